@@ -1,0 +1,293 @@
+"""Tensor-level wrappers over the C ABI (include/nmgp_b200.h).
+
+Each function validates its arguments (CUDA, float64/int32, contiguous), allocates
+outputs with torch (device memory is torch's job; arithmetic is not) and launches the
+sm_100a kernel on torch's current stream.  CPU tensors are rejected: there is no
+fallback path.  ``oracle/kernel_specs.py`` holds a same-named CPU specification of
+every function for the tests.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_double, c_int, c_int64, c_void_p
+
+import torch
+
+from ._lib import check, lib
+
+F64 = torch.float64
+MODE_W, MODE_U = 0, 1
+MAX_Q = 112
+
+
+def _d(t: torch.Tensor) -> c_void_p:
+    if not (t.is_cuda and t.dtype == F64 and t.is_contiguous()):
+        raise TypeError("expected a contiguous CUDA float64 tensor, got %s %s contiguous=%s (no CPU fallback)"
+                        % (t.device, t.dtype, t.is_contiguous()))
+    return c_void_p(t.data_ptr())
+
+
+def _i(t: torch.Tensor) -> c_void_p:
+    if not (t.is_cuda and t.dtype == torch.int32 and t.is_contiguous()):
+        raise TypeError("expected a contiguous CUDA int32 tensor, got %s %s" % (t.device, t.dtype))
+    return c_void_p(t.data_ptr())
+
+
+def _stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _empty(ref, *shape):
+    return torch.empty(*shape, dtype=F64, device=ref.device)
+
+
+def _zeros(ref, *shape):
+    return torch.zeros(*shape, dtype=F64, device=ref.device)
+
+
+def _checkQ(Q):
+    if Q > MAX_Q:
+        raise ValueError("number of inducing points Q=%d exceeds the supported maximum %d" % (Q, MAX_Q))
+
+
+# ---------------------------------------------------------------------------------------------
+def hyper_exp(logs):
+    out = torch.empty_like(logs)
+    check(lib().nmgp_hyper_exp(_d(logs), _d(out), c_int(logs.numel()), _stream()), "nmgp_hyper_exp")
+    return out
+
+
+def segment_offsets(I, D):
+    seg = torch.empty(D + 1, dtype=torch.int32, device=I.device)
+    check(lib().nmgp_segment_offsets(_i(I), _i(seg), c_int64(I.numel()), c_int(D), _stream()), "nmgp_segment_offsets")
+    return seg
+
+
+def tril_syrk_fwd(S):
+    nb, Q, _ = S.shape
+    _checkQ(Q)
+    out = torch.empty_like(S)
+    check(lib().nmgp_tril_syrk_fwd(_d(S), _d(out), c_int(nb), c_int(Q), _stream()), "nmgp_tril_syrk_fwd")
+    return out
+
+
+def tril_syrk_bwd(S, SigBar):
+    nb, Q, _ = S.shape
+    out = torch.empty_like(S)
+    check(lib().nmgp_tril_syrk_bwd(_d(S), _d(SigBar), _d(out), c_int(nb), c_int(Q), _stream()), "nmgp_tril_syrk_bwd")
+    return out
+
+
+def potrf(A, jitter=0.0):
+    """Batched lower Cholesky of A + jitter*I with hld = sum(log(diag)).  Raises RuntimeError
+    (like torch.cholesky in the reference) when a matrix is not positive definite."""
+    nb, Q, _ = A.shape
+    _checkQ(Q)
+    C = torch.empty_like(A)
+    hld = _empty(A, nb)
+    info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    check(lib().nmgp_potrf_batched(_d(A), c_double(jitter), _d(C), _d(hld), _i(info), c_int(nb), c_int(Q), _stream()),
+          "nmgp_potrf_batched")
+    bad = int(info.item())
+    if bad != 0:
+        raise RuntimeError("cholesky: matrix %d of the batch is not positive-definite" % (bad - 1))
+    return C, hld
+
+
+def potrf_bwd(C, Cbar, hldbar):
+    nb, Q, _ = C.shape
+    out = torch.empty_like(C)
+    check(lib().nmgp_potrf_bwd_batched(_d(C), _d(Cbar), _d(hldbar), _d(out), c_int(nb), c_int(Q), _stream()),
+          "nmgp_potrf_bwd_batched")
+    return out
+
+
+def kl_fwd(CS, hldS, mu, R, hldR, exact=False):
+    if exact:
+        raise NotImplementedError("exact KL (flagged variant of quirk q10) is not built yet")
+    nb, Q, _ = CS.shape
+    np_ = R.shape[0]
+    kl = _empty(CS, np_, nb)
+    t = _empty(CS, np_, nb, Q)
+    check(lib().nmgp_kl_fwd(_d(CS), _d(hldS), _d(mu), _d(R), _d(hldR), _d(kl), _d(t),
+                            c_int(np_), c_int(nb), c_int(Q), _stream()), "nmgp_kl_fwd")
+    return kl, t
+
+
+def kl_bwd(klbar, CS, mu, R, t, exact=False):
+    nb, Q, _ = CS.shape
+    np_ = R.shape[0]
+    CSbar = torch.empty_like(CS)
+    hldSbar = _empty(CS, nb)
+    mubar = _empty(CS, nb, Q)
+    Rbar = _zeros(CS, np_, Q, Q)
+    hldRbar = _empty(CS, np_)
+    work = _empty(CS, np_, nb, Q)
+    check(lib().nmgp_kl_bwd(_d(klbar), _d(CS), _d(mu), _d(R), _d(t), _d(CSbar), _d(hldSbar), _d(mubar), _d(Rbar),
+                            _d(hldRbar), _d(work), c_int(np_), c_int(nb), c_int(Q), _stream()), "nmgp_kl_bwd")
+    return CSbar, hldSbar, mubar, Rbar, hldRbar
+
+
+def rbf_build_fwd(x, z, hyp, is2, ilen, jitter=0.0):
+    B, Q = x.numel(), z.numel()
+    K = _empty(x, B, Q)
+    check(lib().nmgp_rbf_build_fwd(_d(x), _d(z), _d(hyp), c_int(is2), c_int(ilen), c_double(jitter), _d(K),
+                                   c_int64(B), c_int(Q), _stream()), "nmgp_rbf_build_fwd")
+    return K
+
+
+def rbf_build_bwd(x, z, hyp, is2, ilen, Kbar, ghyp):
+    B, Q = x.numel(), z.numel()
+    check(lib().nmgp_rbf_build_bwd(_d(x), _d(z), _d(hyp), c_int(is2), c_int(ilen), _d(Kbar), _d(ghyp),
+                                   c_int64(B), c_int(Q), _stream()), "nmgp_rbf_build_bwd")
+
+
+def gibbs_build_fwd(x, z, ellx, ellz, jitter=0.0):
+    ns, B = ellx.shape
+    Q = z.numel()
+    K = _empty(x, ns, B, Q)
+    check(lib().nmgp_gibbs_build_fwd(_d(x), _d(z), _d(ellx), _d(ellz), c_double(jitter), _d(K),
+                                     c_int(ns), c_int64(B), c_int(Q), _stream()), "nmgp_gibbs_build_fwd")
+    return K
+
+
+def gibbs_build_bwd(x, z, ellx, ellz, Kbar, ellxbar, ellzbar):
+    ns, B = ellx.shape
+    Q = z.numel()
+    check(lib().nmgp_gibbs_build_bwd(_d(x), _d(z), _d(ellx), _d(ellz), _d(Kbar), _d(ellxbar), _d(ellzbar),
+                                     c_int(ns), c_int64(B), c_int(Q), _stream()), "nmgp_gibbs_build_bwd")
+
+
+def solve_rows_fwd(K, R):
+    ns, B, Q = K.shape
+    _checkQ(Q)
+    P = torch.empty_like(K)
+    c = _empty(K, ns, B)
+    check(lib().nmgp_solve_rows_fwd(_d(K), _d(R), _d(P), _d(c), c_int(ns), c_int64(B), c_int(Q), _stream()),
+          "nmgp_solve_rows_fwd")
+    return P, c
+
+
+def solve_rows_bwd(Pbar, cbar, K, P, R, Abar):
+    ns, B, Q = K.shape
+    Kbar = torch.empty_like(K)
+    check(lib().nmgp_solve_rows_bwd(_d(Pbar), _d(cbar), _d(K), _d(P), _d(R), _d(Kbar), _d(Abar),
+                                    c_int(ns), c_int64(B), c_int(Q), _stream()), "nmgp_solve_rows_bwd")
+    return Kbar
+
+
+def quadform_fwd(Pa, Pb, I, Sig, Mu, D, mode, seg=None):
+    ns, B, Q = Pa.shape
+    seg = segment_offsets(I, D) if seg is None else seg
+    q = _zeros(Pa, ns, B, D)
+    m = _zeros(Pa, ns, B, D)
+    check(lib().nmgp_quadform_fwd(_d(Pa), _d(Pb), _i(I), _i(seg), _d(Sig), _d(Mu), _d(q), _d(m),
+                                  c_int(ns), c_int64(B), c_int(Q), c_int(D), c_int(mode), _stream()), "nmgp_quadform_fwd")
+    return q, m
+
+
+def quadform_bwd(Pa, Pb, I, Sig, Mu, qbar, mbar, mode, seg=None):
+    ns, B, Q = Pa.shape
+    D = qbar.shape[-1]
+    seg = segment_offsets(I, D) if seg is None else seg
+    Pabar = torch.empty_like(Pa)
+    Pbbar = torch.empty_like(Pa) if mode == MODE_U else Pabar
+    check(lib().nmgp_quadform_bwd(_d(Pa), _d(Pb), _i(I), _i(seg), _d(Sig), _d(Mu), _d(qbar), _d(mbar),
+                                  _d(Pabar), _d(Pbbar), c_int(ns), c_int64(B), c_int(Q), c_int(D), c_int(mode),
+                                  _stream()), "nmgp_quadform_bwd")
+    return Pabar, (Pbbar if mode == MODE_U else None)
+
+
+def weighted_gram(Pa, Pb, I, qbar, mbar, mode, SigBar, MuBar, seg=None):
+    ns, B, Q = Pa.shape
+    D = qbar.shape[-1]
+    seg = segment_offsets(I, D) if seg is None else seg
+    check(lib().nmgp_weighted_gram(_d(Pa), _d(Pb), _i(I), _i(seg), _d(qbar), _d(mbar), _d(SigBar), _d(MuBar),
+                                   c_int(ns), c_int64(B), c_int(Q), c_int(D), c_int(mode), _stream()), "nmgp_weighted_gram")
+
+
+def sample_v_fwd(mu_v, Cv, zv):
+    S, Q = zv.shape
+    v = torch.empty_like(zv)
+    ellz = torch.empty_like(zv)
+    check(lib().nmgp_sample_v_fwd(_d(mu_v), _d(Cv), _d(zv), _d(v), _d(ellz), c_int(S), c_int(Q), _stream()),
+          "nmgp_sample_v_fwd")
+    return v, ellz
+
+
+def sample_v_bwd(ellzbar, vbar, ellz, zv, mu_v_bar, Cvbar):
+    S, Q = zv.shape
+    check(lib().nmgp_sample_v_bwd(_d(ellzbar), _d(vbar), _d(ellz), _d(zv), _d(mu_v_bar), _d(Cvbar),
+                                  c_int(S), c_int(Q), _stream()), "nmgp_sample_v_bwd")
+
+
+def ell_sd_fwd(c_ell, hyp):
+    sd = torch.empty_like(c_ell)
+    check(lib().nmgp_ell_sd_fwd(_d(c_ell), _d(hyp), _d(sd), c_int64(c_ell.numel()), _stream()), "nmgp_ell_sd_fwd")
+    return sd
+
+
+def ell_sd_bwd(sdbar, sd, hyp, ghyp):
+    cbar = torch.empty_like(sd)
+    check(lib().nmgp_ell_sd_bwd(_d(sdbar), _d(sd), _d(hyp), _d(ghyp), _d(cbar), c_int64(sd.numel()), _stream()),
+          "nmgp_ell_sd_bwd")
+    return cbar
+
+
+def ell_rows_fwd(Pell, v, zell, sdell):
+    ns, Q = v.shape
+    B = Pell.shape[0]
+    ellx = _empty(Pell, ns, B)
+    check(lib().nmgp_ell_rows_fwd(_d(Pell), _d(v), _d(zell), _d(sdell), _d(ellx), c_int(ns), c_int64(B), c_int(Q),
+                                  _stream()), "nmgp_ell_rows_fwd")
+    return ellx
+
+
+def ell_rows_bwd(ellxbar, ellx, Pell, v, zell, vbar, Pellbar, sdbar):
+    ns, Q = v.shape
+    B = Pell.shape[0]
+    check(lib().nmgp_ell_rows_bwd(_d(ellxbar), _d(ellx), _d(Pell), _d(v), _d(zell), _d(vbar), _d(Pellbar), _d(sdbar),
+                                  c_int(ns), c_int64(B), c_int(Q), _stream()), "nmgp_ell_rows_bwd")
+
+
+def coef_sd_fwd(q, cL0, cL1, I, hyp):
+    B, D = q.shape
+    sd = torch.empty_like(q)
+    check(lib().nmgp_coef_sd_fwd(_d(q), _d(cL0), _d(cL1), _i(I), _d(hyp), _d(sd), c_int64(B), c_int(D), _stream()),
+          "nmgp_coef_sd_fwd")
+    return sd
+
+
+def coef_sd_bwd(sdbar, sd, I, hyp, ghyp):
+    B, D = sd.shape
+    qbar = torch.empty_like(sd)
+    cL0bar = _empty(sd, B)
+    cL1bar = _empty(sd, B)
+    check(lib().nmgp_coef_sd_bwd(_d(sdbar), _d(sd), _i(I), _d(hyp), _d(ghyp), _d(qbar), _d(cL0bar), _d(cL1bar),
+                                 c_int64(B), c_int(D), _stream()), "nmgp_coef_sd_bwd")
+    return qbar, cL0bar, cL1bar
+
+
+def coef_sample_fwd(m, sd, zL, I):
+    ns, B, D = zL.shape
+    l = torch.empty_like(zL)
+    check(lib().nmgp_coef_sample_fwd(_d(m), _d(sd), _d(zL), _i(I), _d(l), c_int(ns), c_int64(B), c_int(D), _stream()),
+          "nmgp_coef_sample_fwd")
+    return l
+
+
+def coef_sample_bwd(lbar, l, zL, I, mbar, sdbar):
+    ns, B, D = zL.shape
+    check(lib().nmgp_coef_sample_bwd(_d(lbar), _d(l), _d(zL), _i(I), _d(mbar), _d(sdbar), c_int(ns), c_int64(B),
+                                     c_int(D), _stream()), "nmgp_coef_sample_bwd")
+
+
+def lik_rows(l, mg, qg, cG, y, I, hyp, scale, Rsum, ghyp):
+    ns, B, D = l.shape
+    lbar = torch.empty_like(l); mgbar = torch.empty_like(l); qgbar = torch.empty_like(l)
+    cGbar = _empty(l, ns, B)
+    Rsum.zero_()
+    check(lib().nmgp_lik_rows(_d(l), _d(mg), _d(qg), _d(cG), _d(y), _i(I), _d(hyp), c_double(scale), _d(Rsum), _d(ghyp),
+                              _d(lbar), _d(mgbar), _d(qgbar), _d(cGbar), c_int(ns), c_int64(B), c_int(D), _stream()),
+          "nmgp_lik_rows")
+    return lbar, mgbar, qgbar, cGbar

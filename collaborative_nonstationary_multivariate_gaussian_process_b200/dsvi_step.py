@@ -1,0 +1,206 @@
+"""One DSVI iteration (S-sample reparameterised -ELBO and its hand-written gradient).
+
+This is the B200 restatement of ``NMGP.forward`` + ``loss.backward`` of the reference
+(code/nmgp_dsvi.py:157-301 and :847), de-duplicated as described in DESIGN.md:
+
+* the four distinct inducing systems (tilde-ell, L0, L1, Gibbs) are factored once
+  (the reference re-solves them D(D+1)/2 + 2 times, code/utils.py:119,142,230);
+* the coefficient statistics are evaluated only for the (row n, j <= I[n]) pairs the
+  reference keeps at code/nmgp_dsvi.py:238;
+* the latent statistics only for j <= I[n] (the others are multiplied by zero at :255-258);
+* every adjoint is written out -- no autograd graph exists.
+
+Host code here only sequences kernels from ``_ops`` (the C-ABI wrappers) and moves
+buffers; all arithmetic on B-, Q^2- or S-sized data happens in the CUDA kernels.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import _ops as ops
+
+EPS = 1e-4                                   # tridiagonal_jitter, code/utils.py:7
+HYPER_ORDER = ("sigma2_tildeell_log", "length_scales_tildeell_log", "sigma2_L0_log",
+               "length_scales_L0_log", "sigma2_L1_log", "length_scales_L1_log", "sigma2_err_log")
+H_S2_ELL, H_LEN_ELL, H_S2_L0, H_LEN_L0, H_S2_L1, H_LEN_L1, H_S2_ERR = range(7)
+MODE_W, MODE_U = 0, 1
+PARAM_NAMES = ("mu_W", "sqrt_W", "mu_v", "sqrt_v", "mu_U", "sqrt_U") + HYPER_ORDER
+
+_pair_cache: Dict[tuple, torch.Tensor] = {}
+
+
+def packed_pair_index(D: int, device) -> torch.Tensor:
+    """Flat indices i*D+j of the live coefficient pairs, packed as: the D diagonal
+    pairs (i,i) first, then the strictly-lower pairs (i,j<i) row-major
+    (slot D + i(i-1)/2 + j).  Pairs with j > i never receive gradient (quirk q8)."""
+    key = (D, str(device))
+    if key not in _pair_cache:
+        idx = [i * D + i for i in range(D)]
+        idx += [i * D + j for i in range(D) for j in range(i)]
+        _pair_cache[key] = torch.tensor(idx, dtype=torch.int64, device=device)
+    return _pair_cache[key]
+
+
+def default_sample_chunk(S: int, B: int, Q: int, D: int, budget_bytes: float = 6e9) -> int:
+    """Samples processed per pass so the [ns,B,*] temporaries stay within a budget."""
+    per_sample = 8.0 * B * (5 * Q + 7 * D + 8)
+    return max(1, min(S, int(budget_bytes // max(per_sample, 1.0))))
+
+
+def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: torch.Tensor,
+              I: torch.Tensor, N: int, z_v: torch.Tensor, z_ell: torch.Tensor, z_L: torch.Tensor, *,
+              B_total: Optional[int] = None, kl_weight: float = 1.0,
+              sample_chunk: Optional[int] = None, want_grads: bool = True):
+    """Returns (loss, grads) for rows (x, y, I) -- I sorted ascending, int32 -- and noise
+    z_v [S,Q], z_ell [S,B], z_L [S,B,D] (z_L[s,n,j] is the draw for pair (I[n], j)).
+
+    Under row sharding (several ranks each holding a slice of the minibatch) pass the
+    global row count as ``B_total`` and ``kl_weight = 1/world_size``; the sum over
+    ranks of the returned loss/grads is then the full-batch value.
+    """
+    D, Q = p["mu_W"].shape
+    B = x.shape[0]
+    S = z_v.shape[0]
+    dev = x.device
+    f64 = torch.float64
+    scale = float(N) / float((B if B_total is None else B_total) * S)
+    zeros = lambda *s: torch.zeros(*s, dtype=f64, device=dev)
+    ns_max = sample_chunk or default_sample_chunk(S, B, Q, D)
+
+    hyp = ops.hyper_exp(torch.stack([p[k].detach().reshape(()) for k in HYPER_ORDER]))
+    ghyp = zeros(7)
+
+    # ---- variational covariances: Sigma = tril(S) tril(S)^T, C = chol(Sigma + eps I) -------
+    flat = packed_pair_index(D, dev)
+    npair = flat.shape[0]
+    SU = p["sqrt_U"].detach().reshape(D * D, Q, Q).index_select(0, flat)
+    muU = p["mu_U"].detach().reshape(D * D, Q).index_select(0, flat)
+    sqrt_v = p["sqrt_v"].detach().reshape(1, Q, Q)
+    sqrt_W = p["sqrt_W"].detach()
+    mu_W = p["mu_W"].detach()
+    mu_v = p["mu_v"].detach()
+    Sig_v = ops.tril_syrk_fwd(sqrt_v)
+    Sig_W = ops.tril_syrk_fwd(sqrt_W)
+    Sig_U = ops.tril_syrk_fwd(SU)
+    C_v, hld_v = ops.potrf(Sig_v, EPS)
+    C_W, hld_W = ops.potrf(Sig_W, EPS)
+    C_U, hld_U = ops.potrf(Sig_U, EPS)
+
+    # ---- the three stationary inducing systems ------------------------------------------------
+    sysm = {}
+    for name, is2, ilen in (("ell", H_S2_ELL, H_LEN_ELL), ("L0", H_S2_L0, H_LEN_L0), ("L1", H_S2_L1, H_LEN_L1)):
+        A = ops.rbf_build_fwd(Z, Z, hyp, is2, ilen, EPS).reshape(1, Q, Q)
+        R, hldR = ops.potrf(A, 0.0)
+        K12 = ops.rbf_build_fwd(x, Z, hyp, is2, ilen, 0.0).reshape(1, B, Q)
+        P, c = ops.solve_rows_fwd(K12, R)
+        sysm[name] = dict(R=R, hldR=hldR, K12=K12, P=P, c=c, is2=is2, ilen=ilen)
+    sd_ell = ops.ell_sd_fwd(sysm["ell"]["c"][0], hyp)
+    seg = ops.segment_offsets(I, D)
+    qU, mU = ops.quadform_fwd(sysm["L0"]["P"], sysm["L1"]["P"], I, Sig_U, muU, D, MODE_U, seg=seg)
+    sdU = ops.coef_sd_fwd(qU[0], sysm["L0"]["c"][0], sysm["L1"]["c"][0], I, hyp)
+
+    # ---- per-sample inducing draws, Gibbs K22 factor -----------------------------------------
+    v, ellZ = ops.sample_v_fwd(mu_v, C_v[0], z_v)
+    A_G = ops.gibbs_build_fwd(Z, Z, ellZ, ellZ, EPS)
+    R_G, hld_G = ops.potrf(A_G, 0.0)
+
+    # ---- KL terms (reference-exact form, quirk q10) and their cotangents ----------------------
+    kl_W, t_W = ops.kl_fwd(C_W, hld_W, mu_W, R_G, hld_G)
+    kl_v, t_v = ops.kl_fwd(C_v, hld_v, mu_v.reshape(1, Q), sysm["ell"]["R"], sysm["ell"]["hldR"])
+    kl_U1, t_U1 = ops.kl_fwd(C_U[:D], hld_U[:D], muU[:D], sysm["L1"]["R"], sysm["L1"]["hldR"])
+    if npair > D:
+        kl_U0, t_U0 = ops.kl_fwd(C_U[D:], hld_U[D:], muU[D:], sysm["L0"]["R"], sysm["L0"]["hldR"])
+        klU0_sum = kl_U0.sum()
+    else:
+        klU0_sum = zeros(())
+    loss_kl = kl_weight * (kl_W.sum() / S + kl_v.sum() + kl_U1.sum() + klU0_sum)
+
+    full = lambda shape, val: torch.full(shape, val, dtype=f64, device=dev)
+    CWbar, hldWbar, muWbar, RGbar, hldGbar = ops.kl_bwd(full((S, D), kl_weight / S), C_W, mu_W, R_G, t_W)
+    Cvbar, hldvbar, muvbar, Rellbar, hldRellbar = ops.kl_bwd(full((1, 1), kl_weight), C_v, mu_v.reshape(1, Q),
+                                                             sysm["ell"]["R"], t_v)
+    CUbar = zeros(npair, Q, Q); hldUbar = zeros(npair); muUbar = zeros(npair, Q)
+    a, b, c_, RL1bar, hldRL1bar = ops.kl_bwd(full((1, D), kl_weight), C_U[:D], muU[:D], sysm["L1"]["R"], t_U1)
+    CUbar[:D] = a; hldUbar[:D] = b; muUbar[:D] = c_
+    if npair > D:
+        a, b, c_, RL0bar, hldRL0bar = ops.kl_bwd(full((1, npair - D), kl_weight), C_U[D:], muU[D:],
+                                                 sysm["L0"]["R"], t_U0)
+        CUbar[D:] = a; hldUbar[D:] = b; muUbar[D:] = c_
+    else:
+        RL0bar = zeros(1, Q, Q); hldRL0bar = zeros(1)
+    muvbar = muvbar.reshape(Q).clone()
+
+    # ---- accumulators filled by the sample loop ------------------------------------------------
+    SigWbar = zeros(D, Q, Q)
+    Pellbar = zeros(B, Q); sdellbar = zeros(B)
+    mUbar = zeros(B, D); sdUbar = zeros(B, D)
+    AGbar = zeros(S, Q, Q); ellZbar = zeros(S, Q); vbar = zeros(S, Q)
+    Rsum = zeros(S)
+    P_ell = sysm["ell"]["P"][0]
+
+    for s0 in range(0, S, ns_max):
+        sl = slice(s0, min(S, s0 + ns_max))
+        ellx = ops.ell_rows_fwd(P_ell, v[sl], z_ell[sl], sd_ell)
+        l = ops.coef_sample_fwd(mU[0], sdU, z_L[sl], I)
+        KG = ops.gibbs_build_fwd(x, Z, ellx, ellZ[sl], 0.0)
+        PG, cG = ops.solve_rows_fwd(KG, R_G[sl])
+        qg, mg = ops.quadform_fwd(PG, PG, I, Sig_W, mu_W, D, MODE_W, seg=seg)
+        lbar, mgbar, qgbar, cGbar = ops.lik_rows(l, mg, qg, cG, y, I, hyp, scale, Rsum[sl], ghyp)
+        if not want_grads:
+            continue
+        PGbar, _ = ops.quadform_bwd(PG, PG, I, Sig_W, mu_W, qgbar, mgbar, MODE_W, seg=seg)
+        ops.weighted_gram(PG, PG, I, qgbar, mgbar, MODE_W, SigWbar, muWbar, seg=seg)
+        KGbar = ops.solve_rows_bwd(PGbar, cGbar, KG, PG, R_G[sl], AGbar[sl])
+        ellxbar = torch.empty_like(ellx)
+        ops.gibbs_build_bwd(x, Z, ellx, ellZ[sl], KGbar, ellxbar, ellZbar[sl])
+        ops.ell_rows_bwd(ellxbar, ellx, P_ell, v[sl], z_ell[sl], vbar[sl], Pellbar, sdellbar)
+        ops.coef_sample_bwd(lbar, l, z_L[sl], I, mUbar, sdUbar)
+
+    loss = loss_kl - scale * Rsum.sum()
+    if not want_grads:
+        return loss, None
+
+    # ---- backward of the per-sample small stage ------------------------------------------------
+    AGbar += ops.potrf_bwd(R_G, RGbar, hldGbar)
+    tmp = torch.empty_like(ellZbar)
+    ops.gibbs_build_bwd(Z, Z, ellZ, ellZ, AGbar, tmp, ellZbar)
+    ellZbar += tmp
+    Cvbar = Cvbar.reshape(Q, Q).clone()
+    ops.sample_v_bwd(ellZbar, vbar, ellZ, z_v, muvbar, Cvbar)
+
+    # ---- backward of the sample-independent coefficient statistics ------------------------------
+    qUbar, cL0bar, cL1bar = ops.coef_sd_bwd(sdUbar, sdU, I, hyp, ghyp)
+    PL0bar, PL1bar = ops.quadform_bwd(sysm["L0"]["P"], sysm["L1"]["P"], I, Sig_U, muU,
+                                      qUbar.reshape(1, B, D), mUbar.reshape(1, B, D), MODE_U, seg=seg)
+    SigUbar = zeros(npair, Q, Q)
+    ops.weighted_gram(sysm["L0"]["P"], sysm["L1"]["P"], I, qUbar.reshape(1, B, D), mUbar.reshape(1, B, D),
+                      MODE_U, SigUbar, muUbar, seg=seg)
+    cellbar = ops.ell_sd_bwd(sdellbar, sd_ell, hyp, ghyp)
+
+    for name, Pbar, cbar, Rbar, hldRbar in (("ell", Pellbar.reshape(1, B, Q), cellbar.reshape(1, B), Rellbar, hldRellbar),
+                                            ("L0", PL0bar, cL0bar.reshape(1, B), RL0bar, hldRL0bar),
+                                            ("L1", PL1bar, cL1bar.reshape(1, B), RL1bar, hldRL1bar)):
+        sy = sysm[name]
+        Abar = zeros(1, Q, Q)
+        K12bar = ops.solve_rows_bwd(Pbar, cbar, sy["K12"], sy["P"], sy["R"], Abar)
+        Abar += ops.potrf_bwd(sy["R"], Rbar, hldRbar)
+        ops.rbf_build_bwd(x, Z, hyp, sy["is2"], sy["ilen"], K12bar[0], ghyp)
+        ops.rbf_build_bwd(Z, Z, hyp, sy["is2"], sy["ilen"], Abar[0], ghyp)
+
+    # ---- Cholesky / LL^T adjoints back to the sqrt parameters -----------------------------------
+    g_sqrt_v = ops.tril_syrk_bwd(sqrt_v, ops.potrf_bwd(C_v, Cvbar.reshape(1, Q, Q), hldvbar)).reshape(Q, Q)
+    SigWbar += ops.potrf_bwd(C_W, CWbar, hldWbar)
+    g_sqrt_W = ops.tril_syrk_bwd(sqrt_W, SigWbar)
+    SigUbar += ops.potrf_bwd(C_U, CUbar, hldUbar)
+    g_SU = ops.tril_syrk_bwd(SU, SigUbar)
+    g_sqrt_U = zeros(D * D, Q, Q).index_copy_(0, flat, g_SU).reshape(D, D, Q, Q)
+    g_mu_U = zeros(D * D, Q).index_copy_(0, flat, muUbar).reshape(D, D, Q)
+
+    grads = {"mu_W": muWbar, "sqrt_W": g_sqrt_W, "mu_v": muvbar, "sqrt_v": g_sqrt_v,
+             "mu_U": g_mu_U, "sqrt_U": g_sqrt_U}
+    for i, k in enumerate(HYPER_ORDER):
+        grads[k] = ghyp[i]
+    return loss, grads

@@ -1,0 +1,317 @@
+"""Per-kernel CPU specifications -- TEST INFRASTRUCTURE ONLY.
+
+One plain torch-CPU float64 function per entry point of the C ABI
+(include/nmgp_b200.h), with the same tensor-level signature as the thin
+wrappers in ``collaborative_nonstationary_multivariate_gaussian_process_b200/_ops.py``.
+They serve two purposes:
+
+* GPU unit tests compare every CUDA kernel against its spec on seeded inputs;
+* CPU tests monkeypatch ``_ops`` with these functions to check the hand-written
+  adjoint orchestration (``dsvi_step.py``) against the autograd oracle without a GPU.
+
+The product never imports this module.  Formulas follow SURVEY.md Appendix A
+(derived from code/utils.py and code/nmgp_dsvi.py of the reference).
+"""
+import torch
+
+F64 = torch.float64
+EPS = 1e-4                      # code/utils.py:7
+MODE_W, MODE_U = 0, 1
+# hyper-parameter slots (values = exp of the reference's *_log parameters)
+H_S2_ELL, H_LEN_ELL, H_S2_L0, H_LEN_L0, H_S2_L1, H_LEN_L1, H_S2_ERR = range(7)
+
+
+def hyper_exp(logs):
+    return torch.exp(logs)
+
+
+def segment_offsets(I, D):
+    """seg[d] = first row with I >= d (rows sorted by output id); seg[D] = B."""
+    return torch.searchsorted(I.long().contiguous(), torch.arange(D + 1)).to(torch.int32)
+
+
+# ---- small batched Q x Q ---------------------------------------------------------------
+def tril_syrk_fwd(S):
+    L = torch.tril(S)
+    return L @ L.transpose(-1, -2)
+
+
+def tril_syrk_bwd(S, SigBar):
+    L = torch.tril(S)
+    return torch.tril((SigBar + SigBar.transpose(-1, -2)) @ L)
+
+
+def potrf(A, jitter=0.0):
+    n = A.shape[-1]
+    C = torch.linalg.cholesky(A + jitter * torch.eye(n, dtype=F64))
+    return C, C.diagonal(dim1=-2, dim2=-1).log().sum(-1)
+
+
+def potrf_bwd(C, Cbar, hldbar):
+    """Abar (symmetric) for C = chol(A); hld = sum log diag C folded in."""
+    Cb = torch.tril(Cbar) + torch.diag_embed(hldbar.unsqueeze(-1) / C.diagonal(dim1=-2, dim2=-1))
+    Pm = torch.tril(C.transpose(-1, -2) @ Cb)
+    Pm = Pm - 0.5 * torch.diag_embed(Pm.diagonal(dim1=-2, dim2=-1))
+    X = torch.linalg.solve_triangular(C.transpose(-1, -2), Pm, upper=True)             # C^-T Phi
+    Y = torch.linalg.solve_triangular(C.transpose(-1, -2), X.transpose(-1, -2), upper=True)  # C^-T (C^-T Phi)^T
+    Ab = Y.transpose(-1, -2)                                                            # C^-T Phi C^-1
+    return 0.5 * (Ab + Ab.transpose(-1, -2))
+
+
+def kl_fwd(CS, hldS, mu, R, hldR, exact=False):
+    """kl[p,b] = hldR[p] - hldS[b] + 0.5 (term2 + ||R_p^-1 mu_b||^2 - Q); term2 is the
+    reference's diagonal-only form (quirk q10) unless exact."""
+    np_, nb, Q = R.shape[0], CS.shape[0], CS.shape[-1]
+    # t[p,b,:] = R_p^-1 mu_b
+    t = torch.linalg.solve_triangular(R, mu.t().unsqueeze(0).expand(np_, Q, nb), upper=False).transpose(1, 2)
+    term3 = (t * t).sum(-1)
+    if exact:
+        sol = torch.linalg.solve_triangular(R.unsqueeze(1), CS.unsqueeze(0), upper=False)
+        term2 = (sol * sol).sum((-1, -2))
+    else:
+        rs = (CS * CS).sum(-1)                                  # [nb,Q]
+        w = 1.0 / R.diagonal(dim1=-2, dim2=-1) ** 2             # [np,Q]
+        term2 = w @ rs.t()
+    kl = hldR.unsqueeze(1) - hldS.unsqueeze(0) + 0.5 * (term2 + term3 - Q)
+    return kl, t.contiguous()
+
+
+def kl_bwd(klbar, CS, mu, R, t, exact=False):
+    assert not exact, "exact-KL adjoint is not part of the reference path"
+    np_, nb, Q = R.shape[0], CS.shape[0], CS.shape[-1]
+    d = R.diagonal(dim1=-2, dim2=-1)                            # [np,Q]
+    w = 1.0 / d ** 2
+    rs = (CS * CS).sum(-1)
+    hldRbar = klbar.sum(1)
+    hldSbar = -klbar.sum(0)
+    # term2: 0.5 * sum_a w[p,a] rs[b,a]
+    wbar = 0.5 * klbar @ rs                                     # [np,Q]
+    rsbar = 0.5 * klbar.t() @ w                                 # [nb,Q]
+    CSbar = torch.tril(2.0 * rsbar.unsqueeze(-1) * CS)
+    Rbar = torch.diag_embed(wbar * (-2.0) / d ** 3)
+    # term3: 0.5 * ||t||^2, t = R^-1 mu
+    tbar = klbar.unsqueeze(-1) * t                              # [np,nb,Q]
+    mb = torch.linalg.solve_triangular(R.transpose(-1, -2), tbar.transpose(1, 2), upper=True)   # [np,Q,nb] = R^-T tbar
+    mubar = mb.sum(0).t().contiguous()
+    Rbar = Rbar - torch.tril(mb @ t)                            # -sum_b (R^-T tbar_b) t_b^T
+    return CSbar, hldSbar, mubar, Rbar, hldRbar
+
+
+# ---- kernel builds ---------------------------------------------------------------------
+def rbf_build_fwd(x, z, hyp, is2, ilen, jitter=0.0):
+    r = x.view(-1, 1) / hyp[ilen] - z.view(1, -1) / hyp[ilen]
+    K = hyp[is2] * torch.exp(-0.5 * r * r)
+    if jitter:
+        K = K + jitter * torch.eye(K.shape[0], K.shape[1], dtype=F64)
+    return K
+
+
+def rbf_build_bwd(x, z, hyp, is2, ilen, Kbar, ghyp):
+    r = x.view(-1, 1) / hyp[ilen] - z.view(1, -1) / hyp[ilen]
+    K = hyp[is2] * torch.exp(-0.5 * r * r)
+    ghyp[is2] += (Kbar * K).sum()
+    ghyp[ilen] += (Kbar * K * r * r).sum()
+
+
+def gibbs_build_fwd(x, z, ellx, ellz, jitter=0.0):
+    r2 = (x.view(1, -1, 1) - z.view(1, 1, -1)) ** 2
+    a = ellx.unsqueeze(2); b = ellz.unsqueeze(1)
+    den = a * a + b * b
+    K = torch.sqrt(2 * (a * b) / den) * torch.exp(-r2 / den)
+    if jitter:
+        K = K + jitter * torch.eye(K.shape[1], K.shape[2], dtype=F64)
+    return K
+
+
+def gibbs_build_bwd(x, z, ellx, ellz, Kbar, ellxbar, ellzbar):
+    """ellxbar[ns,B] = ; ellzbar[ns,Q] += (cotangents w.r.t. ell itself, not its log)."""
+    r2 = (x.view(1, -1, 1) - z.view(1, 1, -1)) ** 2
+    a = ellx.unsqueeze(2); b = ellz.unsqueeze(1)
+    den = a * a + b * b
+    K = torch.sqrt(2 * (a * b) / den) * torch.exp(-r2 / den)
+    G = Kbar * K
+    da = G * (0.5 / a - a / den + 2 * a * r2 / den ** 2)
+    db = G * (0.5 / b - b / den + 2 * b * r2 / den ** 2)
+    ellxbar.copy_(da.sum(2))
+    ellzbar += db.sum(1)
+
+
+# ---- row solves through the Cholesky factor of K22 + eps I ---------------------------------
+def solve_rows_fwd(K, R):
+    """P = K A^-1 (A = R R^T), c = rowsum(P o K)."""
+    Y = torch.linalg.solve_triangular(R, K.transpose(1, 2), upper=False)
+    P = torch.linalg.solve_triangular(R.transpose(1, 2), Y, upper=True).transpose(1, 2).contiguous()
+    return P, (P * K).sum(-1)
+
+
+def solve_rows_bwd(Pbar, cbar, K, P, R, Abar):
+    g = Pbar + cbar.unsqueeze(-1) * K
+    Y = torch.linalg.solve_triangular(R, g.transpose(1, 2), upper=False)
+    t = torch.linalg.solve_triangular(R.transpose(1, 2), Y, upper=True).transpose(1, 2)
+    Abar -= t.transpose(1, 2) @ P
+    return (t + cbar.unsqueeze(-1) * P).contiguous()
+
+
+# ---- quadratic forms through the variational covariances ----------------------------------
+def _pair_index(I, j, mode, D):
+    """Matrix slot used by row n for latent/coefficient j: MODE_W -> j; MODE_U -> the
+    packed pair (I[n], j): diagonal pairs occupy slots 0..D-1, strictly-lower pairs
+    (i, j<i) slot D + i(i-1)/2 + j (see dsvi_step.packed_pair_index)."""
+    Il = I.long()
+    if mode == MODE_W:
+        return torch.full_like(Il, j)
+    return torch.where(Il == j, Il, D + (Il * (Il - 1)) // 2 + j)
+
+
+def quadform_fwd(Pa, Pb, I, Sig, Mu, D, mode, seg=None):
+    ns, B, Q = Pa.shape
+    q = torch.zeros(ns, B, D, dtype=F64); m = torch.zeros(ns, B, D, dtype=F64)
+    Il = I.long()
+    for j in range(D):
+        rows = torch.nonzero(Il >= j).view(-1)
+        if rows.numel() == 0:
+            continue
+        idx = _pair_index(I[rows], j, mode, D)
+        p = Pa[:, rows, :]
+        if mode == MODE_U:
+            diag = (Il[rows] == j).view(1, -1, 1)
+            p = torch.where(diag, Pb[:, rows, :], p)
+        S = Sig[idx]                                           # [r,Q,Q]
+        V = torch.einsum("sra,rab->srb", p, S)
+        q[:, rows, j] = (V * p).sum(-1)
+        m[:, rows, j] = (p * Mu[idx].unsqueeze(0)).sum(-1)
+    return q, m
+
+
+def quadform_bwd(Pa, Pb, I, Sig, Mu, qbar, mbar, mode, seg=None):
+    ns, B, Q = Pa.shape
+    D = qbar.shape[-1]
+    Pabar = torch.zeros_like(Pa)
+    Pbbar = torch.zeros_like(Pa) if mode == MODE_U else None
+    Il = I.long()
+    for j in range(D):
+        rows = torch.nonzero(Il >= j).view(-1)
+        if rows.numel() == 0:
+            continue
+        idx = _pair_index(I[rows], j, mode, D)
+        p = Pa[:, rows, :]
+        diag = (Il[rows] == j).view(1, -1, 1)
+        if mode == MODE_U:
+            p = torch.where(diag, Pb[:, rows, :], p)
+        S = Sig[idx]
+        V = torch.einsum("sra,rab->srb", p, S + S.transpose(-1, -2))
+        g = qbar[:, rows, j].unsqueeze(-1) * V + mbar[:, rows, j].unsqueeze(-1) * Mu[idx].unsqueeze(0)
+        if mode == MODE_U:
+            Pbbar[:, rows, :] += torch.where(diag, g, torch.zeros_like(g))
+            Pabar[:, rows, :] += torch.where(diag, torch.zeros_like(g), g)
+        else:
+            Pabar[:, rows, :] += g
+    return Pabar, Pbbar
+
+
+def weighted_gram(Pa, Pb, I, qbar, mbar, mode, SigBar, MuBar, seg=None):
+    ns, B, Q = Pa.shape
+    D = qbar.shape[-1]
+    Il = I.long()
+    for j in range(D):
+        rows = torch.nonzero(Il >= j).view(-1)
+        if rows.numel() == 0:
+            continue
+        idx = _pair_index(I[rows], j, mode, D)
+        p = Pa[:, rows, :]
+        if mode == MODE_U:
+            p = torch.where((Il[rows] == j).view(1, -1, 1), Pb[:, rows, :], p)
+        outer = torch.einsum("sr,sra,srb->rab", qbar[:, rows, j], p, p)
+        SigBar.index_add_(0, idx, outer)
+        MuBar.index_add_(0, idx, torch.einsum("sr,sra->ra", mbar[:, rows, j], p))
+
+
+# ---- per-sample small stage -----------------------------------------------------------------
+def sample_v_fwd(mu_v, Cv, zv):
+    v = mu_v.unsqueeze(0) + zv @ Cv.t()
+    return v, torch.exp(v)
+
+
+def sample_v_bwd(ellzbar, vbar, ellz, zv, mu_v_bar, Cvbar):
+    vb = vbar + ellzbar * ellz
+    mu_v_bar += vb.sum(0)
+    Cvbar += torch.tril(vb.t() @ zv)
+
+
+# ---- row-wise element kernels ----------------------------------------------------------------
+def ell_sd_fwd(c_ell, hyp):
+    return torch.sqrt(hyp[H_S2_ELL] - c_ell + EPS)
+
+
+def ell_sd_bwd(sdbar, sd, hyp, ghyp):
+    vb = sdbar / (2.0 * sd)
+    ghyp[H_S2_ELL] += vb.sum() * hyp[H_S2_ELL]
+    return -vb
+
+
+def ell_rows_fwd(Pell, v, zell, sdell):
+    return torch.exp(v @ Pell.t() + zell * sdell.unsqueeze(0))
+
+
+def ell_rows_bwd(ellxbar, ellx, Pell, v, zell, vbar, Pellbar, sdbar):
+    tb = ellxbar * ellx                          # cotangent of tilde-ell  [ns,B]
+    vbar += tb @ Pell
+    Pellbar += tb.t() @ v
+    sdbar += (tb * zell).sum(0)
+
+
+def coef_sd_fwd(q, cL0, cL1, I, hyp):
+    B, D = q.shape
+    j = torch.arange(D).view(1, -1); Il = I.long().view(-1, 1)
+    var = torch.where(j == Il, hyp[H_S2_L1] - cL1.view(-1, 1), hyp[H_S2_L0] - cL0.view(-1, 1)) + q
+    return torch.where(j <= Il, torch.sqrt(var + EPS), torch.zeros_like(var))
+
+
+def coef_sd_bwd(sdbar, sd, I, hyp, ghyp):
+    B, D = sd.shape
+    j = torch.arange(D).view(1, -1); Il = I.long().view(-1, 1)
+    live = j <= Il
+    qbar = torch.where(live, sdbar / (2.0 * torch.where(live, sd, torch.ones_like(sd))), torch.zeros_like(sd))
+    dg = torch.where(j == Il, qbar, torch.zeros_like(qbar)).sum(1)
+    off = qbar.sum(1) - dg
+    ghyp[H_S2_L1] += dg.sum() * hyp[H_S2_L1]
+    ghyp[H_S2_L0] += off.sum() * hyp[H_S2_L0]
+    return qbar, -off, -dg
+
+
+def coef_sample_fwd(m, sd, zL, I):
+    D = m.shape[-1]
+    j = torch.arange(D).view(1, 1, -1); Il = I.long().view(1, -1, 1)
+    raw = m.unsqueeze(0) + zL * sd.unsqueeze(0)
+    l = torch.where(j == Il, torch.exp(raw), raw)
+    return torch.where(j <= Il, l, torch.zeros_like(l))
+
+
+def coef_sample_bwd(lbar, l, zL, I, mbar, sdbar):
+    D = l.shape[-1]
+    j = torch.arange(D).view(1, 1, -1); Il = I.long().view(1, -1, 1)
+    rb = torch.where(j == Il, lbar * l, lbar)
+    rb = torch.where(j <= Il, rb, torch.zeros_like(rb))
+    mbar += rb.sum(0)
+    sdbar += (rb * zL).sum(0)
+
+
+def lik_rows(l, mg, qg, cG, y, I, hyp, scale, Rsum, ghyp):
+    """Expected log-likelihood of a sample chunk and its cotangents (loss = -scale * sum_s R_s + ...)."""
+    ns, B, D = l.shape
+    j = torch.arange(D).view(1, 1, -1); Il = I.long().view(1, -1, 1)
+    live = (j <= Il).to(F64)
+    s2e = hyp[H_S2_ERR]
+    s2g = (1.0 - cG.unsqueeze(-1) + qg) * live
+    F = (l * mg * live).sum(-1)
+    r = y.view(1, -1) - F
+    pen = (l * l * s2g).sum(-1)
+    import math
+    Rsum.copy_((-(r * r) / (2 * s2e) - 0.5 * torch.log(s2e) - math.log(math.sqrt(2 * math.pi))).sum(1) - 0.5 / s2e * pen.sum(1))
+    ghyp[H_S2_ERR] += -scale * ((r * r / (2 * s2e) - 0.5).sum() + 0.5 / s2e * pen.sum())
+    rr = (r / s2e).unsqueeze(-1)
+    mgbar = -scale * rr * l * live
+    qgbar = scale * (0.5 / s2e) * l * l * live
+    cGbar = -qgbar.sum(-1)
+    lbar = -scale * (rr * mg - (1.0 / s2e) * l * s2g) * live
+    return lbar, mgbar, qgbar, cGbar
