@@ -1,0 +1,213 @@
+// Covariance builds: stationary RBF (code/utils.py:75-94), Gibbs/Paciorek nonstationary RBF
+// (code/utils.py:97-103) with adjoints, and the SIM_code builds (code/SIM_code/Utility/kernels.py:5-73).
+// Bound by HBM stores and the FP64 exp/sqrt/div ALU sequences; one element per thread, coalesced
+// along the inducing/column index.
+#include "common.cuh"
+
+// K[n,q] = s2 * exp(-0.5 (x_n/len - z_q/len)^2) (+ jitter on n==q)
+__global__ void k_rbf_fwd(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ hyp,
+                          int is2, int ilen, double jitter, double* __restrict__ K, long long B, int Q) {
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= B * Q) return;
+    long long n = gid / Q;
+    int q = (int)(gid - n * Q);
+    const double s2 = hyp[is2], len = hyp[ilen];
+    double r = x[n] / len - z[q] / len;
+    double k = s2 * exp(-0.5 * (r * r));
+    if (jitter != 0.0 && n == q) k += jitter;
+    K[gid] = k;
+}
+NMGP_API int nmgp_rbf_build_fwd(const double* x, const double* z, const double* hyp, int is2, int ilen, double jitter,
+                                double* K, long long B, int Q, cudaStream_t st) {
+    NMGP_REQUIRE(B >= 0 && Q > 0 && is2 >= 0 && is2 < H_COUNT && ilen >= 0 && ilen < H_COUNT, "nmgp_rbf_build_fwd");
+    if (B == 0) return 0;
+    long long n = B * Q;
+    k_rbf_fwd<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, z, hyp, is2, ilen, jitter, K, B, Q);
+    return nmgp_launch_status("nmgp_rbf_build_fwd");
+}
+
+// ghyp[is2] += sum Kbar*K (d/dlog s2);  ghyp[ilen] += sum Kbar*K*r^2 (d/dlog len)
+__global__ void k_rbf_bwd(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ hyp,
+                          int is2, int ilen, const double* __restrict__ Kbar, double* __restrict__ ghyp, long long B,
+                          int Q) {
+    const double s2 = hyp[is2], len = hyp[ilen];
+    double a0 = 0.0, a1 = 0.0;
+    const long long total = B * Q;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+         gid += (long long)gridDim.x * blockDim.x) {
+        long long n = gid / Q;
+        int q = (int)(gid - n * Q);
+        double r = x[n] / len - z[q] / len;
+        double r2 = r * r;
+        double g = Kbar[gid] * (s2 * exp(-0.5 * r2));
+        a0 += g;
+        a1 = fma(g, r2, a1);
+    }
+    a0 = block_sum(a0);
+    a1 = block_sum(a1);
+    if (threadIdx.x == 0) {
+        atomicAdd(&ghyp[is2], a0);
+        atomicAdd(&ghyp[ilen], a1);
+    }
+}
+NMGP_API int nmgp_rbf_build_bwd(const double* x, const double* z, const double* hyp, int is2, int ilen,
+                                const double* Kbar, double* ghyp, long long B, int Q, cudaStream_t st) {
+    NMGP_REQUIRE(B >= 0 && Q > 0 && is2 >= 0 && is2 < H_COUNT && ilen >= 0 && ilen < H_COUNT, "nmgp_rbf_build_bwd");
+    if (B == 0) return 0;
+    long long n = B * Q;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_rbf_bwd<<<(unsigned)blocks, 256, 0, st>>>(x, z, hyp, is2, ilen, Kbar, ghyp, B, Q);
+    return nmgp_launch_status("nmgp_rbf_build_bwd");
+}
+
+// ---- Gibbs kernel -----------------------------------------------------------------------------
+__device__ __forceinline__ double gibbs_value(double xn, double zq, double a, double b) {
+    double d = xn - zq;
+    double r2 = d * d;
+    double den = a * a + b * b;
+    return sqrt(2.0 * (a * b) / den) * exp(-r2 / den);
+}
+
+__global__ void k_gibbs_fwd(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ ellx,
+                            const double* __restrict__ ellz, double jitter, double* __restrict__ K, long long B, int Q) {
+    const int s = blockIdx.y;
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= B * Q) return;
+    long long n = gid / Q;
+    int q = (int)(gid - n * Q);
+    double k = gibbs_value(x[n], z[q], ellx[(size_t)s * B + n], ellz[(size_t)s * Q + q]);
+    if (jitter != 0.0 && n == q) k += jitter;
+    K[(size_t)s * B * Q + gid] = k;
+}
+NMGP_API int nmgp_gibbs_build_fwd(const double* x, const double* z, const double* ellx, const double* ellz,
+                                  double jitter, double* K, int ns, long long B, int Q, cudaStream_t st) {
+    NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && Q > 0, "nmgp_gibbs_build_fwd");
+    if (B == 0 || ns == 0) return 0;
+    long long n = B * Q;
+    dim3 grid((unsigned)((n + 255) / 256), ns);
+    k_gibbs_fwd<<<grid, 256, 0, st>>>(x, z, ellx, ellz, jitter, K, B, Q);
+    return nmgp_launch_status("nmgp_gibbs_build_fwd");
+}
+
+// ellxbar[s,n] = sum_q Kbar k dlog k/da ;  ellzbar[s,q] += sum_n Kbar k dlog k/db
+// dlog k/da = 1/(2a) - a/den + 2 a r2/den^2.  One warp per row, lanes over q.
+#define GB_ROWS_PER_WARP 8
+__global__ void k_gibbs_bwd(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ ellx,
+                            const double* __restrict__ ellz, const double* __restrict__ Kbar,
+                            double* __restrict__ ellxbar, double* __restrict__ ellzbar, long long B, int Q) {
+    extern __shared__ double colsum[];  // [Q]
+    const int s = blockIdx.y;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) colsum[q] = 0.0;
+    __syncthreads();
+    const long long row0 = ((long long)blockIdx.x * nw + w) * GB_ROWS_PER_WARP;
+    double cacc[4] = {0.0, 0.0, 0.0, 0.0};  // Q <= 128
+    for (int rr = 0; rr < GB_ROWS_PER_WARP; ++rr) {
+        long long n = row0 + rr;
+        if (n >= B) break;
+        const double a = ellx[(size_t)s * B + n], xn = x[n];
+        const double* kb = Kbar + ((size_t)s * B + n) * Q;
+        double racc = 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int q = lane + 32 * u;
+            if (q < Q) {
+                double b = ellz[(size_t)s * Q + q];
+                double d = xn - z[q];
+                double r2 = d * d, den = a * a + b * b;
+                double k = sqrt(2.0 * (a * b) / den) * exp(-r2 / den);
+                double g = kb[q] * k;
+                double common = 2.0 * r2 / (den * den) - 1.0 / den;
+                racc = fma(g, 0.5 / a + a * common, racc);
+                cacc[u] = fma(g, 0.5 / b + b * common, cacc[u]);
+            }
+        }
+        racc = warp_sum(racc);
+        if (lane == 0) ellxbar[(size_t)s * B + n] = racc;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        int q = lane + 32 * u;
+        if (q < Q && cacc[u] != 0.0) atomicAdd(&colsum[q], cacc[u]);
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < Q; q += blockDim.x)
+        if (colsum[q] != 0.0) atomicAdd(&ellzbar[(size_t)s * Q + q], colsum[q]);
+}
+NMGP_API int nmgp_gibbs_build_bwd(const double* x, const double* z, const double* ellx, const double* ellz,
+                                  const double* Kbar, double* ellxbar, double* ellzbar, int ns, long long B, int Q,
+                                  cudaStream_t st) {
+    NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && Q > 0 && Q <= 128, "nmgp_gibbs_build_bwd");
+    if (B == 0 || ns == 0) return 0;
+    const int threads = 256, rows_per_block = (threads / 32) * GB_ROWS_PER_WARP;
+    dim3 grid((unsigned)((B + rows_per_block - 1) / rows_per_block), ns);
+    k_gibbs_bwd<<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, ellxbar, ellzbar, B, Q);
+    return nmgp_launch_status("nmgp_gibbs_build_bwd");
+}
+
+// ---- SIM_code builds (kernels.py) ----------------------------------------------------------------
+// dist = |x|^2 + |y|^2 - 2 x.y (GEMM form, may be slightly negative, not clamped: kernels.py:14-21)
+__device__ __forceinline__ double sim_dist(const double* __restrict__ X1, const double* __restrict__ X2, long long i,
+                                           long long j, int dx) {
+    double xn = 0.0, yn = 0.0, xy = 0.0;
+    for (int k = 0; k < dx; ++k) {
+        double a = X1[i * dx + k], b = X2[j * dx + k];
+        xn = fma(a, a, xn);
+        yn = fma(b, b, yn);
+        xy = fma(a, b, xy);
+    }
+    return xn + yn - 2.0 * xy;
+}
+// Nonstationary_RBF_cov (kernels.py:46-73): C*sqrt(2B/A)*exp(-dist/A) (+1e-6 I when self)
+__global__ void k_nonstat_cov(const double* __restrict__ X1, const double* __restrict__ sg1, const double* __restrict__ l1,
+                              const double* __restrict__ X2, const double* __restrict__ sg2, const double* __restrict__ l2,
+                              double jitter, double* __restrict__ K, long long row0, long long T2, int dx) {
+    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long i = row0 + blockIdx.y;
+    if (j >= T2) return;
+    double a = l1 ? l1[i] : 1.0, b = l2 ? l2[j] : 1.0;
+    double c = (sg1 ? sg1[i] : 1.0) * (sg2 ? sg2[j] : 1.0);
+    double A = a * a + b * b;
+    double k = c * sqrt(2.0 * (a * b) / A) * exp(-sim_dist(X1, X2, i, j, dx) / A);
+    if (i == j) k += jitter;
+    K[i * T2 + j] = k;
+}
+NMGP_API int nmgp_nonstationary_cov(const double* X1, const double* sigma1, const double* ell1, const double* X2,
+                                    const double* sigma2, const double* ell2, double jitter, double* K, long long T1,
+                                    long long T2, int dx, cudaStream_t st) {
+    NMGP_REQUIRE(T1 >= 0 && T2 >= 0 && dx > 0, "nmgp_nonstationary_cov");
+    if (T1 == 0 || T2 == 0) return 0;
+    for (long long r0 = 0; r0 < T1; r0 += 65535) {  // grid.y is limited to 65535
+        long long rows = T1 - r0 < 65535 ? T1 - r0 : 65535;
+        dim3 grid((unsigned)((T2 + 255) / 256), (unsigned)rows);
+        k_nonstat_cov<<<grid, 256, 0, st>>>(X1, sigma1, ell1, X2, sigma2, ell2, jitter, K, r0, T2, dx);
+    }
+    return nmgp_launch_status("nmgp_nonstationary_cov");
+}
+// RBF_cov (kernels.py:24-43): alpha^2 exp(-0.5 dist(X1/beta, X2/beta)) (+1e-6 I when self)
+__global__ void k_sim_rbf_cov(const double* __restrict__ X1, const double* __restrict__ X2, double alpha, double beta,
+                              double jitter, double* __restrict__ K, long long T1, long long T2, int dx) {
+    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long i = blockIdx.y;
+    if (j >= T2) return;
+    double xn = 0.0, yn = 0.0, xy = 0.0;
+    for (int k = 0; k < dx; ++k) {
+        double a = X1[i * dx + k] / beta, b = X2[j * dx + k] / beta;
+        xn = fma(a, a, xn);
+        yn = fma(b, b, yn);
+        xy = fma(a, b, xy);
+    }
+    double dist = xn + yn - 2.0 * xy;
+    double k = exp(-0.5 * dist) * (alpha * alpha);
+    if (i == j) k += jitter;
+    K[i * T2 + j] = k;
+}
+NMGP_API int nmgp_sim_rbf_cov(const double* X1, const double* X2, double alpha, double beta, double jitter, double* K,
+                              long long T1, long long T2, int dx, cudaStream_t st) {
+    NMGP_REQUIRE(T1 >= 0 && T2 >= 0 && dx > 0 && T1 <= 65535, "nmgp_sim_rbf_cov");
+    if (T1 == 0 || T2 == 0) return 0;
+    dim3 grid((unsigned)((T2 + 255) / 256), (unsigned)T1);
+    k_sim_rbf_cov<<<grid, 256, 0, st>>>(X1, X2, alpha, beta, jitter, K, T1, T2, dx);
+    return nmgp_launch_status("nmgp_sim_rbf_cov");
+}

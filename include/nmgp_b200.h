@@ -1,0 +1,134 @@
+/*
+ * nmgp_b200.h -- C ABI of libnmgp_b200.so: the B200 (sm_100a, FP64) kernels behind the NMGP DSVI hot path.
+ *
+ * The reference (Corleno/Collaborative_Nonstationary_Multivariate_Gaussian_Process) is pure Python/torch and has no
+ * FFI; its boundary is the Python call surface of code/utils.py, code/nmgp_dsvi.py and code/SIM_code/Utility/*.py.
+ * Each entry point below names the reference site(s) it replaces.  INTEGRATION.md shows the ctypes stub a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous row-major data; `double` unless noted; `int` is 32-bit;
+ *   - sizes: B rows in the minibatch, Q inducing points (<= 112), D outputs, ns Monte-Carlo samples of a chunk,
+ *     nb / np batch counts of Q x Q matrices;
+ *   - `hyp` is the vector of exponentiated hyper-parameters in the order
+ *     {s2_tildeell, len_tildeell, s2_L0, len_L0, s2_L1, len_L1, s2_err} (code/nmgp_dsvi.py:180-188);
+ *     `ghyp` accumulates gradients w.r.t. the corresponding *_log parameters;
+ *   - rows are sorted by output id I[n]; seg[d] = first row with I >= d, seg[D] = B;
+ *   - "+=" marks accumulating outputs (caller zero-initialises), "=" overwriting ones;
+ *   - all work is enqueued on `stream` (a cudaStream_t); no internal allocation, no global state;
+ *   - return value: 0 ok, < 0 argument/launch error, > 0 numerical failure; nmgp_last_error() gives the text
+ *     (thread-local).
+ */
+#ifndef NMGP_B200_H
+#define NMGP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* nmgp_stream_t; /* cudaStream_t */
+
+const char* nmgp_last_error(void);
+int nmgp_version(void);
+
+/* hyp[i] = exp(logs[i])                                                    code/nmgp_dsvi.py:180-188 */
+int nmgp_hyper_exp(const double* logs, double* hyp, int n, nmgp_stream_t stream);
+/* seg[0..D] from the sorted output ids                                     code/nmgp_dsvi.py:163-167 */
+int nmgp_segment_offsets(const int* I, int* seg, long long B, int D, nmgp_stream_t stream);
+
+/* Sigma = tril(S) tril(S)^T, batched                                       utils.py:68-72 + nmgp_dsvi.py:172-177 */
+int nmgp_tril_syrk_fwd(const double* S, double* Sigma, int nb, int Q, nmgp_stream_t stream);
+int nmgp_tril_syrk_bwd(const double* S, const double* SigBar, double* Sbar, int nb, int Q, nmgp_stream_t stream);
+
+/* C = chol(A + jitter I) (lower), hld = sum log diag C; *info = 1 + index of a non-PD matrix (0 if none)
+ *                                                                          utils.py:46,276,347-348 (torch.cholesky) */
+int nmgp_potrf_batched(const double* A, double jitter, double* C, double* hld, int* info, int nb, int Q,
+                       nmgp_stream_t stream);
+/* Abar = sym(C^-T Phi(C^T Cbar') C^-1), Cbar' = tril(Cbar) + diag(hldbar / diag C)   (autograd of the above) */
+int nmgp_potrf_bwd_batched(const double* C, const double* Cbar, const double* hldbar, double* Abar, int nb, int Q,
+                           nmgp_stream_t stream);
+
+/* kl[p,b] = KL(N(mu_b, CS_b CS_b^T) || N(0, R_p R_p^T)) in the reference's form (quirk q10); t[p,b,:] = R_p^-1 mu_b
+ *                                                                          utils.py:332-351 KL_Gaussian */
+int nmgp_kl_fwd(const double* CS, const double* hldS, const double* mu, const double* R, const double* hldR,
+                double* kl, double* t, int np, int nb, int Q, nmgp_stream_t stream);
+int nmgp_kl_bwd(const double* klbar, const double* CS, const double* mu, const double* R, const double* t,
+                double* CSbar, double* hldSbar, double* mubar, double* Rbar /* += */, double* hldRbar,
+                double* work /* [np,nb,Q] */, int np, int nb, int Q, nmgp_stream_t stream);
+
+/* K[n,q] = hyp[is2] exp(-(x_n/len - z_q/len)^2 / 2) (+ jitter on n == q)    utils.py:75-94 create_RBF */
+int nmgp_rbf_build_fwd(const double* x, const double* z, const double* hyp, int is2, int ilen, double jitter,
+                       double* K, long long B, int Q, nmgp_stream_t stream);
+int nmgp_rbf_build_bwd(const double* x, const double* z, const double* hyp, int is2, int ilen, const double* Kbar,
+                       double* ghyp /* += */, long long B, int Q, nmgp_stream_t stream);
+
+/* K[s,n,q] = sqrt(2ab/(a^2+b^2)) exp(-(x_n-z_q)^2/(a^2+b^2)), a = ellx[s,n], b = ellz[s,q]   utils.py:97-103 create_Gibbs */
+int nmgp_gibbs_build_fwd(const double* x, const double* z, const double* ellx, const double* ellz, double jitter,
+                         double* K, int ns, long long B, int Q, nmgp_stream_t stream);
+int nmgp_gibbs_build_bwd(const double* x, const double* z, const double* ellx, const double* ellz, const double* Kbar,
+                         double* ellxbar /* = */, double* ellzbar /* += */, int ns, long long B, int Q,
+                         nmgp_stream_t stream);
+
+/* P = K (R R^T)^-1, c = rowsum(P o K)                                      utils.py:117-122 (torch.solve of K22 + eps I) */
+int nmgp_solve_rows_fwd(const double* K, const double* R, double* P, double* c, int ns, long long B, int Q,
+                        nmgp_stream_t stream);
+int nmgp_solve_rows_bwd(const double* Pbar, const double* cbar, const double* K, const double* P, const double* R,
+                        double* Kbar /* = */, double* Abar /* += */, int ns, long long B, int Q, nmgp_stream_t stream);
+
+/* q[s,n,j] = p^T Sig[idx] p, m[s,n,j] = p . Mu[idx] for j <= I[n]          utils.py:120-122,143-144 (MGP_d, MGP_mu_sigma2)
+ * mode 0 (latent functions): idx = j; mode 1 (coefficients): idx = packed pair (I[n], j), p = Pb row if j == I[n] */
+int nmgp_quadform_fwd(const double* Pa, const double* Pb, const int* I, const int* seg, const double* Sig,
+                      const double* Mu, double* q, double* m, int ns, long long B, int Q, int D, int mode,
+                      nmgp_stream_t stream);
+int nmgp_quadform_bwd(const double* Pa, const double* Pb, const int* I, const int* seg, const double* Sig,
+                      const double* Mu, const double* qbar, const double* mbar, double* Pabar, double* Pbbar, int ns,
+                      long long B, int Q, int D, int mode, nmgp_stream_t stream);
+int nmgp_weighted_gram(const double* Pa, const double* Pb, const int* I, const int* seg, const double* qbar,
+                       const double* mbar, double* SigBar /* += */, double* MuBar /* += */, int ns, long long B, int Q,
+                       int D, int mode, nmgp_stream_t stream);
+
+/* v = mu_v + C_v z, ellz = exp(v)                                          utils.py:225-227, nmgp_dsvi.py:215 */
+int nmgp_sample_v_fwd(const double* mu_v, const double* Cv, const double* zv, double* v, double* ellz, int S, int Q,
+                      nmgp_stream_t stream);
+int nmgp_sample_v_bwd(const double* ellzbar, const double* vbar, const double* ellz, const double* zv,
+                      double* mu_v_bar /* += */, double* Cvbar /* += */, int S, int Q, nmgp_stream_t stream);
+
+/* sd = sqrt(s2_tildeell - c + eps)                                         utils.py:233 + :32 */
+int nmgp_ell_sd_fwd(const double* c, const double* hyp, double* sd, long long B, nmgp_stream_t stream);
+int nmgp_ell_sd_bwd(const double* sdbar, const double* sd, const double* hyp, double* ghyp, double* cbar, long long B,
+                    nmgp_stream_t stream);
+/* ellx[s,n] = exp(P_ell[n,:] . v[s,:] + z[s,n] sd[n])                      utils.py:231-235, nmgp_dsvi.py:216 */
+int nmgp_ell_rows_fwd(const double* Pell, const double* v, const double* zell, const double* sd, double* ellx, int ns,
+                      long long B, int Q, nmgp_stream_t stream);
+int nmgp_ell_rows_bwd(const double* ellxbar, const double* ellx, const double* Pell, const double* v,
+                      const double* zell, double* vbar /* += */, double* Pellbar /* += */, double* sdbar /* += */,
+                      int ns, long long B, int Q, nmgp_stream_t stream);
+
+/* sd[n,j] = sqrt(s2_k - c_k[n] + q[n,j] + eps)                             utils.py:122 + :32 (inside MGP_d) */
+int nmgp_coef_sd_fwd(const double* q, const double* cL0, const double* cL1, const int* I, const double* hyp,
+                     double* sd, long long B, int D, nmgp_stream_t stream);
+int nmgp_coef_sd_bwd(const double* sdbar, const double* sd, const int* I, const double* hyp, double* ghyp,
+                     double* qbar, double* cL0bar, double* cL1bar, long long B, int D, nmgp_stream_t stream);
+/* l[s,n,j] = m + z sd (exp on the diagonal coefficient)                    nmgp_dsvi.py:228-238 */
+int nmgp_coef_sample_fwd(const double* m, const double* sd, const double* zL, const int* I, double* l, int ns,
+                         long long B, int D, nmgp_stream_t stream);
+int nmgp_coef_sample_bwd(const double* lbar, const double* l, const double* zL, const int* I, double* mbar /* += */,
+                         double* sdbar /* += */, int ns, long long B, int D, nmgp_stream_t stream);
+
+/* expected log-likelihood of a sample chunk and its cotangents             nmgp_dsvi.py:255-258, utils.py:268-272 */
+int nmgp_lik_rows(const double* l, const double* mg, const double* qg, const double* cG, const double* y, const int* I,
+                  const double* hyp, double scale, double* Rsum /* += */, double* ghyp /* += */, double* lbar,
+                  double* mgbar, double* qgbar, double* cGbar, int ns, long long B, int D, nmgp_stream_t stream);
+
+/* SIM_code line: code/SIM_code/Utility/kernels.py:46-73 Nonstationary_RBF_cov and :24-43 RBF_cov.
+ * sigma/ell pointers may be NULL (= ones).  jitter (1e-6) is added on i == j; pass 0 for cross-covariances. */
+int nmgp_nonstationary_cov(const double* X1, const double* sigma1, const double* ell1, const double* X2,
+                           const double* sigma2, const double* ell2, double jitter, double* K, long long T1,
+                           long long T2, int dx, nmgp_stream_t stream);
+int nmgp_sim_rbf_cov(const double* X1, const double* X2, double alpha, double beta, double jitter, double* K,
+                     long long T1, long long T2, int dx, nmgp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMGP_B200_H */
