@@ -291,3 +291,19 @@ def lik_rows(l, mg, qg, cG, y, I, hyp, scale, Rsum, ghyp):
                               _d(lbar), _d(mgbar), _d(qgbar), _d(cGbar), c_int(ns), c_int64(B), c_int(D), _stream()),
           "nmgp_lik_rows")
     return lbar, mgbar, qgbar, cGbar
+
+
+def pair_means(Pa, Pb, I, Mu, D, mode):
+    ns, B, Q = Pa.shape
+    m = _empty(Pa, ns, B, D)
+    check(lib().nmgp_pair_means(_d(Pa), _d(Pb), _i(I), _d(Mu), _d(m), c_int(ns), c_int64(B), c_int(Q), c_int(D),
+                                c_int(mode), _stream()), "nmgp_pair_means")
+    return m
+
+
+def rowdot_live(l, g, I):
+    ns, B, D = l.shape
+    F = _empty(l, ns, B)
+    check(lib().nmgp_rowdot_live(_d(l), _d(g), _i(I), _d(F), c_int(ns), c_int64(B), c_int(D), _stream()),
+          "nmgp_rowdot_live")
+    return F

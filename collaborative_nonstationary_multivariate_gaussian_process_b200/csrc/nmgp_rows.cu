@@ -424,3 +424,70 @@ NMGP_API int nmgp_lik_rows(const double* l, const double* mg, const double* qg, 
     k_lik_rows<<<grid, 256, 0, st>>>(l, mg, qg, cG, y, I, hyp, scale, Rsum, ghyp, lbar, mgbar, qgbar, cGbar, B, D);
     return nmgp_launch_status("nmgp_lik_rows");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Means only (no quadratic forms): m[s,n,j] = p . Mu[idx] for j <= I[n]   (code/utils.py:149-157 MGP_mu,
+// used by predict_Y, code/nmgp_dsvi.py:698-718).  Warp per (s,n), lanes over q.
+__global__ void k_pair_means(const double* __restrict__ Pa, const double* __restrict__ Pb, const int* __restrict__ I,
+                             const double* __restrict__ Mu, double* __restrict__ m, long long B, int Q, int D,
+                             int mode) {
+    const int s = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    long long n = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= B) return;
+    const int i = I[n];
+    const size_t prow = ((size_t)s * B + n) * Q;
+    double pa[4], pb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        int q = lane + 32 * u;
+        pa[u] = q < Q ? Pa[prow + q] : 0.0;
+        pb[u] = (mode == MODE_U && q < Q) ? Pb[prow + q] : pa[u];
+    }
+    double* mo = m + ((size_t)s * B + n) * D;
+    for (int j = 0; j < D; ++j) {
+        double acc = 0.0;
+        if (j <= i) {
+            const int idx = (mode == MODE_U) ? pair_slot(i, j, D) : j;
+            const bool useB = (mode == MODE_U) && (j == i);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int q = lane + 32 * u;
+                if (q < Q) acc = fma(useB ? pb[u] : pa[u], Mu[(size_t)idx * Q + q], acc);
+            }
+            acc = warp_sum(acc);
+        }
+        if (lane == 0) mo[j] = acc;
+    }
+}
+NMGP_API int nmgp_pair_means(const double* Pa, const double* Pb, const int* I, const double* Mu, double* m, int ns,
+                             long long B, int Q, int D, int mode, cudaStream_t st) {
+    NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && Q > 0 && Q <= 128 && D > 0, "nmgp_pair_means");
+    if (ns == 0 || B == 0) return 0;
+    dim3 grid((unsigned)((B + 7) / 8), ns);
+    k_pair_means<<<grid, 256, 0, st>>>(Pa, Pb, I, Mu, m, B, Q, D, mode);
+    return nmgp_launch_status("nmgp_pair_means");
+}
+
+// F[s,n] = sum_{j <= I[n]} l[s,n,j] g[s,n,j]     (code/nmgp_dsvi.py:255 and :721-722)
+__global__ void k_rowdot_live(const double* __restrict__ l, const double* __restrict__ g, const int* __restrict__ I,
+                              double* __restrict__ F, long long B, int D) {
+    const int s = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    long long n = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= B) return;
+    const int i = I[n];
+    const size_t o = ((size_t)s * B + n) * D;
+    double acc = 0.0;
+    for (int j = lane; j <= i; j += 32) acc = fma(l[o + j], g[o + j], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) F[(size_t)s * B + n] = acc;
+}
+NMGP_API int nmgp_rowdot_live(const double* l, const double* g, const int* I, double* F, int ns, long long B, int D,
+                              cudaStream_t st) {
+    NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && D > 0, "nmgp_rowdot_live");
+    if (ns == 0 || B == 0) return 0;
+    dim3 grid((unsigned)((B + 7) / 8), ns);
+    k_rowdot_live<<<grid, 256, 0, st>>>(l, g, I, F, B, D);
+    return nmgp_launch_status("nmgp_rowdot_live");
+}

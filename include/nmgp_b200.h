@@ -120,6 +120,13 @@ int nmgp_lik_rows(const double* l, const double* mg, const double* qg, const dou
                   const double* hyp, double scale, double* Rsum /* += */, double* ghyp /* += */, double* lbar,
                   double* mgbar, double* qgbar, double* cGbar, int ns, long long B, int D, nmgp_stream_t stream);
 
+/* means only: m[s,n,j] = p . Mu[idx], j <= I[n]                            utils.py:149-157 MGP_mu (predict_Y) */
+int nmgp_pair_means(const double* Pa, const double* Pb, const int* I, const double* Mu, double* m, int ns, long long B,
+                    int Q, int D, int mode, nmgp_stream_t stream);
+/* F[s,n] = sum_{j <= I[n]} l[s,n,j] g[s,n,j]                               nmgp_dsvi.py:255, :721-722 */
+int nmgp_rowdot_live(const double* l, const double* g, const int* I, double* F, int ns, long long B, int D,
+                     nmgp_stream_t stream);
+
 /* SIM_code line: code/SIM_code/Utility/kernels.py:46-73 Nonstationary_RBF_cov and :24-43 RBF_cov.
  * sigma/ell pointers may be NULL (= ones).  jitter (1e-6) is added on i == j; pass 0 for cross-covariances. */
 int nmgp_nonstationary_cov(const double* X1, const double* sigma1, const double* ell1, const double* X2,

@@ -315,3 +315,25 @@ def lik_rows(l, mg, qg, cG, y, I, hyp, scale, Rsum, ghyp):
     cGbar = -qgbar.sum(-1)
     lbar = -scale * (rr * mg - (1.0 / s2e) * l * s2g) * live
     return lbar, mgbar, qgbar, cGbar
+
+
+def pair_means(Pa, Pb, I, Mu, D, mode):
+    ns, B, Q = Pa.shape
+    m = torch.zeros(ns, B, D, dtype=F64)
+    Il = I.long()
+    for j in range(D):
+        rows = torch.nonzero(Il >= j).view(-1)
+        if rows.numel() == 0:
+            continue
+        idx = _pair_index(I[rows], j, mode, D)
+        p = Pa[:, rows, :]
+        if mode == MODE_U:
+            p = torch.where((Il[rows] == j).view(1, -1, 1), Pb[:, rows, :], p)
+        m[:, rows, j] = (p * Mu[idx].unsqueeze(0)).sum(-1)
+    return m
+
+
+def rowdot_live(l, g, I):
+    D = l.shape[-1]
+    live = (torch.arange(D).view(1, 1, -1) <= I.long().view(1, -1, 1)).to(F64)
+    return (l * g * live).sum(-1)
