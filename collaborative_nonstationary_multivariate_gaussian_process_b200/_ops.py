@@ -307,3 +307,49 @@ def rowdot_live(l, g, I):
     check(lib().nmgp_rowdot_live(_d(l), _d(g), _i(I), _d(F), c_int(ns), c_int64(B), c_int(D), _stream()),
           "nmgp_rowdot_live")
     return F
+
+
+# ---- optional per-call CUDA-event timing (used by bench.py; off by default) -------------------------
+import functools as _functools
+
+_PROFILE = None
+_CALLS = [0]
+
+
+def _profile_begin():
+    global _PROFILE
+    _PROFILE = []
+    _CALLS[0] = 0
+
+
+def _profile_end():
+    """Returns {op name: (calls, total milliseconds)} and the number of C-ABI calls since _profile_begin()."""
+    global _PROFILE
+    rec, _PROFILE = _PROFILE or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in rec:
+        c, t = out.get(name, (0, 0.0))
+        out[name] = (c + 1, t + e0.elapsed_time(e1))
+    return out, _CALLS[0]
+
+
+def _instrument(fn):
+    @_functools.wraps(fn)
+    def wrapped(*a, **k):
+        _CALLS[0] += 1
+        if _PROFILE is None:
+            return fn(*a, **k)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*a, **k)
+        e1.record()
+        _PROFILE.append((fn.__name__, e0, e1))
+        return r
+    return wrapped
+
+
+for _name, _fn in list(globals().items()):
+    if callable(_fn) and not _name.startswith("_") and getattr(_fn, "__module__", None) == __name__ \
+            and _name not in ("check", "lib"):
+        globals()[_name] = _instrument(_fn)

@@ -154,11 +154,19 @@ class NMGP(torch.nn.Module):
         return zv, zell, zL
 
     def _device_noise(self, B, n_mc):
+        """float32 normals cast to float64 like the reference's (quirk q2), drawn on the device.  Under row
+        sharding ``gen_shared`` (same seed on every rank) feeds the draw of v, ``gen_local`` the row noise."""
         dev = self.device
-        zv = torch.randn(n_mc, self.M, device=dev, dtype=torch.float32).to(F64)
-        zell = torch.randn(n_mc, B, device=dev, dtype=torch.float32).to(F64)
-        zL = torch.randn(n_mc, B, self.D, device=dev, dtype=torch.float32).to(F64)
+        gs, gl = getattr(self, "gen_shared", None), getattr(self, "gen_local", None)
+        zv = torch.randn(n_mc, self.M, device=dev, dtype=torch.float32, generator=gs).to(F64)
+        zell = torch.randn(n_mc, B, device=dev, dtype=torch.float32, generator=gl).to(F64)
+        zL = torch.randn(n_mc, B, self.D, device=dev, dtype=torch.float32, generator=gl).to(F64)
         return zv, zell, zL
+
+    def forward_rows(self, x, y, I, n_mc=1, explicit_noise=None):
+        """Same as forward() for rows already on the device: x, y float64 [B], I int32 [B] sorted by output."""
+        zv, zell, zL = explicit_noise if explicit_noise is not None else self._device_noise(x.shape[0], n_mc)
+        return _DSVILoss.apply(self, x, y, I, self.N, zv, zell, zL, dict(self.step_options), *self._param_list())
 
     # -- the hot path -----------------------------------------------------------------------------
     def forward(self, inputs_list, outputs_list, index=None, verbose=False, n_mc=1, noise=None, explicit_noise=None):

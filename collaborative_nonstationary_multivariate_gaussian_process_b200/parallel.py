@@ -1,0 +1,44 @@
+"""Multi-GPU plumbing for the DSVI step: one process per GPU, rows of the minibatch sharded across ranks,
+ONE all-reduce (NCCL over NVLink/NVSwitch, sum, float64) of the packed gradient + loss per step.
+
+The reference has no distributed code; the decomposition follows SURVEY.md 8e: every
+adjoint is linear in its cotangent, so each rank can run the complete backward on its row shard with the
+KL terms weighted 1/world_size, and the sum over ranks is the full-batch gradient.  Parameters stay
+replicated; every rank applies the identical Adam update.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_rows_per_output(counts: Sequence[int], rank: int, world: int) -> List[np.ndarray]:
+    """Row indices (within each output) owned by ``rank``: a stride-``world`` slice of every output, so each
+    rank sees every output and the per-row cost (proportional to I[n]+1) is balanced."""
+    return [np.arange(rank, int(c), world) for c in counts]
+
+
+def configure_model_for_sharding(model, total_rows: int, rank: int, world: int, seed: int = 1234):
+    model.step_options = dict(B_total=int(total_rows), kl_weight=1.0 / world)
+    dev = model.device
+    if dev.type == "cuda":
+        model.gen_shared = torch.Generator(device=dev); model.gen_shared.manual_seed(seed)
+        model.gen_local = torch.Generator(device=dev); model.gen_local.manual_seed(seed + 1 + rank)
+
+
+def allreduce_loss_and_grads(loss: torch.Tensor, params: Sequence[torch.nn.Parameter], group=None) -> torch.Tensor:
+    """Sum loss and all gradients over ranks with a single collective on one flat float64 buffer."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return loss.detach()
+    live = [p for p in params if p.grad is not None]
+    flat = torch.cat([loss.detach().reshape(1)] + [p.grad.reshape(-1) for p in live])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 1
+    for p in live:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+    return flat[0]
