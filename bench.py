@@ -270,15 +270,17 @@ def run_b200(args, w):
         # roofline of the dominant kernels: dense convention, 2 Q^2 flop per (row, used pair) quadratic form
         pairs_per_sample = float(sum((d + 1) * int(Xh[d].shape[0]) for d in range(D)))
         kern = {}
-        for name, per_pair in (("quadform_fwd", 2.0 * Q * Q), ("quadform_bwd", 2.0 * Q * Q), ("weighted_gram", 2.0 * Q * Q),
-                               ("latent_fused", 6.0 * Q * Q)):
+        # dense convention: 2 Q^2 flop per (row, used pair) for each of V = P Sigma, its adjoint and
+        # the Gram accumulation; the fused latent kernel covers the first two for the S samples, the coefficient
+        # (U) side runs once per step.
+        for name, per_pair, nsamp in (("quadform_fwd", 2.0 * Q * Q, 1), ("quadform_bwd", 2.0 * Q * Q, 1),
+                                      ("weighted_gram", 2.0 * Q * Q, S + 1), ("latent_fused", 4.0 * Q * Q, S)):
             if name in prof:
                 calls, tms = prof[name]
-                # W-side launches carry S samples in total per step; the U-side launch is one more "sample"
-                nsamp = (S + 1) if name != "latent_fused" else S
                 flops = args.steps * nsamp * pairs_per_sample * per_pair
                 kern[name] = {"calls": calls, "ms_total": tms, "share_of_step": tms / ms,
                               "tflops": flops / (tms * 1e-3) / 1e12}
+        others = {k: {"calls": c, "ms_total": t_, "share_of_step": t_ / ms} for k, (c, t_) in prof.items() if k not in kern}
         dom = max(kern, key=lambda k: kern[k]["ms_total"]) if kern else None
         roof = None
         if dom:
@@ -297,7 +299,7 @@ def run_b200(args, w):
                            "noise": "device", "optimizer": "Adam lr=0.005"},
                 "step_tflops_fp64": F_step / (ms_step * 1e-3) / 1e12,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(ncalls),
-                "roofline": roof, "kernels": kern, "loss": float(last)}
+                "roofline": roof, "kernels": kern, "other_ops": others, "loss": float(last)}
         if args.cpu_baseline == "auto" and world == 1:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)

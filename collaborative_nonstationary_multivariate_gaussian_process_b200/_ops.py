@@ -309,6 +309,28 @@ def rowdot_live(l, g, I):
     return F
 
 
+def latent_fused(PG, cG, l, y, I, SigW, muW, hyp, scale, Rsum, ghyp, seg=None):
+    """Latent-function statistics, expected log-likelihood and every row cotangent of one sample chunk in a
+    single DMMA kernel (Q <= 64).  Returns (lbar, mgbar, qgbar, cGbar, PGbar); Rsum (=) and ghyp (+=) in place."""
+    ns, B, Q = PG.shape
+    D = l.shape[-1]
+    seg = segment_offsets(I, D) if seg is None else seg
+    lbar = torch.empty_like(l); mgbar = torch.empty_like(l); qgbar = torch.empty_like(l)
+    cGbar = _empty(l, ns, B)
+    PGbar = torch.empty_like(PG)
+    Rsum.zero_()
+    if Q > 64:
+        wq_, wm_ = _zeros(l, ns, B, D), _zeros(l, ns, B, D)
+        pq, pm = _d(wq_), _d(wm_)
+    else:
+        pq = pm = c_void_p(0)
+    check(lib().nmgp_latent_fused(_d(PG), _d(cG), _d(l), _d(y), _i(I), _i(seg), _d(SigW), _d(muW), _d(hyp),
+                                  c_double(scale), _d(Rsum), _d(ghyp), _d(lbar), _d(mgbar), _d(qgbar), _d(cGbar),
+                                  _d(PGbar), pq, pm, c_int(ns), c_int64(B), c_int(Q), c_int(D), _stream()),
+          "nmgp_latent_fused")
+    return lbar, mgbar, qgbar, cGbar, PGbar
+
+
 # ---- optional per-call CUDA-event timing (used by bench.py; off by default) -------------------------
 import functools as _functools
 

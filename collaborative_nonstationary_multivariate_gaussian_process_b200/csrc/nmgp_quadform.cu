@@ -12,13 +12,6 @@
 
 #define QF_SUB 4  // threads per row
 
-struct QfTask {
-    int idx;      // matrix slot
-    int i_sel;    // MODE_U: rows with I == i_sel; MODE_W: rows with I >= j_sel
-    int j;
-    bool useB;
-};
-
 __device__ __forceinline__ void load_matrix(double* __restrict__ dst, const double* __restrict__ src, int n) {
     for (int e = threadIdx.x; e < n; e += blockDim.x) dst[e] = src[e];
 }
@@ -234,6 +227,9 @@ __global__ void k_weighted_gram(const double* __restrict__ Pa, const double* __r
     for (int e = threadIdx.x; e < Q * Q; e += blockDim.x) atomicAdd(&SigBar[(size_t)task * Q * Q + e], Acc[e]);
     for (int a = threadIdx.x; a < Q; a += blockDim.x) atomicAdd(&MuBar[(size_t)task * Q + a], MAcc[a]);
 }
+int nmgp_weighted_gram_mma(const double* Pa, const double* Pb, const int* seg, const double* qbar, const double* mbar,
+                           double* SigBar, double* MuBar, int ns, long long B, int Q, int D, int mode, cudaStream_t st);
+
 NMGP_API int nmgp_weighted_gram(const double* Pa, const double* Pb, const int* I, const int* seg, const double* qbar,
                                 const double* mbar, double* SigBar, double* MuBar, int ns, long long B, int Q, int D,
                                 int mode, cudaStream_t st) {
@@ -241,6 +237,7 @@ NMGP_API int nmgp_weighted_gram(const double* Pa, const double* Pb, const int* I
     NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && Q > 0 && Q <= 128 && D > 0 && (mode == MODE_W || mode == MODE_U),
                  "nmgp_weighted_gram");
     if (ns == 0 || B == 0) return 0;
+    if (Q <= 64) return nmgp_weighted_gram_mma(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
     const int ntasks = (mode == MODE_W) ? D : D * (D + 1) / 2;
     NMGP_REQUIRE(ntasks <= 65535, "nmgp_weighted_gram");
     size_t smem = sizeof(double) * ((size_t)Q * Q + Q + (size_t)WG_SUB * (Q + 1) + 2 * WG_SUB);

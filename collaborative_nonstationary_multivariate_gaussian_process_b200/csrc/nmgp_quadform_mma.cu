@@ -1,0 +1,500 @@
+// FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4) formulation of the FLOP-dominant kernels.
+//
+//  k_latent_fused : per (sample, 128-row tile), for every latent j <= I[n]
+//        V = P Sigma_W[j]           (DMMA, A = P tile held in registers for the whole j loop,
+//                                    B = Sigma_W[j] streamed through a cp.async double buffer)
+//        q = rowdot(V, P)           -> s2_g, expected log-likelihood, all row cotangents
+//        Pbar += 2 qbar V + mbar mu -> the adjoint w.r.t. P reuses V (no second GEMM)
+//     = quadform_fwd + lik_rows + quadform_bwd of nmgp_quadform.cu / nmgp_rows.cu in one pass
+//     (reference: code/utils.py:143-144 + code/nmgp_dsvi.py:255-258 and their autograd).
+//  k_gram_mma     : SigBar[idx] += P^T diag(qbar[:,j]) P, MuBar[idx] += P^T mbar[:,j] over the rows of one output,
+//                   NG latents per CTA, lower-triangular 8x8 blocks only (symmetric result).
+//
+// Register-resident design: valid for Q <= 64 (NB = ceil(Q/8) <= 8); larger Q uses the shared-memory FMA kernels.
+#include "common.cuh"
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__host__ __device__ constexpr int pad4mod8(int n) { return ((n + 3) / 8) * 8 + 4; }   // smallest m >= n, m % 8 == 4
+
+// ------------------------------------------------------------------------------------------------------------
+#define LF_ROWS 128
+#define LF_THREADS 256
+
+template <int NB, int KS>
+struct LFShape {
+    static constexpr int NP = 8 * NB;                      // padded N (columns of Sigma / P in C layout)
+    static constexpr int KP = 4 * KS;                      // padded K
+    static constexpr int LDP = pad4mod8(NP > KP ? NP : KP);
+    static constexpr int LDS = pad4mod8(NP);
+    static constexpr size_t smem_doubles = (size_t)LF_ROWS * LDP + 2 * (size_t)KP * LDS + 2 * NP + 2 * LF_ROWS + 2 * LF_ROWS;
+    static constexpr size_t smem_bytes = smem_doubles * 8 + LF_ROWS * 4;
+};
+
+template <int NB, int KS>
+__global__ void __launch_bounds__(LF_THREADS, 1)
+k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, const double* __restrict__ l,
+               const double* __restrict__ y, const int* __restrict__ I, const double* __restrict__ SigW,
+               const double* __restrict__ muW, const double* __restrict__ hyp, double scale,
+               double* __restrict__ Rsum, double* __restrict__ ghyp, double* __restrict__ lbar,
+               double* __restrict__ mgbar, double* __restrict__ qgbar, double* __restrict__ cGbar,
+               double* __restrict__ PGbar, long long B, int Q, int D) {
+    using SH = LFShape<NB, KS>;
+    constexpr int LDP = SH::LDP, LDS = SH::LDS, NP = SH::NP, KP = SH::KP;
+    extern __shared__ __align__(16) double sm[];
+    double* Ps = sm;                                   // [LF_ROWS][LDP]
+    double* Ss = Ps + (size_t)LF_ROWS * LDP;           // [2][KP][LDS]
+    double* mus = Ss + 2 * (size_t)KP * LDS;           // [2][NP]
+    double* lcol = mus + 2 * NP;                       // [2][LF_ROWS]
+    double* rrs = lcol + 2 * LF_ROWS;                  // [LF_ROWS]
+    double* omcs = rrs + LF_ROWS;                      // [LF_ROWS]
+    int* Is = reinterpret_cast<int*>(omcs + LF_ROWS);  // [LF_ROWS]
+
+    const int s = blockIdx.y;
+    const long long row0 = (long long)blockIdx.x * LF_ROWS;
+    const int nrows = (int)min((long long)LF_ROWS, B - row0);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const size_t rbase = (size_t)s * B + row0;          // first row of this tile in [ns*B]
+    const double s2e = hyp[H_S2_ERR];
+
+    for (int e = tid; e < LF_ROWS * LDP; e += LF_THREADS) {
+        int r = e / LDP, a = e - r * LDP;
+        Ps[e] = (r < nrows && a < Q) ? PG[(rbase + r) * Q + a] : 0.0;
+    }
+    for (int e = tid; e < 2 * KP * LDS + 2 * NP; e += LF_THREADS) Ss[e] = 0.0;   // Ss and mus are contiguous
+    for (int r = tid; r < LF_ROWS; r += LF_THREADS) {
+        Is[r] = r < nrows ? I[row0 + r] : -1;
+        omcs[r] = r < nrows ? 1.0 - cG[rbase + r] : 0.0;
+    }
+    __syncthreads();
+
+    // A fragments of this warp's 16 rows: rows 16w + 8mb + g, k = 4ks + t
+    double afr[2][KS];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) afr[mb][ks] = Ps[(16 * w + 8 * mb + g) * LDP + 4 * ks + t];
+    const int rloc[2] = {16 * w + g, 16 * w + 8 + g};
+    const int myI[2] = {Is[rloc[0]], Is[rloc[1]]};
+
+    // ---- phase 1: m[n,j] = p_n . mu_W[j], F_n, residual -------------------------------------------------
+    double Fp[2] = {0.0, 0.0};
+    for (int jb = 0; jb * 8 < D; ++jb) {
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        const int jn = 8 * jb + g;                       // B-fragment column (latent) of this lane
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const int k = 4 * ks + t;
+            double b = (jn < D && k < Q) ? __ldg(&muW[(size_t)jn * Q + k]) : 0.0;
+            dmma884(acc[0][0], acc[0][1], afr[0][ks], b);
+            dmma884(acc[1][0], acc[1][1], afr[1][ks], b);
+        }
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+            if (rloc[mb] < nrows) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = 8 * jb + 2 * t + e;
+                    if (j < D) {
+                        const size_t o = (rbase + rloc[mb]) * D + j;
+                        double mval = 0.0;
+                        if (j <= myI[mb]) {
+                            mval = acc[mb][e];
+                            Fp[mb] = fma(l[o], mval, Fp[mb]);
+                        }
+                        lbar[o] = mval;                 // parked here until the residual is known
+                    }
+                }
+            }
+        }
+    }
+    double racc = 0.0, gacc = 0.0;                       // per-thread partial sums of the sample statistics
+    double rr[2];
+    const double cst = -0.5 * log(s2e) - log(sqrt(2.0 * 3.14159265358979323846));
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) {
+        double F = Fp[mb];
+        F += __shfl_xor_sync(0xffffffffu, F, 1);
+        F += __shfl_xor_sync(0xffffffffu, F, 2);
+        double r = 0.0;
+        if (rloc[mb] < nrows) r = y[row0 + rloc[mb]] - F;
+        rr[mb] = r / s2e;
+        if (t == 0 && rloc[mb] < nrows) {
+            rrs[rloc[mb]] = rr[mb];
+            racc += -(r * r) / (2.0 * s2e) + cst;
+            gacc += (r * r) / (2.0 * s2e) - 0.5;
+        }
+    }
+    for (int jb = 0; jb * 8 < D; ++jb) {
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+            if (rloc[mb] < nrows) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = 8 * jb + 2 * t + e;
+                    if (j < D) {
+                        const size_t o = (rbase + rloc[mb]) * D + j;
+                        lbar[o] = -scale * rr[mb] * lbar[o];
+                        if (j > myI[mb]) {
+                            mgbar[o] = 0.0;
+                            qgbar[o] = 0.0;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- phase 2: quadratic forms, j loop with a cp.async double buffer -----------------------------------
+    const int jmax = Is[nrows - 1];
+    const int warpmaxI = (16 * w < nrows) ? Is[min(16 * w + 15, nrows - 1)] : -1;
+    auto stage = [&](int j, int buf) {
+        const double* Sg = SigW + (size_t)j * Q * Q;
+        double* Sd = Ss + (size_t)buf * KP * LDS;
+        for (int e = tid; e < Q * Q; e += LF_THREADS) {
+            int a = e / Q, b = e - a * Q;
+            cp_async8(&Sd[a * LDS + b], &Sg[e]);
+        }
+        for (int c = tid; c < Q; c += LF_THREADS) cp_async8(&mus[buf * NP + c], &muW[(size_t)j * Q + c]);
+        for (int r = tid; r < nrows; r += LF_THREADS) cp_async8(&lcol[buf * LF_ROWS + r], &l[(rbase + r) * D + j]);
+    };
+    double pacc[2][NB][2];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) pacc[mb][nb][0] = pacc[mb][nb][1] = 0.0;
+    double pen[2] = {0.0, 0.0}, gsum[2] = {0.0, 0.0};
+
+    stage(0, 0);
+    cp_async_commit();
+    for (int j = 0; j <= jmax; ++j) {
+        const int buf = j & 1;
+        cp_async_wait<0>();
+        __syncthreads();                                  // buffer `buf` landed; everyone is done with the other one
+        if (j + 1 <= jmax) stage(j + 1, buf ^ 1);
+        cp_async_commit();
+        if (warpmaxI < j) continue;                        // warp-uniform: none of this warp's rows uses latent j
+        const double* Sd = Ss + (size_t)buf * KP * LDS;
+        double V[2][NB][2];
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) V[mb][nb][0] = V[mb][nb][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                const double b = Sd[(4 * ks + t) * LDS + 8 * nb + g];
+                dmma884(V[0][nb][0], V[0][nb][1], afr[0][ks], b);
+                dmma884(V[1][nb][0], V[1][nb][1], afr[1][ks], b);
+            }
+        }
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+            const int rl = rloc[mb];
+            double qp = 0.0;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                qp = fma(V[mb][nb][0], Ps[rl * LDP + 8 * nb + 2 * t], qp);
+                qp = fma(V[mb][nb][1], Ps[rl * LDP + 8 * nb + 2 * t + 1], qp);
+            }
+            qp += __shfl_xor_sync(0xffffffffu, qp, 1);
+            qp += __shfl_xor_sync(0xffffffffu, qp, 2);
+            const bool live = (rl < nrows) && (j <= myI[mb]);
+            const double lj = live ? lcol[buf * LF_ROWS + rl] : 0.0;
+            const double gq = scale * (0.5 / s2e) * lj * lj;          // cotangent of s2_g[n,j]
+            const double gm = -scale * rr[mb] * lj;                    // cotangent of mu_g[n,j]
+            const double s2g = omcs[rl] + qp;
+            if (live && t == 0) {
+                const size_t o = (rbase + rl) * D + j;
+                pen[mb] = fma(lj * lj, s2g, pen[mb]);
+                gsum[mb] += gq;
+                lbar[o] += scale * (1.0 / s2e) * lj * s2g;
+                qgbar[o] = gq;
+                mgbar[o] = gm;
+            }
+            const double g2 = 2.0 * gq;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                pacc[mb][nb][0] = fma(g2, V[mb][nb][0], fma(gm, mus[buf * NP + 8 * nb + 2 * t], pacc[mb][nb][0]));
+                pacc[mb][nb][1] = fma(g2, V[mb][nb][1], fma(gm, mus[buf * NP + 8 * nb + 2 * t + 1], pacc[mb][nb][1]));
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- outputs ---------------------------------------------------------------------------------------------
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) {
+        const int rl = rloc[mb];
+        if (rl < nrows) {
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = 8 * nb + 2 * t + e;
+                    if (c < Q) PGbar[(rbase + rl) * Q + c] = pacc[mb][nb][e];
+                }
+            }
+            if (t == 0) {
+                cGbar[rbase + rl] = -gsum[mb];
+                racc -= (0.5 / s2e) * pen[mb];
+                gacc += (0.5 / s2e) * pen[mb];
+            }
+        }
+    }
+    racc = block_sum(racc);
+    gacc = block_sum(gacc);
+    if (tid == 0) {
+        atomicAdd(&Rsum[s], racc);
+        atomicAdd(&ghyp[H_S2_ERR], -scale * gacc);
+    }
+}
+
+template <int NB, int KS>
+static int launch_latent_fused(const double* PG, const double* cG, const double* l, const double* y, const int* I,
+                               const double* SigW, const double* muW, const double* hyp, double scale, double* Rsum,
+                               double* ghyp, double* lbar, double* mgbar, double* qgbar, double* cGbar, double* PGbar,
+                               int ns, long long B, int Q, int D, cudaStream_t st) {
+    size_t smem = LFShape<NB, KS>::smem_bytes;
+    if (int r = nmgp_opt_in_smem(k_latent_fused<NB, KS>, smem, "nmgp_latent_fused")) return r;
+    dim3 grid((unsigned)((B + LF_ROWS - 1) / LF_ROWS), ns);
+    k_latent_fused<NB, KS><<<grid, LF_THREADS, smem, st>>>(PG, cG, l, y, I, SigW, muW, hyp, scale, Rsum, ghyp, lbar,
+                                                           mgbar, qgbar, cGbar, PGbar, B, Q, D);
+    return nmgp_launch_status("nmgp_latent_fused");
+}
+
+// generic-Q fallbacks (nmgp_quadform.cu / nmgp_rows.cu)
+extern "C" int nmgp_quadform_fwd(const double*, const double*, const int*, const int*, const double*, const double*,
+                                 double*, double*, int, long long, int, int, int, cudaStream_t);
+extern "C" int nmgp_quadform_bwd(const double*, const double*, const int*, const int*, const double*, const double*,
+                                 const double*, const double*, double*, double*, int, long long, int, int, int,
+                                 cudaStream_t);
+extern "C" int nmgp_lik_rows(const double*, const double*, const double*, const double*, const double*, const int*,
+                             const double*, double, double*, double*, double*, double*, double*, double*, int,
+                             long long, int, cudaStream_t);
+
+#define LF_CASE(nb, ks)                                                                                              \
+    if (NBr == nb && KSr == ks)                                                                                      \
+        return launch_latent_fused<nb, ks>(PG, cG, l, y, I, SigW, muW, hyp, scale, Rsum, ghyp, lbar, mgbar, qgbar,   \
+                                           cGbar, PGbar, ns, B, Q, D, st);
+
+// Fused latent-function statistics + expected log-likelihood + cotangents.  `work_q`, `work_m` ([ns,B,D] each) are
+// only used on the generic-Q path (they receive q and m).
+NMGP_API int nmgp_latent_fused(const double* PG, const double* cG, const double* l, const double* y, const int* I,
+                               const int* seg, const double* SigW, const double* muW, const double* hyp, double scale,
+                               double* Rsum, double* ghyp, double* lbar, double* mgbar, double* qgbar, double* cGbar,
+                               double* PGbar, double* work_q, double* work_m, int ns, long long B, int Q, int D,
+                               cudaStream_t st) {
+    NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && Q > 0 && Q <= 128 && D > 0, "nmgp_latent_fused");
+    if (ns == 0 || B == 0) return 0;
+    const int NBr = (Q + 7) / 8, KSr = (Q + 3) / 4;
+    if (NBr <= 8) {
+        LF_CASE(1, 1) LF_CASE(1, 2) LF_CASE(2, 3) LF_CASE(2, 4) LF_CASE(3, 5) LF_CASE(3, 6) LF_CASE(4, 7) LF_CASE(4, 8)
+        LF_CASE(5, 9) LF_CASE(5, 10) LF_CASE(6, 11) LF_CASE(6, 12) LF_CASE(7, 13) LF_CASE(7, 14) LF_CASE(8, 15)
+        LF_CASE(8, 16)
+    }
+    // Q > 64: three-kernel path
+    if (int r = nmgp_quadform_fwd(PG, PG, I, seg, SigW, muW, work_q, work_m, ns, B, Q, D, MODE_W, st)) return r;
+    if (int r = nmgp_lik_rows(l, work_m, work_q, cG, y, I, hyp, scale, Rsum, ghyp, lbar, mgbar, qgbar, cGbar, ns, B, D,
+                              st))
+        return r;
+    return nmgp_quadform_bwd(PG, PG, I, seg, SigW, muW, qgbar, mgbar, PGbar, PGbar, ns, B, Q, D, MODE_W, st);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Weighted Gram matrices on DMMA.  grid (D outputs, jgroups [+1 for the MODE_U diagonal pair], ns), 128 threads.
+#define GM_NG 4         // latents per CTA
+#define GM_TROWS 32     // rows per staged tile (8 k-steps)
+#define GM_THREADS 128
+
+template <int NB>
+struct GMShape {
+    static constexpr int NP = 8 * NB;
+    static constexpr int LDP = pad4mod8(NP);
+    static constexpr size_t smem_doubles = 2 * (size_t)GM_TROWS * LDP + 2 * 2 * GM_NG * GM_TROWS;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(GM_THREADS)
+k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const int* __restrict__ seg,
+           const double* __restrict__ qbar, const double* __restrict__ mbar, double* __restrict__ SigBar,
+           double* __restrict__ MuBar, long long B, int Q, int D, int mode) {
+    using SH = GMShape<NB>;
+    constexpr int LDP = SH::LDP;
+    extern __shared__ __align__(16) double sm[];
+    double* Pt = sm;                                        // [2][GM_TROWS][LDP]
+    double* wq = Pt + 2 * (size_t)GM_TROWS * LDP;           // [2][GM_NG][GM_TROWS]
+    double* wm = wq + 2 * GM_NG * GM_TROWS;                 // [2][GM_NG][GM_TROWS]
+    const int i = blockIdx.x, s = blockIdx.z;
+    const int ngroups = (D + GM_NG - 1) / GM_NG;
+    int j0, nj;
+    const double* P = Pa;
+    if (mode == MODE_U && (int)blockIdx.y == ngroups) {     // the diagonal coefficient pair (i,i): L1 system rows
+        j0 = i; nj = 1; P = Pb;
+    } else {
+        j0 = GM_NG * blockIdx.y;
+        const int jlast = (mode == MODE_U) ? i - 1 : i;      // MODE_U groups cover the strictly-lower pairs only
+        if (j0 > jlast) return;
+        nj = min(GM_NG, jlast - j0 + 1);
+    }
+    const long long rbeg = seg[i], rend = seg[i + 1];
+    if (rbeg >= rend) return;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int a1 = w, a2 = NB - 1 - w;
+    const bool active = a1 <= a2;
+    const int nslots = !active ? 0 : (a1 == a2 ? a1 + 1 : NB + 1);
+
+    for (int e = tid; e < (int)SH::smem_doubles; e += GM_THREADS) sm[e] = 0.0;
+    __syncthreads();
+
+    double acc[GM_NG][NB + 1][2];
+    double accm[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+    for (int u = 0; u < GM_NG; ++u)
+#pragma unroll
+        for (int sl = 0; sl <= NB; ++sl) acc[u][sl][0] = acc[u][sl][1] = 0.0;
+
+    const long long ntiles = (rend - rbeg + GM_TROWS - 1) / GM_TROWS;
+    auto stage = [&](long long tile, int buf) {
+        const long long r0 = rbeg + tile * GM_TROWS;
+        const int nr = (int)min((long long)GM_TROWS, rend - r0);
+        double* Pd = Pt + (size_t)buf * GM_TROWS * LDP;
+        for (int e = tid; e < GM_TROWS * Q; e += GM_THREADS) {
+            int r = e / Q, c = e - r * Q;
+            if (r < nr) cp_async8(&Pd[r * LDP + c], &P[((size_t)s * B + r0 + r) * Q + c]);
+            else Pd[r * LDP + c] = 0.0;
+        }
+        for (int e = tid; e < GM_NG * GM_TROWS; e += GM_THREADS) {
+            int u = e / GM_TROWS, r = e - u * GM_TROWS;
+            double* dq = &wq[(buf * GM_NG + u) * GM_TROWS + r];
+            double* dm = &wm[(buf * GM_NG + u) * GM_TROWS + r];
+            if (r < nr && u < nj) {
+                const size_t o = ((size_t)s * B + r0 + r) * D + j0 + u;
+                cp_async8(dq, &qbar[o]);
+                cp_async8(dm, &mbar[o]);
+            } else {
+                *dq = 0.0;
+                *dm = 0.0;
+            }
+        }
+    };
+    stage(0, 0);
+    cp_async_commit();
+    for (long long tile = 0; tile < ntiles; ++tile) {
+        const int buf = (int)(tile & 1);
+        cp_async_wait<0>();
+        __syncthreads();
+        if (tile + 1 < ntiles) stage(tile + 1, buf ^ 1);
+        cp_async_commit();
+        if (!active) continue;
+        const double* Pd = Pt + (size_t)buf * GM_TROWS * LDP;
+#pragma unroll
+        for (int kk = 0; kk < GM_TROWS / 4; ++kk) {
+            const int n = 4 * kk + t;                        // row of the tile this lane feeds as k index
+            const double ra1 = Pd[n * LDP + 8 * a1 + g];     // A fragment (a = 8 a1 + g, k = n), unscaled
+            const double ra2 = Pd[n * LDP + 8 * a2 + g];
+            double sa1[GM_NG], sa2[GM_NG];
+#pragma unroll
+            for (int u = 0; u < GM_NG; ++u) {
+                const double wv = wq[(buf * GM_NG + u) * GM_TROWS + n];
+                sa1[u] = ra1 * wv;
+                sa2[u] = ra2 * wv;
+            }
+#pragma unroll
+            for (int sl = 0; sl <= NB; ++sl) {
+                if (sl < nslots) {
+                    const bool first = sl <= a1;
+                    const int bb = first ? sl : sl - a1 - 1;
+                    const double bf = Pd[n * LDP + 8 * bb + g];   // B fragment (k = n, col = 8 bb + g)
+#pragma unroll
+                    for (int u = 0; u < GM_NG; ++u)
+                        dmma884(acc[u][sl][0], acc[u][sl][1], first ? sa1[u] : sa2[u], bf);
+                }
+            }
+            // MuBar: (Q x rows)(rows x NG): B fragment column g carries mbar of latent g (< NG), k = n
+            const double bm = (g < GM_NG) ? wm[(buf * GM_NG + g) * GM_TROWS + n] : 0.0;
+            dmma884(accm[0][0], accm[0][1], ra1, bm);
+            if (a2 != a1) dmma884(accm[1][0], accm[1][1], ra2, bm);
+        }
+    }
+    cp_async_wait<0>();
+    if (!active) return;
+    // ---- write-out: block (a, bb) holds rows 8a+g, cols 8bb+2t+e; mirror the strictly-lower blocks ----------
+#pragma unroll
+    for (int u = 0; u < GM_NG; ++u) {
+        if (u < nj) {
+            const int idx = (mode == MODE_U) ? pair_slot(i, j0 + u, D) : j0 + u;
+            double* Sb = SigBar + (size_t)idx * Q * Q;
+#pragma unroll
+            for (int sl = 0; sl <= NB; ++sl) {
+                if (sl < nslots) {
+                    const bool first = sl <= a1;
+                    const int a = first ? a1 : a2, bb = first ? sl : sl - a1 - 1;
+                    const int r = 8 * a + g;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int c = 8 * bb + 2 * t + e;
+                        if (r < Q && c < Q) {
+                            atomicAdd(&Sb[(size_t)r * Q + c], acc[u][sl][e]);
+                            if (a != bb) atomicAdd(&Sb[(size_t)c * Q + r], acc[u][sl][e]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int st2 = 0; st2 < 2; ++st2) {
+        if (st2 == 1 && a2 == a1) break;
+        const int a = st2 == 0 ? a1 : a2;
+        const int r = 8 * a + g;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int u = 2 * t + e;
+            if (u < nj && r < Q) {
+                const int idx = (mode == MODE_U) ? pair_slot(i, j0 + u, D) : j0 + u;
+                atomicAdd(&MuBar[(size_t)idx * Q + r], accm[st2][e]);
+            }
+        }
+    }
+}
+
+template <int NB>
+static int launch_gram(const double* Pa, const double* Pb, const int* seg, const double* qbar, const double* mbar,
+                       double* SigBar, double* MuBar, int ns, long long B, int Q, int D, int mode, cudaStream_t st) {
+    size_t smem = GMShape<NB>::smem_doubles * sizeof(double);
+    if (int r = nmgp_opt_in_smem(k_gram_mma<NB>, smem, "nmgp_weighted_gram")) return r;
+    const int ngroups = (D + GM_NG - 1) / GM_NG;
+    dim3 grid(D, ngroups + (mode == MODE_U ? 1 : 0), ns);
+    k_gram_mma<NB><<<grid, GM_THREADS, smem, st>>>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, B, Q, D, mode);
+    return nmgp_launch_status("nmgp_weighted_gram(mma)");
+}
+
+// returns 1 if Q is outside the register-resident range (caller falls back to the FMA kernel)
+int nmgp_weighted_gram_mma(const double* Pa, const double* Pb, const int* seg, const double* qbar, const double* mbar,
+                           double* SigBar, double* MuBar, int ns, long long B, int Q, int D, int mode,
+                           cudaStream_t st) {
+    switch ((Q + 7) / 8) {
+        case 1: return launch_gram<1>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+        case 2: return launch_gram<2>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+        case 3: return launch_gram<3>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+        case 4: return launch_gram<4>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+        case 5: return launch_gram<5>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+        case 6: return launch_gram<6>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+        case 7: return launch_gram<7>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+        case 8: return launch_gram<8>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+        default: return 1;
+    }
+}

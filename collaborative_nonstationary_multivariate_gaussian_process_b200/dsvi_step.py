@@ -147,11 +147,10 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
         l = ops.coef_sample_fwd(mU[0], sdU, z_L[sl], I)
         KG = ops.gibbs_build_fwd(x, Z, ellx, ellZ[sl], 0.0)
         PG, cG = ops.solve_rows_fwd(KG, R_G[sl])
-        qg, mg = ops.quadform_fwd(PG, PG, I, Sig_W, mu_W, D, MODE_W, seg=seg)
-        lbar, mgbar, qgbar, cGbar = ops.lik_rows(l, mg, qg, cG, y, I, hyp, scale, Rsum[sl], ghyp)
+        lbar, mgbar, qgbar, cGbar, PGbar = ops.latent_fused(PG, cG, l, y, I, Sig_W, mu_W, hyp, scale, Rsum[sl], ghyp,
+                                                            seg=seg)
         if not want_grads:
             continue
-        PGbar, _ = ops.quadform_bwd(PG, PG, I, Sig_W, mu_W, qgbar, mgbar, MODE_W, seg=seg)
         ops.weighted_gram(PG, PG, I, qgbar, mgbar, MODE_W, SigWbar, muWbar, seg=seg)
         KGbar = ops.solve_rows_bwd(PGbar, cGbar, KG, PG, R_G[sl], AGbar[sl])
         ellxbar = torch.empty_like(ellx)

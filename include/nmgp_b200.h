@@ -87,6 +87,15 @@ int nmgp_weighted_gram(const double* Pa, const double* Pb, const int* I, const i
                        const double* mbar, double* SigBar /* += */, double* MuBar /* += */, int ns, long long B, int Q,
                        int D, int mode, nmgp_stream_t stream);
 
+/* quadform_fwd (mode 0) + lik_rows + quadform_bwd in one pass over 128-row tiles on the FP64 tensor cores
+ * (DMMA) for Q <= 64; larger Q runs the three kernels (work_q, work_m: [ns,B,D] scratch, may be NULL if Q <= 64)
+ *                                                                          utils.py:143-144 + nmgp_dsvi.py:255-258 */
+int nmgp_latent_fused(const double* PG, const double* cG, const double* l, const double* y, const int* I,
+                      const int* seg, const double* SigW, const double* muW, const double* hyp, double scale,
+                      double* Rsum /* += */, double* ghyp /* += */, double* lbar, double* mgbar, double* qgbar,
+                      double* cGbar, double* PGbar, double* work_q, double* work_m, int ns, long long B, int Q, int D,
+                      nmgp_stream_t stream);
+
 /* v = mu_v + C_v z, ellz = exp(v)                                          utils.py:225-227, nmgp_dsvi.py:215 */
 int nmgp_sample_v_fwd(const double* mu_v, const double* Cv, const double* zv, double* v, double* ellz, int S, int Q,
                       nmgp_stream_t stream);

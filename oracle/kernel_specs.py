@@ -337,3 +337,12 @@ def rowdot_live(l, g, I):
     D = l.shape[-1]
     live = (torch.arange(D).view(1, 1, -1) <= I.long().view(1, -1, 1)).to(F64)
     return (l * g * live).sum(-1)
+
+
+def latent_fused(PG, cG, l, y, I, SigW, muW, hyp, scale, Rsum, ghyp, seg=None):
+    """= quadform_fwd(MODE_W) -> lik_rows -> quadform_bwd(MODE_W)."""
+    D = l.shape[-1]
+    qg, mg = quadform_fwd(PG, PG, I, SigW, muW, D, MODE_W)
+    lbar, mgbar, qgbar, cGbar = lik_rows(l, mg, qg, cG, y, I, hyp, scale, Rsum, ghyp)
+    PGbar, _ = quadform_bwd(PG, PG, I, SigW, muW, qgbar, mgbar, MODE_W)
+    return lbar, mgbar, qgbar, cGbar, PGbar

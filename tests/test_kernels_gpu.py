@@ -231,3 +231,25 @@ def test_row_elementwise(Q, D, B):
 def test_cpu_tensors_are_rejected():
     with pytest.raises(TypeError):
         ops.tril_syrk_fwd(torch.zeros(1, 4, 4, dtype=torch.float64))
+
+
+@pytest.mark.parametrize("Q,D,B", [(20, 3, 37), (50, 8, 300), (50, 70, 517), (64, 5, 131), (100, 4, 90), (8, 2, 129)])
+def test_latent_fused(Q, D, B):
+    """DMMA fused kernel (Q <= 64) and the three-kernel path (Q > 64) against the composed specification."""
+    gen = torch.Generator().manual_seed(B + 11)
+    ns = 2
+    rn = lambda *s: torch.randn(*s, generator=gen, dtype=torch.float64)
+    hyp = torch.tensor([1.3, 2.5, 0.7, 3.0, 1.1, 0.9, 0.05], dtype=torch.float64)
+    I = make_I(gen, B, D, empty=(1,) if D > 2 else ())
+    SigW = spd(D, Q, gen); muW = rn(D, Q)
+    PG = rn(ns, B, Q) * 0.3; cG = torch.rand(ns, B, generator=gen, dtype=torch.float64)
+    j = torch.arange(D).view(1, 1, -1)
+    l = rn(ns, B, D) * (j <= I.long().view(1, -1, 1))
+    y = rn(B)
+    Rs = torch.zeros(ns, dtype=torch.float64); gh = torch.zeros(7, dtype=torch.float64)
+    Rsd, ghd = g(Rs.clone()), g(gh.clone())
+    ref = specs.latent_fused(PG, cG, l, y, I, SigW, muW, hyp, 0.37, Rs, gh)
+    got = ops.latent_fused(g(PG), g(cG), g(l), g(y), g(I), g(SigW), g(muW), g(hyp), 0.37, Rsd, ghd)
+    for a, b, n in zip(got, ref, ("lbar", "mgbar", "qgbar", "cGbar", "PGbar")):
+        check(a, b, 1e-12, "latent_fused " + n)
+    check(Rsd, Rs, 1e-12, "latent_fused Rsum"); check(ghd, gh, 1e-11, "latent_fused ghyp")
