@@ -171,7 +171,8 @@ def solve_rows_fwd(K, R):
 def solve_rows_bwd(Pbar, cbar, K, P, R, Abar):
     ns, B, Q = K.shape
     Kbar = torch.empty_like(K)
-    check(lib().nmgp_solve_rows_bwd(_d(Pbar), _d(cbar), _d(K), _d(P), _d(R), _d(Kbar), _d(Abar),
+    work = _d(torch.empty_like(K)) if Q <= 64 else c_void_p(0)
+    check(lib().nmgp_solve_rows_bwd(_d(Pbar), _d(cbar), _d(K), _d(P), _d(R), _d(Kbar), _d(Abar), work,
                                     c_int(ns), c_int64(B), c_int(Q), _stream()), "nmgp_solve_rows_bwd")
     return Kbar
 

@@ -73,7 +73,8 @@ int nmgp_gibbs_build_bwd(const double* x, const double* z, const double* ellx, c
 int nmgp_solve_rows_fwd(const double* K, const double* R, double* P, double* c, int ns, long long B, int Q,
                         nmgp_stream_t stream);
 int nmgp_solve_rows_bwd(const double* Pbar, const double* cbar, const double* K, const double* P, const double* R,
-                        double* Kbar /* = */, double* Abar /* += */, int ns, long long B, int Q, nmgp_stream_t stream);
+                        double* Kbar /* = */, double* Abar /* += */, double* work /* [ns,B,Q] scratch, Q <= 64 */,
+                        int ns, long long B, int Q, nmgp_stream_t stream);
 
 /* q[s,n,j] = p^T Sig[idx] p, m[s,n,j] = p . Mu[idx] for j <= I[n]          utils.py:120-122,143-144 (MGP_d, MGP_mu_sigma2)
  * mode 0 (latent functions): idx = j; mode 1 (coefficients): idx = packed pair (I[n], j), p = Pb row if j == I[n] */
