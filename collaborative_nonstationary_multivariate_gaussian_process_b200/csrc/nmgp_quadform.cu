@@ -12,6 +12,11 @@
 
 #define QF_SUB 4  // threads per row
 
+// DMMA formulations (nmgp_quadform_mma.cu), Q <= 64
+int nmgp_coef_quadform_mma(bool bwd, const double* Pa, const double* Pb, const int* I, const double* Sig,
+                           const double* Mu, double* q, double* m, const double* qbar, const double* mbar,
+                           double* Pabar, double* Pbbar, int ns, long long B, int Q, int D, cudaStream_t st);
+
 __device__ __forceinline__ void load_matrix(double* __restrict__ dst, const double* __restrict__ src, int n) {
     for (int e = threadIdx.x; e < n; e += blockDim.x) dst[e] = src[e];
 }
@@ -137,6 +142,8 @@ NMGP_API int nmgp_quadform_fwd(const double* Pa, const double* Pb, const int* I,
     NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && Q > 0 && Q <= 128 && D > 0 && (mode == MODE_W || mode == MODE_U),
                  "nmgp_quadform_fwd");
     if (ns == 0 || B == 0) return 0;
+    if (mode == MODE_U && Q <= 64)
+        return nmgp_coef_quadform_mma(false, Pa, Pb, I, Sig, Mu, q, m, nullptr, nullptr, nullptr, nullptr, ns, B, Q, D, st);
     const int TR = quadform_rows(Q, mode, false);
     size_t smem = quadform_smem(Q, mode, false, TR);
     if (int r = nmgp_opt_in_smem(k_quadform<false>, smem, "nmgp_quadform_fwd")) return r;
@@ -153,6 +160,9 @@ NMGP_API int nmgp_quadform_bwd(const double* Pa, const double* Pb, const int* I,
     NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && Q > 0 && Q <= 128 && D > 0 && (mode == MODE_W || mode == MODE_U),
                  "nmgp_quadform_bwd");
     if (ns == 0 || B == 0) return 0;
+    if (mode == MODE_U && Q <= 64)
+        return nmgp_coef_quadform_mma(true, Pa, Pb, I, Sig, Mu, nullptr, nullptr, qbar, mbar, Pabar, Pbbar, ns, B, Q, D,
+                                      st);
     const int TR = quadform_rows(Q, mode, true);
     size_t smem = quadform_smem(Q, mode, true, TR);
     if (int r = nmgp_opt_in_smem(k_quadform<true>, smem, "nmgp_quadform_bwd")) return r;

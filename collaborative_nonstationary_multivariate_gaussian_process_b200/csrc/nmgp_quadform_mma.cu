@@ -27,6 +27,9 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 __host__ __device__ constexpr int pad4mod8(int n) { return ((n + 3) / 8) * 8 + 4; }   // smallest m >= n, m % 8 == 4
+// smallest m >= n with m % 16 == 8: rows of the P tile are then read conflict-free as 16-byte (2-column) accesses by
+// the C-fragment layout of the epilogue (8 rows x 4 column pairs per warp)
+__host__ __device__ constexpr int pad8mod16(int n) { return ((n + 7) / 16) * 16 + 8; }
 
 // ------------------------------------------------------------------------------------------------------------
 #define LF_ROWS 128
@@ -36,7 +39,7 @@ template <int NB, int KS>
 struct LFShape {
     static constexpr int NP = 8 * NB;                      // padded N (columns of Sigma / P in C layout)
     static constexpr int KP = 4 * KS;                      // padded K
-    static constexpr int LDP = pad4mod8(NP > KP ? NP : KP);
+    static constexpr int LDP = pad8mod16(NP > KP ? NP : KP);
     static constexpr int LDS = pad4mod8(NP);
     static constexpr size_t smem_doubles = (size_t)LF_ROWS * LDP + 2 * (size_t)KP * LDS + 2 * NP + 2 * LF_ROWS + 2 * LF_ROWS;
     static constexpr size_t smem_bytes = smem_doubles * 8 + LF_ROWS * 4;
@@ -108,12 +111,7 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
                     const int j = 8 * jb + 2 * t + e;
                     if (j < D) {
                         const size_t o = (rbase + rloc[mb]) * D + j;
-                        double mval = 0.0;
-                        if (j <= myI[mb]) {
-                            mval = acc[mb][e];
-                            Fp[mb] = fma(l[o], mval, Fp[mb]);
-                        }
-                        lbar[o] = mval;                 // parked here until the residual is known
+                        if (j <= myI[mb]) Fp[mb] = fma(l[o], acc[mb][e], Fp[mb]);
                     }
                 }
             }
@@ -136,26 +134,16 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
             gacc += (r * r) / (2.0 * s2e) - 0.5;
         }
     }
-    for (int jb = 0; jb * 8 < D; ++jb) {
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) {
-            if (rloc[mb] < nrows) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int j = 8 * jb + 2 * t + e;
-                    if (j < D) {
-                        const size_t o = (rbase + rloc[mb]) * D + j;
-                        lbar[o] = -scale * rr[mb] * lbar[o];
-                        if (j > myI[mb]) {
-                            mgbar[o] = 0.0;
-                            qgbar[o] = 0.0;
-                        }
-                    }
-                }
-            }
+    // entries of latents a row does not use (j > I[n]) are exact zeros in every [ns,B,D] output
+    for (int e = tid; e < nrows * D; e += LF_THREADS) {
+        const int r = e / D, j = e - r * D;
+        if (j > Is[r]) {
+            const size_t o = (rbase + r) * D + j;
+            lbar[o] = 0.0;
+            mgbar[o] = 0.0;
+            qgbar[o] = 0.0;
         }
     }
-
     // ---- phase 2: quadratic forms, j loop with a cp.async double buffer -----------------------------------
     const int jmax = Is[nrows - 1];
     const int warpmaxI = (16 * w < nrows) ? Is[min(16 * w + 15, nrows - 1)] : -1;
@@ -203,14 +191,22 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {
             const int rl = rloc[mb];
-            double qp = 0.0;
+            double qp = 0.0, qp1 = 0.0, mp = 0.0, mp1 = 0.0;
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) {
-                qp = fma(V[mb][nb][0], Ps[rl * LDP + 8 * nb + 2 * t], qp);
-                qp = fma(V[mb][nb][1], Ps[rl * LDP + 8 * nb + 2 * t + 1], qp);
+                const double2 pv = *reinterpret_cast<const double2*>(&Ps[rl * LDP + 8 * nb + 2 * t]);
+                const double2 mv = *reinterpret_cast<const double2*>(&mus[buf * NP + 8 * nb + 2 * t]);
+                qp = fma(V[mb][nb][0], pv.x, qp);
+                qp1 = fma(V[mb][nb][1], pv.y, qp1);
+                mp = fma(mv.x, pv.x, mp);
+                mp1 = fma(mv.y, pv.y, mp1);
             }
+            qp += qp1;
+            mp += mp1;
             qp += __shfl_xor_sync(0xffffffffu, qp, 1);
             qp += __shfl_xor_sync(0xffffffffu, qp, 2);
+            mp += __shfl_xor_sync(0xffffffffu, mp, 1);
+            mp += __shfl_xor_sync(0xffffffffu, mp, 2);
             const bool live = (rl < nrows) && (j <= myI[mb]);
             const double lj = live ? lcol[buf * LF_ROWS + rl] : 0.0;
             const double gq = scale * (0.5 / s2e) * lj * lj;          // cotangent of s2_g[n,j]
@@ -220,7 +216,7 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
                 const size_t o = (rbase + rl) * D + j;
                 pen[mb] = fma(lj * lj, s2g, pen[mb]);
                 gsum[mb] += gq;
-                lbar[o] += scale * (1.0 / s2e) * lj * s2g;
+                lbar[o] = -scale * (rr[mb] * mp - (1.0 / s2e) * lj * s2g);
                 qgbar[o] = gq;
                 mgbar[o] = gm;
             }
@@ -311,6 +307,209 @@ NMGP_API int nmgp_latent_fused(const double* PG, const double* cG, const double*
                               st))
         return r;
     return nmgp_quadform_bwd(PG, PG, I, seg, SigW, muW, qgbar, mgbar, PGbar, PGbar, ns, B, Q, D, MODE_W, st);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Coefficient-side quadratic forms on DMMA (MODE_U): for the rows of output i and every j <= i
+//     q[n,j] = p^T Sigma_U[pair(i,j)] p,  m[n,j] = p . mu_U[pair(i,j)],   p = P_L1[n] if j == i else P_L0[n]
+// (forward, code/utils.py:120-122 inside the D(D+1)/2 loop of code/nmgp_dsvi.py:228-237, only for the pairs the row
+// consumes) and the adjoint  Pbar += 2 qbar Sigma p + mbar mu  (backward).  Same tiling as k_latent_fused: 128-row
+// tiles, A = P tile in registers (reloaded when the source system changes), B = Sigma_U[pair] through a cp.async
+// double buffer; the tile walks the (i, j) pairs of every output present in it.
+template <int NB, int KS, bool BWD>
+__global__ void __launch_bounds__(LF_THREADS, 1)
+k_coef_quadform_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const int* __restrict__ I,
+                    const double* __restrict__ Sig, const double* __restrict__ Mu, double* __restrict__ qout,
+                    double* __restrict__ mout, const double* __restrict__ qbar, const double* __restrict__ mbar,
+                    double* __restrict__ Pabar, double* __restrict__ Pbbar, long long B, int Q, int D) {
+    using SH = LFShape<NB, KS>;
+    constexpr int LDP = SH::LDP, LDS = SH::LDS, NP = SH::NP, KP = SH::KP;
+    extern __shared__ __align__(16) double sm[];
+    double* PaS = sm;                                   // [LF_ROWS][LDP]
+    double* PbS = PaS + (size_t)LF_ROWS * LDP;          // [LF_ROWS][LDP]
+    double* Ss = PbS + (size_t)LF_ROWS * LDP;           // [2][KP][LDS]
+    double* mus = Ss + 2 * (size_t)KP * LDS;            // [2][NP]
+    double* qcol = mus + 2 * NP;                        // [2][LF_ROWS]  (BWD: qbar column of the task)
+    double* mcol = qcol + 2 * LF_ROWS;                  // [2][LF_ROWS]
+    int* Is = reinterpret_cast<int*>(mcol + 2 * LF_ROWS);
+
+    const int s = blockIdx.y;
+    const long long row0 = (long long)blockIdx.x * LF_ROWS;
+    const int nrows = (int)min((long long)LF_ROWS, B - row0);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const size_t rbase = (size_t)s * B + row0;
+
+    for (int e = tid; e < LF_ROWS * LDP; e += LF_THREADS) {
+        int r = e / LDP, a = e - r * LDP;
+        bool ok = r < nrows && a < Q;
+        PaS[e] = ok ? Pa[(rbase + r) * Q + a] : 0.0;
+        PbS[e] = ok ? Pb[(rbase + r) * Q + a] : 0.0;
+    }
+    for (int e = tid; e < 2 * KP * LDS + 2 * NP; e += LF_THREADS) Ss[e] = 0.0;
+    for (int r = tid; r < LF_ROWS; r += LF_THREADS) Is[r] = r < nrows ? I[row0 + r] : -1;
+    __syncthreads();
+
+    const int rloc[2] = {16 * w + g, 16 * w + 8 + g};
+    const int myI[2] = {Is[rloc[0]], Is[rloc[1]]};
+    const int wlo = (16 * w < nrows) ? Is[16 * w] : 1 << 30;                         // outputs spanned by this warp
+    const int whi = (16 * w < nrows) ? Is[min(16 * w + 15, nrows - 1)] : -1;
+    const int i_lo = Is[0], i_hi = Is[nrows - 1];
+
+    auto stage = [&](int i, int j, int buf) {
+        const int idx = pair_slot(i, j, D);
+        const double* Sg = Sig + (size_t)idx * Q * Q;
+        double* Sd = Ss + (size_t)buf * KP * LDS;
+        for (int e = tid; e < Q * Q; e += LF_THREADS) {
+            int a = e / Q, b = e - a * Q;
+            cp_async8(&Sd[a * LDS + b], &Sg[e]);
+        }
+        for (int c = tid; c < Q; c += LF_THREADS) cp_async8(&mus[buf * NP + c], &Mu[(size_t)idx * Q + c]);
+        if (BWD) {
+            for (int r = tid; r < nrows; r += LF_THREADS) {
+                cp_async8(&qcol[buf * LF_ROWS + r], &qbar[(rbase + r) * D + j]);
+                cp_async8(&mcol[buf * LF_ROWS + r], &mbar[(rbase + r) * D + j]);
+            }
+        }
+    };
+
+    double afr[2][KS];
+    double pacc[2][NB][2];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) pacc[mb][nb][0] = pacc[mb][nb][1] = 0.0;
+    int cursrc = -1;                                   // 0: Pa fragments loaded, 1: Pb fragments loaded
+
+    int i = i_lo, j = 0, it = 0;
+    stage(i, j, 0);
+    cp_async_commit();
+    while (i <= i_hi) {
+        const int buf = it & 1;
+        int ni = i, nj = j + 1;
+        if (nj > i) { ni = i + 1; nj = 0; }
+        cp_async_wait<0>();
+        __syncthreads();
+        if (ni <= i_hi) stage(ni, nj, buf ^ 1);
+        cp_async_commit();
+        if (i >= wlo && i <= whi) {                    // warp-uniform: some row of this warp belongs to output i
+            const int src = (j == i) ? 1 : 0;
+            const double* Psrc = src ? PbS : PaS;
+            if (src != cursrc) {
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) afr[mb][ks] = Psrc[(16 * w + 8 * mb + g) * LDP + 4 * ks + t];
+                cursrc = src;
+            }
+            const double* Sd = Ss + (size_t)buf * KP * LDS;
+            double V[2][NB][2];
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) V[mb][nb][0] = V[mb][nb][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    const double b = Sd[(4 * ks + t) * LDS + 8 * nb + g];
+                    dmma884(V[0][nb][0], V[0][nb][1], afr[0][ks], b);
+                    dmma884(V[1][nb][0], V[1][nb][1], afr[1][ks], b);
+                }
+            }
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+                const int rl = rloc[mb];
+                const bool live = (rl < nrows) && (myI[mb] == i);
+                if (!BWD) {
+                    double qp = 0.0, mp = 0.0;
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) {
+                        const double p0 = Psrc[rl * LDP + 8 * nb + 2 * t], p1 = Psrc[rl * LDP + 8 * nb + 2 * t + 1];
+                        qp = fma(V[mb][nb][0], p0, qp);
+                        qp = fma(V[mb][nb][1], p1, qp);
+                        mp = fma(mus[buf * NP + 8 * nb + 2 * t], p0, mp);
+                        mp = fma(mus[buf * NP + 8 * nb + 2 * t + 1], p1, mp);
+                    }
+                    qp += __shfl_xor_sync(0xffffffffu, qp, 1);
+                    qp += __shfl_xor_sync(0xffffffffu, qp, 2);
+                    mp += __shfl_xor_sync(0xffffffffu, mp, 1);
+                    mp += __shfl_xor_sync(0xffffffffu, mp, 2);
+                    if (live && t == 0) {
+                        qout[(rbase + rl) * D + j] = qp;
+                        mout[(rbase + rl) * D + j] = mp;
+                    }
+                } else {
+                    const double g2 = live ? 2.0 * qcol[buf * LF_ROWS + rl] : 0.0;
+                    const double gm = live ? mcol[buf * LF_ROWS + rl] : 0.0;
+                    if (src == 0) {
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb) {
+                            pacc[mb][nb][0] = fma(g2, V[mb][nb][0], fma(gm, mus[buf * NP + 8 * nb + 2 * t], pacc[mb][nb][0]));
+                            pacc[mb][nb][1] = fma(g2, V[mb][nb][1], fma(gm, mus[buf * NP + 8 * nb + 2 * t + 1], pacc[mb][nb][1]));
+                        }
+                    } else if (live) {                 // the single diagonal pair of this row: direct store
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int c = 8 * nb + 2 * t + e;
+                                if (c < Q)
+                                    Pbbar[(rbase + rl) * Q + c] = fma(g2, V[mb][nb][e], gm * mus[buf * NP + c]);
+                            }
+                    }
+                }
+            }
+        }
+        i = ni; j = nj; ++it;
+    }
+    cp_async_wait<0>();
+    if (BWD) {
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+            const int rl = rloc[mb];
+            if (rl < nrows) {
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int c = 8 * nb + 2 * t + e;
+                        if (c < Q) Pabar[(rbase + rl) * Q + c] = pacc[mb][nb][e];
+                    }
+            }
+        }
+    }
+}
+
+template <int NB, int KS, bool BWD>
+static int launch_coef_quadform(const double* Pa, const double* Pb, const int* I, const double* Sig, const double* Mu,
+                                double* q, double* m, const double* qbar, const double* mbar, double* Pabar,
+                                double* Pbbar, int ns, long long B, int Q, int D, cudaStream_t st) {
+    using SH = LFShape<NB, KS>;
+    size_t smem = 8 * (2 * (size_t)LF_ROWS * SH::LDP + 2 * (size_t)SH::KP * SH::LDS + 2 * SH::NP + 4 * LF_ROWS) + LF_ROWS * 4;
+    if (int r = nmgp_opt_in_smem(k_coef_quadform_mma<NB, KS, BWD>, smem, "nmgp_quadform(mma)")) return r;
+    dim3 grid((unsigned)((B + LF_ROWS - 1) / LF_ROWS), ns);
+    k_coef_quadform_mma<NB, KS, BWD><<<grid, LF_THREADS, smem, st>>>(Pa, Pb, I, Sig, Mu, q, m, qbar, mbar, Pabar, Pbbar,
+                                                                     B, Q, D);
+    return nmgp_launch_status("nmgp_quadform(mma)");
+}
+
+#define CQ_CASE(nb, ks)                                                                                               \
+    if (NBr == nb && KSr == ks)                                                                                       \
+        return bwd ? launch_coef_quadform<nb, ks, true>(Pa, Pb, I, Sig, Mu, q, m, qbar, mbar, Pabar, Pbbar, ns, B, Q, \
+                                                        D, st)                                                        \
+                   : launch_coef_quadform<nb, ks, false>(Pa, Pb, I, Sig, Mu, q, m, qbar, mbar, Pabar, Pbbar, ns, B,   \
+                                                         Q, D, st);
+
+// MODE_U forward (bwd = false: q, m) / backward (bwd = true: Pabar, Pbbar).  Returns 1 when Q > 64 (caller falls back).
+int nmgp_coef_quadform_mma(bool bwd, const double* Pa, const double* Pb, const int* I, const double* Sig,
+                           const double* Mu, double* q, double* m, const double* qbar, const double* mbar,
+                           double* Pabar, double* Pbbar, int ns, long long B, int Q, int D, cudaStream_t st) {
+    const int NBr = (Q + 7) / 8, KSr = (Q + 3) / 4;
+    if (NBr > 8) return 1;
+    CQ_CASE(1, 1) CQ_CASE(1, 2) CQ_CASE(2, 3) CQ_CASE(2, 4) CQ_CASE(3, 5) CQ_CASE(3, 6) CQ_CASE(4, 7) CQ_CASE(4, 8)
+    CQ_CASE(5, 9) CQ_CASE(5, 10) CQ_CASE(6, 11) CQ_CASE(6, 12) CQ_CASE(7, 13) CQ_CASE(7, 14) CQ_CASE(8, 15)
+    CQ_CASE(8, 16)
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------------------------
