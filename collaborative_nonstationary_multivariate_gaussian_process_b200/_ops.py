@@ -332,6 +332,104 @@ def latent_fused(PG, cG, l, y, I, SigW, muW, hyp, scale, Rsum, ghyp, seg=None):
     return lbar, mgbar, qgbar, cGbar, PGbar
 
 
+# ---- SIM_code (exact / Kronecker) line --------------------------------------------------------------
+def _optd(t):
+    return c_void_p(0) if t is None else _d(t)
+
+
+def nonstationary_cov(X1, sigma1, ell1, X2, sigma2, ell2, jitter):
+    T1, dx = X1.shape
+    T2 = X2.shape[0]
+    K = _empty(X1, T1, T2)
+    check(lib().nmgp_nonstationary_cov(_d(X1), _optd(sigma1), _optd(ell1), _d(X2), _optd(sigma2), _optd(ell2),
+                                       c_double(jitter), _d(K), c_int64(T1), c_int64(T2), c_int(dx), _stream()),
+          "nmgp_nonstationary_cov")
+    return K
+
+
+def sim_rbf_cov(X1, X2, alpha, beta, jitter):
+    T1, dx = X1.shape
+    T2 = X2.shape[0]
+    K = _empty(X1, T1, T2)
+    check(lib().nmgp_sim_rbf_cov(_d(X1), _d(X2), c_double(alpha), c_double(beta), c_double(jitter), _d(K),
+                                 c_int64(T1), c_int64(T2), c_int(dx), _stream()), "nmgp_sim_rbf_cov")
+    return K
+
+
+def pairwise_dist(X1, X2):
+    T1, dx = X1.shape
+    T2 = X2.shape[0]
+    out = _empty(X1, T1, T2)
+    check(lib().nmgp_pairwise_dist(_d(X1), _d(X2), _d(out), c_int64(T1), c_int64(T2), c_int(dx), _stream()),
+          "nmgp_pairwise_dist")
+    return out
+
+
+def gemm_nt(A, Bm, alpha=1.0, beta=0.0, C=None):
+    """C = alpha * A @ Bm.T + beta * C  (A [M,K], Bm [N,K] row-major) on the FP64 tensor cores."""
+    M, K = A.shape
+    N = Bm.shape[0]
+    if C is None:
+        C = _empty(A, M, N)
+        beta = 0.0
+    check(lib().nmgp_gemm_nt(_d(A), _d(Bm), _d(C), c_int64(M), c_int64(N), c_int64(K), c_int64(K), c_int64(K),
+                             c_int64(N), c_double(alpha), c_double(beta), _stream()), "nmgp_gemm_nt")
+    return C
+
+
+def potrf_big(A):
+    """In-place blocked lower Cholesky of the square matrix A; returns (A, sum(log(diag)))."""
+    T = A.shape[0]
+    hld = _empty(A, 1)
+    info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    check(lib().nmgp_potrf_big(_d(A), c_int64(T), c_int64(T), _d(hld), _i(info), _stream()), "nmgp_potrf_big")
+    bad = int(info.item())
+    if bad != 0:
+        raise RuntimeError("cholesky: the leading minor of order %d is not positive-definite" % bad)
+    return A, hld
+
+
+def potrs_vec(L, b):
+    x = b.clone()
+    check(lib().nmgp_potrs_vec(_d(L), c_int64(L.shape[0]), c_int64(L.shape[0]), _d(x), _stream()), "nmgp_potrs_vec")
+    return x
+
+
+def scale_add_diag(K, alpha, sigma2):
+    A = torch.empty_like(K)
+    check(lib().nmgp_scale_add_diag(_d(K), _d(A), c_int64(K.shape[0]), c_double(alpha), c_double(sigma2), _stream()),
+          "nmgp_scale_add_diag")
+    return A
+
+
+def kron_product(t1, t2):
+    h1, w1 = t1.shape
+    h2, w2 = t2.shape
+    out = _empty(t1, h1 * h2, w1 * w2)
+    check(lib().nmgp_kron_product(_d(t1), _d(t2), _d(out), c_int(h1), c_int(w1), c_int64(h2), c_int64(w2), _stream()),
+          "nmgp_kron_product")
+    return out
+
+
+def eigh_small(A):
+    n = A.shape[0]
+    w = _empty(A, n); V = _empty(A, n, n); work = _empty(A, n, n)
+    check(lib().nmgp_eigh_small(_d(A), _d(w), _d(V), _d(work), c_int(n), _stream()), "nmgp_eigh_small")
+    return w, V
+
+
+def axpby(x, y, a, b):
+    out = torch.empty_like(x)
+    check(lib().nmgp_axpby(_d(x), _d(y), _d(out), c_int64(x.numel()), c_double(a), c_double(b), _stream()), "nmgp_axpby")
+    return out
+
+
+def dot(x, y):
+    out = _zeros(x, 1)
+    check(lib().nmgp_dot(_d(x), _d(y), _d(out), c_int64(x.numel()), _stream()), "nmgp_dot")
+    return out
+
+
 # ---- optional per-call CUDA-event timing (used by bench.py; off by default) -------------------------
 import functools as _functools
 
@@ -376,3 +474,5 @@ for _name, _fn in list(globals().items()):
     if callable(_fn) and not _name.startswith("_") and getattr(_fn, "__module__", None) == __name__ \
             and _name not in ("check", "lib"):
         globals()[_name] = _instrument(_fn)
+
+

@@ -1,0 +1,511 @@
+// Large dense FP64 kernels of the SIM_code (exact/Kronecker) line:
+//   nmgp_gemm_nt      C = alpha A B^T + beta C on the FP64 tensor cores (DMMA m8n8k4), 128x128 CTA tiles
+//   nmgp_potrf_big    blocked right-looking Cholesky (lower) of a T x T matrix: diagonal block in one CTA,
+//                     panel TRSM one thread per row, trailing SYRK through the DMMA GEMM (lower tiles only)
+//   nmgp_potrs_vec    solve L L^T x = b for one right-hand side (blocked substitution)
+//   nmgp_eigh_small   cyclic Jacobi eigen-decomposition of a small symmetric matrix (the D x D output covariance)
+//   helpers           A = alpha K + sigma2 I, Kronecker products
+// They replace torch.symeig / torch.inverse / torch.logdet / torch.mm at
+// code/SIM_code/Utility/kronecker_operation.py:36-85 and distributions.py:26-113 (SURVEY.md 7.2 "Kronecker without
+// eigen of K": sigma2 I + B (x) K = (V (x) I) blkdiag_m(sigma2 I + lambda_m K) (V^T (x) I)).
+#include "common.cuh"
+
+__device__ __forceinline__ void dmma884d(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cpd8(double* smem_dst, const double* gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cpd16(double* smem_dst, const double* gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cpd_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cpd_wait0() { asm volatile("cp.async.wait_group 0;\n" ::); }
+
+// ------------------------------------------------------------------------------------------------------------
+// C[M,N] = alpha * A[M,K] * B[N,K]^T + beta * C      (row-major, leading dimensions lda/ldb/ldc)
+// CTA tile 128 x 128, 8 warps as 4 (m) x 2 (n): warp tile 32 x 64 = 4 x 8 DMMA blocks, K staged 32 at a time in a
+// cp.async double buffer.  lower_only: skip tiles strictly above the diagonal (SYRK-style trailing update).
+#define GT_M 128
+#define GT_N 128
+#define GT_K 32
+#define GT_LD 36          // 36 % 8 == 4: conflict-free fragment loads (see pad4mod8 in nmgp_quadform_mma.cu)
+#define GT_THREADS 256
+
+__global__ void __launch_bounds__(GT_THREADS, 1)
+k_gemm_nt(const double* __restrict__ A, const double* __restrict__ Bm, double* __restrict__ C, long long M,
+          long long N, long long K, long long lda, long long ldb, long long ldc, double alpha, double beta,
+          int lower_only) {
+    extern __shared__ __align__(16) double sm[];
+    double* As = sm;                              // [2][GT_M][GT_LD]
+    double* Bs = As + 2 * GT_M * GT_LD;           // [2][GT_N][GT_LD]
+    const long long m0 = (long long)blockIdx.y * GT_M, n0 = (long long)blockIdx.x * GT_N;
+    if (lower_only && n0 > m0 + GT_M - 1) return;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int wm = w >> 1, wn = w & 1;            // warp position: rows 32*wm, cols 64*wn
+    const bool vec_ok = ((lda & 1) == 0) && ((ldb & 1) == 0) && ((((size_t)A) & 15) == 0) && ((((size_t)Bm) & 15) == 0);
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    auto stage = [&](long long k0, int buf) {
+        double* Ad = As + buf * GT_M * GT_LD;
+        double* Bd = Bs + buf * GT_N * GT_LD;
+        // 128 rows x 32 k each: 16 double2 per row
+        for (int e = tid; e < GT_M * (GT_K / 2); e += GT_THREADS) {
+            int r = e / (GT_K / 2), c2 = (e - r * (GT_K / 2)) * 2;
+            long long gr = m0 + r, gk = k0 + c2;
+            double* d = &Ad[r * GT_LD + c2];
+            if (gr < M && gk + 1 < K && vec_ok) cpd16(d, &A[gr * lda + gk]);
+            else {
+                d[0] = (gr < M && gk < K) ? A[gr * lda + gk] : 0.0;
+                d[1] = (gr < M && gk + 1 < K) ? A[gr * lda + gk + 1] : 0.0;
+            }
+            gr = n0 + r;
+            d = &Bd[r * GT_LD + c2];
+            if (gr < N && gk + 1 < K && vec_ok) cpd16(d, &Bm[gr * ldb + gk]);
+            else {
+                d[0] = (gr < N && gk < K) ? Bm[gr * ldb + gk] : 0.0;
+                d[1] = (gr < N && gk + 1 < K) ? Bm[gr * ldb + gk + 1] : 0.0;
+            }
+        }
+    };
+    const long long nk = (K + GT_K - 1) / GT_K;
+    stage(0, 0);
+    cpd_commit();
+    for (long long kt = 0; kt < nk; ++kt) {
+        const int buf = (int)(kt & 1);
+        cpd_wait0();
+        __syncthreads();
+        if (kt + 1 < nk) stage((kt + 1) * GT_K, buf ^ 1);
+        cpd_commit();
+        const double* Ad = As + buf * GT_M * GT_LD + (32 * wm) * GT_LD;
+        const double* Bd = Bs + buf * GT_N * GT_LD + (64 * wn) * GT_LD;
+#pragma unroll
+        for (int ks = 0; ks < GT_K / 4; ++ks) {
+            double af[4], bf[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = Ad[(8 * i + g) * GT_LD + 4 * ks + t];      // A[row][k]
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bf[j] = Bd[(8 * j + g) * GT_LD + 4 * ks + t];      // B^T[k][col] = B[col][k]
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma884d(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cpd_wait0();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long r = m0 + 32 * wm + 8 * i + g;
+        if (r >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const long long c = n0 + 64 * wn + 8 * j + 2 * t + e;
+                if (c < N) {
+                    double* p = &C[r * ldc + c];
+                    double v = alpha * acc[i][j][e];
+                    if (beta != 0.0) v = fma(beta, *p, v);
+                    *p = v;
+                }
+            }
+        }
+    }
+}
+static int gemm_nt_launch(const double* A, const double* Bm, double* C, long long M, long long N, long long K,
+                          long long lda, long long ldb, long long ldc, double alpha, double beta, int lower_only,
+                          cudaStream_t st) {
+    if (M <= 0 || N <= 0) return 0;
+    size_t smem = sizeof(double) * 2 * (GT_M + GT_N) * GT_LD;
+    if (int r = nmgp_opt_in_smem(k_gemm_nt, smem, "nmgp_gemm_nt")) return r;
+    dim3 grid((unsigned)((N + GT_N - 1) / GT_N), (unsigned)((M + GT_M - 1) / GT_M));
+    k_gemm_nt<<<grid, GT_THREADS, smem, st>>>(A, Bm, C, M, N, K, lda, ldb, ldc, alpha, beta, lower_only);
+    return nmgp_launch_status("nmgp_gemm_nt");
+}
+NMGP_API int nmgp_gemm_nt(const double* A, const double* Bm, double* C, long long M, long long N, long long K,
+                          long long lda, long long ldb, long long ldc, double alpha, double beta, cudaStream_t st) {
+    NMGP_REQUIRE(M >= 0 && N >= 0 && K >= 0 && lda >= K && ldb >= K && ldc >= N, "nmgp_gemm_nt");
+    return gemm_nt_launch(A, Bm, C, M, N, K, lda, ldb, ldc, alpha, beta, 0, st);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Blocked Cholesky.  PB = panel width.
+#define PB 128
+
+// diagonal block: in-place lower Cholesky of the nb x nb block at A (leading dimension lda), one CTA, block in smem
+__global__ void __launch_bounds__(PB)
+k_potrf_diag(double* __restrict__ A, long long lda, int nb, int* __restrict__ info, int blockno) {
+    extern __shared__ double sm[];
+    __shared__ double s_piv;
+    const int ld = nb | 1, i = threadIdx.x;
+    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
+        int a = e / nb, b = e - a * nb;
+        sm[a * ld + b] = A[(long long)a * lda + b];
+    }
+    __syncthreads();
+    for (int k = 0; k < nb; ++k) {
+        double s = 0.0;
+        if (i >= k && i < nb) {
+            double s0 = sm[i * ld + k], s1 = 0.0;
+            int c = 0;
+            for (; c + 1 < k; c += 2) {
+                s0 = fma(-sm[i * ld + c], sm[k * ld + c], s0);
+                s1 = fma(-sm[i * ld + c + 1], sm[k * ld + c + 1], s1);
+            }
+            if (c < k) s0 = fma(-sm[i * ld + c], sm[k * ld + c], s0);
+            s = s0 + s1;
+            if (i == k) {
+                if (!(s > 0.0)) atomicMax(info, blockno * PB + k + 1);
+                s_piv = sqrt(s);
+            }
+        }
+        __syncthreads();
+        if (i >= k && i < nb) sm[i * ld + k] = (i == k) ? s_piv : s / s_piv;
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
+        int a = e / nb, b = e - a * nb;
+        A[(long long)a * lda + b] = (b <= a) ? sm[a * ld + b] : 0.0;
+    }
+}
+// panel: rows below the diagonal block, X L11^T = A21  ->  one thread per row, forward substitution, L11 in smem
+__global__ void __launch_bounds__(128)
+k_trsm_panel(const double* __restrict__ L11, double* __restrict__ A21, long long lda, long long nrows, int nb) {
+    extern __shared__ double sm[];
+    double* Ls = sm;                         // [nb][nb]
+    double* tile = Ls + nb * nb;             // [128][nb+1]
+    const int ldt = nb + 1, tid = threadIdx.x;
+    const long long r0 = (long long)blockIdx.x * 128;
+    const int nr = (int)min(128LL, nrows - r0);
+    for (int e = tid; e < nb * nb; e += 128) {
+        int a = e / nb, b = e - a * nb;
+        Ls[e] = L11[(long long)a * lda + b];
+    }
+    for (int e = tid; e < nr * nb; e += 128) {
+        int r = e / nb, a = e - r * nb;
+        tile[r * ldt + a] = A21[(r0 + r) * lda + a];
+    }
+    __syncthreads();
+    if (tid < nr) {
+        double* y = tile + tid * ldt;
+        for (int a = 0; a < nb; ++a) {
+            double s0 = y[a], s1 = 0.0;
+            int c = 0;
+            for (; c + 1 < a; c += 2) {
+                s0 = fma(-Ls[a * nb + c], y[c], s0);
+                s1 = fma(-Ls[a * nb + c + 1], y[c + 1], s1);
+            }
+            if (c < a) s0 = fma(-Ls[a * nb + c], y[c], s0);
+            y[a] = (s0 + s1) / Ls[a * nb + a];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < nr * nb; e += 128) {
+        int r = e / nb, a = e - r * nb;
+        A21[(r0 + r) * lda + a] = tile[r * ldt + a];
+    }
+}
+__global__ void k_zero_upper(double* __restrict__ A, long long T, long long lda) {
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c < T && c > r) A[r * lda + c] = 0.0;
+}
+__global__ void k_logdiag_sum(const double* __restrict__ A, long long T, long long lda, double* __restrict__ out) {
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < T; i += blockDim.x) s += log(A[i * lda + i]);
+    s = block_sum(s);
+    if (threadIdx.x == 0) out[0] = s;
+}
+// In-place lower Cholesky of A (T x T, leading dimension lda); strict upper triangle zeroed; hld = sum log diag(L);
+// *info = 1 + index of the first non-positive pivot (0 if none).  Reference sites: torch.logdet / torch.inverse
+// at distributions.py:109-110 and logpos.py:352-353 (dense path), and the per-eigen-block factorisations of the
+// Kronecker path.
+NMGP_API int nmgp_potrf_big(double* A, long long T, long long lda, double* hld, int* info, cudaStream_t st) {
+    NMGP_REQUIRE(T > 0 && lda >= T, "nmgp_potrf_big");
+    const size_t smem_d = sizeof(double) * PB * (PB | 1);
+    const size_t smem_t = sizeof(double) * (64 * 64 + 128 * (64 + 1));
+    if (int r = nmgp_opt_in_smem(k_potrf_diag, smem_d, "nmgp_potrf_big")) return r;
+    if (int r = nmgp_opt_in_smem(k_trsm_panel, smem_t, "nmgp_potrf_big")) return r;
+    for (long long k = 0; k < T; k += PB) {
+        const int nb = (int)min((long long)PB, T - k);
+        double* Akk = A + k * lda + k;
+        k_potrf_diag<<<1, PB, sizeof(double) * nb * (nb | 1), st>>>(Akk, lda, nb, info, (int)(k / PB));
+        const long long rest = T - k - nb;
+        if (rest > 0) {
+            double* A21 = A + (k + nb) * lda + k;
+            // panel solve X L11^T = A21 in column halves of <= 64 (the row tile must fit shared memory):
+            //   X1 = A21[:, :h] L11[:h,:h]^-T ;  A21[:, h:] -= X1 L11[h:, :h]^T ;  X2 = A21[:, h:] L11[h:,h:]^-T
+            const int h = nb > 64 ? 64 : nb;
+            k_trsm_panel<<<(unsigned)((rest + 127) / 128), 128, sizeof(double) * (h * h + 128 * (h + 1)), st>>>(
+                Akk, A21, lda, rest, h);
+            if (nb > h) {
+                const int h2 = nb - h;
+                if (int r = gemm_nt_launch(A21, Akk + (long long)h * lda, A21 + h, rest, h2, h, lda, lda, lda, -1.0, 1.0, 0, st))
+                    return r;
+                k_trsm_panel<<<(unsigned)((rest + 127) / 128), 128, sizeof(double) * (h2 * h2 + 128 * (h2 + 1)), st>>>(
+                    Akk + (long long)h * lda + h, A21 + h, lda, rest, h2);
+            }
+            double* A22 = A + (k + nb) * lda + (k + nb);
+            if (int r = gemm_nt_launch(A21, A21, A22, rest, rest, nb, lda, lda, lda, -1.0, 1.0, 1, st)) return r;
+        }
+    }
+    dim3 gz((unsigned)((T + 255) / 256), (unsigned)min(T, 65535LL));
+    if (T <= 65535) k_zero_upper<<<gz, 256, 0, st>>>(A, T, lda);
+    if (hld) k_logdiag_sum<<<1, 1024, 0, st>>>(A, T, lda, hld);
+    return nmgp_launch_status("nmgp_potrf_big");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// x <- (L L^T)^-1 x for one vector: blocked forward then backward substitution (PB-wide diagonal solves in one CTA,
+// the remaining update as a memory-bound matrix-vector product).
+__global__ void __launch_bounds__(PB)
+k_trsv_diag(const double* __restrict__ L, long long lda, double* __restrict__ x, int nb, int transposed) {
+    extern __shared__ double sm[];
+    double* Ls = sm;            // [nb][nb|1]
+    double* xs = Ls + nb * (nb | 1);
+    const int ld = nb | 1, tid = threadIdx.x;
+    for (int e = tid; e < nb * nb; e += blockDim.x) {
+        int a = e / nb, b = e - a * nb;
+        Ls[a * ld + b] = L[(long long)a * lda + b];
+    }
+    if (tid < nb) xs[tid] = x[tid];
+    __syncthreads();
+    if (!transposed) {
+        for (int a = 0; a < nb; ++a) {
+            if (tid == a) xs[a] /= Ls[a * ld + a];
+            __syncthreads();
+            if (tid > a && tid < nb) xs[tid] = fma(-Ls[tid * ld + a], xs[a], xs[tid]);
+            __syncthreads();
+        }
+    } else {
+        for (int a = nb - 1; a >= 0; --a) {
+            if (tid == a) xs[a] /= Ls[a * ld + a];
+            __syncthreads();
+            if (tid < a) xs[tid] = fma(-Ls[a * ld + tid], xs[a], xs[tid]);
+            __syncthreads();
+        }
+    }
+    if (tid < nb) x[tid] = xs[tid];
+}
+// y[r] -= sum_c M[r,c] x[c] (not transposed: M is rows x nb) or y[c] -= sum_r M[r,c] x[r] (transposed: M is nb.. rows)
+__global__ void k_gemv_sub(const double* __restrict__ Mx, long long lda, const double* __restrict__ x,
+                           double* __restrict__ y, long long rows, int nb) {
+    // one warp per row of M: y[row] -= M[row, 0:nb] . x
+    const int lane = threadIdx.x & 31;
+    long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    double acc = 0.0;
+    for (int c = lane; c < nb; c += 32) acc = fma(Mx[row * lda + c], x[c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) y[row] -= acc;
+}
+__global__ void k_gemv_t_sub(const double* __restrict__ Mx, long long lda, const double* __restrict__ x,
+                             double* __restrict__ y, int rows, long long ncols) {
+    // y[c] -= sum_{r < rows} M[r, c] x[r]   (one thread per column, coalesced across columns)
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    double acc = 0.0;
+    for (int r = 0; r < rows; ++r) acc = fma(Mx[r * lda + c], x[r], acc);
+    y[c] -= acc;
+}
+NMGP_API int nmgp_potrs_vec(const double* L, long long T, long long lda, double* x, cudaStream_t st) {
+    NMGP_REQUIRE(T > 0 && lda >= T, "nmgp_potrs_vec");
+    const size_t smem = sizeof(double) * (PB * (PB | 1) + PB);
+    if (int r = nmgp_opt_in_smem(k_trsv_diag, smem, "nmgp_potrs_vec")) return r;
+    for (long long k = 0; k < T; k += PB) {                       // L y = b
+        const int nb = (int)min((long long)PB, T - k);
+        k_trsv_diag<<<1, PB, sizeof(double) * (nb * (nb | 1) + nb), st>>>(L + k * lda + k, lda, x + k, nb, 0);
+        const long long rest = T - k - nb;
+        if (rest > 0)
+            k_gemv_sub<<<(unsigned)((rest + 7) / 8), 256, 0, st>>>(L + (k + nb) * lda + k, lda, x + k, x + k + nb, rest, nb);
+    }
+    for (long long k = ((T - 1) / PB) * PB; k >= 0; k -= PB) {    // L^T x = y
+        const int nb = (int)min((long long)PB, T - k);
+        k_trsv_diag<<<1, PB, sizeof(double) * (nb * (nb | 1) + nb), st>>>(L + k * lda + k, lda, x + k, nb, 1);
+        if (k > 0)   // x[0:k] -= L[k:k+nb, 0:k]^T x[k:k+nb]
+            k_gemv_t_sub<<<(unsigned)((k + 127) / 128), 128, 0, st>>>(L + k * lda, lda, x + k, x, nb, k);
+    }
+    return nmgp_launch_status("nmgp_potrs_vec");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// A = alpha K + sigma2 I
+__global__ void k_scale_add_diag(const double* __restrict__ K, double* __restrict__ A, long long T, double alpha,
+                                 double sigma2) {
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y + (long long)blockIdx.z * 65535;
+    if (c < T && r < T) A[r * T + c] = fma(alpha, K[r * T + c], (r == c) ? sigma2 : 0.0);
+}
+NMGP_API int nmgp_scale_add_diag(const double* K, double* A, long long T, double alpha, double sigma2,
+                                 cudaStream_t st) {
+    NMGP_REQUIRE(T > 0, "nmgp_scale_add_diag");
+    dim3 grid((unsigned)((T + 255) / 256), (unsigned)min(T, 65535LL), (unsigned)((T + 65534) / 65535));
+    k_scale_add_diag<<<grid, 256, 0, st>>>(K, A, T, alpha, sigma2);
+    return nmgp_launch_status("nmgp_scale_add_diag");
+}
+// out[(i1*h2+i2), (j1*w2+j2)] = t1[i1,j1] * t2[i2,j2]     (kronecker_operation.py:5-22)
+__global__ void k_kron(const double* __restrict__ t1, const double* __restrict__ t2, double* __restrict__ out, int h1,
+                       int w1, long long h2, long long w2) {
+    long long total = (long long)h1 * h2 * w1 * w2;
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    long long W = (long long)w1 * w2;
+    long long r = gid / W, c = gid - r * W;
+    long long i1 = r / h2, i2 = r - i1 * h2, j1 = c / w2, j2 = c - j1 * w2;
+    out[gid] = t1[i1 * w1 + j1] * t2[i2 * w2 + j2];
+}
+NMGP_API int nmgp_kron_product(const double* t1, const double* t2, double* out, int h1, int w1, long long h2,
+                               long long w2, cudaStream_t st) {
+    long long total = (long long)h1 * h2 * w1 * w2;
+    NMGP_REQUIRE(total >= 0 && total < (1LL << 40), "nmgp_kron_product");
+    if (total == 0) return 0;
+    k_kron<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t1, t2, out, h1, w1, h2, w2);
+    return nmgp_launch_status("nmgp_kron_product");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Cyclic Jacobi eigen-decomposition of a small symmetric n x n matrix (n <= 128), one CTA.  Reads the UPPER triangle
+// (torch.symeig's default, kronecker_operation.py:45).  Eigenvalues ascending in w, eigenvectors in the columns of V.
+__global__ void __launch_bounds__(128)
+k_eigh_jacobi(const double* __restrict__ A, double* __restrict__ w, double* __restrict__ V,
+              double* __restrict__ Vwork, int n) {
+    extern __shared__ double sm[];
+    double* S = sm;              // [n][n]
+    double* U = Vwork;           // [n][n] eigenvector accumulator (global scratch, L2-resident)
+    __shared__ double cs[2];
+    __shared__ int order[128];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < n * n; e += blockDim.x) {
+        int a = e / n, b = e - a * n;
+        S[e] = (b >= a) ? A[a * n + b] : A[b * n + a];
+        U[e] = (a == b) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0;
+        for (int e = tid; e < n * n; e += blockDim.x) {
+            int a = e / n, b = e - a * n;
+            if (a != b) off = fma(S[e], S[e], off);
+        }
+        off = block_sum(off);
+        double diag = 0.0;
+        for (int a = tid; a < n; a += blockDim.x) diag = fma(S[a * n + a], S[a * n + a], diag);
+        diag = block_sum(diag);
+        if (off <= 1e-34 * diag) break;
+        for (int p = 0; p < n - 1; ++p) {
+            for (int q = p + 1; q < n; ++q) {
+                if (tid == 0) {
+                    double apq = S[p * n + q];
+                    double c = 1.0, s = 0.0;
+                    if (apq != 0.0) {
+                        double tau = (S[q * n + q] - S[p * n + p]) / (2.0 * apq);
+                        double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = 1.0 / sqrt(1.0 + tt * tt);
+                        s = tt * c;
+                    }
+                    cs[0] = c; cs[1] = s;
+                }
+                __syncthreads();
+                const double c = cs[0], s = cs[1];
+                if (s != 0.0) {
+                    for (int k = tid; k < n; k += blockDim.x) {      // columns p, q of S and U
+                        double skp = S[k * n + p], skq = S[k * n + q];
+                        S[k * n + p] = c * skp - s * skq;
+                        S[k * n + q] = s * skp + c * skq;
+                        double ukp = U[k * n + p], ukq = U[k * n + q];
+                        U[k * n + p] = c * ukp - s * ukq;
+                        U[k * n + q] = s * ukp + c * ukq;
+                    }
+                    __syncthreads();
+                    for (int k = tid; k < n; k += blockDim.x) {      // rows p, q of S
+                        double spk = S[p * n + k], sqk = S[q * n + k];
+                        S[p * n + k] = c * spk - s * sqk;
+                        S[q * n + k] = s * spk + c * sqk;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    // sort ascending (n small): rank by counting
+    if (tid < n) {
+        double v = S[tid * n + tid];
+        int rank = 0;
+        for (int k = 0; k < n; ++k) {
+            double u = S[k * n + k];
+            if (u < v || (u == v && k < tid)) ++rank;
+        }
+        order[rank] = tid;
+    }
+    __syncthreads();
+    if (tid < n) w[tid] = S[order[tid] * n + order[tid]];
+    for (int e = tid; e < n * n; e += blockDim.x) {
+        int a = e / n, b = e - a * n;
+        V[e] = U[a * n + order[b]];
+    }
+}
+NMGP_API int nmgp_eigh_small(const double* A, double* w, double* V, double* work /* n*n */, int n, cudaStream_t st) {
+    NMGP_REQUIRE(n > 0 && n <= 128 && work != nullptr, "nmgp_eigh_small");
+    size_t smem = sizeof(double) * n * n;
+    if (int r = nmgp_opt_in_smem(k_eigh_jacobi, smem, "nmgp_eigh_small")) return r;
+    k_eigh_jacobi<<<1, 128, smem, st>>>(A, w, V, work, n);
+    return nmgp_launch_status("nmgp_eigh_small");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// small vector helpers of the Kronecker log-density (distributions.py:42-51)
+__global__ void k_axpby(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out,
+                        long long n, double a, double b) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a * x[i] + b * y[i];
+}
+NMGP_API int nmgp_axpby(const double* x, const double* y, double* out, long long n, double a, double b,
+                        cudaStream_t st) {
+    if (n <= 0) return 0;
+    k_axpby<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, out, n, a, b);
+    return nmgp_launch_status("nmgp_axpby");
+}
+__global__ void k_dot(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out,
+                      long long n) {
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        s = fma(x[i], y[i], s);
+    s = block_sum(s);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+}
+NMGP_API int nmgp_dot(const double* x, const double* y, double* out /* += */, long long n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    k_dot<<<(unsigned)blocks, 256, 0, st>>>(x, y, out, n);
+    return nmgp_launch_status("nmgp_dot");
+}
+// dist[i,j] = |x_i|^2 + |y_j|^2 - 2 x_i.y_j   (kernels.py:5-21)
+__global__ void k_pairwise(const double* __restrict__ X1, const double* __restrict__ X2, double* __restrict__ out,
+                           long long T1, long long T2, int dx) {
+    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y + (long long)blockIdx.z * 65535;
+    if (j >= T2 || i >= T1) return;
+    double xn = 0.0, yn = 0.0, xy = 0.0;
+    for (int k = 0; k < dx; ++k) {
+        double a = X1[i * dx + k], b = X2[j * dx + k];
+        xn = fma(a, a, xn);
+        yn = fma(b, b, yn);
+        xy = fma(a, b, xy);
+    }
+    out[i * T2 + j] = xn + yn - 2.0 * xy;
+}
+NMGP_API int nmgp_pairwise_dist(const double* X1, const double* X2, double* out, long long T1, long long T2, int dx,
+                                cudaStream_t st) {
+    NMGP_REQUIRE(T1 >= 0 && T2 >= 0 && dx > 0, "nmgp_pairwise_dist");
+    if (T1 == 0 || T2 == 0) return 0;
+    dim3 grid((unsigned)((T2 + 255) / 256), (unsigned)min(T1, 65535LL), (unsigned)((T1 + 65534) / 65535));
+    k_pairwise<<<grid, 256, 0, st>>>(X1, X2, out, T1, T2, dx);
+    return nmgp_launch_status("nmgp_pairwise_dist");
+}

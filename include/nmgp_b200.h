@@ -145,6 +145,29 @@ int nmgp_nonstationary_cov(const double* X1, const double* sigma1, const double*
 int nmgp_sim_rbf_cov(const double* X1, const double* X2, double alpha, double beta, double jitter, double* K,
                      long long T1, long long T2, int dx, nmgp_stream_t stream);
 
+int nmgp_pairwise_dist(const double* X1, const double* X2, double* out, long long T1, long long T2, int dx,
+                       nmgp_stream_t stream);                               /* kernels.py:5-21 */
+
+/* C = alpha A B^T + beta C on the FP64 tensor cores (A [M,K], B [N,K], row-major)
+ *                                                    kronecker_operation.py:72-85 kron_mv (torch.mm x2), trailing updates */
+int nmgp_gemm_nt(const double* A, const double* B, double* C, long long M, long long N, long long K, long long lda,
+                 long long ldb, long long ldc, double alpha, double beta, nmgp_stream_t stream);
+/* in-place blocked lower Cholesky, hld = sum log diag L      replaces torch.symeig / torch.logdet / torch.inverse at
+ *                                                    kronecker_operation.py:45-47,66-67; distributions.py:37-40,109-110 */
+int nmgp_potrf_big(double* A, long long T, long long lda, double* hld, int* info, nmgp_stream_t stream);
+/* x <- (L L^T)^-1 x */
+int nmgp_potrs_vec(const double* L, long long T, long long lda, double* x, nmgp_stream_t stream);
+/* A = alpha K + sigma2 I (the eigen-block sigma2 I + lambda_m K of sigma2 I + B (x) K) */
+int nmgp_scale_add_diag(const double* K, double* A, long long T, double alpha, double sigma2, nmgp_stream_t stream);
+/* dense Kronecker product                                                  kronecker_operation.py:5-33 */
+int nmgp_kron_product(const double* t1, const double* t2, double* out, int h1, int w1, long long h2, long long w2,
+                      nmgp_stream_t stream);
+/* Jacobi eigen-decomposition of a small symmetric matrix (upper triangle read), ascending eigenvalues
+ *                                                                          torch.symeig(B) at kronecker_operation.py:45 */
+int nmgp_eigh_small(const double* A, double* w, double* V, double* work, int n, nmgp_stream_t stream);
+int nmgp_axpby(const double* x, const double* y, double* out, long long n, double a, double b, nmgp_stream_t stream);
+int nmgp_dot(const double* x, const double* y, double* out /* += */, long long n, nmgp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -346,3 +346,63 @@ def latent_fused(PG, cG, l, y, I, SigW, muW, hyp, scale, Rsum, ghyp, seg=None):
     lbar, mgbar, qgbar, cGbar = lik_rows(l, mg, qg, cG, y, I, hyp, scale, Rsum, ghyp)
     PGbar, _ = quadform_bwd(PG, PG, I, SigW, muW, qgbar, mgbar, MODE_W)
     return lbar, mgbar, qgbar, cGbar, PGbar
+
+
+# ---- SIM_code line ---------------------------------------------------------------------------------------
+def nonstationary_cov(X1, sigma1, ell1, X2, sigma2, ell2, jitter):
+    n1, n2 = X1.shape[0], X2.shape[0]
+    s1 = torch.ones(n1, dtype=F64) if sigma1 is None else sigma1
+    s2 = torch.ones(n2, dtype=F64) if sigma2 is None else sigma2
+    l1 = torch.ones(n1, dtype=F64) if ell1 is None else ell1
+    l2 = torch.ones(n2, dtype=F64) if ell2 is None else ell2
+    d = pairwise_dist(X1, X2)
+    A = (l1 ** 2).view(-1, 1) + (l2 ** 2).view(1, -1)
+    K = (s1.view(-1, 1) * s2.view(1, -1)) * torch.sqrt(2.0 * (l1.view(-1, 1) * l2.view(1, -1)) / A) * torch.exp(-d / A)
+    return K + jitter * torch.eye(n1, n2, dtype=F64)
+
+
+def sim_rbf_cov(X1, X2, alpha, beta, jitter):
+    d = pairwise_dist(X1 / beta, X2 / beta)
+    return torch.exp(-0.5 * d) * alpha ** 2 + jitter * torch.eye(X1.shape[0], X2.shape[0], dtype=F64)
+
+
+def pairwise_dist(X1, X2):
+    return (X1 ** 2).sum(1).view(-1, 1) + (X2 ** 2).sum(1).view(1, -1) - 2.0 * X1 @ X2.t()
+
+
+def gemm_nt(A, Bm, alpha=1.0, beta=0.0, C=None):
+    out = alpha * (A @ Bm.t())
+    if C is not None:
+        C.copy_(out + beta * C)
+        return C
+    return out
+
+
+def potrf_big(A):
+    L = torch.linalg.cholesky(A)
+    A.copy_(L)
+    return A, L.diagonal().log().sum().reshape(1)
+
+
+def potrs_vec(L, b):
+    return torch.cholesky_solve(b.view(-1, 1), L).view(-1)
+
+
+def scale_add_diag(K, alpha, sigma2):
+    return alpha * K + sigma2 * torch.eye(K.shape[0], dtype=F64)
+
+
+def kron_product(t1, t2):
+    return torch.kron(t1, t2)
+
+
+def eigh_small(A):
+    return torch.linalg.eigh(A, UPLO="U")
+
+
+def axpby(x, y, a, b):
+    return a * x + b * y
+
+
+def dot(x, y):
+    return (x * y).sum().reshape(1)

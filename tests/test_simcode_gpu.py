@@ -1,0 +1,117 @@
+"""SIM_code (exact / Kronecker) line on the GPU against the reference's golden vectors and the CPU oracle.
+Tolerances: 1e-12 relative for the element-wise kernel builds, 1e-9 for anything that goes through a
+factorisation (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kernel_specs as specs
+from oracle import nmgp_oracle as orc
+from tests import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+from collaborative_nonstationary_multivariate_gaussian_process_b200 import _ops as ops  # noqa: E402
+from collaborative_nonstationary_multivariate_gaussian_process_b200 import distributions, kernels, kronecker_operation  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def d(a):
+    return torch.as_tensor(a, dtype=torch.float64).to(DEV).contiguous()
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().cpu().double().reshape(-1); b = torch.as_tensor(b).detach().cpu().double().reshape(-1)
+    return float(torch.linalg.norm(a - b) / max(float(torch.linalg.norm(b)), 1e-300))
+
+
+def test_kernel_builds_match_reference_golden():
+    g = gu.load("sim_code")
+    x1 = d(g["x1"]).view(-1, 1); x2 = d(g["x2"]).view(-1, 1)
+    assert rel(kernels.Nonstationary_RBF_cov(x1, sigma1=d(g["sg1"]), ell1=d(g["ell1"])), g["K_self"]) < 1e-13
+    assert rel(kernels.Nonstationary_RBF_cov(x1, d(g["sg1"]), d(g["ell1"]), x2, d(g["sg2"]), d(g["ell2"])), g["K_cross"]) < 1e-13
+    assert rel(kernels.Nonstationary_RBF_cov(x1), g["K_def"]) < 1e-13
+    assert rel(kernels.RBF_cov(x1, alpha=1.3, beta=0.2), g["R_self"]) < 1e-13
+    assert rel(kernels.RBF_cov(x1, x2, alpha=0.7, beta=0.35), g["R_cross"]) < 1e-13
+    xc = torch.from_numpy(g["x1"]).view(-1, 1)
+    assert rel(kernels.pairwise_distances(x1), orc.sq_dists_gemm(xc)) < 1e-13
+
+
+def test_kronecker_and_logpdf_match_reference_golden():
+    g = gu.load("sim_code")
+    K = d(g["K_self"]); Bf = d(g["Bf"]); y = d(g["y"]); mu = d(g["mu"]); s2 = torch.tensor(float(g["s2"]), dtype=torch.float64)
+    assert rel(kronecker_operation.kron_mv(Bf, K, y), g["kron_mv"]) < 1e-12
+    assert rel(kronecker_operation.kronecker_product(Bf, K[:5, :4].contiguous()), g["kron_prod"]) < 1e-14
+    assert rel(kronecker_operation.kronecker_product_diag(torch.diagonal(Bf).contiguous(), torch.diagonal(K).contiguous()), g["kron_diag"]) < 1e-14
+    ld = float(kronecker_operation.kron_logdet(s2, Bf, K).cpu())
+    assert abs(ld - float(g["kron_logdet"])) <= 1e-9 * abs(float(g["kron_logdet"]))
+    inv = kronecker_operation.kron_inv(s2, Bf, K).cpu()
+    assert np.allclose(torch.diagonal(inv).numpy(), g["kron_inv_diag"], rtol=1e-8)
+    assert np.allclose(inv[7].numpy(), g["kron_inv_row7"], rtol=1e-7, atol=1e-8)
+    lp0 = float(distributions.multivariate_normal_logpdf0(y, mu, Bf, K, s2).cpu())
+    lp2 = float(distributions.multivariate_normal_logpdf2(y, mu, Bf, K, s2).cpu())
+    assert abs(lp0 - float(g["logpdf0"])) <= 1e-9 * abs(lp0), (lp0, float(g["logpdf0"]))
+    assert abs(lp2 - float(g["logpdf2"])) <= 1e-9 * abs(lp2)
+    torch.manual_seed(9)
+    lp1 = float(distributions.multivariate_normal_logpdf1(y, mu, Bf, K, s2).cpu())
+    assert abs(lp1 - float(g["logpdf1"])) <= 1e-9 * abs(lp1)
+    # dense-path helper (distributions.py:10-23)
+    lp = float(distributions.multivariate_normal_logpdf(y, mu, torch.tensor(ld, device=DEV), d(inv)).cpu())
+    assert abs(lp - float(g["logpdf2"])) <= 1e-8 * abs(lp)
+
+
+def test_t200_logpdf():
+    g = gu.load("sim_code_t200")
+    x1 = d(g["x1"]).view(-1, 1)
+    K = kernels.Nonstationary_RBF_cov(x1, ell1=d(g["ell1"]))
+    assert rel(K[17], g["K_row17"]) < 1e-13
+    y = d(g["y"]); Bf = d(g["Bf"]); s2 = torch.tensor(float(g["s2"]), dtype=torch.float64)
+    lp0 = float(distributions.multivariate_normal_logpdf0(y, torch.zeros_like(y), Bf, K, s2).cpu())
+    assert abs(lp0 - float(g["logpdf0"])) <= 1e-9 * abs(lp0), (lp0, float(g["logpdf0"]))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (300, 77, 45), (1, 5, 3), (513, 260, 129)])
+def test_gemm_nt(M, N, K):
+    gen = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=gen, dtype=torch.float64); B = torch.randn(N, K, generator=gen, dtype=torch.float64)
+    assert rel(ops.gemm_nt(d(A), d(B)), A @ B.t()) < 1e-14
+    C = torch.randn(M, N, generator=gen, dtype=torch.float64); Cd = d(C.clone())
+    ops.gemm_nt(d(A), d(B), alpha=-0.5, beta=2.0, C=Cd)
+    assert rel(Cd, -0.5 * (A @ B.t()) + 2.0 * C) < 1e-14
+
+
+@pytest.mark.parametrize("T", [7, 128, 200, 1000, 1537])
+def test_potrf_big_and_solve(T):
+    gen = torch.Generator().manual_seed(T)
+    x = torch.sort(torch.rand(T, generator=gen, dtype=torch.float64))[0].view(-1, 1)
+    K = orc.sim_nonstationary_cov(x, ell1=torch.exp(3 * (x.view(-1) - 1) ** 3 - 2.0)) + 1e-2 * torch.eye(T, dtype=torch.float64)
+    L, hld = ops.potrf_big(d(K.clone()))
+    Lr = torch.linalg.cholesky(K)
+    assert rel(L, Lr) < 1e-9
+    assert abs(float(hld.cpu()) - float(Lr.diagonal().log().sum())) <= 1e-11 * max(1.0, abs(float(Lr.diagonal().log().sum())))
+    assert float(torch.triu(L, 1).abs().max()) == 0.0
+    b = torch.randn(T, generator=gen, dtype=torch.float64)
+    xs = ops.potrs_vec(d(Lr), d(b))
+    assert rel(xs, torch.cholesky_solve(b.view(-1, 1), Lr).view(-1)) < 1e-9
+    # size-independent property: residual of the factorisation itself
+    Ld = L.cpu()
+    assert rel(Ld @ Ld.t(), K) < 1e-13
+
+
+def test_potrf_big_raises_on_non_pd():
+    A = torch.eye(300, dtype=torch.float64); A[250, 250] = -1.0
+    with pytest.raises(RuntimeError):
+        ops.potrf_big(d(A))
+
+
+@pytest.mark.parametrize("n", [2, 3, 16, 64])
+def test_eigh_small(n):
+    gen = torch.Generator().manual_seed(n)
+    L = torch.tril(torch.randn(n, n, generator=gen, dtype=torch.float64)); A = L @ L.t()
+    w, V = ops.eigh_small(d(A))
+    wr, _ = torch.linalg.eigh(A)
+    assert rel(w, wr) < 1e-12
+    Vc = V.cpu()
+    assert rel(Vc @ torch.diag(w.cpu()) @ Vc.t(), A) < 1e-12
+    assert rel(Vc.t() @ Vc, torch.eye(n, dtype=torch.float64)) < 1e-12
