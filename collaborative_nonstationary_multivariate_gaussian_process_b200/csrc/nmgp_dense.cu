@@ -141,38 +141,39 @@ NMGP_API int nmgp_gemm_nt(const double* A, const double* Bm, double* C, long lon
 // Blocked Cholesky.  PB = panel width.
 #define PB 128
 
-// diagonal block: in-place lower Cholesky of the nb x nb block at A (leading dimension lda), one CTA, block in smem
-__global__ void __launch_bounds__(PB)
+// diagonal block: in-place lower Cholesky of the nb x nb block at A (leading dimension lda), one CTA of 32 x 16
+// threads, block resident in shared memory, right-looking (every step updates the whole trailing block in parallel)
+#define PD_TX 32
+#define PD_TY 16
+__global__ void __launch_bounds__(PD_TX * PD_TY)
 k_potrf_diag(double* __restrict__ A, long long lda, int nb, int* __restrict__ info, int blockno) {
     extern __shared__ double sm[];
-    __shared__ double s_piv;
-    const int ld = nb | 1, i = threadIdx.x;
-    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
+    __shared__ double s_rinv;
+    const int ld = nb | 1, tid = threadIdx.x, tx = tid & (PD_TX - 1), ty = tid / PD_TX;
+    for (int e = tid; e < nb * nb; e += blockDim.x) {
         int a = e / nb, b = e - a * nb;
         sm[a * ld + b] = A[(long long)a * lda + b];
     }
     __syncthreads();
     for (int k = 0; k < nb; ++k) {
-        double s = 0.0;
-        if (i >= k && i < nb) {
-            double s0 = sm[i * ld + k], s1 = 0.0;
-            int c = 0;
-            for (; c + 1 < k; c += 2) {
-                s0 = fma(-sm[i * ld + c], sm[k * ld + c], s0);
-                s1 = fma(-sm[i * ld + c + 1], sm[k * ld + c + 1], s1);
-            }
-            if (c < k) s0 = fma(-sm[i * ld + c], sm[k * ld + c], s0);
-            s = s0 + s1;
-            if (i == k) {
-                if (!(s > 0.0)) atomicMax(info, blockno * PB + k + 1);
-                s_piv = sqrt(s);
-            }
+        if (tid == 0) {
+            double dkk = sm[k * ld + k];
+            if (!(dkk > 0.0)) atomicMax(info, blockno + k + 1);
+            double piv = sqrt(dkk);
+            sm[k * ld + k] = piv;
+            s_rinv = 1.0 / piv;
         }
         __syncthreads();
-        if (i >= k && i < nb) sm[i * ld + k] = (i == k) ? s_piv : s / s_piv;
+        const double rinv = s_rinv;
+        for (int i = k + 1 + tid; i < nb; i += blockDim.x) sm[i * ld + k] *= rinv;
+        __syncthreads();
+        for (int i = k + 1 + ty; i < nb; i += PD_TY) {
+            const double lik = sm[i * ld + k];
+            for (int j = k + 1 + tx; j <= i; j += PD_TX) sm[i * ld + j] = fma(-lik, sm[j * ld + k], sm[i * ld + j]);
+        }
         __syncthreads();
     }
-    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
+    for (int e = tid; e < nb * nb; e += blockDim.x) {
         int a = e / nb, b = e - a * nb;
         A[(long long)a * lda + b] = (b <= a) ? sm[a * ld + b] : 0.0;
     }
@@ -214,6 +215,51 @@ k_trsm_panel(const double* __restrict__ L11, double* __restrict__ A21, long long
         A21[(r0 + r) * lda + a] = tile[r * ldt + a];
     }
 }
+// same panel solve with the row held in registers (nb padded to 64 with an identity tail): X L^T = A
+__global__ void __launch_bounds__(128)
+k_trsm_panel_reg64(const double* __restrict__ L11, double* __restrict__ A21, long long lda, long long nrows, int nb) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int QP = 64, LDT = QP + 1;
+    double* Ls = sm;                 // [64][64], identity padded
+    double* rinv = Ls + QP * QP;     // [64]
+    double* tile = rinv + QP;        // [128][65]
+    const int tid = threadIdx.x;
+    const long long r0 = (long long)blockIdx.x * 128;
+    const int nr = (int)min(128LL, nrows - r0);
+    for (int e = tid; e < QP * QP; e += 128) {
+        int a = e / QP, b = e - a * QP;
+        Ls[e] = (a < nb && b < nb) ? ((b <= a) ? L11[(long long)a * lda + b] : 0.0) : (a == b ? 1.0 : 0.0);
+    }
+    for (int a = tid; a < QP; a += 128) rinv[a] = a < nb ? 1.0 / L11[(long long)a * lda + a] : 1.0;
+    for (int e = tid; e < 128 * QP; e += 128) {
+        int r = e / QP, a = e - r * QP;
+        tile[r * LDT + a] = (r < nr && a < nb) ? A21[(r0 + r) * lda + a] : 0.0;
+    }
+    __syncthreads();
+    double yv[QP];
+#pragma unroll
+    for (int a = 0; a < QP; ++a) yv[a] = tile[tid * LDT + a];
+#pragma unroll
+    for (int a = 0; a < QP; ++a) {
+        double s0 = yv[a], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int c = 0; c < a; ++c) {
+            const double rv = Ls[a * QP + c];
+            if ((c & 3) == 0) s0 = fma(-rv, yv[c], s0);
+            else if ((c & 3) == 1) s1 = fma(-rv, yv[c], s1);
+            else if ((c & 3) == 2) s2 = fma(-rv, yv[c], s2);
+            else s3 = fma(-rv, yv[c], s3);
+        }
+        yv[a] = ((s0 + s1) + (s2 + s3)) * rinv[a];
+    }
+#pragma unroll
+    for (int a = 0; a < QP; ++a) tile[tid * LDT + a] = yv[a];
+    __syncthreads();
+    for (int e = tid; e < nr * nb; e += 128) {
+        int r = e / nb, a = e - r * nb;
+        A21[(r0 + r) * lda + a] = tile[r * LDT + a];
+    }
+}
 __global__ void k_zero_upper(double* __restrict__ A, long long T, long long lda) {
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
     if (c < T && c > r) A[r * lda + c] = 0.0;
@@ -224,39 +270,46 @@ __global__ void k_logdiag_sum(const double* __restrict__ A, long long T, long lo
     s = block_sum(s);
     if (threadIdx.x == 0) out[0] = s;
 }
-// In-place lower Cholesky of A (T x T, leading dimension lda); strict upper triangle zeroed; hld = sum log diag(L);
-// *info = 1 + index of the first non-positive pivot (0 if none).  Reference sites: torch.logdet / torch.inverse
-// at distributions.py:109-110 and logpos.py:352-353 (dense path), and the per-eigen-block factorisations of the
-// Kronecker path.
-NMGP_API int nmgp_potrf_big(double* A, long long T, long long lda, double* hld, int* info, cudaStream_t st) {
-    NMGP_REQUIRE(T > 0 && lda >= T, "nmgp_potrf_big");
-    const size_t smem_d = sizeof(double) * PB * (PB | 1);
-    const size_t smem_t = sizeof(double) * (64 * 64 + 128 * (64 + 1));
-    if (int r = nmgp_opt_in_smem(k_potrf_diag, smem_d, "nmgp_potrf_big")) return r;
-    if (int r = nmgp_opt_in_smem(k_trsm_panel, smem_t, "nmgp_potrf_big")) return r;
-    for (long long k = 0; k < T; k += PB) {
-        const int nb = (int)min((long long)PB, T - k);
+// blocked right-looking factorisation with panel width pb (64 or 128); diagonal blocks wider than 64 recurse with pb=64
+static int potrf_blocked(double* A, long long T, long long lda, int pb, int* info, int pivot_base, cudaStream_t st) {
+    const size_t smem_r = sizeof(double) * (64 * 64 + 64 + 128 * 65);
+    for (long long k = 0; k < T; k += pb) {
+        const int nb = (int)min((long long)pb, T - k);
         double* Akk = A + k * lda + k;
-        k_potrf_diag<<<1, PB, sizeof(double) * nb * (nb | 1), st>>>(Akk, lda, nb, info, (int)(k / PB));
+        if (nb > 64) {
+            if (int r = potrf_blocked(Akk, nb, lda, 64, info, pivot_base + (int)k, st)) return r;
+        } else {
+            k_potrf_diag<<<1, PD_TX * PD_TY, sizeof(double) * nb * (nb | 1), st>>>(Akk, lda, nb, info, pivot_base + (int)k);
+        }
         const long long rest = T - k - nb;
         if (rest > 0) {
             double* A21 = A + (k + nb) * lda + k;
-            // panel solve X L11^T = A21 in column halves of <= 64 (the row tile must fit shared memory):
+            // panel solve X L11^T = A21 in column halves of <= 64 (register-resident rows):
             //   X1 = A21[:, :h] L11[:h,:h]^-T ;  A21[:, h:] -= X1 L11[h:, :h]^T ;  X2 = A21[:, h:] L11[h:,h:]^-T
             const int h = nb > 64 ? 64 : nb;
-            k_trsm_panel<<<(unsigned)((rest + 127) / 128), 128, sizeof(double) * (h * h + 128 * (h + 1)), st>>>(
-                Akk, A21, lda, rest, h);
+            k_trsm_panel_reg64<<<(unsigned)((rest + 127) / 128), 128, smem_r, st>>>(Akk, A21, lda, rest, h);
             if (nb > h) {
                 const int h2 = nb - h;
                 if (int r = gemm_nt_launch(A21, Akk + (long long)h * lda, A21 + h, rest, h2, h, lda, lda, lda, -1.0, 1.0, 0, st))
                     return r;
-                k_trsm_panel<<<(unsigned)((rest + 127) / 128), 128, sizeof(double) * (h2 * h2 + 128 * (h2 + 1)), st>>>(
-                    Akk + (long long)h * lda + h, A21 + h, lda, rest, h2);
+                k_trsm_panel_reg64<<<(unsigned)((rest + 127) / 128), 128, smem_r, st>>>(Akk + (long long)h * lda + h,
+                                                                                         A21 + h, lda, rest, h2);
             }
             double* A22 = A + (k + nb) * lda + (k + nb);
             if (int r = gemm_nt_launch(A21, A21, A22, rest, rest, nb, lda, lda, lda, -1.0, 1.0, 1, st)) return r;
         }
     }
+    return 0;
+}
+// In-place lower Cholesky of A (T x T, leading dimension lda); strict upper triangle zeroed; hld = sum log diag(L);
+// *info = 1 + index of the first non-positive pivot (0 if none).  Reference sites: torch.logdet / torch.inverse
+// at distributions.py:109-110 and logpos.py:352-353 (dense path), and the per-eigen-block factorisations of the
+// Kronecker path.
+NMGP_API int nmgp_potrf_big(double* A, long long T, long long lda, double* hld, int* info, cudaStream_t st) {
+    NMGP_REQUIRE(T > 0 && lda >= T && T < 2147483647LL, "nmgp_potrf_big");
+    if (int r = nmgp_opt_in_smem(k_potrf_diag, sizeof(double) * 64 * 65, "nmgp_potrf_big")) return r;
+    if (int r = nmgp_opt_in_smem(k_trsm_panel_reg64, sizeof(double) * (64 * 64 + 64 + 128 * 65), "nmgp_potrf_big")) return r;
+    if (int r = potrf_blocked(A, T, lda, T > 1024 ? PB : 64, info, 0, st)) return r;
     dim3 gz((unsigned)((T + 255) / 256), (unsigned)min(T, 65535LL));
     if (T <= 65535) k_zero_upper<<<gz, 256, 0, st>>>(A, T, lda);
     if (hld) k_logdiag_sum<<<1, 1024, 0, st>>>(A, T, lda, hld);
