@@ -332,6 +332,26 @@ def latent_fused(PG, cG, l, y, I, SigW, muW, hyp, scale, Rsum, ghyp, seg=None):
     return lbar, mgbar, qgbar, cGbar, PGbar
 
 
+def reparam_diag(mean, var, z):
+    out = torch.empty_like(mean)
+    check(lib().nmgp_reparam_diag(_d(mean), _d(var), _d(z), _d(out), c_int64(mean.numel()), _stream()), "nmgp_reparam_diag")
+    return out
+
+
+def normal_logprob_sum(loc, scale, y):
+    out = _zeros(loc, 1)
+    check(lib().nmgp_normal_logprob_sum(_d(loc), _d(scale), _d(y), _d(out), c_int64(loc.numel()), _stream()),
+          "nmgp_normal_logprob_sum")
+    return out
+
+
+def sumsq_rows(x):
+    rows, cols = x.shape
+    out = _empty(x, rows)
+    check(lib().nmgp_sumsq_rows(_d(x), _d(out), c_int64(rows), c_int64(cols), _stream()), "nmgp_sumsq_rows")
+    return out
+
+
 # ---- SIM_code (exact / Kronecker) line --------------------------------------------------------------
 def _optd(t):
     return c_void_p(0) if t is None else _d(t)

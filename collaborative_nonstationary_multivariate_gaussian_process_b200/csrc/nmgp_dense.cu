@@ -8,6 +8,8 @@
 // They replace torch.symeig / torch.inverse / torch.logdet / torch.mm at
 // code/SIM_code/Utility/kronecker_operation.py:36-85 and distributions.py:26-113 (SURVEY.md 7.2 "Kronecker without
 // eigen of K": sigma2 I + B (x) K = (V (x) I) blkdiag_m(sigma2 I + lambda_m K) (V^T (x) I)).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 __device__ __forceinline__ void dmma884d(double& d0, double& d1, double a, double b) {
@@ -36,17 +38,19 @@ __device__ __forceinline__ void cpd_wait0() { asm volatile("cp.async.wait_group 
 #define GT_LD 36          // 36 % 8 == 4: conflict-free fragment loads (see pad4mod8 in nmgp_quadform_mma.cu)
 #define GT_THREADS 256
 
-__global__ void __launch_bounds__(GT_THREADS, 1)
+template <int NWN>
+__global__ void __launch_bounds__(128 * NWN, NWN == 2 ? 1 : 2)
 k_gemm_nt(const double* __restrict__ A, const double* __restrict__ Bm, double* __restrict__ C, long long M,
           long long N, long long K, long long lda, long long ldb, long long ldc, double alpha, double beta,
           int lower_only) {
     extern __shared__ __align__(16) double sm[];
     double* As = sm;                              // [2][GT_M][GT_LD]
-    double* Bs = As + 2 * GT_M * GT_LD;           // [2][GT_N][GT_LD]
-    const long long m0 = (long long)blockIdx.y * GT_M, n0 = (long long)blockIdx.x * GT_N;
+    constexpr int TN = 64 * NWN, NTHREADS = 128 * NWN;
+    double* Bs = As + 2 * GT_M * GT_LD;           // [2][TN][GT_LD]
+    const long long m0 = (long long)blockIdx.y * GT_M, n0 = (long long)blockIdx.x * TN;
     if (lower_only && n0 > m0 + GT_M - 1) return;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
-    const int wm = w >> 1, wn = w & 1;            // warp position: rows 32*wm, cols 64*wn
+    const int wm = w / NWN, wn = w % NWN;         // warp position: rows 32*wm, cols 64*wn
     const bool vec_ok = ((lda & 1) == 0) && ((ldb & 1) == 0) && ((((size_t)A) & 15) == 0) && ((((size_t)Bm) & 15) == 0);
 
     double acc[4][8][2];
@@ -57,9 +61,9 @@ k_gemm_nt(const double* __restrict__ A, const double* __restrict__ Bm, double* _
 
     auto stage = [&](long long k0, int buf) {
         double* Ad = As + buf * GT_M * GT_LD;
-        double* Bd = Bs + buf * GT_N * GT_LD;
-        // 128 rows x 32 k each: 16 double2 per row
-        for (int e = tid; e < GT_M * (GT_K / 2); e += GT_THREADS) {
+        double* Bd = Bs + buf * TN * GT_LD;
+        // 128 (A) / TN (B) rows x 32 k each: 16 double2 per row
+        for (int e = tid; e < GT_M * (GT_K / 2); e += NTHREADS) {
             int r = e / (GT_K / 2), c2 = (e - r * (GT_K / 2)) * 2;
             long long gr = m0 + r, gk = k0 + c2;
             double* d = &Ad[r * GT_LD + c2];
@@ -68,8 +72,11 @@ k_gemm_nt(const double* __restrict__ A, const double* __restrict__ Bm, double* _
                 d[0] = (gr < M && gk < K) ? A[gr * lda + gk] : 0.0;
                 d[1] = (gr < M && gk + 1 < K) ? A[gr * lda + gk + 1] : 0.0;
             }
-            gr = n0 + r;
-            d = &Bd[r * GT_LD + c2];
+        }
+        for (int e = tid; e < TN * (GT_K / 2); e += NTHREADS) {
+            int r = e / (GT_K / 2), c2 = (e - r * (GT_K / 2)) * 2;
+            long long gr = n0 + r, gk = k0 + c2;
+            double* d = &Bd[r * GT_LD + c2];
             if (gr < N && gk + 1 < K && vec_ok) cpd16(d, &Bm[gr * ldb + gk]);
             else {
                 d[0] = (gr < N && gk < K) ? Bm[gr * ldb + gk] : 0.0;
@@ -87,7 +94,7 @@ k_gemm_nt(const double* __restrict__ A, const double* __restrict__ Bm, double* _
         if (kt + 1 < nk) stage((kt + 1) * GT_K, buf ^ 1);
         cpd_commit();
         const double* Ad = As + buf * GT_M * GT_LD + (32 * wm) * GT_LD;
-        const double* Bd = Bs + buf * GT_N * GT_LD + (64 * wn) * GT_LD;
+        const double* Bd = Bs + buf * TN * GT_LD + (64 * wn) * GT_LD;
 #pragma unroll
         for (int ks = 0; ks < GT_K / 4; ++ks) {
             double af[4], bf[8];
@@ -121,14 +128,27 @@ k_gemm_nt(const double* __restrict__ A, const double* __restrict__ Bm, double* _
         }
     }
 }
+static int g_gemm_narrow = -1;   // 1: 128x64 CTA tiles, two CTAs per SM (epilogue of one overlaps the MMAs of the other)
 static int gemm_nt_launch(const double* A, const double* Bm, double* C, long long M, long long N, long long K,
                           long long lda, long long ldb, long long ldc, double alpha, double beta, int lower_only,
                           cudaStream_t st) {
     if (M <= 0 || N <= 0) return 0;
-    size_t smem = sizeof(double) * 2 * (GT_M + GT_N) * GT_LD;
-    if (int r = nmgp_opt_in_smem(k_gemm_nt, smem, "nmgp_gemm_nt")) return r;
-    dim3 grid((unsigned)((N + GT_N - 1) / GT_N), (unsigned)((M + GT_M - 1) / GT_M));
-    k_gemm_nt<<<grid, GT_THREADS, smem, st>>>(A, Bm, C, M, N, K, lda, ldb, ldc, alpha, beta, lower_only);
+    if (g_gemm_narrow < 0) {
+        const char* e = getenv("NMGP_GEMM_TILE");
+        g_gemm_narrow = (e && e[0] == 'w') ? 0 : 1;
+    }
+    const bool narrow = g_gemm_narrow || N <= 64 || K <= 256;
+    if (narrow) {
+        size_t smem = sizeof(double) * 2 * (GT_M + 64) * GT_LD;
+        if (int r = nmgp_opt_in_smem(k_gemm_nt<1>, smem, "nmgp_gemm_nt")) return r;
+        dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + GT_M - 1) / GT_M));
+        k_gemm_nt<1><<<grid, 128, smem, st>>>(A, Bm, C, M, N, K, lda, ldb, ldc, alpha, beta, lower_only);
+    } else {
+        size_t smem = sizeof(double) * 2 * (GT_M + GT_N) * GT_LD;
+        if (int r = nmgp_opt_in_smem(k_gemm_nt<2>, smem, "nmgp_gemm_nt")) return r;
+        dim3 grid((unsigned)((N + GT_N - 1) / GT_N), (unsigned)((M + GT_M - 1) / GT_M));
+        k_gemm_nt<2><<<grid, 256, smem, st>>>(A, Bm, C, M, N, K, lda, ldb, ldc, alpha, beta, lower_only);
+    }
     return nmgp_launch_status("nmgp_gemm_nt");
 }
 NMGP_API int nmgp_gemm_nt(const double* A, const double* Bm, double* C, long long M, long long N, long long K,
@@ -270,34 +290,86 @@ __global__ void k_logdiag_sum(const double* __restrict__ A, long long T, long lo
     s = block_sum(s);
     if (threadIdx.x == 0) out[0] = s;
 }
-// blocked right-looking factorisation with panel width pb (64 or 128); diagonal blocks wider than 64 recurse with pb=64
-static int potrf_blocked(double* A, long long T, long long lda, int pb, int* info, int pivot_base, cudaStream_t st) {
+// factor one panel: diagonal block (recursing with 64-wide blocks when wider than 64) and the rows below it
+static int potrf_blocked(double* A, long long T, long long lda, int pb, int* info, int pivot_base, cudaStream_t st);
+static int factor_panel(double* Akk, long long lda, int nb, long long rest, int* info, int pivot_base, cudaStream_t st) {
     const size_t smem_r = sizeof(double) * (64 * 64 + 64 + 128 * 65);
+    if (nb > 64) {
+        if (int r = potrf_blocked(Akk, nb, lda, 64, info, pivot_base, st)) return r;
+    } else {
+        k_potrf_diag<<<1, PD_TX * PD_TY, sizeof(double) * nb * (nb | 1), st>>>(Akk, lda, nb, info, pivot_base);
+    }
+    if (rest > 0) {
+        // panel solve X L11^T = A21 by 64-wide column blocks with register-resident rows:
+        //   A21[:, c0:c0+h] -= X[:, :c0] L11[c0:c0+h, :c0]^T ;  X[:, c0:c0+h] = A21[:, c0:c0+h] L11[c0.., c0..]^-T
+        double* A21 = Akk + (long long)nb * lda;
+        for (int c0 = 0; c0 < nb; c0 += 64) {
+            const int h = nb - c0 > 64 ? 64 : nb - c0;
+            if (c0 > 0)
+                if (int r = gemm_nt_launch(A21, Akk + (long long)c0 * lda, A21 + c0, rest, h, c0, lda, lda, lda, -1.0, 1.0, 0, st))
+                    return r;
+            k_trsm_panel_reg64<<<(unsigned)((rest + 127) / 128), 128, smem_r, st>>>(Akk + (long long)c0 * lda + c0, A21 + c0,
+                                                                                     lda, rest, h);
+        }
+    }
+    return 0;
+}
+// blocked right-looking factorisation, panel width pb, everything on one stream (used for the diagonal blocks)
+static int potrf_blocked(double* A, long long T, long long lda, int pb, int* info, int pivot_base, cudaStream_t st) {
     for (long long k = 0; k < T; k += pb) {
         const int nb = (int)min((long long)pb, T - k);
-        double* Akk = A + k * lda + k;
-        if (nb > 64) {
-            if (int r = potrf_blocked(Akk, nb, lda, 64, info, pivot_base + (int)k, st)) return r;
-        } else {
-            k_potrf_diag<<<1, PD_TX * PD_TY, sizeof(double) * nb * (nb | 1), st>>>(Akk, lda, nb, info, pivot_base + (int)k);
-        }
         const long long rest = T - k - nb;
+        double* Akk = A + k * lda + k;
+        if (int r = factor_panel(Akk, lda, nb, rest, info, pivot_base + (int)k, st)) return r;
         if (rest > 0) {
-            double* A21 = A + (k + nb) * lda + k;
-            // panel solve X L11^T = A21 in column halves of <= 64 (register-resident rows):
-            //   X1 = A21[:, :h] L11[:h,:h]^-T ;  A21[:, h:] -= X1 L11[h:, :h]^T ;  X2 = A21[:, h:] L11[h:,h:]^-T
-            const int h = nb > 64 ? 64 : nb;
-            k_trsm_panel_reg64<<<(unsigned)((rest + 127) / 128), 128, smem_r, st>>>(Akk, A21, lda, rest, h);
-            if (nb > h) {
-                const int h2 = nb - h;
-                if (int r = gemm_nt_launch(A21, Akk + (long long)h * lda, A21 + h, rest, h2, h, lda, lda, lda, -1.0, 1.0, 0, st))
-                    return r;
-                k_trsm_panel_reg64<<<(unsigned)((rest + 127) / 128), 128, smem_r, st>>>(Akk + (long long)h * lda + h,
-                                                                                         A21 + h, lda, rest, h2);
-            }
-            double* A22 = A + (k + nb) * lda + (k + nb);
-            if (int r = gemm_nt_launch(A21, A21, A22, rest, rest, nb, lda, lda, lda, -1.0, 1.0, 1, st)) return r;
+            double* A21 = Akk + (long long)nb * lda;
+            if (int r = gemm_nt_launch(A21, A21, A21 + nb, rest, rest, nb, lda, lda, lda, -1.0, 1.0, 1, st)) return r;
         }
+    }
+    return 0;
+}
+// top level with look-ahead: the next panel is factorised on a helper stream while the main stream applies the bulk
+// of the trailing update, so the latency-bound panel work hides behind the DMMA SYRK.
+static cudaStream_t g_helper_stream = nullptr;
+static cudaEvent_t g_ev_upd = nullptr, g_ev_pan = nullptr;
+static int potrf_lookahead(double* A, long long T, long long lda, int pb, int* info, cudaStream_t s0) {
+    if (!g_helper_stream) {
+        if (cudaStreamCreateWithFlags(&g_helper_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&g_ev_upd, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&g_ev_pan, cudaEventDisableTiming) != cudaSuccess) {
+            nmgp_set_error("nmgp_potrf_big: cannot create the look-ahead stream");
+            return -4;
+        }
+    }
+    cudaStream_t s1 = g_helper_stream;
+    {   // panel 0 on the main stream
+        const int nb = (int)min((long long)pb, T);
+        if (int r = factor_panel(A, lda, nb, T - nb, info, 0, s0)) return r;
+    }
+    for (long long k = 0; k < T; k += pb) {
+        const int nb = (int)min((long long)pb, T - k);
+        const long long rest = T - k - nb;
+        if (rest <= 0) break;
+        double* A21 = A + (k + nb) * lda + k;            // rest x nb   (factorised panel k, rows below the diagonal block)
+        double* A22 = A + (k + nb) * lda + (k + nb);     // rest x rest (trailing matrix)
+        const int nb2 = (int)min((long long)pb, rest);   // width of the next panel
+        // 1. bring the next panel's columns up to date (main stream)
+        if (int r = gemm_nt_launch(A21, A21, A22, rest, nb2, nb, lda, lda, lda, -1.0, 1.0, 0, s0)) return r;
+        cudaEventRecord(g_ev_upd, s0);
+        // 2. factorise the next panel on the helper stream
+        cudaStreamWaitEvent(s1, g_ev_upd, 0);
+        if (int r = factor_panel(A22, lda, nb2, rest - nb2, info, (int)(k + nb), s1)) return r;
+        cudaEventRecord(g_ev_pan, s1);
+        // 3. rest of the trailing update (columns beyond the next panel, lower tiles only) on the main stream
+        const long long rest2 = rest - nb2;
+        if (rest2 > 0) {
+            double* B21 = A21 + (long long)nb2 * lda;
+            if (int r = gemm_nt_launch(B21, B21, A22 + (long long)nb2 * lda + nb2, rest2, rest2, nb, lda, lda, lda, -1.0, 1.0,
+                                       1, s0))
+                return r;
+        }
+        // 4. the next iteration (and anything after us on the main stream) needs the factorised panel
+        cudaStreamWaitEvent(s0, g_ev_pan, 0);
     }
     return 0;
 }
@@ -309,7 +381,11 @@ NMGP_API int nmgp_potrf_big(double* A, long long T, long long lda, double* hld, 
     NMGP_REQUIRE(T > 0 && lda >= T && T < 2147483647LL, "nmgp_potrf_big");
     if (int r = nmgp_opt_in_smem(k_potrf_diag, sizeof(double) * 64 * 65, "nmgp_potrf_big")) return r;
     if (int r = nmgp_opt_in_smem(k_trsm_panel_reg64, sizeof(double) * (64 * 64 + 64 + 128 * 65), "nmgp_potrf_big")) return r;
-    if (int r = potrf_blocked(A, T, lda, T > 1024 ? PB : 64, info, 0, st)) return r;
+    if (T > 1024) {
+        if (int r = potrf_lookahead(A, T, lda, PB, info, st)) return r;
+    } else {
+        if (int r = potrf_blocked(A, T, lda, 64, info, 0, st)) return r;
+    }
     dim3 gz((unsigned)((T + 255) / 256), (unsigned)min(T, 65535LL));
     if (T <= 65535) k_zero_upper<<<gz, 256, 0, st>>>(A, T, lda);
     if (hld) k_logdiag_sum<<<1, 1024, 0, st>>>(A, T, lda, hld);

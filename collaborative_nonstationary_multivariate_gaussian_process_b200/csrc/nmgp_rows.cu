@@ -503,3 +503,57 @@ NMGP_API int nmgp_rowdot_live(const double* l, const double* g, const int* I, do
     k_rowdot_live<<<grid, 256, 0, st>>>(l, g, I, F, B, D);
     return nmgp_launch_status("nmgp_rowdot_live");
 }
+
+// ------------------------------------------------------------------------------------------------
+// element helpers behind the reference's small utilities (code/utils.py:15-33, 268-287)
+// out = mean + z * sqrt(var + eps)
+__global__ void k_reparam_diag(const double* __restrict__ mean, const double* __restrict__ var,
+                               const double* __restrict__ z, double* __restrict__ out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = fma(z[i], sqrt(var[i] + NMGP_EPS), mean[i]);
+}
+NMGP_API int nmgp_reparam_diag(const double* mean, const double* var, const double* z, double* out, long long n,
+                               cudaStream_t st) {
+    if (n <= 0) return 0;
+    k_reparam_diag<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mean, var, z, out, n);
+    return nmgp_launch_status("nmgp_reparam_diag");
+}
+// out += sum_i [ -(y-loc)^2/(2 scale^2) - log(scale) - log(sqrt(2 pi)) ]   (scale: scalar on device)
+__global__ void k_normal_logprob(const double* __restrict__ loc, const double* __restrict__ scale,
+                                 const double* __restrict__ y, double* __restrict__ out, long long n) {
+    const double sc = scale[0], var = sc * sc;
+    const double cst = -log(sc) - log(sqrt(2.0 * 3.14159265358979323846));
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double r = y[i] - loc[i];
+        s += -(r * r) / (2.0 * var) + cst;
+    }
+    s = block_sum(s);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+}
+NMGP_API int nmgp_normal_logprob_sum(const double* loc, const double* scale, const double* y, double* out /* += */,
+                                     long long n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    k_normal_logprob<<<(unsigned)blocks, 256, 0, st>>>(loc, scale, y, out, n);
+    return nmgp_launch_status("nmgp_normal_logprob_sum");
+}
+// out[r] = sum_k x[r,k]^2   (warp per row)
+__global__ void k_sumsq_rows(const double* __restrict__ x, double* __restrict__ out, long long rows, long long cols) {
+    const int lane = threadIdx.x & 31;
+    long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    double s = 0.0;
+    for (long long k = lane; k < cols; k += 32) {
+        double v = x[r * cols + k];
+        s = fma(v, v, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) out[r] = s;
+}
+NMGP_API int nmgp_sumsq_rows(const double* x, double* out, long long rows, long long cols, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    k_sumsq_rows<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, out, rows, cols);
+    return nmgp_launch_status("nmgp_sumsq_rows");
+}

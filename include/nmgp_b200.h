@@ -137,6 +137,13 @@ int nmgp_pair_means(const double* Pa, const double* Pb, const int* I, const doub
 int nmgp_rowdot_live(const double* l, const double* g, const int* I, double* F, int ns, long long B, int D,
                      nmgp_stream_t stream);
 
+/* small utilities: reparameterize (diagonal), Normal_logprob, batch_trace_XXT      utils.py:15-33, 268-287 */
+int nmgp_reparam_diag(const double* mean, const double* var, const double* z, double* out, long long n,
+                      nmgp_stream_t stream);
+int nmgp_normal_logprob_sum(const double* loc, const double* scale /* device scalar */, const double* y,
+                            double* out /* += */, long long n, nmgp_stream_t stream);
+int nmgp_sumsq_rows(const double* x, double* out, long long rows, long long cols, nmgp_stream_t stream);
+
 /* SIM_code line: code/SIM_code/Utility/kernels.py:46-73 Nonstationary_RBF_cov and :24-43 RBF_cov.
  * sigma/ell pointers may be NULL (= ones).  jitter (1e-6) is added on i == j; pass 0 for cross-covariances. */
 int nmgp_nonstationary_cov(const double* X1, const double* sigma1, const double* ell1, const double* X2,

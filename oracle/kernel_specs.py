@@ -406,3 +406,17 @@ def axpby(x, y, a, b):
 
 def dot(x, y):
     return (x * y).sum().reshape(1)
+
+
+def reparam_diag(mean, var, z):
+    return mean + z * torch.sqrt(var + EPS)
+
+
+def normal_logprob_sum(loc, scale, y):
+    import math
+    var = scale.reshape(()) ** 2
+    return (-((y - loc) ** 2) / (2 * var) - torch.log(scale.reshape(())) - math.log(math.sqrt(2 * math.pi))).sum().reshape(1)
+
+
+def sumsq_rows(x):
+    return (x * x).sum(-1)
