@@ -382,7 +382,9 @@ NMGP_API int nmgp_potrf_big(double* A, long long T, long long lda, double* hld, 
     if (int r = nmgp_opt_in_smem(k_potrf_diag, sizeof(double) * 64 * 65, "nmgp_potrf_big")) return r;
     if (int r = nmgp_opt_in_smem(k_trsm_panel_reg64, sizeof(double) * (64 * 64 + 64 + 128 * 65), "nmgp_potrf_big")) return r;
     if (T > 1024) {
-        if (int r = potrf_lookahead(A, T, lda, PB, info, st)) return r;
+        int pb = T >= 12288 ? 512 : (T >= 6144 ? 256 : PB);   // measured best on B200 (profiles/README.md)
+        if (const char* e = getenv("NMGP_POTRF_PB")) pb = atoi(e) >= 64 ? (atoi(e) / 64) * 64 : pb;   // tuning knob
+        if (int r = potrf_lookahead(A, T, lda, pb, info, st)) return r;
     } else {
         if (int r = potrf_blocked(A, T, lda, 64, info, 0, st)) return r;
     }
