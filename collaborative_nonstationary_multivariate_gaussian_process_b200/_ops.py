@@ -352,6 +352,13 @@ def sumsq_rows(x):
     return out
 
 
+def lcorr(L):
+    nmat, D = L.shape[0], L.shape[-1]
+    out = torch.empty_like(L)
+    check(lib().nmgp_lcorr(_d(L), _d(out), c_int64(nmat), c_int(D), _stream()), "nmgp_lcorr")
+    return out
+
+
 # ---- SIM_code (exact / Kronecker) line --------------------------------------------------------------
 def _optd(t):
     return c_void_p(0) if t is None else _d(t)

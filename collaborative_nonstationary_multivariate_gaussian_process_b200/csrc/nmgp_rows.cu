@@ -557,3 +557,28 @@ NMGP_API int nmgp_sumsq_rows(const double* x, double* out, long long rows, long 
     k_sumsq_rows<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, out, rows, cols);
     return nmgp_launch_status("nmgp_sumsq_rows");
 }
+
+// corr[m] = diag(cov)^-1/2 cov diag(cov)^-1/2 with cov = L[m] L[m]^T for a batch of small D x D lower factors
+// (code/nmgp_dsvi.py:567-569, the per-point output correlations of sample_FY).  One thread per (m, a, b).
+__global__ void k_lcorr(const double* __restrict__ L, double* __restrict__ corr, long long nmat, int D) {
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nmat * D * D) return;
+    long long m = gid / (D * D);
+    int r = (int)(gid - m * D * D), a = r / D, b = r - a * D;
+    const double* Lm = L + m * D * D;
+    double cab = 0.0, caa = 0.0, cbb = 0.0;
+    for (int k = 0; k < D; ++k) {
+        double la = Lm[a * D + k], lb = Lm[b * D + k];
+        cab = fma(la, lb, cab);
+        caa = fma(la, la, caa);
+        cbb = fma(lb, lb, cbb);
+    }
+    corr[gid] = sqrt(1.0 / caa) * cab * sqrt(1.0 / cbb);
+}
+NMGP_API int nmgp_lcorr(const double* L, double* corr, long long nmat, int D, cudaStream_t st) {
+    NMGP_REQUIRE(nmat >= 0 && D > 0, "nmgp_lcorr");
+    if (nmat == 0) return 0;
+    long long n = nmat * D * D;
+    k_lcorr<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, corr, nmat, D);
+    return nmgp_launch_status("nmgp_lcorr");
+}

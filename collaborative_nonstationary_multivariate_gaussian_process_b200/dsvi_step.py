@@ -53,13 +53,18 @@ def default_sample_chunk(S: int, B: int, Q: int, D: int, budget_bytes: float = 6
 def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: torch.Tensor,
               I: torch.Tensor, N: int, z_v: torch.Tensor, z_ell: torch.Tensor, z_L: torch.Tensor, *,
               B_total: Optional[int] = None, kl_weight: float = 1.0,
-              sample_chunk: Optional[int] = None, want_grads: bool = True):
+              sample_chunk: Optional[int] = None, want_grads: bool = True, pair_index: Optional[torch.Tensor] = None,
+              latent_order: Optional[torch.Tensor] = None, aux: Optional[dict] = None):
     """Returns (loss, grads) for rows (x, y, I) -- I sorted ascending, int32 -- and noise
     z_v [S,Q], z_ell [S,B], z_L [S,B,D] (z_L[s,n,j] is the draw for pair (I[n], j)).
 
     Under row sharding (several ranks each holding a slice of the minibatch) pass the
     global row count as ``B_total`` and ``kl_weight = 1/world_size``; the sum over
     ranks of the returned loss/grads is then the full-batch value.
+
+    ``pair_index`` (flat i*D+j per packed pair slot) and ``latent_order`` (permutation of the D latent functions)
+    override the default packing; compute_ELBO uses them to evaluate the reference's transposed coefficient gather
+    (quirk q5) with the same kernels.  ``aux`` (a dict) receives the per-sample pieces of the estimate.
     """
     D, Q = p["mu_W"].shape
     B = x.shape[0]
@@ -74,13 +79,17 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
     ghyp = zeros(7)
 
     # ---- variational covariances: Sigma = tril(S) tril(S)^T, C = chol(Sigma + eps I) -------
-    flat = packed_pair_index(D, dev)
+    flat = packed_pair_index(D, dev) if pair_index is None else pair_index
     npair = flat.shape[0]
     SU = p["sqrt_U"].detach().reshape(D * D, Q, Q).index_select(0, flat)
     muU = p["mu_U"].detach().reshape(D * D, Q).index_select(0, flat)
     sqrt_v = p["sqrt_v"].detach().reshape(1, Q, Q)
     sqrt_W = p["sqrt_W"].detach()
     mu_W = p["mu_W"].detach()
+    if latent_order is not None:
+        assert not want_grads
+        sqrt_W = sqrt_W.index_select(0, latent_order).contiguous()
+        mu_W = mu_W.index_select(0, latent_order).contiguous()
     mu_v = p["mu_v"].detach()
     Sig_v = ops.tril_syrk_fwd(sqrt_v)
     Sig_W = ops.tril_syrk_fwd(sqrt_W)
@@ -119,19 +128,20 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
     loss_kl = kl_weight * (kl_W.sum() / S + kl_v.sum() + kl_U1.sum() + klU0_sum)
 
     full = lambda shape, val: torch.full(shape, val, dtype=f64, device=dev)
-    CWbar, hldWbar, muWbar, RGbar, hldGbar = ops.kl_bwd(full((S, D), kl_weight / S), C_W, mu_W, R_G, t_W)
-    Cvbar, hldvbar, muvbar, Rellbar, hldRellbar = ops.kl_bwd(full((1, 1), kl_weight), C_v, mu_v.reshape(1, Q),
-                                                             sysm["ell"]["R"], t_v)
-    CUbar = zeros(npair, Q, Q); hldUbar = zeros(npair); muUbar = zeros(npair, Q)
-    a, b, c_, RL1bar, hldRL1bar = ops.kl_bwd(full((1, D), kl_weight), C_U[:D], muU[:D], sysm["L1"]["R"], t_U1)
-    CUbar[:D] = a; hldUbar[:D] = b; muUbar[:D] = c_
-    if npair > D:
-        a, b, c_, RL0bar, hldRL0bar = ops.kl_bwd(full((1, npair - D), kl_weight), C_U[D:], muU[D:],
-                                                 sysm["L0"]["R"], t_U0)
-        CUbar[D:] = a; hldUbar[D:] = b; muUbar[D:] = c_
-    else:
-        RL0bar = zeros(1, Q, Q); hldRL0bar = zeros(1)
-    muvbar = muvbar.reshape(Q).clone()
+    if want_grads:
+        CWbar, hldWbar, muWbar, RGbar, hldGbar = ops.kl_bwd(full((S, D), kl_weight / S), C_W, mu_W, R_G, t_W)
+        Cvbar, hldvbar, muvbar, Rellbar, hldRellbar = ops.kl_bwd(full((1, 1), kl_weight), C_v, mu_v.reshape(1, Q),
+                                                                 sysm["ell"]["R"], t_v)
+        CUbar = zeros(npair, Q, Q); hldUbar = zeros(npair); muUbar = zeros(npair, Q)
+        a, b, c_, RL1bar, hldRL1bar = ops.kl_bwd(full((1, D), kl_weight), C_U[:D], muU[:D], sysm["L1"]["R"], t_U1)
+        CUbar[:D] = a; hldUbar[:D] = b; muUbar[:D] = c_
+        if npair > D:
+            a, b, c_, RL0bar, hldRL0bar = ops.kl_bwd(full((1, npair - D), kl_weight), C_U[D:], muU[D:],
+                                                     sysm["L0"]["R"], t_U0)
+            CUbar[D:] = a; hldUbar[D:] = b; muUbar[D:] = c_
+        else:
+            RL0bar = zeros(1, Q, Q); hldRL0bar = zeros(1)
+        muvbar = muvbar.reshape(Q).clone()
 
     # ---- accumulators filled by the sample loop ------------------------------------------------
     SigWbar = zeros(D, Q, Q)
@@ -159,6 +169,8 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
         ops.coef_sample_bwd(lbar, l, z_L[sl], I, mUbar, sdUbar)
 
     loss = loss_kl - scale * Rsum.sum()
+    if aux is not None:
+        aux.update(Rsum=Rsum, kl_W=kl_W, kl_v=kl_v.sum(), kl_U=kl_U1.sum() + klU0_sum)
     if not want_grads:
         return loss, None
 

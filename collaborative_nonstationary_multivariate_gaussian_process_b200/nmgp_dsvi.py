@@ -214,9 +214,22 @@ class NMGP(torch.nn.Module):
             out = inv
         return out
 
-    def compute_ELBO(self, inputs_list, outputs_list, index=None, n_sample=1000, verbose=False):
+    def sample_Y(self, inputs_list, index=None, n_sample=1000, **kw):
+        """code/nmgp_dsvi.py:406-491 -> (sampled_Ys [S,B], sampled_Ls [S,B,D], sampled_Gs [S,D,B], tilde_ells [S,B])."""
+        from .predict import sample_Y as _sy
+        return _sy(self, inputs_list, index=index, n_sample=n_sample, **kw)
+
+    sample_Y_gpu = sample_Y          # code/nmgp_dsvi.py:582-664: the reference's device variant of the same sampler
+
+    def sample_FY(self, inputs, n_sample=1000, **kw):
+        """code/nmgp_dsvi.py:493-580 -> (tilde_ells [S,B], Ys [S,B,D], corrs [S,B,D,D])."""
+        from .predict import sample_FY as _sf
+        return _sf(self, inputs, n_sample=n_sample, **kw)
+
+    def compute_ELBO(self, inputs_list, outputs_list, index=None, n_sample=1000, verbose=False, **kw):
+        """code/nmgp_dsvi.py:303-404 (quirk q5 reproduced); extra keywords: noise, chunk."""
         from .predict import mc_elbo
-        return mc_elbo(self, inputs_list, outputs_list, index=index, n_sample=n_sample, verbose=verbose)
+        return mc_elbo(self, inputs_list, outputs_list, index=index, n_sample=n_sample, verbose=verbose, **kw)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -335,6 +348,21 @@ def inference(X_train_list, Y_train_list, z, batch_size, dim_outputs, hyperpars=
     if X_test_list is not None:
         return model, loss_list, rmse_test_list, time_list
     return model, loss_list, time_list
+
+
+def sample_Y(model, X_list, n_sample=1000):
+    """code/nmgp_dsvi.py:912-918."""
+    X_list = [torch.from_numpy(np.asarray(x)).type(TensorType) for x in X_list]
+    Ys, Ls, Gs, ells = model.sample_Y(X_list, n_sample=n_sample)
+    return Ys.data.cpu().numpy(), Ls.data.cpu().numpy(), Gs.data.cpu().numpy(), ells.data.cpu().numpy()
+
+
+def sample_FY(model, x, n_sample=1000):
+    """code/nmgp_dsvi.py:921-924 (the reference unpacks the model's (tilde_ells, Ys, corrs) into differently named
+    variables; the positional order of the returned arrays is kept)."""
+    x = torch.from_numpy(np.asarray(x)).type(TensorType)
+    a, b, c = model.sample_FY(x, n_sample=n_sample)
+    return a.data.cpu().numpy(), b.data.cpu().numpy(), c.data.cpu().numpy()
 
 
 def predict_Y(model, X_list):

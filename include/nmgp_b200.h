@@ -144,6 +144,9 @@ int nmgp_normal_logprob_sum(const double* loc, const double* scale /* device sca
                             double* out /* += */, long long n, nmgp_stream_t stream);
 int nmgp_sumsq_rows(const double* x, double* out, long long rows, long long cols, nmgp_stream_t stream);
 
+/* per-point output correlation matrices from the sampled mixing factors      nmgp_dsvi.py:567-569 (sample_FY) */
+int nmgp_lcorr(const double* L, double* corr, long long nmat, int D, nmgp_stream_t stream);
+
 /* SIM_code line: code/SIM_code/Utility/kernels.py:46-73 Nonstationary_RBF_cov and :24-43 RBF_cov.
  * sigma/ell pointers may be NULL (= ones).  jitter (1e-6) is added on i == j; pass 0 for cross-covariances. */
 int nmgp_nonstationary_cov(const double* X1, const double* sigma1, const double* ell1, const double* X2,

@@ -199,6 +199,26 @@ def main():
                         n_per_output=np.array([len(x) for x in X_list]))
     print("compute_ELBO", float(elbo))
 
+    # ---- posterior sampling: sample_Y / sample_FY with 2 draws -----------------------------
+    Xs_small = [torch.from_numpy(Xt_list[0][:7]).type(T), torch.from_numpy(Xt_list[1][:5]).type(T)]
+    torch.manual_seed(31)
+    with Recorder() as rec:
+        sYs, sLs, sGs, sEll = m.sample_Y(Xs_small, n_sample=2)
+    np.savez_compressed(os.path.join(OUT, "sample_Y_modelpt.npz"), X=np.concatenate([a.numpy().reshape(-1) for a in Xs_small]),
+                        n_per_output=np.array([7, 5]), Ys=sYs.numpy(), Ls=sLs.numpy(), Gs=sGs.numpy(), ells=sEll.numpy())
+    m3 = nmgp_dsvi.NMGP(50, 3, torch.from_numpy(np.linspace(0, 1, 8)).type(T).unsqueeze(1), seed=4,
+                        mu_v=-1.0 * np.ones(8))
+    for k, v in {"length_scales_tildeell_log": -1.0, "length_scales_L0_log": -0.5, "length_scales_L1_log": -0.8,
+                 "sigma2_err_log": -3.0}.items():
+        getattr(m3, k).data.fill_(v)
+    grid = torch.from_numpy(np.linspace(0.05, 0.95, 9)).type(T)
+    torch.manual_seed(32)
+    tE, tY, tC = m3.sample_FY(grid, n_sample=2)
+    out3 = {"param_" + k: v.detach().numpy() for k, v in m3.state_dict().items()}
+    out3.update(grid=grid.numpy(), ells=tE.numpy(), Ys=tY.numpy(), corrs=tC.numpy(), Z=np.linspace(0, 1, 8))
+    np.savez_compressed(os.path.join(OUT, "sample_FY_d3.npz"), **out3)
+    print("sample_Y/FY", sYs.shape, sLs.shape, sGs.shape, sEll.shape, tE.shape, tY.shape, tC.shape)
+
     # ---- small ragged case with an empty output, N != B, trainable length-scales, S=2 ---
     rng = np.random.default_rng(5)
     counts = [15, 0, 25, 9]

@@ -420,3 +420,9 @@ def normal_logprob_sum(loc, scale, y):
 
 def sumsq_rows(x):
     return (x * x).sum(-1)
+
+
+def lcorr(L):
+    cov = L @ L.transpose(-1, -2)
+    inv = torch.sqrt(torch.diag_embed(1.0 / torch.diagonal(cov, dim1=-2, dim2=-1)))
+    return inv @ cov @ inv

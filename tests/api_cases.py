@@ -83,3 +83,38 @@ def inference_trace(device):
     pred = nmgp_dsvi.predict_Y(model, split(g["Xt"], g["nt_per_output"]))
     assert np.max(np.abs(pred - g["pred_after"])) <= 1e-8 * np.max(np.abs(g["pred_after"]))
     assert len(time_list) == 5
+
+
+def compute_elbo_replay(device):
+    """compute_ELBO (quirk q5 included) with the reference's random stream: 3 draws on low_freq with model.pt."""
+    g = gu.load("elbo_modelpt"); gm = gu.load("predict_modelpt")
+    m = nmgp_dsvi.NMGP(200, 2, torch.from_numpy(gm["Z"]).view(-1, 1), device=device)
+    m.load_state_dict({k[6:]: torch.from_numpy(v) for k, v in gm.items() if k.startswith("param_")})
+    Xl = [torch.from_numpy(a) for a in split(g["X"], g["n_per_output"])]
+    Yl = [torch.from_numpy(a) for a in split(g["Y"], g["n_per_output"])]
+    torch.manual_seed(77)
+    e = float(m.compute_ELBO(Xl, Yl, n_sample=3))
+    assert abs(e - float(g["elbo"])) <= RTOL * abs(float(g["elbo"])), (e, float(g["elbo"]))
+    torch.manual_seed(77)
+    e2 = float(m.compute_ELBO(Xl, Yl, n_sample=3, chunk=2))          # chunking must not change the random stream
+    assert abs(e2 - e) <= 1e-12 * abs(e)
+
+
+def posterior_sampling_replay(device):
+    """sample_Y / sample_FY with the reference's random stream (2 draws each)."""
+    g = gu.load("sample_Y_modelpt"); gm = gu.load("predict_modelpt")
+    m = nmgp_dsvi.NMGP(200, 2, torch.from_numpy(gm["Z"]).view(-1, 1), device=device)
+    m.load_state_dict({k[6:]: torch.from_numpy(v) for k, v in gm.items() if k.startswith("param_")})
+    torch.manual_seed(31)
+    Ys, Ls, Gs, ells = nmgp_dsvi.sample_Y(m, split(g["X"], g["n_per_output"]), n_sample=2)
+    for got, ref, name in ((Ys, g["Ys"], "Ys"), (Ls, g["Ls"], "Ls"), (Gs, g["Gs"], "Gs"), (ells, g["ells"], "ells")):
+        assert got.shape == ref.shape, (name, got.shape, ref.shape)
+        assert np.max(np.abs(got - ref)) <= RTOL * np.max(np.abs(ref)), (name, np.max(np.abs(got - ref)))
+    g3 = gu.load("sample_FY_d3")
+    m3 = nmgp_dsvi.NMGP(50, 3, torch.from_numpy(g3["Z"]).view(-1, 1), device=device)
+    m3.load_state_dict({k[6:]: torch.from_numpy(v) for k, v in g3.items() if k.startswith("param_")})
+    torch.manual_seed(32)
+    E, Y, C = nmgp_dsvi.sample_FY(m3, g3["grid"], n_sample=2)
+    for got, ref, name in ((E, g3["ells"], "ells"), (Y, g3["Ys"], "Ys"), (C, g3["corrs"], "corrs")):
+        assert got.shape == ref.shape, (name, got.shape, ref.shape)
+        assert np.max(np.abs(got - ref)) <= RTOL * max(1.0, np.max(np.abs(ref))), (name, np.max(np.abs(got - ref)))

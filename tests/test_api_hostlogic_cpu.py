@@ -31,3 +31,11 @@ def test_unsorted_index():
 
 def test_inference_trace():
     api_cases.inference_trace("cpu")
+
+
+def test_compute_elbo_replay():
+    api_cases.compute_elbo_replay("cpu")
+
+
+def test_posterior_sampling_replay():
+    api_cases.posterior_sampling_replay("cpu")
