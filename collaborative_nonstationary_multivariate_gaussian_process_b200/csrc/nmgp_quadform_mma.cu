@@ -22,6 +22,22 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc));
 }
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc));
+}
+// copy a Q x Q row-major matrix into a padded shared tile (row stride ld): one warp per row, no integer division,
+// 16-byte chunks when the rows are 16-byte aligned (Q even)
+__device__ __forceinline__ void stage_matrix(double* __restrict__ dst, const double* __restrict__ src, int Q, int ld,
+                                             int warp, int nwarps, int lane) {
+    if ((Q & 1) == 0) {
+        for (int a = warp; a < Q; a += nwarps)
+            for (int c = 2 * lane; c < Q; c += 64) cp_async16(&dst[a * ld + c], &src[(size_t)a * Q + c]);
+    } else {
+        for (int a = warp; a < Q; a += nwarps)
+            for (int c = lane; c < Q; c += 32) cp_async8(&dst[a * ld + c], &src[(size_t)a * Q + c]);
+    }
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
@@ -32,6 +48,8 @@ __host__ __device__ constexpr int pad4mod8(int n) { return ((n + 3) / 8) * 8 + 4
 __host__ __device__ constexpr int pad8mod16(int n) { return ((n + 7) / 16) * 16 + 8; }
 
 // ------------------------------------------------------------------------------------------------------------
+// 128-row tiles, 8 warps, one CTA per SM (measured: two 64-row CTAs per SM are 18% slower -- every CTA stages its
+// own copy of Sigma_W[j], profiles/README.md)
 #define LF_ROWS 128
 #define LF_THREADS 256
 
@@ -526,7 +544,7 @@ struct GMShape {
 };
 
 template <int NB>
-__global__ void __launch_bounds__(GM_THREADS)
+__global__ void __launch_bounds__(GM_THREADS, NB <= 6 ? 3 : 2)
 k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const int* __restrict__ seg,
            const double* __restrict__ qbar, const double* __restrict__ mbar, double* __restrict__ SigBar,
            double* __restrict__ MuBar, long long B, int Q, int D, int mode) {
@@ -570,10 +588,17 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
         const long long r0 = rbeg + tile * GM_TROWS;
         const int nr = (int)min((long long)GM_TROWS, rend - r0);
         double* Pd = Pt + (size_t)buf * GM_TROWS * LDP;
-        for (int e = tid; e < GM_TROWS * Q; e += GM_THREADS) {
-            int r = e / Q, c = e - r * Q;
-            if (r < nr) cp_async8(&Pd[r * LDP + c], &P[((size_t)s * B + r0 + r) * Q + c]);
-            else Pd[r * LDP + c] = 0.0;
+        for (int r = w; r < GM_TROWS; r += GM_THREADS / 32) {
+            if (r < nr) {
+                const double* src = &P[((size_t)s * B + r0 + r) * Q];
+                if ((Q & 1) == 0) {
+                    for (int c = 2 * lane; c < Q; c += 64) cp_async16(&Pd[r * LDP + c], &src[c]);
+                } else {
+                    for (int c = lane; c < Q; c += 32) cp_async8(&Pd[r * LDP + c], &src[c]);
+                }
+            } else {
+                for (int c = lane; c < Q; c += 32) Pd[r * LDP + c] = 0.0;
+            }
         }
         for (int e = tid; e < GM_NG * GM_TROWS; e += GM_THREADS) {
             int u = e / GM_TROWS, r = e - u * GM_TROWS;

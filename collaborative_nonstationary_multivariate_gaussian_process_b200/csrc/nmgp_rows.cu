@@ -95,9 +95,9 @@ static int solve_rows_tile(int Q, bool bwd) {
     while (TR > 32 && 8.0 * ((double)Q * Q + (bwd ? 2.0 : 1.0) * Q * (TR + 1)) > 200.0 * 1024) TR >>= 1;
     return TR;
 }
-int nmgp_solve_rows_fwd_reg(const double* K, const double* R, double* P, double* c, int ns, long long B, int Q,
+int nmgp_solve_rows_fwd_mma(const double* K, const double* R, double* P, double* c, int ns, long long B, int Q,
                             cudaStream_t st);
-int nmgp_solve_rows_bwd_reg(const double* Pbar, const double* cbar, const double* K, const double* P, const double* R,
+int nmgp_solve_rows_bwd_mma(const double* Pbar, const double* cbar, const double* K, const double* P, const double* R,
                             double* Kbar, double* Tout, int ns, long long B, int Q, cudaStream_t st);
 int nmgp_atb_mma(const double* A, const double* Bm, double* C, double sign, int ns, long long B, int Q, cudaStream_t st);
 
@@ -105,7 +105,7 @@ NMGP_API int nmgp_solve_rows_fwd(const double* K, const double* R, double* P, do
                                  cudaStream_t st) {
     NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && Q > 0 && Q <= 128, "nmgp_solve_rows_fwd");
     if (ns == 0 || B == 0) return 0;
-    if (Q <= 64) return nmgp_solve_rows_fwd_reg(K, R, P, c, ns, B, Q, st);
+    if (Q <= 64) return nmgp_solve_rows_fwd_mma(K, R, P, c, ns, B, Q, st);
     const int TR = solve_rows_tile(Q, false);
     size_t smem = sizeof(double) * ((size_t)Q * Q + (size_t)Q * (TR + 1));
     if (int r = nmgp_opt_in_smem(k_solve_rows<false>, smem, "nmgp_solve_rows_fwd")) return r;
@@ -120,7 +120,7 @@ NMGP_API int nmgp_solve_rows_bwd(const double* Pbar, const double* cbar, const d
     if (ns == 0 || B == 0) return 0;
     if (Q <= 64) {
         NMGP_REQUIRE(work != nullptr, "nmgp_solve_rows_bwd");
-        if (int r = nmgp_solve_rows_bwd_reg(Pbar, cbar, K, P, R, Kbar, work, ns, B, Q, st)) return r;
+        if (int r = nmgp_solve_rows_bwd_mma(Pbar, cbar, K, P, R, Kbar, work, ns, B, Q, st)) return r;
         return nmgp_atb_mma(work, P, Abar, -1.0, ns, B, Q, st);      // Abar -= T^T P
     }
     const int TR = solve_rows_tile(Q, true);
