@@ -209,11 +209,12 @@ def run_b200(args, w):
     Bloc = sum(int(x.shape[0]) for x in Xh)
     xd = torch.cat(Xh).to(dev); yd = torch.cat(Yh).to(dev)
     Id = torch.from_numpy(np.repeat(np.arange(D, dtype=np.int32), [int(x.shape[0]) for x in Xh])).to(dev)
+    gid = torch.from_numpy(parallel.global_row_ids([T] * D, rows)).to(dev)
     params = list(model.parameters())
 
     def step_resident():
         opt.zero_grad(set_to_none=True)
-        loss = model.forward_rows(xd, yd, Id, n_mc=S)
+        loss = model.forward_rows(xd, yd, Id, n_mc=S, row_gid=gid)
         loss.backward()
         tot = parallel.allreduce_loss_and_grads(loss, params)
         opt.step()
@@ -221,7 +222,7 @@ def run_b200(args, w):
 
     def step_e2e():
         opt.zero_grad(set_to_none=True)
-        loss = model(Xh, Yh, n_mc=S, noise="device")                   # host lists -> H2D inside
+        loss = model(Xh, Yh, n_mc=S, noise="device", row_gid=gid)                   # host lists -> H2D inside
         loss.backward()
         tot = parallel.allreduce_loss_and_grads(loss, params)
         opt.step()
@@ -296,7 +297,7 @@ def run_b200(args, w):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(args, w), "rows_per_gpu": Bloc, "sharding": "rows strided over ranks",
                            "l2": "per-step working set (>= 5 B*Q doubles per sample chunk, >1 GB) exceeds the 126 MB L2",
-                           "noise": "device", "optimizer": "Adam lr=0.005"},
+                           "noise": "device (counter-based, in-kernel)", "optimizer": "Adam lr=0.005"},
                 "step_tflops_fp64": F_step / (ms_step * 1e-3) / 1e12,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(ncalls),
                 "roofline": roof, "kernels": kern, "other_ops": others, "loss": float(last)}

@@ -33,6 +33,10 @@ def _i(t: torch.Tensor) -> c_void_p:
     return c_void_p(t.data_ptr())
 
 
+def _optd(t):
+    return c_void_p(0) if t is None else _d(t)
+
+
 def _stream() -> c_void_p:
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -269,18 +273,44 @@ def coef_sd_bwd(sdbar, sd, I, hyp, ghyp):
     return qbar, cL0bar, cL1bar
 
 
-def coef_sample_fwd(m, sd, zL, I):
-    ns, B, D = zL.shape
-    l = torch.empty_like(zL)
-    check(lib().nmgp_coef_sample_fwd(_d(m), _d(sd), _d(zL), _i(I), _d(l), c_int(ns), c_int64(B), c_int(D), _stream()),
-          "nmgp_coef_sample_fwd")
+def _l(t):
+    if t is None:
+        return c_void_p(0)
+    if not (t.is_cuda and t.dtype == torch.int64 and t.is_contiguous()):
+        raise TypeError("expected a contiguous CUDA int64 tensor")
+    return c_void_p(t.data_ptr())
+
+
+def _noise_args(noise):
+    """noise = (seed, stream_id, s0, ns, gid) for in-kernel generation; None when explicit draws are passed."""
+    if noise is None:
+        return ctypes.c_uint64(0), ctypes.c_uint64(0), c_int(0), c_void_p(0)
+    seed, stream_id, s0, _, gid = noise
+    return ctypes.c_uint64(seed), ctypes.c_uint64(stream_id), c_int(s0), _l(gid)
+
+
+def coef_sample_fwd(m, sd, zL, I, noise=None):
+    B, D = m.shape
+    ns = zL.shape[0] if zL is not None else noise[3]
+    l = _empty(m, ns, B, D)
+    a = _noise_args(noise)
+    check(lib().nmgp_coef_sample_fwd(_d(m), _d(sd), _optd(zL), _i(I), _d(l), c_int(ns), c_int64(B), c_int(D),
+                                     a[0], a[1], a[2], a[3], _stream()), "nmgp_coef_sample_fwd")
     return l
 
 
-def coef_sample_bwd(lbar, l, zL, I, mbar, sdbar):
-    ns, B, D = zL.shape
-    check(lib().nmgp_coef_sample_bwd(_d(lbar), _d(l), _d(zL), _i(I), _d(mbar), _d(sdbar), c_int(ns), c_int64(B),
-                                     c_int(D), _stream()), "nmgp_coef_sample_bwd")
+def coef_sample_bwd(lbar, l, zL, I, mbar, sdbar, noise=None):
+    ns, B, D = l.shape
+    a = _noise_args(noise)
+    check(lib().nmgp_coef_sample_bwd(_d(lbar), _d(l), _optd(zL), _i(I), _d(mbar), _d(sdbar), c_int(ns), c_int64(B),
+                                     c_int(D), a[0], a[1], a[2], a[3], _stream()), "nmgp_coef_sample_bwd")
+
+
+def noise_fill(ns, B, C, seed, stream_id, s0, gid, device):
+    out = torch.empty(ns, B, C, dtype=F64, device=device)
+    check(lib().nmgp_noise_fill(_d(out), c_int(ns), c_int64(B), c_int(C), ctypes.c_uint64(seed),
+                                ctypes.c_uint64(stream_id), c_int(s0), _l(gid), _stream()), "nmgp_noise_fill")
+    return out
 
 
 def lik_rows(l, mg, qg, cG, y, I, hyp, scale, Rsum, ghyp):
@@ -360,10 +390,6 @@ def lcorr(L):
 
 
 # ---- SIM_code (exact / Kronecker) line --------------------------------------------------------------
-def _optd(t):
-    return c_void_p(0) if t is None else _d(t)
-
-
 def nonstationary_cov(X1, sigma1, ell1, X2, sigma2, ell2, jitter):
     T1, dx = X1.shape
     T2 = X2.shape[0]

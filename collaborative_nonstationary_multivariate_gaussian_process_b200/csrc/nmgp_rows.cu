@@ -3,6 +3,7 @@
 // (code/utils.py:32,120-124,231-235; code/nmgp_dsvi.py:215-238) and the expected log-likelihood
 // (code/nmgp_dsvi.py:255-258) with all cotangents.
 #include "common.cuh"
+#include "philox.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // solve_rows: per row k (Q), p = A^-1 k with A = R R^T: forward then backward substitution.
@@ -318,55 +319,99 @@ NMGP_API int nmgp_coef_sd_bwd(const double* sdbar, const double* sd, const int* 
 }
 
 // l[s,n,j] = m + z sd  (exp on j == I[n]), 0 for j > I[n]    (code/nmgp_dsvi.py:228-238)
+// zL == NULL: the noise is generated in the kernel (counter-based, philox.cuh) from (key, s0 + s, gid[n], j) and never
+// touches HBM; the backward kernel regenerates the same values.
+__device__ __forceinline__ double coef_noise(const double* __restrict__ zL, size_t o, NoiseKey key, int sglob,
+                                             long long gid, int j) {
+    if (zL) return zL[o];
+    float z[4];
+    philox_normal4(key, (unsigned)sglob, (unsigned long long)gid, (unsigned)(j >> 2), z);
+    return (double)z[j & 3];
+}
 __global__ void k_coef_sample_fwd(const double* __restrict__ m, const double* __restrict__ sd,
                                   const double* __restrict__ zL, const int* __restrict__ I, double* __restrict__ l,
-                                  long long B, int D) {
+                                  long long B, int D, NoiseKey key, int s0, const long long* __restrict__ gid) {
     const int s = blockIdx.y;
-    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= B * D) return;
-    long long n = gid / D;
-    int j = (int)(gid - n * D), i = I[n];
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B * D) return;
+    long long n = e / D;
+    int j = (int)(e - n * D), i = I[n];
     double out = 0.0;
     if (j <= i) {
-        out = fma(zL[(size_t)s * B * D + gid], sd[gid], m[gid]);
+        const double z = coef_noise(zL, (size_t)s * B * D + e, key, s0 + s, gid ? gid[n] : n, j);
+        out = fma(z, sd[e], m[e]);
         if (j == i) out = exp(out);
     }
-    l[(size_t)s * B * D + gid] = out;
+    l[(size_t)s * B * D + e] = out;
 }
 NMGP_API int nmgp_coef_sample_fwd(const double* m, const double* sd, const double* zL, const int* I, double* l, int ns,
-                                  long long B, int D, cudaStream_t st) {
+                                  long long B, int D, unsigned long long seed, unsigned long long stream_id, int s0,
+                                  const long long* gid, cudaStream_t st) {
     NMGP_REQUIRE(ns >= 0 && ns <= 65535, "nmgp_coef_sample_fwd");
     if (B == 0 || ns == 0) return 0;
     long long n = B * D;
     dim3 grid((unsigned)((n + 255) / 256), ns);
-    k_coef_sample_fwd<<<grid, 256, 0, st>>>(m, sd, zL, I, l, B, D);
+    NoiseKey key{seed, stream_id};
+    k_coef_sample_fwd<<<grid, 256, 0, st>>>(m, sd, zL, I, l, B, D, key, s0, gid);
     return nmgp_launch_status("nmgp_coef_sample_fwd");
 }
 __global__ void k_coef_sample_bwd(const double* __restrict__ lbar, const double* __restrict__ l,
                                   const double* __restrict__ zL, const int* __restrict__ I, double* __restrict__ mbar,
-                                  double* __restrict__ sdbar, int ns, long long B, int D) {
-    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= B * D) return;
-    long long n = gid / D;
-    int j = (int)(gid - n * D), i = I[n];
+                                  double* __restrict__ sdbar, int ns, long long B, int D, NoiseKey key, int s0,
+                                  const long long* __restrict__ gid) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B * D) return;
+    long long n = e / D;
+    int j = (int)(e - n * D), i = I[n];
     if (j > i) return;
+    const long long g = gid ? gid[n] : n;
     double am = 0.0, as = 0.0;
     for (int s = 0; s < ns; ++s) {
-        size_t o = (size_t)s * B * D + gid;
+        size_t o = (size_t)s * B * D + e;
         double rb = lbar[o];
         if (j == i) rb *= l[o];
         am += rb;
-        as = fma(rb, zL[o], as);
+        as = fma(rb, coef_noise(zL, o, key, s0 + s, g, j), as);
     }
-    mbar[gid] += am;
-    sdbar[gid] += as;
+    mbar[e] += am;
+    sdbar[e] += as;
 }
 NMGP_API int nmgp_coef_sample_bwd(const double* lbar, const double* l, const double* zL, const int* I, double* mbar,
-                                  double* sdbar, int ns, long long B, int D, cudaStream_t st) {
+                                  double* sdbar, int ns, long long B, int D, unsigned long long seed,
+                                  unsigned long long stream_id, int s0, const long long* gid, cudaStream_t st) {
     if (B == 0 || ns == 0) return 0;
     long long n = B * D;
-    k_coef_sample_bwd<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(lbar, l, zL, I, mbar, sdbar, ns, B, D);
+    NoiseKey key{seed, stream_id};
+    k_coef_sample_bwd<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(lbar, l, zL, I, mbar, sdbar, ns, B, D, key, s0, gid);
     return nmgp_launch_status("nmgp_coef_sample_bwd");
+}
+
+// out[s, n, c] = N(0,1) (float32 precision) for columns c < C: the explicit form of the same generator
+__global__ void k_noise_fill(double* __restrict__ out, long long B, int C, NoiseKey key, int s0,
+                             const long long* __restrict__ gid) {
+    const int s = blockIdx.y;
+    const int nq = (C + 3) / 4;
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B * nq) return;
+    long long n = e / nq;
+    int q4 = (int)(e - n * nq);
+    float z[4];
+    philox_normal4(key, (unsigned)(s0 + s), (unsigned long long)(gid ? gid[n] : n), (unsigned)q4, z);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int c = 4 * q4 + k;
+        if (c < C) out[((size_t)s * B + n) * C + c] = (double)z[k];
+    }
+}
+NMGP_API int nmgp_noise_fill(double* out, int ns, long long B, int C, unsigned long long seed,
+                             unsigned long long stream_id, int s0, const long long* gid, cudaStream_t st) {
+    NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && C > 0, "nmgp_noise_fill");
+    if (B == 0 || ns == 0) return 0;
+    long long n = B * ((C + 3) / 4);
+    dim3 grid((unsigned)((n + 255) / 256), ns);
+    NoiseKey key{seed, stream_id};
+    k_noise_fill<<<grid, 256, 0, st>>>(out, B, C, key, s0, gid);
+    return nmgp_launch_status("nmgp_noise_fill");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -54,13 +54,22 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
               I: torch.Tensor, N: int, z_v: torch.Tensor, z_ell: torch.Tensor, z_L: torch.Tensor, *,
               B_total: Optional[int] = None, kl_weight: float = 1.0,
               sample_chunk: Optional[int] = None, want_grads: bool = True, pair_index: Optional[torch.Tensor] = None,
-              latent_order: Optional[torch.Tensor] = None, aux: Optional[dict] = None):
+              latent_order: Optional[torch.Tensor] = None, aux: Optional[dict] = None,
+              kl_shard: Optional[tuple] = None, noise_key: Optional[tuple] = None,
+              row_gid: Optional[torch.Tensor] = None):
     """Returns (loss, grads) for rows (x, y, I) -- I sorted ascending, int32 -- and noise
     z_v [S,Q], z_ell [S,B], z_L [S,B,D] (z_L[s,n,j] is the draw for pair (I[n], j)).
 
     Under row sharding (several ranks each holding a slice of the minibatch) pass the
     global row count as ``B_total`` and ``kl_weight = 1/world_size``; the sum over
     ranks of the returned loss/grads is then the full-batch value.
+
+    ``z_L`` may be None: the coefficient noise is then generated inside the sampling kernels from
+    ``noise_key = (seed, stream_id)`` and ``row_gid`` (int64 global row ids; default arange(B)), see nmgp_noise_fill.
+
+    ``kl_shard = (rank, world)`` additionally splits the batched small-matrix work of the KL terms (Cholesky of the
+    P coefficient covariances, KL forward/backward) over the ranks instead of replicating it: each KL_U pair and each
+    sample's KL_W is then evaluated by exactly one rank with weight 1 (KL_v stays replicated with ``kl_weight``).
 
     ``pair_index`` (flat i*D+j per packed pair slot) and ``latent_order`` (permutation of the D latent functions)
     override the default packing; compute_ELBO uses them to evaluate the reference's transposed coefficient gather
@@ -96,7 +105,17 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
     Sig_U = ops.tril_syrk_fwd(SU)
     C_v, hld_v = ops.potrf(Sig_v, EPS)
     C_W, hld_W = ops.potrf(Sig_W, EPS)
-    C_U, hld_U = ops.potrf(Sig_U, EPS)
+    rank_, world_ = kl_shard if kl_shard is not None else (0, 1)
+    part = lambda n: slice((n * rank_) // world_, (n * (rank_ + 1)) // world_)
+    sl1 = part(D)                                             # diagonal pairs handled here
+    sl0 = slice(D + part(npair - D).start, D + part(npair - D).stop)   # strictly-lower pairs handled here
+    slS = part(S)                                             # samples whose KL_W is evaluated here
+    w_sh = kl_weight if kl_shard is None else 1.0
+    n1, n0, nS = sl1.stop - sl1.start, sl0.stop - sl0.start, slS.stop - slS.start
+    if n1:
+        C_U1, hld_U1 = ops.potrf(Sig_U[sl1], EPS)
+    if n0:
+        C_U0, hld_U0 = ops.potrf(Sig_U[sl0], EPS)
 
     # ---- the three stationary inducing systems ------------------------------------------------
     sysm = {}
@@ -117,30 +136,40 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
     R_G, hld_G = ops.potrf(A_G, 0.0)
 
     # ---- KL terms (reference-exact form, quirk q10) and their cotangents ----------------------
-    kl_W, t_W = ops.kl_fwd(C_W, hld_W, mu_W, R_G, hld_G)
     kl_v, t_v = ops.kl_fwd(C_v, hld_v, mu_v.reshape(1, Q), sysm["ell"]["R"], sysm["ell"]["hldR"])
-    kl_U1, t_U1 = ops.kl_fwd(C_U[:D], hld_U[:D], muU[:D], sysm["L1"]["R"], sysm["L1"]["hldR"])
-    if npair > D:
-        kl_U0, t_U0 = ops.kl_fwd(C_U[D:], hld_U[D:], muU[D:], sysm["L0"]["R"], sysm["L0"]["hldR"])
-        klU0_sum = kl_U0.sum()
-    else:
-        klU0_sum = zeros(())
-    loss_kl = kl_weight * (kl_W.sum() / S + kl_v.sum() + kl_U1.sum() + klU0_sum)
+    loss_kl = kl_weight * kl_v.sum()
+    kl_W = None
+    if nS:
+        kl_W, t_W = ops.kl_fwd(C_W, hld_W, mu_W, R_G[slS], hld_G[slS])
+        loss_kl = loss_kl + w_sh * kl_W.sum() / S
+    klU_sum = zeros(())
+    if n1:
+        kl_U1, t_U1 = ops.kl_fwd(C_U1, hld_U1, muU[sl1], sysm["L1"]["R"], sysm["L1"]["hldR"])
+        klU_sum = klU_sum + kl_U1.sum()
+    if n0:
+        kl_U0, t_U0 = ops.kl_fwd(C_U0, hld_U0, muU[sl0], sysm["L0"]["R"], sysm["L0"]["hldR"])
+        klU_sum = klU_sum + kl_U0.sum()
+    loss_kl = loss_kl + w_sh * klU_sum
 
     full = lambda shape, val: torch.full(shape, val, dtype=f64, device=dev)
     if want_grads:
-        CWbar, hldWbar, muWbar, RGbar, hldGbar = ops.kl_bwd(full((S, D), kl_weight / S), C_W, mu_W, R_G, t_W)
+        CWbar = zeros(D, Q, Q); hldWbar = zeros(D); muWbar = zeros(D, Q)
+        RGbar = zeros(S, Q, Q); hldGbar = zeros(S)
+        if nS:
+            a, b, c_, rg, hg = ops.kl_bwd(full((nS, D), w_sh / S), C_W, mu_W, R_G[slS], t_W)
+            CWbar, hldWbar, muWbar = a, b, c_
+            RGbar[slS] = rg; hldGbar[slS] = hg
         Cvbar, hldvbar, muvbar, Rellbar, hldRellbar = ops.kl_bwd(full((1, 1), kl_weight), C_v, mu_v.reshape(1, Q),
                                                                  sysm["ell"]["R"], t_v)
-        CUbar = zeros(npair, Q, Q); hldUbar = zeros(npair); muUbar = zeros(npair, Q)
-        a, b, c_, RL1bar, hldRL1bar = ops.kl_bwd(full((1, D), kl_weight), C_U[:D], muU[:D], sysm["L1"]["R"], t_U1)
-        CUbar[:D] = a; hldUbar[:D] = b; muUbar[:D] = c_
-        if npair > D:
-            a, b, c_, RL0bar, hldRL0bar = ops.kl_bwd(full((1, npair - D), kl_weight), C_U[D:], muU[D:],
-                                                     sysm["L0"]["R"], t_U0)
-            CUbar[D:] = a; hldUbar[D:] = b; muUbar[D:] = c_
-        else:
-            RL0bar = zeros(1, Q, Q); hldRL0bar = zeros(1)
+        CUbar1 = hldUbar1 = CUbar0 = hldUbar0 = None
+        muUbar = zeros(npair, Q)
+        RL1bar = zeros(1, Q, Q); hldRL1bar = zeros(1); RL0bar = zeros(1, Q, Q); hldRL0bar = zeros(1)
+        if n1:
+            CUbar1, hldUbar1, c_, RL1bar, hldRL1bar = ops.kl_bwd(full((1, n1), w_sh), C_U1, muU[sl1], sysm["L1"]["R"], t_U1)
+            muUbar[sl1] = c_
+        if n0:
+            CUbar0, hldUbar0, c_, RL0bar, hldRL0bar = ops.kl_bwd(full((1, n0), w_sh), C_U0, muU[sl0], sysm["L0"]["R"], t_U0)
+            muUbar[sl0] = c_
         muvbar = muvbar.reshape(Q).clone()
 
     # ---- accumulators filled by the sample loop ------------------------------------------------
@@ -154,7 +183,11 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
     for s0 in range(0, S, ns_max):
         sl = slice(s0, min(S, s0 + ns_max))
         ellx = ops.ell_rows_fwd(P_ell, v[sl], z_ell[sl], sd_ell)
-        l = ops.coef_sample_fwd(mU[0], sdU, z_L[sl], I)
+        if z_L is not None:
+            zl_, nz_ = z_L[sl], None
+        else:
+            zl_, nz_ = None, (int(noise_key[0]), int(noise_key[1]), sl.start, sl.stop - sl.start, row_gid)
+        l = ops.coef_sample_fwd(mU[0], sdU, zl_, I, noise=nz_)
         KG = ops.gibbs_build_fwd(x, Z, ellx, ellZ[sl], 0.0)
         PG, cG = ops.solve_rows_fwd(KG, R_G[sl])
         lbar, mgbar, qgbar, cGbar, PGbar = ops.latent_fused(PG, cG, l, y, I, Sig_W, mu_W, hyp, scale, Rsum[sl], ghyp,
@@ -166,11 +199,11 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
         ellxbar = torch.empty_like(ellx)
         ops.gibbs_build_bwd(x, Z, ellx, ellZ[sl], KGbar, ellxbar, ellZbar[sl])
         ops.ell_rows_bwd(ellxbar, ellx, P_ell, v[sl], z_ell[sl], vbar[sl], Pellbar, sdellbar)
-        ops.coef_sample_bwd(lbar, l, z_L[sl], I, mUbar, sdUbar)
+        ops.coef_sample_bwd(lbar, l, zl_, I, mUbar, sdUbar, noise=nz_)
 
     loss = loss_kl - scale * Rsum.sum()
     if aux is not None:
-        aux.update(Rsum=Rsum, kl_W=kl_W, kl_v=kl_v.sum(), kl_U=kl_U1.sum() + klU0_sum)
+        aux.update(Rsum=Rsum, kl_W=kl_W, kl_v=kl_v.sum(), kl_U=klU_sum)
     if not want_grads:
         return loss, None
 
@@ -205,7 +238,10 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
     g_sqrt_v = ops.tril_syrk_bwd(sqrt_v, ops.potrf_bwd(C_v, Cvbar.reshape(1, Q, Q), hldvbar)).reshape(Q, Q)
     SigWbar += ops.potrf_bwd(C_W, CWbar, hldWbar)
     g_sqrt_W = ops.tril_syrk_bwd(sqrt_W, SigWbar)
-    SigUbar += ops.potrf_bwd(C_U, CUbar, hldUbar)
+    if n1:
+        SigUbar[sl1] += ops.potrf_bwd(C_U1, CUbar1, hldUbar1)
+    if n0:
+        SigUbar[sl0] += ops.potrf_bwd(C_U0, CUbar0, hldUbar0)
     g_SU = ops.tril_syrk_bwd(SU, SigUbar)
     g_sqrt_U = zeros(D * D, Q, Q).index_copy_(0, flat, g_SU).reshape(D, D, Q, Q)
     g_mu_U = zeros(D * D, Q).index_copy_(0, flat, muUbar).reshape(D, D, Q)

@@ -92,6 +92,8 @@ class NMGP(torch.nn.Module):
         self.D = dim_outputs
         self.batch_size = minibatch_size
         self.noise = noise
+        self.noise_seed = seed            # key of the counter-based device noise ("device" mode)
+        self._noise_step = 0
         self.step_options = {}
         D, M = self.D, self.M
 
@@ -153,23 +155,33 @@ class NMGP(torch.nn.Module):
                         zL[s, sel[i], j] = zs[sel[i]]
         return zv, zell, zL
 
-    def _device_noise(self, B, n_mc):
-        """float32 normals cast to float64 like the reference's (quirk q2), drawn on the device.  Under row
-        sharding ``gen_shared`` (same seed on every rank) feeds the draw of v, ``gen_local`` the row noise."""
+    def _device_noise(self, B, n_mc, row_gid=None):
+        """Counter-based device noise (csrc/philox.cuh): float32 normals widened to float64 like the reference's
+        (quirk q2), a pure function of (noise_seed, step, sample, global row id, column) -- identical however the rows
+        are sharded over ranks.  z_v and z_ell are materialised (small); the B*D coefficient draws are generated inside
+        the sampling kernels and never stored (returned as None plus the key)."""
         dev = self.device
-        gs, gl = getattr(self, "gen_shared", None), getattr(self, "gen_local", None)
-        zv = torch.randn(n_mc, self.M, device=dev, dtype=torch.float32, generator=gs).to(F64)
-        zell = torch.randn(n_mc, B, device=dev, dtype=torch.float32, generator=gl).to(F64)
-        zL = torch.randn(n_mc, B, self.D, device=dev, dtype=torch.float32, generator=gl).to(F64)
-        return zv, zell, zL
+        step = self._noise_step
+        self._noise_step += 1
+        seed = int(self.noise_seed)
+        zv = ops.noise_fill(1, n_mc, self.M, seed, (step << 8) | 0, 0, None, dev)[0]
+        zell = ops.noise_fill(n_mc, B, 1, seed, (step << 8) | 1, 0, row_gid, dev).reshape(n_mc, B)
+        return zv, zell, None, (seed, (step << 8) | 2)
 
-    def forward_rows(self, x, y, I, n_mc=1, explicit_noise=None):
-        """Same as forward() for rows already on the device: x, y float64 [B], I int32 [B] sorted by output."""
-        zv, zell, zL = explicit_noise if explicit_noise is not None else self._device_noise(x.shape[0], n_mc)
-        return _DSVILoss.apply(self, x, y, I, self.N, zv, zell, zL, dict(self.step_options), *self._param_list())
+    def forward_rows(self, x, y, I, n_mc=1, explicit_noise=None, row_gid=None):
+        """Same as forward() for rows already on the device: x, y float64 [B], I int32 [B] sorted by output;
+        ``row_gid`` (int64 [B]) are the rows' global ids when the minibatch is sharded over ranks."""
+        kw = dict(self.step_options)
+        if explicit_noise is not None:
+            zv, zell, zL = explicit_noise
+        else:
+            zv, zell, zL, key = self._device_noise(x.shape[0], n_mc, row_gid)
+            kw.update(noise_key=key, row_gid=row_gid)
+        return _DSVILoss.apply(self, x, y, I, self.N, zv, zell, zL, kw, *self._param_list())
 
     # -- the hot path -----------------------------------------------------------------------------
-    def forward(self, inputs_list, outputs_list, index=None, verbose=False, n_mc=1, noise=None, explicit_noise=None):
+    def forward(self, inputs_list, outputs_list, index=None, verbose=False, n_mc=1, noise=None, explicit_noise=None,
+                row_gid=None):
         """-SELBO of one minibatch (code/nmgp_dsvi.py:157-301)."""
         t1 = time.time() if verbose else None
         x, y, I, perm = _rows_from_lists(inputs_list, outputs_list, self.D, index)
@@ -177,19 +189,20 @@ class NMGP(torch.nn.Module):
         if perm is not None:
             x, y, I = x[torch.from_numpy(perm).to(x.device)], y[torch.from_numpy(perm).to(y.device)], I[perm]
         noise = noise or self.noise
+        dev = self.device
+        kw = dict(self.step_options)
         if explicit_noise is not None:
             zv, zell, zL = explicit_noise
         elif noise == "reference":
             zv, zell, zL = self._reference_noise(B, I, perm, n_mc)
         elif noise == "device":
-            zv, zell, zL = self._device_noise(B, n_mc)
+            zv, zell, zL, key = self._device_noise(B, n_mc, row_gid)
+            kw.update(noise_key=key, row_gid=row_gid)
         else:
             raise ValueError("noise must be 'reference' or 'device'")
-        dev = self.device
-        up = lambda t: t.to(dev, dtype=F64, non_blocking=True).contiguous()
+        up = lambda t: None if t is None else t.to(dev, dtype=F64, non_blocking=True).contiguous()
         Id = torch.from_numpy(I.astype(np.int32)).to(dev, non_blocking=True)
-        loss = _DSVILoss.apply(self, up(x), up(y), Id, self.N, up(zv), up(zell), up(zL), dict(self.step_options),
-                               *self._param_list())
+        loss = _DSVILoss.apply(self, up(x), up(y), Id, self.N, up(zv), up(zell), up(zL), kw, *self._param_list())
         if verbose:
             torch.cuda.synchronize()
             print("forward+gradient (fused) costs {}s".format(time.time() - t1))

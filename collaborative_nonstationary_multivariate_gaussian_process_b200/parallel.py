@@ -21,12 +21,17 @@ def shard_rows_per_output(counts: Sequence[int], rank: int, world: int) -> List[
     return [np.arange(rank, int(c), world) for c in counts]
 
 
-def configure_model_for_sharding(model, total_rows: int, rank: int, world: int, seed: int = 1234):
-    model.step_options = dict(B_total=int(total_rows), kl_weight=1.0 / world)
-    dev = model.device
-    if dev.type == "cuda":
-        model.gen_shared = torch.Generator(device=dev); model.gen_shared.manual_seed(seed)
-        model.gen_local = torch.Generator(device=dev); model.gen_local.manual_seed(seed + 1 + rank)
+def configure_model_for_sharding(model, total_rows: int, rank: int, world: int):
+    """Row sharding: global row count for the N/B scaling, KL terms split over the ranks.  The device noise is
+    counter-based and keyed by global row ids (pass ``row_gid`` to ``forward_rows``), so no per-rank generator state."""
+    model.step_options = dict(B_total=int(total_rows), kl_weight=1.0 / world,
+                              kl_shard=(rank, world) if world > 1 else None)
+
+
+def global_row_ids(counts: Sequence[int], rows_per_output: Sequence[np.ndarray]) -> np.ndarray:
+    """Global ids (position in the unsharded, output-sorted minibatch) of a rank's rows."""
+    starts = np.cumsum([0] + [int(c) for c in counts[:-1]])
+    return np.concatenate([starts[d] + np.asarray(r, dtype=np.int64) for d, r in enumerate(rows_per_output)]).astype(np.int64)
 
 
 def allreduce_loss_and_grads(loss: torch.Tensor, params: Sequence[torch.nn.Parameter], group=None) -> torch.Tensor:

@@ -119,11 +119,19 @@ int nmgp_coef_sd_fwd(const double* q, const double* cL0, const double* cL1, cons
                      double* sd, long long B, int D, nmgp_stream_t stream);
 int nmgp_coef_sd_bwd(const double* sdbar, const double* sd, const int* I, const double* hyp, double* ghyp,
                      double* qbar, double* cL0bar, double* cL1bar, long long B, int D, nmgp_stream_t stream);
-/* l[s,n,j] = m + z sd (exp on the diagonal coefficient)                    nmgp_dsvi.py:228-238 */
+/* l[s,n,j] = m + z sd (exp on the diagonal coefficient)                    nmgp_dsvi.py:228-238
+ * zL == NULL: the N(0,1) draws are generated inside the kernel by the counter-based generator of nmgp_noise_fill
+ * from (seed, stream_id, s0 + s, gid[n] (or n), j) and never stored; the backward kernel regenerates them. */
 int nmgp_coef_sample_fwd(const double* m, const double* sd, const double* zL, const int* I, double* l, int ns,
-                         long long B, int D, nmgp_stream_t stream);
+                         long long B, int D, unsigned long long seed, unsigned long long stream_id, int s0,
+                         const long long* gid, nmgp_stream_t stream);
 int nmgp_coef_sample_bwd(const double* lbar, const double* l, const double* zL, const int* I, double* mbar /* += */,
-                         double* sdbar /* += */, int ns, long long B, int D, nmgp_stream_t stream);
+                         double* sdbar /* += */, int ns, long long B, int D, unsigned long long seed,
+                         unsigned long long stream_id, int s0, const long long* gid, nmgp_stream_t stream);
+/* out[s,n,c] = N(0,1), float32 draws widened to double (quirk q2: utils.py:123,226,234), Philox4x32-10 keyed by
+ * (seed, stream_id) with counter (gid[n] or n, s0 + s, c/4): independent of how rows are sharded over ranks */
+int nmgp_noise_fill(double* out, int ns, long long B, int C, unsigned long long seed, unsigned long long stream_id,
+                    int s0, const long long* gid, nmgp_stream_t stream);
 
 /* expected log-likelihood of a sample chunk and its cotangents             nmgp_dsvi.py:255-258, utils.py:268-272 */
 int nmgp_lik_rows(const double* l, const double* mg, const double* qg, const double* cG, const double* y, const int* I,

@@ -279,16 +279,64 @@ def coef_sd_bwd(sdbar, sd, I, hyp, ghyp):
     return qbar, -off, -dg
 
 
-def coef_sample_fwd(m, sd, zL, I):
+def _philox4x32_10(c, k):
+    """c: uint32 array [...,4], k: uint32 array [...,2] (numpy, vectorised)."""
+    import numpy as np
+    c = [c[..., i].astype(np.uint64) for i in range(4)]
+    k0 = k[..., 0].astype(np.uint64); k1 = k[..., 1].astype(np.uint64)
+    M0, M1, W0, W1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = M0 * c[0]; p1 = M1 * c[2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
+        hi1, lo1 = p1 >> np.uint64(32), p1 & MASK
+        c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+        k0 = (k0 + W0) & MASK; k1 = (k1 + W1) & MASK
+    return np.stack(c, -1).astype(np.uint32)
+
+
+def noise_fill(ns, B, C, seed, stream_id, s0, gid, device=None):
+    """Counter-based N(0,1) noise of csrc/philox.cuh restated in numpy (float32 Box-Muller, widened to double)."""
+    import numpy as np
+    nq = (C + 3) // 4
+    g = np.arange(B, dtype=np.uint64) if gid is None else np.asarray(gid.cpu() if torch.is_tensor(gid) else gid).astype(np.uint64)
+    ctr = np.zeros((ns, B, nq, 4), dtype=np.uint32)
+    ctr[..., 0] = (g & np.uint64(0xFFFFFFFF)).astype(np.uint32)[None, :, None]
+    ctr[..., 1] = (g >> np.uint64(32)).astype(np.uint32)[None, :, None]
+    ctr[..., 2] = (np.arange(ns, dtype=np.uint32) + np.uint32(s0))[:, None, None]
+    ctr[..., 3] = np.arange(nq, dtype=np.uint32)[None, None, :]
+    key = np.zeros((ns, B, nq, 2), dtype=np.uint32)
+    key[..., 0] = np.uint32((seed ^ stream_id) & 0xFFFFFFFF)
+    key[..., 1] = np.uint32(((seed >> 32) ^ (stream_id >> 32)) & 0xFFFFFFFF)
+    u = _philox4x32_10(ctr, key)
+    uf = ((u >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+    z = np.empty((ns, B, nq, 4), dtype=np.float32)
+    for h in range(2):
+        r = np.sqrt(np.float32(-2.0) * np.log(uf[..., 2 * h]))
+        ang = np.float32(6.28318530717958647692) * uf[..., 2 * h + 1]
+        z[..., 2 * h] = r * np.cos(ang)
+        z[..., 2 * h + 1] = r * np.sin(ang)
+    return torch.from_numpy(z.reshape(ns, B, nq * 4)[..., :C].astype(np.float64)).contiguous()
+
+
+def _explicit_noise(zL, noise, B, D):
+    if zL is not None:
+        return zL
+    seed, stream_id, s0, ns, gid = noise
+    return noise_fill(ns, B, D, seed, stream_id, s0, gid)
+
+
+def coef_sample_fwd(m, sd, zL, I, noise=None):
     D = m.shape[-1]
+    zL = _explicit_noise(zL, noise, m.shape[0], D)
     j = torch.arange(D).view(1, 1, -1); Il = I.long().view(1, -1, 1)
     raw = m.unsqueeze(0) + zL * sd.unsqueeze(0)
     l = torch.where(j == Il, torch.exp(raw), raw)
     return torch.where(j <= Il, l, torch.zeros_like(l))
 
 
-def coef_sample_bwd(lbar, l, zL, I, mbar, sdbar):
+def coef_sample_bwd(lbar, l, zL, I, mbar, sdbar, noise=None):
     D = l.shape[-1]
+    zL = _explicit_noise(zL, noise, l.shape[1], D)
     j = torch.arange(D).view(1, 1, -1); Il = I.long().view(1, -1, 1)
     rb = torch.where(j == Il, lbar * l, lbar)
     rb = torch.where(j <= Il, rb, torch.zeros_like(rb))

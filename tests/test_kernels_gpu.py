@@ -253,3 +253,29 @@ def test_latent_fused(Q, D, B):
     for a, b, n in zip(got, ref, ("lbar", "mgbar", "qgbar", "cGbar", "PGbar")):
         check(a, b, 1e-12, "latent_fused " + n)
     check(Rsd, Rs, 1e-12, "latent_fused Rsum"); check(ghd, gh, 1e-11, "latent_fused ghyp")
+
+
+def test_counter_noise_kernel_and_in_kernel_sampling():
+    """nmgp_noise_fill against its numpy restatement (float32 transcendental rounding: 1e-6), and the in-kernel noise
+    of coef_sample_fwd/bwd against the explicit-noise path fed with the same generator's output (exact)."""
+    gen = torch.Generator().manual_seed(3)
+    B, D, ns = 333, 7, 3
+    gid = torch.randperm(10 ** 6, generator=gen)[:B].to(torch.int64)
+    seed, stream = 424242, (5 << 8) | 2
+    z = ops.noise_fill(ns, B, D, seed, stream, 4, g(gid), DEV)
+    zr = specs.noise_fill(ns, B, D, seed, stream, 4, gid)
+    assert relerr(z, zr) < 1e-5
+    assert abs(float(z.mean())) < 0.05 and abs(float(z.var()) - 1.0) < 0.05
+    I = make_I(gen, B, D)
+    m = torch.randn(B, D, generator=gen, dtype=torch.float64) * 0.3
+    sd = torch.rand(B, D, generator=gen, dtype=torch.float64)
+    noise = (seed, stream, 4, ns, g(gid))
+    l_in = ops.coef_sample_fwd(g(m), g(sd), None, g(I), noise=noise)
+    l_ex = ops.coef_sample_fwd(g(m), g(sd), z, g(I))
+    assert torch.equal(l_in, l_ex)
+    lb = torch.randn(ns, B, D, generator=gen, dtype=torch.float64)
+    mb1, sb1 = g(torch.zeros(B, D, dtype=torch.float64)), g(torch.zeros(B, D, dtype=torch.float64))
+    mb2, sb2 = mb1.clone(), sb1.clone()
+    ops.coef_sample_bwd(g(lb), l_in, None, g(I), mb1, sb1, noise=noise)
+    ops.coef_sample_bwd(g(lb), l_ex, z, g(I), mb2, sb2)
+    assert torch.equal(mb1, mb2) and torch.equal(sb1, sb2)
