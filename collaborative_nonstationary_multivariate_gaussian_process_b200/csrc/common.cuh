@@ -64,5 +64,21 @@ __device__ __forceinline__ double block_sum(double v) {
     return total;
 }
 
+// Division of a 32-bit index by a launch-invariant divisor in three instructions (Granlund-Montgomery): the staging
+// loops turn flat element indices into (row, column) and a hardware-emulated integer division there costs more issue
+// slots than the copy itself.
+struct FastDiv {
+    unsigned int d, m, s;
+    __host__ explicit FastDiv(unsigned int div = 1) : d(div) {
+        s = 0;
+        while ((1ull << s) < div) ++s;
+        m = (unsigned int)(((1ull << 32) * ((1ull << s) - div)) / div + 1);
+    }
+    __device__ __forceinline__ unsigned int div(unsigned int n) const {
+        const unsigned int t = __umulhi(m, n);
+        return (t + n) >> s;   // valid while t + n does not overflow: n < 2^31 (all uses are tile-local indices)
+    }
+};
+
 // slot of the packed coefficient pair (i, j<=i): diagonal pairs first, then strictly-lower row-major
 __device__ __forceinline__ int pair_slot(int i, int j, int D) { return i == j ? i : D + (i * (i - 1)) / 2 + j; }

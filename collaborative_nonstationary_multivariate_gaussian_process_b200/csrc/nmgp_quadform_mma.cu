@@ -70,7 +70,7 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
                const double* __restrict__ muW, const double* __restrict__ hyp, double scale,
                double* __restrict__ Rsum, double* __restrict__ ghyp, double* __restrict__ lbar,
                double* __restrict__ mgbar, double* __restrict__ qgbar, double* __restrict__ cGbar,
-               double* __restrict__ PGbar, long long B, int Q, int D) {
+               double* __restrict__ PGbar, long long B, int Q, int D, FastDiv qdiv) {
     using SH = LFShape<NB, KS>;
     constexpr int LDP = SH::LDP, LDS = SH::LDS, NP = SH::NP, KP = SH::KP;
     extern __shared__ __align__(16) double sm[];
@@ -169,7 +169,7 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
         const double* Sg = SigW + (size_t)j * Q * Q;
         double* Sd = Ss + (size_t)buf * KP * LDS;
         for (int e = tid; e < Q * Q; e += LF_THREADS) {
-            int a = e / Q, b = e - a * Q;
+            int a = (int)qdiv.div((unsigned)e), b = e - a * Q;
             cp_async8(&Sd[a * LDS + b], &Sg[e]);
         }
         for (int c = tid; c < Q; c += LF_THREADS) cp_async8(&mus[buf * NP + c], &muW[(size_t)j * Q + c]);
@@ -285,7 +285,8 @@ static int launch_latent_fused(const double* PG, const double* cG, const double*
     if (int r = nmgp_opt_in_smem(k_latent_fused<NB, KS>, smem, "nmgp_latent_fused")) return r;
     dim3 grid((unsigned)((B + LF_ROWS - 1) / LF_ROWS), ns);
     k_latent_fused<NB, KS><<<grid, LF_THREADS, smem, st>>>(PG, cG, l, y, I, SigW, muW, hyp, scale, Rsum, ghyp, lbar,
-                                                           mgbar, qgbar, cGbar, PGbar, B, Q, D);
+                                                           mgbar, qgbar, cGbar, PGbar, B, Q, D,
+                                                           FastDiv((unsigned)Q));
     return nmgp_launch_status("nmgp_latent_fused");
 }
 
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1)
 k_coef_quadform_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const int* __restrict__ I,
                     const double* __restrict__ Sig, const double* __restrict__ Mu, double* __restrict__ qout,
                     double* __restrict__ mout, const double* __restrict__ qbar, const double* __restrict__ mbar,
-                    double* __restrict__ Pabar, double* __restrict__ Pbbar, long long B, int Q, int D) {
+                    double* __restrict__ Pabar, double* __restrict__ Pbbar, long long B, int Q, int D, FastDiv qdiv) {
     using SH = LFShape<NB, KS>;
     constexpr int LDP = SH::LDP, LDS = SH::LDS, NP = SH::NP, KP = SH::KP;
     extern __shared__ __align__(16) double sm[];
@@ -378,7 +379,7 @@ k_coef_quadform_mma(const double* __restrict__ Pa, const double* __restrict__ Pb
         const double* Sg = Sig + (size_t)idx * Q * Q;
         double* Sd = Ss + (size_t)buf * KP * LDS;
         for (int e = tid; e < Q * Q; e += LF_THREADS) {
-            int a = e / Q, b = e - a * Q;
+            int a = (int)qdiv.div((unsigned)e), b = e - a * Q;
             cp_async8(&Sd[a * LDS + b], &Sg[e]);
         }
         for (int c = tid; c < Q; c += LF_THREADS) cp_async8(&mus[buf * NP + c], &Mu[(size_t)idx * Q + c]);
@@ -507,7 +508,7 @@ static int launch_coef_quadform(const double* Pa, const double* Pb, const int* I
     if (int r = nmgp_opt_in_smem(k_coef_quadform_mma<NB, KS, BWD>, smem, "nmgp_quadform(mma)")) return r;
     dim3 grid((unsigned)((B + LF_ROWS - 1) / LF_ROWS), ns);
     k_coef_quadform_mma<NB, KS, BWD><<<grid, LF_THREADS, smem, st>>>(Pa, Pb, I, Sig, Mu, q, m, qbar, mbar, Pabar, Pbbar,
-                                                                     B, Q, D);
+                                                                     B, Q, D, FastDiv((unsigned)Q));
     return nmgp_launch_status("nmgp_quadform(mma)");
 }
 

@@ -321,35 +321,51 @@ NMGP_API int nmgp_coef_sd_bwd(const double* sdbar, const double* sd, const int* 
 // l[s,n,j] = m + z sd  (exp on j == I[n]), 0 for j > I[n]    (code/nmgp_dsvi.py:228-238)
 // zL == NULL: the noise is generated in the kernel (counter-based, philox.cuh) from (key, s0 + s, gid[n], j) and never
 // touches HBM; the backward kernel regenerates the same values.
-__device__ __forceinline__ double coef_noise(const double* __restrict__ zL, size_t o, NoiseKey key, int sglob,
-                                             long long gid, int j) {
-    if (zL) return zL[o];
-    float z[4];
-    philox_normal4(key, (unsigned)sglob, (unsigned long long)gid, (unsigned)(j >> 2), z);
-    return (double)z[j & 3];
+// One thread per (row, quad of 4 consecutive columns): a Philox call yields the 4 normals of the quad.
+__device__ __forceinline__ void coef_noise4(const double* __restrict__ zL, size_t o, int jn, NoiseKey key, int sglob,
+                                            long long gid, int q4, double z[4]) {
+    if (zL) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z[k] = k < jn ? zL[o + k] : 0.0;
+    } else {
+        float zf[4];
+        philox_normal4(key, (unsigned)sglob, (unsigned long long)gid, (unsigned)q4, zf);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z[k] = (double)zf[k];
+    }
 }
 __global__ void k_coef_sample_fwd(const double* __restrict__ m, const double* __restrict__ sd,
                                   const double* __restrict__ zL, const int* __restrict__ I, double* __restrict__ l,
                                   long long B, int D, NoiseKey key, int s0, const long long* __restrict__ gid) {
     const int s = blockIdx.y;
+    const int nq = (D + 3) >> 2;
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= B * D) return;
-    long long n = e / D;
-    int j = (int)(e - n * D), i = I[n];
-    double out = 0.0;
-    if (j <= i) {
-        const double z = coef_noise(zL, (size_t)s * B * D + e, key, s0 + s, gid ? gid[n] : n, j);
-        out = fma(z, sd[e], m[e]);
-        if (j == i) out = exp(out);
+    if (e >= B * nq) return;
+    long long n = e / nq;
+    const int q4 = (int)(e - n * nq), j0 = 4 * q4, i = I[n];
+    const int jn = min(4, D - j0);
+    const size_t o = (size_t)n * D + j0, os = (size_t)s * B * D + o;
+    double z[4] = {0.0, 0.0, 0.0, 0.0};
+    if (j0 <= i) coef_noise4(zL, os, jn, key, s0 + s, gid ? gid[n] : n, q4, z);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < jn) {
+            const int j = j0 + k;
+            double out = 0.0;
+            if (j <= i) {
+                out = fma(z[k], sd[o + k], m[o + k]);
+                if (j == i) out = exp(out);
+            }
+            l[os + k] = out;
+        }
     }
-    l[(size_t)s * B * D + e] = out;
 }
 NMGP_API int nmgp_coef_sample_fwd(const double* m, const double* sd, const double* zL, const int* I, double* l, int ns,
                                   long long B, int D, unsigned long long seed, unsigned long long stream_id, int s0,
                                   const long long* gid, cudaStream_t st) {
     NMGP_REQUIRE(ns >= 0 && ns <= 65535, "nmgp_coef_sample_fwd");
     if (B == 0 || ns == 0) return 0;
-    long long n = B * D;
+    long long n = B * ((D + 3) / 4);
     dim3 grid((unsigned)((n + 255) / 256), ns);
     NoiseKey key{seed, stream_id};
     k_coef_sample_fwd<<<grid, 256, 0, st>>>(m, sd, zL, I, l, B, D, key, s0, gid);
@@ -359,28 +375,43 @@ __global__ void k_coef_sample_bwd(const double* __restrict__ lbar, const double*
                                   const double* __restrict__ zL, const int* __restrict__ I, double* __restrict__ mbar,
                                   double* __restrict__ sdbar, int ns, long long B, int D, NoiseKey key, int s0,
                                   const long long* __restrict__ gid) {
+    const int nq = (D + 3) >> 2;
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= B * D) return;
-    long long n = e / D;
-    int j = (int)(e - n * D), i = I[n];
-    if (j > i) return;
+    if (e >= B * nq) return;
+    long long n = e / nq;
+    const int q4 = (int)(e - n * nq), j0 = 4 * q4, i = I[n];
+    if (j0 > i) return;
+    const int jn = min(4, D - j0);
     const long long g = gid ? gid[n] : n;
-    double am = 0.0, as = 0.0;
+    const size_t o = (size_t)n * D + j0;
+    double am[4] = {0.0, 0.0, 0.0, 0.0}, as[4] = {0.0, 0.0, 0.0, 0.0};
     for (int s = 0; s < ns; ++s) {
-        size_t o = (size_t)s * B * D + e;
-        double rb = lbar[o];
-        if (j == i) rb *= l[o];
-        am += rb;
-        as = fma(rb, coef_noise(zL, o, key, s0 + s, g, j), as);
+        const size_t os = (size_t)s * B * D + o;
+        double z[4];
+        coef_noise4(zL, os, jn, key, s0 + s, g, q4, z);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < jn && j0 + k <= i) {
+                double rb = lbar[os + k];
+                if (j0 + k == i) rb *= l[os + k];
+                am[k] += rb;
+                as[k] = fma(rb, z[k], as[k]);
+            }
+        }
     }
-    mbar[e] += am;
-    sdbar[e] += as;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < jn && j0 + k <= i) {
+            mbar[o + k] += am[k];
+            sdbar[o + k] += as[k];
+        }
+    }
 }
 NMGP_API int nmgp_coef_sample_bwd(const double* lbar, const double* l, const double* zL, const int* I, double* mbar,
                                   double* sdbar, int ns, long long B, int D, unsigned long long seed,
                                   unsigned long long stream_id, int s0, const long long* gid, cudaStream_t st) {
     if (B == 0 || ns == 0) return 0;
-    long long n = B * D;
+    long long n = B * ((D + 3) / 4);
     NoiseKey key{seed, stream_id};
     k_coef_sample_bwd<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(lbar, l, zL, I, mbar, sdbar, ns, B, D, key, s0, gid);
     return nmgp_launch_status("nmgp_coef_sample_bwd");
