@@ -8,6 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "libnmgp_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+PTXAS_OPT = {"nmgp_quadform_mma.cu": os.environ.get("NMGP_PTXAS_QUADFORM", "-O3")}
 
 
 def nvcc_path():
@@ -37,8 +38,11 @@ def build(force=False, verbose=False):
     procs = []
     for src in sources():
         obj = src[:-3] + ".o"
+        # per-file ptxas level (tuning knob): -O1 keeps the source's k-step-major DMMA order in the quadratic-form kernels
+        # where -O3 regroups it into two dependent accumulator chains, but measured 6% slower overall (profiles/README.md)
+        popt = PTXAS_OPT.get(os.path.basename(src), "-O3")
         cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-fvisibility=hidden",
-               "-Xptxas", "-v" if verbose else "-O3", "-c", src, "-o", obj]
+               "-Xptxas", popt] + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False
