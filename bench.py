@@ -301,12 +301,36 @@ def run_b200(args, w):
         dom = max(kern, key=lambda k: kern[k]["ms_total"]) if kern else None
         roof = None
         if dom:
+            # DRAM traffic per launch of the dominant kernel from the committed ncu --set full capture (profiles/)
+            traffic = None
+            try:
+                summ = json.load(open(os.path.join(ROOT, "profiles", "ncu_r1_full_summary.json")))
+                key = {"latent_fused": "k_latent_fused", "weighted_gram": "k_gram_mma"}.get(dom)
+                for kname, rec in summ.items():
+                    if key and kname.startswith(key):
+                        scale_u = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+                        ur = scale_u.get(rec["units"]["dram__bytes_read.sum"], 1.0)
+                        uw = scale_u.get(rec["units"]["dram__bytes_write.sum"], 1.0)
+                        traffic = rec["dram__bytes_read.sum"] * ur + rec["dram__bytes_write.sum"] * uw
+            except Exception:
+                traffic = None
+            # flops the kernel really issues per (row, pair): one padded V = P Sigma GEMM (latent_fused) / the lower
+            # 8x8 blocks of the Gram matrix (weighted_gram) -- the dense convention counts 4 Q^2 / 2 Q^2
+            KSp, NBp = (Q + 3) // 4, (Q + 7) // 8
+            executed_per_pair = {"latent_fused": 2.0 * (4 * KSp) * (8 * NBp),
+                                 "weighted_gram": 2.0 * 64 * (NBp * (NBp + 1) // 2)}.get(dom)
             roof = {"kernel": dom, "bound": "tensor", "achieved": kern[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
-                    "frac": kern[dom]["tflops"] / peak, "traffic": None,
+                    "frac": kern[dom]["tflops"] / peak, "traffic": traffic,
                     "peak_source": "FP64 DGEMM (torch.matmul, cuBLAS) 8192^3 measured in this run; "
                                    "MEASURED_PEAKS.json holds no FP64 figure",
+                    "convention": "achieved = dense-convention flops of SURVEY.md 8d (2 Q^2 per quadratic form and per "
+                                  "adjoint); the kernel re-uses V = P Sigma for the adjoint, see executed_tflops",
                     "avg_launch_ms": kern[dom]["ms_total"] / kern[dom]["calls"],
                     "share_of_step": kern[dom]["share_of_step"]}
+            if executed_per_pair:
+                nsamp = S if dom == "latent_fused" else S + 1
+                roof["executed_tflops"] = args.steps * nsamp * pairs_per_sample * executed_per_pair / (kern[dom]["ms_total"] * 1e-3) / 1e12
+                roof["executed_frac"] = roof["executed_tflops"] / peak
         F_step = 3.0 * ((S + 1) * pairs_per_sample * (2.0 * Q * Q + 2.0 * Q) + S * 2.0 * Bloc * Q * Q) * world
         line = {"metric": METRIC, "value": 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
