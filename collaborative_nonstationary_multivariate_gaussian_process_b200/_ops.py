@@ -82,20 +82,28 @@ def tril_syrk_bwd(S, SigBar):
     return out
 
 
-def potrf(A, jitter=0.0):
-    """Batched lower Cholesky of A + jitter*I with hld = sum(log(diag)).  Raises RuntimeError
-    (like torch.cholesky in the reference) when a matrix is not positive definite."""
+def potrf(A, jitter=0.0, info=None):
+    """Batched lower Cholesky of A + jitter*I with hld = sum(log(diag)).  Raises RuntimeError (like torch.cholesky in
+    the reference) when a matrix is not positive definite.  With ``info`` (an int32 device scalar that accumulates
+    1 + index of a failing matrix) the check is deferred to the caller -- no host synchronisation here."""
     nb, Q, _ = A.shape
     _checkQ(Q)
     C = torch.empty_like(A)
     hld = _empty(A, nb)
-    info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    deferred = info is not None
+    if not deferred:
+        info = torch.zeros(1, dtype=torch.int32, device=A.device)
     check(lib().nmgp_potrf_batched(_d(A), c_double(jitter), _d(C), _d(hld), _i(info), c_int(nb), c_int(Q), _stream()),
           "nmgp_potrf_batched")
+    if not deferred:
+        raise_if_not_pd(info)
+    return C, hld
+
+
+def raise_if_not_pd(info):
     bad = int(info.item())
     if bad != 0:
-        raise RuntimeError("cholesky: matrix %d of the batch is not positive-definite" % (bad - 1))
-    return C, hld
+        raise RuntimeError("cholesky: matrix %d of a batch is not positive-definite" % (bad - 1))
 
 
 def potrf_bwd(C, Cbar, hldbar):

@@ -15,6 +15,7 @@ buffers; all arithmetic on B-, Q^2- or S-sized data happens in the CUDA kernels.
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Dict, Optional
 
@@ -30,6 +31,14 @@ MODE_W, MODE_U = 0, 1
 PARAM_NAMES = ("mu_W", "sqrt_W", "mu_v", "sqrt_v", "mu_U", "sqrt_U") + HYPER_ORDER
 
 _pair_cache: Dict[tuple, torch.Tensor] = {}
+_side_streams: Dict[str, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(dev):
+    key = str(dev)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=dev)
+    return _side_streams[key]
 
 
 def packed_pair_index(D: int, device) -> torch.Tensor:
@@ -84,6 +93,7 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
     zeros = lambda *s: torch.zeros(*s, dtype=f64, device=dev)
     ns_max = sample_chunk or default_sample_chunk(S, B, Q, D)
 
+    pd_info = torch.zeros(1, dtype=torch.int32, device=dev)     # one deferred positive-definiteness check per step
     hyp = ops.hyper_exp(torch.stack([p[k].detach().reshape(()) for k in HYPER_ORDER]))
     ghyp = zeros(7)
 
@@ -103,8 +113,8 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
     Sig_v = ops.tril_syrk_fwd(sqrt_v)
     Sig_W = ops.tril_syrk_fwd(sqrt_W)
     Sig_U = ops.tril_syrk_fwd(SU)
-    C_v, hld_v = ops.potrf(Sig_v, EPS)
-    C_W, hld_W = ops.potrf(Sig_W, EPS)
+    C_v, hld_v = ops.potrf(Sig_v, EPS, info=pd_info)
+    C_W, hld_W = ops.potrf(Sig_W, EPS, info=pd_info)
     rank_, world_ = kl_shard if kl_shard is not None else (0, 1)
     part = lambda n: slice((n * rank_) // world_, (n * (rank_ + 1)) // world_)
     sl1 = part(D)                                             # diagonal pairs handled here
@@ -112,16 +122,12 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
     slS = part(S)                                             # samples whose KL_W is evaluated here
     w_sh = kl_weight if kl_shard is None else 1.0
     n1, n0, nS = sl1.stop - sl1.start, sl0.stop - sl0.start, slS.stop - slS.start
-    if n1:
-        C_U1, hld_U1 = ops.potrf(Sig_U[sl1], EPS)
-    if n0:
-        C_U0, hld_U0 = ops.potrf(Sig_U[sl0], EPS)
 
     # ---- the three stationary inducing systems ------------------------------------------------
     sysm = {}
     for name, is2, ilen in (("ell", H_S2_ELL, H_LEN_ELL), ("L0", H_S2_L0, H_LEN_L0), ("L1", H_S2_L1, H_LEN_L1)):
         A = ops.rbf_build_fwd(Z, Z, hyp, is2, ilen, EPS).reshape(1, Q, Q)
-        R, hldR = ops.potrf(A, 0.0)
+        R, hldR = ops.potrf(A, 0.0, info=pd_info)
         K12 = ops.rbf_build_fwd(x, Z, hyp, is2, ilen, 0.0).reshape(1, B, Q)
         P, c = ops.solve_rows_fwd(K12, R)
         sysm[name] = dict(R=R, hldR=hldR, K12=K12, P=P, c=c, is2=is2, ilen=ilen)
@@ -133,44 +139,60 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
     # ---- per-sample inducing draws, Gibbs K22 factor -----------------------------------------
     v, ellZ = ops.sample_v_fwd(mu_v, C_v[0], z_v)
     A_G = ops.gibbs_build_fwd(Z, Z, ellZ, ellZ, EPS)
-    R_G, hld_G = ops.potrf(A_G, 0.0)
+    R_G, hld_G = ops.potrf(A_G, 0.0, info=pd_info)
 
-    # ---- KL terms (reference-exact form, quirk q10) and their cotangents ----------------------
-    kl_v, t_v = ops.kl_fwd(C_v, hld_v, mu_v.reshape(1, Q), sysm["ell"]["R"], sysm["ell"]["hldR"])
-    loss_kl = kl_weight * kl_v.sum()
-    kl_W = None
-    if nS:
-        kl_W, t_W = ops.kl_fwd(C_W, hld_W, mu_W, R_G[slS], hld_G[slS])
-        loss_kl = loss_kl + w_sh * kl_W.sum() / S
-    klU_sum = zeros(())
-    if n1:
-        kl_U1, t_U1 = ops.kl_fwd(C_U1, hld_U1, muU[sl1], sysm["L1"]["R"], sysm["L1"]["hldR"])
-        klU_sum = klU_sum + kl_U1.sum()
-    if n0:
-        kl_U0, t_U0 = ops.kl_fwd(C_U0, hld_U0, muU[sl0], sysm["L0"]["R"], sysm["L0"]["hldR"])
-        klU_sum = klU_sum + kl_U0.sum()
-    loss_kl = loss_kl + w_sh * klU_sum
-
-    full = lambda shape, val: torch.full(shape, val, dtype=f64, device=dev)
-    if want_grads:
-        CWbar = zeros(D, Q, Q); hldWbar = zeros(D); muWbar = zeros(D, Q)
-        RGbar = zeros(S, Q, Q); hldGbar = zeros(S)
-        if nS:
-            a, b, c_, rg, hg = ops.kl_bwd(full((nS, D), w_sh / S), C_W, mu_W, R_G[slS], t_W)
-            CWbar, hldWbar, muWbar = a, b, c_
-            RGbar[slS] = rg; hldGbar[slS] = hg
-        Cvbar, hldvbar, muvbar, Rellbar, hldRellbar = ops.kl_bwd(full((1, 1), kl_weight), C_v, mu_v.reshape(1, Q),
-                                                                 sysm["ell"]["R"], t_v)
-        CUbar1 = hldUbar1 = CUbar0 = hldUbar0 = None
-        muUbar = zeros(npair, Q)
-        RL1bar = zeros(1, Q, Q); hldRL1bar = zeros(1); RL0bar = zeros(1, Q, Q); hldRL0bar = zeros(1)
+    # The KL terms touch only Q x Q matrices (n_K of them): latency-bound work that is independent of the row kernels
+    # of the sample loop, so it runs on a side stream and overlaps them (it is the serial fraction under row sharding).
+    side = _side_stream(dev) if x.is_cuda else None
+    main = torch.cuda.current_stream(dev) if x.is_cuda else None
+    if side is not None:
+        side.wait_stream(main)
+    with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+        # ---- KL terms (reference-exact form, quirk q10) and their cotangents ----------------------
         if n1:
-            CUbar1, hldUbar1, c_, RL1bar, hldRL1bar = ops.kl_bwd(full((1, n1), w_sh), C_U1, muU[sl1], sysm["L1"]["R"], t_U1)
-            muUbar[sl1] = c_
+            C_U1, hld_U1 = ops.potrf(Sig_U[sl1], EPS, info=pd_info)
         if n0:
-            CUbar0, hldUbar0, c_, RL0bar, hldRL0bar = ops.kl_bwd(full((1, n0), w_sh), C_U0, muU[sl0], sysm["L0"]["R"], t_U0)
-            muUbar[sl0] = c_
-        muvbar = muvbar.reshape(Q).clone()
+            C_U0, hld_U0 = ops.potrf(Sig_U[sl0], EPS, info=pd_info)
+        kl_v, t_v = ops.kl_fwd(C_v, hld_v, mu_v.reshape(1, Q), sysm["ell"]["R"], sysm["ell"]["hldR"])
+        loss_kl = kl_weight * kl_v.sum()
+        kl_W = None
+        if nS:
+            kl_W, t_W = ops.kl_fwd(C_W, hld_W, mu_W, R_G[slS], hld_G[slS])
+            loss_kl = loss_kl + w_sh * kl_W.sum() / S
+        klU_sum = zeros(())
+        if n1:
+            kl_U1, t_U1 = ops.kl_fwd(C_U1, hld_U1, muU[sl1], sysm["L1"]["R"], sysm["L1"]["hldR"])
+            klU_sum = klU_sum + kl_U1.sum()
+        if n0:
+            kl_U0, t_U0 = ops.kl_fwd(C_U0, hld_U0, muU[sl0], sysm["L0"]["R"], sysm["L0"]["hldR"])
+            klU_sum = klU_sum + kl_U0.sum()
+        loss_kl = loss_kl + w_sh * klU_sum
+
+        full = lambda shape, val: torch.full(shape, val, dtype=f64, device=dev)
+        if want_grads:
+            CWbar = zeros(D, Q, Q); hldWbar = zeros(D); muWbar = zeros(D, Q)
+            RGbar = zeros(S, Q, Q); hldGbar = zeros(S)
+            if nS:
+                a, b, c_, rg, hg = ops.kl_bwd(full((nS, D), w_sh / S), C_W, mu_W, R_G[slS], t_W)
+                CWbar, hldWbar, muWbar = a, b, c_
+                RGbar[slS] = rg; hldGbar[slS] = hg
+            Cvbar, hldvbar, muvbar, Rellbar, hldRellbar = ops.kl_bwd(full((1, 1), kl_weight), C_v, mu_v.reshape(1, Q),
+                                                                     sysm["ell"]["R"], t_v)
+            CUbar1 = hldUbar1 = CUbar0 = hldUbar0 = None
+            muUbar = zeros(npair, Q)
+            RL1bar = zeros(1, Q, Q); hldRL1bar = zeros(1); RL0bar = zeros(1, Q, Q); hldRL0bar = zeros(1)
+            if n1:
+                CUbar1, hldUbar1, c_, RL1bar, hldRL1bar = ops.kl_bwd(full((1, n1), w_sh), C_U1, muU[sl1], sysm["L1"]["R"], t_U1)
+                muUbar[sl1] = c_
+            if n0:
+                CUbar0, hldUbar0, c_, RL0bar, hldRL0bar = ops.kl_bwd(full((1, n0), w_sh), C_U0, muU[sl0], sysm["L0"]["R"], t_U0)
+                muUbar[sl0] = c_
+            muvbar = muvbar.reshape(Q).clone()
+            # Cholesky adjoints that depend on the KL terms only
+            AG_kl = ops.potrf_bwd(R_G, RGbar, hldGbar)
+            SigW_kl = ops.potrf_bwd(C_W, CWbar, hldWbar)
+            SigU_kl1 = ops.potrf_bwd(C_U1, CUbar1, hldUbar1) if n1 else None
+            SigU_kl0 = ops.potrf_bwd(C_U0, CUbar0, hldUbar0) if n0 else None
 
     # ---- accumulators filled by the sample loop ------------------------------------------------
     SigWbar = zeros(D, Q, Q)
@@ -201,14 +223,25 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
         ops.ell_rows_bwd(ellxbar, ellx, P_ell, v[sl], z_ell[sl], vbar[sl], Pellbar, sdellbar)
         ops.coef_sample_bwd(lbar, l, zl_, I, mUbar, sdUbar, noise=nz_)
 
+    if side is not None:
+        main.wait_stream(side)
+        for t_ in (loss_kl, kl_v, kl_W):
+            if t_ is not None:
+                t_.record_stream(main)
     loss = loss_kl - scale * Rsum.sum()
     if aux is not None:
         aux.update(Rsum=Rsum, kl_W=kl_W, kl_v=kl_v.sum(), kl_U=klU_sum)
     if not want_grads:
+        ops.raise_if_not_pd(pd_info)
         return loss, None
 
     # ---- backward of the per-sample small stage ------------------------------------------------
-    AGbar += ops.potrf_bwd(R_G, RGbar, hldGbar)
+    if side is not None:
+        for t_ in (AG_kl, SigW_kl, SigU_kl1, SigU_kl0, muWbar, muUbar, muvbar, Cvbar, hldvbar, Rellbar, hldRellbar,
+                   RL1bar, hldRL1bar, RL0bar, hldRL0bar):
+            if t_ is not None:
+                t_.record_stream(main)
+    AGbar += AG_kl
     tmp = torch.empty_like(ellZbar)
     ops.gibbs_build_bwd(Z, Z, ellZ, ellZ, AGbar, tmp, ellZbar)
     ellZbar += tmp
@@ -236,12 +269,12 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
 
     # ---- Cholesky / LL^T adjoints back to the sqrt parameters -----------------------------------
     g_sqrt_v = ops.tril_syrk_bwd(sqrt_v, ops.potrf_bwd(C_v, Cvbar.reshape(1, Q, Q), hldvbar)).reshape(Q, Q)
-    SigWbar += ops.potrf_bwd(C_W, CWbar, hldWbar)
+    SigWbar += SigW_kl
     g_sqrt_W = ops.tril_syrk_bwd(sqrt_W, SigWbar)
     if n1:
-        SigUbar[sl1] += ops.potrf_bwd(C_U1, CUbar1, hldUbar1)
+        SigUbar[sl1] += SigU_kl1
     if n0:
-        SigUbar[sl0] += ops.potrf_bwd(C_U0, CUbar0, hldUbar0)
+        SigUbar[sl0] += SigU_kl0
     g_SU = ops.tril_syrk_bwd(SU, SigUbar)
     g_sqrt_U = zeros(D * D, Q, Q).index_copy_(0, flat, g_SU).reshape(D, D, Q, Q)
     g_mu_U = zeros(D * D, Q).index_copy_(0, flat, muUbar).reshape(D, D, Q)
@@ -250,4 +283,6 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
              "mu_U": g_mu_U, "sqrt_U": g_sqrt_U}
     for i, k in enumerate(HYPER_ORDER):
         grads[k] = ghyp[i]
+    # the only host synchronisation of the step, after everything is enqueued (torch.cholesky's RuntimeError)
+    ops.raise_if_not_pd(pd_info)
     return loss, grads

@@ -41,7 +41,12 @@ def tril_syrk_bwd(S, SigBar):
     return torch.tril((SigBar + SigBar.transpose(-1, -2)) @ L)
 
 
-def potrf(A, jitter=0.0):
+def raise_if_not_pd(info):
+    if int(info.item()) != 0:
+        raise RuntimeError("cholesky: not positive-definite")
+
+
+def potrf(A, jitter=0.0, info=None):
     n = A.shape[-1]
     C = torch.linalg.cholesky(A + jitter * torch.eye(n, dtype=F64))
     return C, C.diagonal(dim1=-2, dim2=-1).log().sum(-1)
