@@ -195,7 +195,7 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
             SigU_kl0 = ops.potrf_bwd(C_U0, CUbar0, hldUbar0) if n0 else None
 
     # ---- accumulators filled by the sample loop ------------------------------------------------
-    SigWbar = zeros(D, Q, Q)
+    SigWbar = zeros(D, Q, Q); muWrows = zeros(D, Q)     # row-kernel parts; the KL parts join after the side stream
     Pellbar = zeros(B, Q); sdellbar = zeros(B)
     mUbar = zeros(B, D); sdUbar = zeros(B, D)
     AGbar = zeros(S, Q, Q); ellZbar = zeros(S, Q); vbar = zeros(S, Q)
@@ -216,7 +216,7 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
                                                             seg=seg)
         if not want_grads:
             continue
-        ops.weighted_gram(PG, PG, I, qgbar, mgbar, MODE_W, SigWbar, muWbar, seg=seg)
+        ops.weighted_gram(PG, PG, I, qgbar, mgbar, MODE_W, SigWbar, muWrows, seg=seg)
         KGbar = ops.solve_rows_bwd(PGbar, cGbar, KG, PG, R_G[sl], AGbar[sl])
         ellxbar = torch.empty_like(ellx)
         ops.gibbs_build_bwd(x, Z, ellx, ellZ[sl], KGbar, ellxbar, ellZbar[sl])
@@ -242,6 +242,7 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
             if t_ is not None:
                 t_.record_stream(main)
     AGbar += AG_kl
+    muWbar = muWbar + muWrows
     tmp = torch.empty_like(ellZbar)
     ops.gibbs_build_bwd(Z, Z, ellZ, ellZ, AGbar, tmp, ellZbar)
     ellZbar += tmp
