@@ -28,7 +28,7 @@ __host__ __device__ constexpr int atb_pad(int n) { return ((n + 3) / 8) * 8 + 4;
 template <int NB>
 __global__ void __launch_bounds__(ATB_THREADS)
 k_atb_mma(const double* __restrict__ A, const double* __restrict__ Bm, double* __restrict__ C, double sign,
-          long long B, int Q, long long chunk) {
+          long long B, int Q, long long chunk, const double* __restrict__ cbar, double* __restrict__ Kbar) {
     constexpr int LDP = atb_pad(8 * NB);
     extern __shared__ __align__(16) double sm[];
     double* At = sm;                                   // [2][ATB_TROWS][LDP]
@@ -81,9 +81,18 @@ k_atb_mma(const double* __restrict__ A, const double* __restrict__ Bm, double* _
         __syncthreads();
         if (tile + 1 < ntiles) stage(tile + 1, buf ^ 1);
         cpa_commit();
-        if (!on1) continue;
         const double* Ad = At + buf * ATB_TROWS * LDP;
         const double* Bd = Bt + buf * ATB_TROWS * LDP;
+        if (Kbar) {   // adjoint of the solve's right-hand side, Kbar = T + cbar P, written coalesced from the staged tiles
+            const long long r0 = rbeg + tile * ATB_TROWS;
+            const int nr = (int)min((long long)ATB_TROWS, rend - r0);
+            for (int r = w; r < nr; r += ATB_THREADS / 32) {
+                const double cb = cbar[(size_t)s * B + r0 + r];
+                const size_t o = ((size_t)s * B + r0 + r) * Q;
+                for (int cc = lane; cc < Q; cc += 32) Kbar[o + cc] = fma(cb, Bd[r * LDP + cc], Ad[r * LDP + cc]);
+            }
+        }
+        if (!on1) continue;
 #pragma unroll
         for (int kk = 0; kk < ATB_TROWS / 4; ++kk) {
             const int n = 4 * kk + t;
@@ -116,7 +125,7 @@ k_atb_mma(const double* __restrict__ A, const double* __restrict__ Bm, double* _
 
 template <int NB>
 static int launch_atb(const double* A, const double* Bm, double* C, double sign, int ns, long long B, int Q,
-                      cudaStream_t st) {
+                      const double* cbar, double* Kbar, cudaStream_t st) {
     size_t smem = sizeof(double) * 4 * ATB_TROWS * atb_pad(8 * NB);
     if (int r = nmgp_opt_in_smem(k_atb_mma<NB>, smem, "nmgp_atb")) return r;
     // one wave: 148 SMs x 3 resident CTAs (61 KB of shared memory each), split evenly over the ns samples
@@ -124,19 +133,20 @@ static int launch_atb(const double* A, const double* Bm, double* C, double sign,
     long long chunk = ((B + nchunks - 1) / nchunks + ATB_TROWS - 1) / ATB_TROWS * ATB_TROWS;
     if (chunk < 4 * ATB_TROWS) chunk = 4 * ATB_TROWS;
     dim3 grid((unsigned)((B + chunk - 1) / chunk), ns);
-    k_atb_mma<NB><<<grid, ATB_THREADS, smem, st>>>(A, Bm, C, sign, B, Q, chunk);
+    k_atb_mma<NB><<<grid, ATB_THREADS, smem, st>>>(A, Bm, C, sign, B, Q, chunk, cbar, Kbar);
     return nmgp_launch_status("nmgp_atb");
 }
-int nmgp_atb_mma(const double* A, const double* Bm, double* C, double sign, int ns, long long B, int Q, cudaStream_t st) {
+int nmgp_atb_mma(const double* A, const double* Bm, double* C, double sign, int ns, long long B, int Q,
+                 const double* cbar, double* Kbar, cudaStream_t st) {
     switch ((Q + 7) / 8) {
-        case 1: return launch_atb<1>(A, Bm, C, sign, ns, B, Q, st);
-        case 2: return launch_atb<2>(A, Bm, C, sign, ns, B, Q, st);
-        case 3: return launch_atb<3>(A, Bm, C, sign, ns, B, Q, st);
-        case 4: return launch_atb<4>(A, Bm, C, sign, ns, B, Q, st);
-        case 5: return launch_atb<5>(A, Bm, C, sign, ns, B, Q, st);
-        case 6: return launch_atb<6>(A, Bm, C, sign, ns, B, Q, st);
-        case 7: return launch_atb<7>(A, Bm, C, sign, ns, B, Q, st);
-        case 8: return launch_atb<8>(A, Bm, C, sign, ns, B, Q, st);
+        case 1: return launch_atb<1>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
+        case 2: return launch_atb<2>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
+        case 3: return launch_atb<3>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
+        case 4: return launch_atb<4>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
+        case 5: return launch_atb<5>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
+        case 6: return launch_atb<6>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
+        case 7: return launch_atb<7>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
+        case 8: return launch_atb<8>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
         default: return 1;
     }
 }

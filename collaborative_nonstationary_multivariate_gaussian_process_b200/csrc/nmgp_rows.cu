@@ -100,7 +100,8 @@ int nmgp_solve_rows_fwd_mma(const double* K, const double* R, double* P, double*
                             cudaStream_t st);
 int nmgp_solve_rows_bwd_mma(const double* Pbar, const double* cbar, const double* K, const double* P, const double* R,
                             double* Kbar, double* Tout, int ns, long long B, int Q, cudaStream_t st);
-int nmgp_atb_mma(const double* A, const double* Bm, double* C, double sign, int ns, long long B, int Q, cudaStream_t st);
+int nmgp_atb_mma(const double* A, const double* Bm, double* C, double sign, int ns, long long B, int Q,
+                 const double* cbar, double* Kbar, cudaStream_t st);
 
 NMGP_API int nmgp_solve_rows_fwd(const double* K, const double* R, double* P, double* c, int ns, long long B, int Q,
                                  cudaStream_t st) {
@@ -122,7 +123,7 @@ NMGP_API int nmgp_solve_rows_bwd(const double* Pbar, const double* cbar, const d
     if (Q <= 64) {
         NMGP_REQUIRE(work != nullptr, "nmgp_solve_rows_bwd");
         if (int r = nmgp_solve_rows_bwd_mma(Pbar, cbar, K, P, R, Kbar, work, ns, B, Q, st)) return r;
-        return nmgp_atb_mma(work, P, Abar, -1.0, ns, B, Q, st);      // Abar -= T^T P
+        return nmgp_atb_mma(work, P, Abar, -1.0, ns, B, Q, cbar, Kbar, st);      // Abar -= T^T P ; Kbar = T + cbar P
     }
     const int TR = solve_rows_tile(Q, true);
     size_t smem = sizeof(double) * ((size_t)Q * Q + 2 * (size_t)Q * (TR + 1));

@@ -100,13 +100,16 @@ k_solve_rows_mma(const double* __restrict__ K, const double* __restrict__ R, dou
     };
 
     double yA[2][NB][2];      // A-fragments of finished blocks (forward: Y, then reused for P in the backward sweep)
-    double yC[2][NB][2];      // C-fragments of Y (start values of the backward sweep)
+    double yC[2][NB][2];      // right-hand sides first (all global loads in flight at once), then C-fragments of Y
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        load_rhs(0, b, yC[0][b][0], yC[0][b][1]);
+        load_rhs(1, b, yC[1][b][0], yC[1][b][1]);
+    }
     // ---- forward sweep ---------------------------------------------------------------------------------------
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        double acc[2][2];
-        load_rhs(0, b, acc[0][0], acc[0][1]);
-        load_rhs(1, b, acc[1][0], acc[1][1]);
+        double acc[2][2] = {{yC[0][b][0], yC[0][b][1]}, {yC[1][b][0], yC[1][b][1]}};
 #pragma unroll
         for (int c = 0; c < b; ++c) {
 #pragma unroll
@@ -156,8 +159,8 @@ k_solve_rows_mma(const double* __restrict__ K, const double* __restrict__ R, dou
                     if (c0 < Q) { P[rb[mb] + c0] = p0; csum[mb] = fma(p0, K[rb[mb] + c0], csum[mb]); }
                     if (c0 + 1 < Q) { P[rb[mb] + c0 + 1] = p1; csum[mb] = fma(p1, K[rb[mb] + c0 + 1], csum[mb]); }
                 } else {
-                    if (c0 < Q) { Tout[rb[mb] + c0] = p0; Kbar[rb[mb] + c0] = fma(cb[mb], Pin[rb[mb] + c0], p0); }
-                    if (c0 + 1 < Q) { Tout[rb[mb] + c0 + 1] = p1; Kbar[rb[mb] + c0 + 1] = fma(cb[mb], Pin[rb[mb] + c0 + 1], p1); }
+                    if (c0 < Q) Tout[rb[mb] + c0] = p0;          // Kbar = T + cbar P is written (coalesced) by k_atb_mma
+                    if (c0 + 1 < Q) Tout[rb[mb] + c0 + 1] = p1;
                 }
             }
         }
