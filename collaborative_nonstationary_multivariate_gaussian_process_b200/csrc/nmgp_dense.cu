@@ -52,6 +52,12 @@ k_gemm_nt(const double* __restrict__ A, const double* __restrict__ Bm, double* _
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
     const int wm = w / NWN, wn = w % NWN;         // warp position: rows 32*wm, cols 64*wn
     const bool vec_ok = ((lda & 1) == 0) && ((ldb & 1) == 0) && ((((size_t)A) & 15) == 0) && ((((size_t)Bm) & 15) == 0);
+    if (beta != 0.0) {   // pull the C tile towards L2 while the K loop runs
+        for (int e = tid; e < GT_M * (TN / 16); e += NTHREADS) {
+            const long long r = m0 + e / (TN / 16), c = n0 + (e % (TN / 16)) * 16;
+            if (r < M && c < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(&C[r * ldc + c]));
+        }
+    }
 
     double acc[4][8][2];
 #pragma unroll
@@ -109,20 +115,46 @@ k_gemm_nt(const double* __restrict__ A, const double* __restrict__ Bm, double* _
         }
     }
     cpd_wait0();
+    // epilogue: all of the thread's C values are fetched as independent 16-byte loads before the first store, so the
+    // read-modify-write costs one memory round trip instead of one per element (the tile was L2-prefetched at entry)
+    const bool c_vec = ((ldc & 1) == 0) && ((((size_t)C) & 15) == 0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const long long r = m0 + 32 * wm + 8 * i + g;
-        if (r >= M) continue;
+    for (int ih = 0; ih < 4; ih += 2) {
+        double2 cv[2][8];
+        if (beta != 0.0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+            for (int i = 0; i < 2; ++i) {
+                const long long r = m0 + 32 * wm + 8 * (ih + i) + g;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const long long c = n0 + 64 * wn + 8 * j + 2 * t + e;
-                if (c < N) {
-                    double* p = &C[r * ldc + c];
-                    double v = alpha * acc[i][j][e];
-                    if (beta != 0.0) v = fma(beta, *p, v);
-                    *p = v;
+                for (int j = 0; j < 8; ++j) {
+                    const long long c = n0 + 64 * wn + 8 * j + 2 * t;
+                    cv[i][j] = make_double2(0.0, 0.0);
+                    if (r < M) {
+                        if (c_vec && c + 1 < N) cv[i][j] = *reinterpret_cast<const double2*>(&C[r * ldc + c]);
+                        else {
+                            if (c < N) cv[i][j].x = C[r * ldc + c];
+                            if (c + 1 < N) cv[i][j].y = C[r * ldc + c + 1];
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const long long r = m0 + 32 * wm + 8 * (ih + i) + g;
+            if (r >= M) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const long long c = n0 + 64 * wn + 8 * j + 2 * t;
+                double2 v = make_double2(alpha * acc[ih + i][j][0], alpha * acc[ih + i][j][1]);
+                if (beta != 0.0) {
+                    v.x = fma(beta, cv[i][j].x, v.x);
+                    v.y = fma(beta, cv[i][j].y, v.y);
+                }
+                if (c_vec && c + 1 < N) *reinterpret_cast<double2*>(&C[r * ldc + c]) = v;
+                else {
+                    if (c < N) C[r * ldc + c] = v.x;
+                    if (c + 1 < N) C[r * ldc + c + 1] = v.y;
                 }
             }
         }
@@ -130,14 +162,16 @@ k_gemm_nt(const double* __restrict__ A, const double* __restrict__ Bm, double* _
 }
 static int g_gemm_narrow = -1;   // 1: 128x64 CTA tiles, two CTAs per SM (epilogue of one overlaps the MMAs of the other)
 static int gemm_nt_launch(const double* A, const double* Bm, double* C, long long M, long long N, long long K,
-                          long long lda, long long ldb, long long ldc, double alpha, double beta, int lower_only,
+                          long long lda, long long ldb, long long ldc, double alpha, double beta, int mode,
                           cudaStream_t st) {
+    // mode bit 0: lower tiles only (SYRK); bit 1: 128-wide tiles (one CTA per row block when N <= 128: C may alias A)
     if (M <= 0 || N <= 0) return 0;
+    const int lower_only = mode & 1;
     if (g_gemm_narrow < 0) {
         const char* e = getenv("NMGP_GEMM_TILE");
         g_gemm_narrow = (e && e[0] == 'w') ? 0 : 1;
     }
-    const bool narrow = g_gemm_narrow || N <= 64 || K <= 256;
+    const bool narrow = !(mode & 2) && (g_gemm_narrow || N <= 64 || K <= 256);
     if (narrow) {
         size_t smem = sizeof(double) * 2 * (GT_M + 64) * GT_LD;
         if (int r = nmgp_opt_in_smem(k_gemm_nt<1>, smem, "nmgp_gemm_nt")) return r;
@@ -161,124 +195,179 @@ NMGP_API int nmgp_gemm_nt(const double* A, const double* Bm, double* C, long lon
 // Blocked Cholesky.  PB = panel width.
 #define PB 128
 
-// diagonal block: in-place lower Cholesky of the nb x nb block at A (leading dimension lda), one CTA of 32 x 16
-// threads, block resident in shared memory, right-looking (every step updates the whole trailing block in parallel)
-#define PD_TX 32
-#define PD_TY 16
-__global__ void __launch_bounds__(PD_TX * PD_TY)
-k_potrf_diag(double* __restrict__ A, long long lda, int nb, int* __restrict__ info, int blockno) {
-    extern __shared__ double sm[];
-    __shared__ double s_rinv;
-    const int ld = nb | 1, tid = threadIdx.x, tx = tid & (PD_TX - 1), ty = tid / PD_TX;
-    for (int e = tid; e < nb * nb; e += blockDim.x) {
-        int a = e / nb, b = e - a * nb;
-        sm[a * ld + b] = A[(long long)a * lda + b];
-    }
-    __syncthreads();
-    for (int k = 0; k < nb; ++k) {
-        if (tid == 0) {
-            double dkk = sm[k * ld + k];
-            if (!(dkk > 0.0)) atomicMax(info, blockno + k + 1);
-            double piv = sqrt(dkk);
-            sm[k * ld + k] = piv;
-            s_rinv = 1.0 / piv;
-        }
-        __syncthreads();
-        const double rinv = s_rinv;
-        for (int i = k + 1 + tid; i < nb; i += blockDim.x) sm[i * ld + k] *= rinv;
-        __syncthreads();
-        for (int i = k + 1 + ty; i < nb; i += PD_TY) {
-            const double lik = sm[i * ld + k];
-            for (int j = k + 1 + tx; j <= i; j += PD_TX) sm[i * ld + j] = fma(-lik, sm[j * ld + k], sm[i * ld + j]);
-        }
-        __syncthreads();
-    }
-    for (int e = tid; e < nb * nb; e += blockDim.x) {
-        int a = e / nb, b = e - a * nb;
-        A[(long long)a * lda + b] = (b <= a) ? sm[a * ld + b] : 0.0;
-    }
-}
-// panel: rows below the diagonal block, X L11^T = A21  ->  one thread per row, forward substitution, L11 in smem
-__global__ void __launch_bounds__(128)
-k_trsm_panel(const double* __restrict__ L11, double* __restrict__ A21, long long lda, long long nrows, int nb) {
-    extern __shared__ double sm[];
-    double* Ls = sm;                         // [nb][nb]
-    double* tile = Ls + nb * nb;             // [128][nb+1]
-    const int ldt = nb + 1, tid = threadIdx.x;
-    const long long r0 = (long long)blockIdx.x * 128;
-    const int nr = (int)min(128LL, nrows - r0);
-    for (int e = tid; e < nb * nb; e += 128) {
-        int a = e / nb, b = e - a * nb;
-        Ls[e] = L11[(long long)a * lda + b];
-    }
-    for (int e = tid; e < nr * nb; e += 128) {
-        int r = e / nb, a = e - r * nb;
-        tile[r * ldt + a] = A21[(r0 + r) * lda + a];
-    }
-    __syncthreads();
-    if (tid < nr) {
-        double* y = tile + tid * ldt;
-        for (int a = 0; a < nb; ++a) {
-            double s0 = y[a], s1 = 0.0;
-            int c = 0;
-            for (; c + 1 < a; c += 2) {
-                s0 = fma(-Ls[a * nb + c], y[c], s0);
-                s1 = fma(-Ls[a * nb + c + 1], y[c + 1], s1);
-            }
-            if (c < a) s0 = fma(-Ls[a * nb + c], y[c], s0);
-            y[a] = (s0 + s1) / Ls[a * nb + a];
-        }
-    }
-    __syncthreads();
-    for (int e = tid; e < nr * nb; e += 128) {
-        int r = e / nb, a = e - r * nb;
-        A21[(r0 + r) * lda + a] = tile[r * ldt + a];
-    }
-}
-// same panel solve with the row held in registers (nb padded to 64 with an identity tail): X L^T = A
-__global__ void __launch_bounds__(128)
-k_trsm_panel_reg64(const double* __restrict__ L11, double* __restrict__ A21, long long lda, long long nrows, int nb) {
+// Diagonal block: in-place lower Cholesky of the nb x nb block at A (nb <= 128, leading dimension lda) AND its explicit
+// inverse Linv (128 x 128 row-major, identity-padded beyond nb), one CTA of 16 warps with the block resident in shared
+// memory.  16-column steps: warp 0 factorises the 16 x 16 diagonal sub-block in registers (one row per lane, column
+// broadcasts by shuffle) and inverts it; all warps form the sub-panel X = A D^-T from that inverse and apply the rank-16
+// trailing update with DMMA 8x8x4 tiles.  The inverse turns the panel solve of the rows below into a plain DMMA GEMM
+// (X = A21 Linv^T), which removes the latency-bound substitution kernels from the factorisation's critical path.
+#define DI_N 128
+#define DI_LD 136        // % 16 == 8: conflict-free 16-byte C-fragment accesses of the trailing tiles
+#define DI_XLD 20        // % 8 == 4: conflict-free A/B fragment loads of the sub-panel
+#define DI_THREADS 512
+#define DI_SMEM (sizeof(double) * (DI_N * DI_LD + DI_N * DI_XLD + 8 * 16 * 17))
+__global__ void __launch_bounds__(DI_THREADS)
+k_potrf_diag_inv(double* __restrict__ A, long long lda, int nb, double* Linv, int* __restrict__ info, int blockno) {
     extern __shared__ __align__(16) double sm[];
-    constexpr int QP = 64, LDT = QP + 1;
-    double* Ls = sm;                 // [64][64], identity padded
-    double* rinv = Ls + QP * QP;     // [64]
-    double* tile = rinv + QP;        // [128][65]
-    const int tid = threadIdx.x;
-    const long long r0 = (long long)blockIdx.x * 128;
-    const int nr = (int)min(128LL, nrows - r0);
-    for (int e = tid; e < QP * QP; e += 128) {
-        int a = e / QP, b = e - a * QP;
-        Ls[e] = (a < nb && b < nb) ? ((b <= a) ? L11[(long long)a * lda + b] : 0.0) : (a == b ? 1.0 : 0.0);
-    }
-    for (int a = tid; a < QP; a += 128) rinv[a] = a < nb ? 1.0 / L11[(long long)a * lda + a] : 1.0;
-    for (int e = tid; e < 128 * QP; e += 128) {
-        int r = e / QP, a = e - r * QP;
-        tile[r * LDT + a] = (r < nr && a < nb) ? A21[(r0 + r) * lda + a] : 0.0;
+    double* Ls = sm;                          // [128][DI_LD]
+    double* Xs = Ls + DI_N * DI_LD;           // [128][DI_XLD] sub-panel (DMMA operands); scratch for the inverse
+    double* Di = Xs + DI_N * DI_XLD;          // [8][16][17]   inverses of the diagonal 16 x 16 sub-blocks
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+#pragma unroll 8
+    for (int e = tid; e < DI_N * DI_N; e += DI_THREADS) {
+        const int a = e >> 7, b = e & 127;
+        Ls[a * DI_LD + b] = (a < nb && b < nb) ? A[(long long)a * lda + b] : (a == b ? 1.0 : 0.0);
     }
     __syncthreads();
-    double yv[QP];
+    for (int bk = 0; bk < 8; ++bk) {
+        const int kb = 16 * bk;
+        if (w == 0) {
+            const int i = lane & 15;
+            double r[16], rd[16];
 #pragma unroll
-    for (int a = 0; a < QP; ++a) yv[a] = tile[tid * LDT + a];
+            for (int c = 0; c < 16; ++c) r[c] = Ls[(kb + i) * DI_LD + kb + c];
 #pragma unroll
-    for (int a = 0; a < QP; ++a) {
-        double s0 = yv[a], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (int k = 0; k < 16; ++k) {
+                const double dkk = __shfl_sync(0xffffffffu, r[k], k);
+                if (!(dkk > 0.0) && lane == 0) atomicCAS(info, 0, blockno + kb + k + 1);   // first failing pivot wins
+                const double rinv = rsqrt(dkk);
+                rd[k] = rinv;
+                const double lik = (i == k) ? dkk * rinv : r[k] * rinv;
+                r[k] = lik;
 #pragma unroll
-        for (int c = 0; c < a; ++c) {
-            const double rv = Ls[a * QP + c];
-            if ((c & 3) == 0) s0 = fma(-rv, yv[c], s0);
-            else if ((c & 3) == 1) s1 = fma(-rv, yv[c], s1);
-            else if ((c & 3) == 2) s2 = fma(-rv, yv[c], s2);
-            else s3 = fma(-rv, yv[c], s3);
+                for (int j = k + 1; j < 16; ++j) {
+                    const double v = __shfl_sync(0xffffffffu, lik, j);
+                    r[j] = fma(-lik, v, r[j]);
+                }
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) Ls[(kb + i) * DI_LD + kb + c] = (c <= i) ? r[c] : 0.0;
+            }
+            __syncwarp();
+            // column i of D^-1 by forward substitution (entries above the diagonal come out as exact zeros)
+            double x[16];
+#pragma unroll
+            for (int a = 0; a < 16; ++a) {
+                double s0 = (a == i) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < a; ++k) {
+                    const double lv = Ls[(kb + a) * DI_LD + kb + k];
+                    if (k & 1) s1 = fma(-lv, x[k], s1);
+                    else s0 = fma(-lv, x[k], s0);
+                }
+                x[a] = (s0 + s1) * rd[a];
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int a = 0; a < 16; ++a) Di[(kb + a) * 17 + i] = x[a];
+            }
         }
-        yv[a] = ((s0 + s1) + (s2 + s3)) * rinv[a];
-    }
+        __syncthreads();
+        const int nrem = DI_N - kb - 16;
+        // sub-panel X = A[:, kb:kb+16] Dinv^T on DMMA: one warp per 8 rows (both 8-column halves), written back in place
+        // and to Xs (operand layout of the trailing update)
+        for (int ti = w; ti < (nrem >> 3); ti += DI_THREADS / 32) {
+            double* arow = &Ls[(kb + 16 + 8 * ti + g) * DI_LD + kb];
+            double xa[4][2], xb[4][2];
 #pragma unroll
-    for (int a = 0; a < QP; ++a) tile[tid * LDT + a] = yv[a];
-    __syncthreads();
-    for (int e = tid; e < nr * nb; e += 128) {
-        int r = e / nb, a = e - r * nb;
-        A21[(r0 + r) * lda + a] = tile[r * LDT + a];
+            for (int ks = 0; ks < 4; ++ks) {
+                const double av = arow[4 * ks + t];
+                xa[ks][0] = xa[ks][1] = xb[ks][0] = xb[ks][1] = 0.0;
+                dmma884d(xa[ks][0], xa[ks][1], av, Di[(kb + g) * 17 + 4 * ks + t]);
+                dmma884d(xb[ks][0], xb[ks][1], av, Di[(kb + 8 + g) * 17 + 4 * ks + t]);
+            }
+            const double a0 = (xa[0][0] + xa[1][0]) + (xa[2][0] + xa[3][0]), a1 = (xa[0][1] + xa[1][1]) + (xa[2][1] + xa[3][1]);
+            const double b0 = (xb[0][0] + xb[1][0]) + (xb[2][0] + xb[3][0]), b1 = (xb[0][1] + xb[1][1]) + (xb[2][1] + xb[3][1]);
+            __syncwarp();
+            arow[2 * t] = a0; arow[2 * t + 1] = a1; arow[8 + 2 * t] = b0; arow[8 + 2 * t + 1] = b1;
+            double* xrow = &Xs[(8 * ti + g) * DI_XLD];
+            xrow[2 * t] = a0; xrow[2 * t + 1] = a1; xrow[8 + 2 * t] = b0; xrow[8 + 2 * t + 1] = b1;
+        }
+        __syncthreads();
+        // trailing update with DMMA: lower 8 x 8 tiles (ti >= tj) of the nrem x nrem block, one accumulator per k-step
+        const int nt = nrem >> 3, ntiles = nt * (nt + 1) / 2;
+        for (int tile = w; tile < ntiles; tile += DI_THREADS / 32) {
+            int ti = (int)((sqrtf(8.f * (float)tile + 1.f) - 1.f) * 0.5f);
+            while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+            while (ti * (ti + 1) / 2 > tile) --ti;
+            const int tj = tile - ti * (ti + 1) / 2;
+            double c[4][2];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                c[ks][0] = c[ks][1] = 0.0;
+                dmma884d(c[ks][0], c[ks][1], Xs[(8 * ti + g) * DI_XLD + 4 * ks + t], Xs[(8 * tj + g) * DI_XLD + 4 * ks + t]);
+            }
+            double2* p = reinterpret_cast<double2*>(&Ls[(kb + 16 + 8 * ti + g) * DI_LD + kb + 16 + 8 * tj + 2 * t]);
+            double2 v = *p;
+            v.x -= (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
+            v.y -= (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
+            *p = v;
+        }
+        __syncthreads();
     }
+#pragma unroll 8
+    for (int e = tid; e < DI_N * DI_N; e += DI_THREADS) {
+        const int a = e >> 7, b = e & 127;
+        if (a < nb && b < nb) A[(long long)a * lda + b] = (b <= a) ? Ls[a * DI_LD + b] : 0.0;
+        // inverse: diagonal 16 x 16 sub-blocks from Di, zeros above them
+        if ((b >> 4) >= (a >> 4)) Linv[e] = ((b >> 4) == (a >> 4)) ? Di[a * 17 + (b & 15)] : 0.0;
+    }
+    __syncthreads();
+    // sub-blocks below the diagonal:  Linv[bi][bj] = -Dinv[bi] * sum_{k=bj}^{bi-1} L[bi][k] Linv[k][bj]  as DMMA block
+    // products.  The two 8-column halves of a block column bj are independent, so each of the 16 warps owns one
+    // (bj, half) task and walks down bi with warp-level synchronisation only; the task table balances the DMMA count
+    // per scheduler (448 each).  Finished blocks are kept in the unused upper block (bj, bi) of Ls.
+    {
+        const int sp = w & 3, slot = w >> 2, tj = sp & 1;
+        const int bj = (((sp >> 1) == 0 ? 0x6530 : 0x7421) >> (4 * slot)) & 15;
+        double* Tw = Xs + w * (16 * 9);       // warp-private 16 x 8 scratch
+        for (int bi = bj + 1; bi < 8; ++bi) {
+            const double* ar0 = &Ls[(16 * bi + g) * DI_LD];
+            const double* ar1 = ar0 + 8 * DI_LD;
+            double c[2][4][2];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const double bv = Di[(16 * bj + 4 * ks + t) * 17 + 8 * tj + g];
+                c[0][ks][0] = c[0][ks][1] = c[1][ks][0] = c[1][ks][1] = 0.0;
+                dmma884d(c[0][ks][0], c[0][ks][1], ar0[16 * bj + 4 * ks + t], bv);
+                dmma884d(c[1][ks][0], c[1][ks][1], ar1[16 * bj + 4 * ks + t], bv);
+            }
+            for (int k = bj + 1; k < bi; ++k) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const double bv = Ls[(16 * bj + 4 * ks + t) * DI_LD + 16 * k + 8 * tj + g];
+                    dmma884d(c[0][ks][0], c[0][ks][1], ar0[16 * k + 4 * ks + t], bv);
+                    dmma884d(c[1][ks][0], c[1][ks][1], ar1[16 * k + 4 * ks + t], bv);
+                }
+            }
+#pragma unroll
+            for (int ti = 0; ti < 2; ++ti) {
+                Tw[(8 * ti + g) * 9 + 2 * t] = (c[ti][0][0] + c[ti][1][0]) + (c[ti][2][0] + c[ti][3][0]);
+                Tw[(8 * ti + g) * 9 + 2 * t + 1] = (c[ti][0][1] + c[ti][1][1]) + (c[ti][2][1] + c[ti][3][1]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const double bv = Tw[(4 * ks + t) * 9 + g];
+                c[0][ks][0] = c[0][ks][1] = c[1][ks][0] = c[1][ks][1] = 0.0;
+                dmma884d(c[0][ks][0], c[0][ks][1], Di[(16 * bi + g) * 17 + 4 * ks + t], bv);
+                dmma884d(c[1][ks][0], c[1][ks][1], Di[(16 * bi + 8 + g) * 17 + 4 * ks + t], bv);
+            }
+#pragma unroll
+            for (int ti = 0; ti < 2; ++ti) {
+                const double v0 = -((c[ti][0][0] + c[ti][1][0]) + (c[ti][2][0] + c[ti][3][0]));
+                const double v1 = -((c[ti][0][1] + c[ti][1][1]) + (c[ti][2][1] + c[ti][3][1]));
+                const int rr = 8 * ti + g, cc = 8 * tj + 2 * t;
+                Ls[(16 * bj + rr) * DI_LD + 16 * bi + cc] = v0;
+                Ls[(16 * bj + rr) * DI_LD + 16 * bi + cc + 1] = v1;
+                Linv[(16 * bi + rr) * DI_N + 16 * bj + cc] = v0;
+                Linv[(16 * bi + rr) * DI_N + 16 * bj + cc + 1] = v1;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
 }
 __global__ void k_zero_upper(double* __restrict__ A, long long T, long long lda) {
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
@@ -290,40 +379,28 @@ __global__ void k_logdiag_sum(const double* __restrict__ A, long long T, long lo
     s = block_sum(s);
     if (threadIdx.x == 0) out[0] = s;
 }
-// factor one panel: diagonal block (recursing with 64-wide blocks when wider than 64) and the rows below it
-static int potrf_blocked(double* A, long long T, long long lda, int pb, int* info, int pivot_base, cudaStream_t st);
-static int factor_panel(double* Akk, long long lda, int nb, long long rest, int* info, int pivot_base, cudaStream_t st) {
-    const size_t smem_r = sizeof(double) * (64 * 64 + 64 + 128 * 65);
-    if (nb > 64) {
-        if (int r = potrf_blocked(Akk, nb, lda, 64, info, pivot_base, st)) return r;
-    } else {
-        k_potrf_diag<<<1, PD_TX * PD_TY, sizeof(double) * nb * (nb | 1), st>>>(Akk, lda, nb, info, pivot_base);
-    }
-    if (rest > 0) {
-        // panel solve X L11^T = A21 by 64-wide column blocks with register-resident rows:
-        //   A21[:, c0:c0+h] -= X[:, :c0] L11[c0:c0+h, :c0]^T ;  X[:, c0:c0+h] = A21[:, c0:c0+h] L11[c0.., c0..]^-T
-        double* A21 = Akk + (long long)nb * lda;
-        for (int c0 = 0; c0 < nb; c0 += 64) {
-            const int h = nb - c0 > 64 ? 64 : nb - c0;
-            if (c0 > 0)
-                if (int r = gemm_nt_launch(A21, Akk + (long long)c0 * lda, A21 + c0, rest, h, c0, lda, lda, lda, -1.0, 1.0, 0, st))
-                    return r;
-            k_trsm_panel_reg64<<<(unsigned)((rest + 127) / 128), 128, smem_r, st>>>(Akk + (long long)c0 * lda + c0, A21 + c0,
-                                                                                     lda, rest, h);
-        }
-    }
-    return 0;
-}
-// blocked right-looking factorisation, panel width pb, everything on one stream (used for the diagonal blocks)
-static int potrf_blocked(double* A, long long T, long long lda, int pb, int* info, int pivot_base, cudaStream_t st) {
-    for (long long k = 0; k < T; k += pb) {
-        const int nb = (int)min((long long)pb, T - k);
-        const long long rest = T - k - nb;
-        double* Akk = A + k * lda + k;
-        if (int r = factor_panel(Akk, lda, nb, rest, info, pivot_base + (int)k, st)) return r;
-        if (rest > 0) {
-            double* A21 = Akk + (long long)nb * lda;
-            if (int r = gemm_nt_launch(A21, A21, A21 + nb, rest, rest, nb, lda, lda, lda, -1.0, 1.0, 1, st)) return r;
+// factor one panel of width nb with `rest` rows below it, left-looking over 128-wide column blocks:
+//   block column c0 (rows c0.. of the panel and all rows below) -= X[:, :c0] L[c0:c0+h, :c0]^T      (DMMA GEMM)
+//   diagonal block factorised and inverted by k_potrf_diag_inv
+//   rows below it:  X = A Linv^T                                                                    (DMMA GEMM, in place)
+// linv: 128 x 128 scratch owned by the stream the panel runs on.
+static int factor_panel(double* Akk, long long lda, int nb, long long rest, double* linv, int* info, int pivot_base,
+                        cudaStream_t st) {
+    for (int c0 = 0; c0 < nb; c0 += DI_N) {
+        const int h = nb - c0 > DI_N ? DI_N : nb - c0;
+        double* Dcc = Akk + (long long)c0 * lda + c0;
+        const long long rows = (nb - c0) + rest;            // rows from the diagonal block down
+        if (c0 > 0)
+            if (int r = gemm_nt_launch(Akk + (long long)c0 * lda, Akk + (long long)c0 * lda, Dcc, rows, h, c0, lda, lda, lda,
+                                       -1.0, 1.0, 0, st))
+                return r;
+        k_potrf_diag_inv<<<1, DI_THREADS, DI_SMEM, st>>>(Dcc, lda, h, linv, info, pivot_base + c0);
+        const long long below = rows - h;
+        if (below > 0) {
+            // in place: the 128-wide tile variant gives every row block to one CTA, which reads all of its K columns
+            // before its epilogue writes them
+            double* A21 = Dcc + (long long)h * lda;
+            if (int r = gemm_nt_launch(A21, linv, A21, below, h, h, lda, DI_N, lda, 1.0, 0.0, 2, st)) return r;
         }
     }
     return 0;
@@ -332,9 +409,20 @@ static int potrf_blocked(double* A, long long T, long long lda, int pb, int* inf
 // of the trailing update, so the latency-bound panel work hides behind the DMMA SYRK.
 static cudaStream_t g_helper_stream = nullptr;
 static cudaEvent_t g_ev_upd = nullptr, g_ev_pan = nullptr;
+static double* g_linv = nullptr;   // two 128 x 128 inverse scratch blocks (main stream, helper stream)
+static int potrf_scratch() {
+    if (!g_linv && cudaMalloc(&g_linv, sizeof(double) * 2 * DI_N * DI_N) != cudaSuccess) {
+        nmgp_set_error("nmgp_potrf_big: cannot allocate the 256 KB panel scratch");
+        return -4;
+    }
+    return 0;
+}
 static int potrf_lookahead(double* A, long long T, long long lda, int pb, int* info, cudaStream_t s0) {
     if (!g_helper_stream) {
-        if (cudaStreamCreateWithFlags(&g_helper_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        // highest priority: the panel's CTAs must get SM slots ahead of the queued tiles of the trailing update
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (cudaStreamCreateWithPriority(&g_helper_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
             cudaEventCreateWithFlags(&g_ev_upd, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&g_ev_pan, cudaEventDisableTiming) != cudaSuccess) {
             nmgp_set_error("nmgp_potrf_big: cannot create the look-ahead stream");
@@ -344,7 +432,7 @@ static int potrf_lookahead(double* A, long long T, long long lda, int pb, int* i
     cudaStream_t s1 = g_helper_stream;
     {   // panel 0 on the main stream
         const int nb = (int)min((long long)pb, T);
-        if (int r = factor_panel(A, lda, nb, T - nb, info, 0, s0)) return r;
+        if (int r = factor_panel(A, lda, nb, T - nb, g_linv, info, 0, s0)) return r;
     }
     for (long long k = 0; k < T; k += pb) {
         const int nb = (int)min((long long)pb, T - k);
@@ -358,7 +446,7 @@ static int potrf_lookahead(double* A, long long T, long long lda, int pb, int* i
         cudaEventRecord(g_ev_upd, s0);
         // 2. factorise the next panel on the helper stream
         cudaStreamWaitEvent(s1, g_ev_upd, 0);
-        if (int r = factor_panel(A22, lda, nb2, rest - nb2, info, (int)(k + nb), s1)) return r;
+        if (int r = factor_panel(A22, lda, nb2, rest - nb2, g_linv + DI_N * DI_N, info, (int)(k + nb), s1)) return r;
         cudaEventRecord(g_ev_pan, s1);
         // 3. rest of the trailing update (columns beyond the next panel, lower tiles only) on the main stream
         const long long rest2 = rest - nb2;
@@ -379,14 +467,14 @@ static int potrf_lookahead(double* A, long long T, long long lda, int pb, int* i
 // Kronecker path.
 NMGP_API int nmgp_potrf_big(double* A, long long T, long long lda, double* hld, int* info, cudaStream_t st) {
     NMGP_REQUIRE(T > 0 && lda >= T && T < 2147483647LL, "nmgp_potrf_big");
-    if (int r = nmgp_opt_in_smem(k_potrf_diag, sizeof(double) * 64 * 65, "nmgp_potrf_big")) return r;
-    if (int r = nmgp_opt_in_smem(k_trsm_panel_reg64, sizeof(double) * (64 * 64 + 64 + 128 * 65), "nmgp_potrf_big")) return r;
+    if (int r = nmgp_opt_in_smem(k_potrf_diag_inv, DI_SMEM, "nmgp_potrf_big")) return r;
+    if (int r = potrf_scratch()) return r;
     if (T > 1024) {
         int pb = T >= 12288 ? 512 : (T >= 6144 ? 256 : PB);   // measured best on B200 (profiles/README.md)
-        if (const char* e = getenv("NMGP_POTRF_PB")) pb = atoi(e) >= 64 ? (atoi(e) / 64) * 64 : pb;   // tuning knob
+        if (const char* e = getenv("NMGP_POTRF_PB")) pb = atoi(e) >= 128 ? (atoi(e) / 128) * 128 : pb;   // tuning knob
         if (int r = potrf_lookahead(A, T, lda, pb, info, st)) return r;
     } else {
-        if (int r = potrf_blocked(A, T, lda, 64, info, 0, st)) return r;
+        if (int r = factor_panel(A, lda, (int)T, 0, g_linv, info, 0, st)) return r;
     }
     dim3 gz((unsigned)((T + 255) / 256), (unsigned)min(T, 65535LL));
     if (T <= 65535) k_zero_upper<<<gz, 256, 0, st>>>(A, T, lda);

@@ -81,8 +81,10 @@ def test_gemm_nt(M, N, K):
     assert rel(Cd, -0.5 * (A @ B.t()) + 2.0 * C) < 1e-14
 
 
-@pytest.mark.parametrize("T", [7, 128, 200, 1000, 1537])
-def test_potrf_big_and_solve(T):
+@pytest.mark.parametrize("T,pb", [(7, 0), (128, 0), (200, 0), (1000, 0), (1537, 0), (2500, 0), (1537, 256), (2100, 512)])
+def test_potrf_big_and_solve(T, pb, monkeypatch):
+    if pb:
+        monkeypatch.setenv("NMGP_POTRF_PB", str(pb))   # panel-width knob: exercises the multi-block left-looking panels
     gen = torch.Generator().manual_seed(T)
     x = torch.sort(torch.rand(T, generator=gen, dtype=torch.float64))[0].view(-1, 1)
     K = orc.sim_nonstationary_cov(x, ell1=torch.exp(3 * (x.view(-1) - 1) ** 3 - 2.0)) + 1e-2 * torch.eye(T, dtype=torch.float64)
@@ -102,6 +104,9 @@ def test_potrf_big_and_solve(T):
 def test_potrf_big_raises_on_non_pd():
     A = torch.eye(300, dtype=torch.float64); A[250, 250] = -1.0
     with pytest.raises(RuntimeError):
+        ops.potrf_big(d(A))
+    A = torch.eye(1500, dtype=torch.float64); A[1333, 1333] = -1.0
+    with pytest.raises(RuntimeError, match="1334"):
         ops.potrf_big(d(A))
 
 
