@@ -47,6 +47,44 @@ __host__ __device__ constexpr int pad4mod8(int n) { return ((n + 3) / 8) * 8 + 4
 // the C-fragment layout of the epilogue (8 rows x 4 column pairs per warp)
 __host__ __device__ constexpr int pad8mod16(int n) { return ((n + 7) / 16) * 16 + 8; }
 
+
+// mbarrier + 1-D bulk copy (TMA engine): one elected thread moves a whole padded (Sigma_W[j], mu_W[j]) record
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    unsigned done = 0;
+    const unsigned a = smem_u32(b);
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    }
+}
+// rec[j] = [ Sigma_W[j] padded to KP x LDS | mu_W[j] padded to NP ], zeros in the padding
+__global__ void k_pad_records(const double* __restrict__ SigW, const double* __restrict__ muW, double* __restrict__ rec,
+                              int Q, int KP, int LDS, int NP) {
+    const int j = blockIdx.x, REC = KP * LDS + NP;
+    double* out = rec + (size_t)j * REC;
+    for (int e = threadIdx.x; e < KP * LDS; e += blockDim.x) {
+        const int a = e / LDS, b = e - a * LDS;
+        out[e] = (a < Q && b < Q) ? SigW[((size_t)j * Q + a) * Q + b] : 0.0;
+    }
+    for (int c = threadIdx.x; c < NP; c += blockDim.x) out[KP * LDS + c] = c < Q ? muW[(size_t)j * Q + c] : 0.0;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // 128-row tiles, 8 warps, one CTA per SM (measured: two 64-row CTAs per SM are 18% slower -- every CTA stages its
 // own copy of Sigma_W[j], profiles/README.md)
@@ -59,28 +97,28 @@ struct LFShape {
     static constexpr int KP = 4 * KS;                      // padded K
     static constexpr int LDP = pad8mod16(NP > KP ? NP : KP);
     static constexpr int LDS = pad4mod8(NP);
-    static constexpr size_t smem_doubles = (size_t)LF_ROWS * LDP + 2 * (size_t)KP * LDS + 2 * NP + 2 * LF_ROWS + 2 * LF_ROWS;
+    static constexpr int REC = KP * LDS + NP;              // one latent's padded record: Sigma_W[j] then mu_W[j]
+    static constexpr size_t smem_doubles = (size_t)LF_ROWS * LDP + 2 * (size_t)REC + 2 * LF_ROWS + 2;
     static constexpr size_t smem_bytes = smem_doubles * 8 + LF_ROWS * 4;
 };
 
 template <int NB, int KS>
 __global__ void __launch_bounds__(LF_THREADS, 1)
 k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, const double* __restrict__ l,
-               const double* __restrict__ y, const int* __restrict__ I, const double* __restrict__ SigW,
+               const double* __restrict__ y, const int* __restrict__ I, const double* __restrict__ rec,
                const double* __restrict__ muW, const double* __restrict__ hyp, double scale,
                double* __restrict__ Rsum, double* __restrict__ ghyp, double* __restrict__ lbar,
                double* __restrict__ mgbar, double* __restrict__ qgbar, double* __restrict__ cGbar,
-               double* __restrict__ PGbar, long long B, int Q, int D, FastDiv qdiv) {
+               double* __restrict__ PGbar, long long B, int Q, int D) {
     using SH = LFShape<NB, KS>;
-    constexpr int LDP = SH::LDP, LDS = SH::LDS, NP = SH::NP, KP = SH::KP;
+    constexpr int LDP = SH::LDP, LDS = SH::LDS, NP = SH::NP, KP = SH::KP, REC = SH::REC;
     extern __shared__ __align__(16) double sm[];
     double* Ps = sm;                                   // [LF_ROWS][LDP]
-    double* Ss = Ps + (size_t)LF_ROWS * LDP;           // [2][KP][LDS]
-    double* mus = Ss + 2 * (size_t)KP * LDS;           // [2][NP]
-    double* lcol = mus + 2 * NP;                       // [2][LF_ROWS]
-    double* rrs = lcol + 2 * LF_ROWS;                  // [LF_ROWS]
+    double* Ss = Ps + (size_t)LF_ROWS * LDP;           // [2][REC]: double-buffered records of the latent j
+    double* rrs = Ss + 2 * (size_t)REC;                // [LF_ROWS]
     double* omcs = rrs + LF_ROWS;                      // [LF_ROWS]
-    int* Is = reinterpret_cast<int*>(omcs + LF_ROWS);  // [LF_ROWS]
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(omcs + LF_ROWS);   // [2]
+    int* Is = reinterpret_cast<int*>(mbar + 2);        // [LF_ROWS]
 
     const int s = blockIdx.y;
     const long long row0 = (long long)blockIdx.x * LF_ROWS;
@@ -93,7 +131,11 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
         int r = e / LDP, a = e - r * LDP;
         Ps[e] = (r < nrows && a < Q) ? PG[(rbase + r) * Q + a] : 0.0;
     }
-    for (int e = tid; e < 2 * KP * LDS + 2 * NP; e += LF_THREADS) Ss[e] = 0.0;   // Ss and mus are contiguous
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
     for (int r = tid; r < LF_ROWS; r += LF_THREADS) {
         Is[r] = r < nrows ? I[row0 + r] : -1;
         omcs[r] = r < nrows ? 1.0 - cG[rbase + r] : 0.0;
@@ -153,27 +195,22 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
         }
     }
     // entries of latents a row does not use (j > I[n]) are exact zeros in every [ns,B,D] output
-    for (int e = tid; e < nrows * D; e += LF_THREADS) {
-        const int r = e / D, j = e - r * D;
-        if (j > Is[r]) {
-            const size_t o = (rbase + r) * D + j;
-            lbar[o] = 0.0;
-            mgbar[o] = 0.0;
-            qgbar[o] = 0.0;
-        }
+    {
+        const int r = tid >> 1;                            // two threads per row
+        if (r < nrows)
+            for (int j = Is[r] + 1 + (tid & 1); j < D; j += 2) {
+                const size_t o = (rbase + r) * D + j;
+                lbar[o] = 0.0;
+                mgbar[o] = 0.0;
+                qgbar[o] = 0.0;
+            }
     }
     // ---- phase 2: quadratic forms, j loop with a cp.async double buffer -----------------------------------
     const int jmax = Is[nrows - 1];
     const int warpmaxI = (16 * w < nrows) ? Is[min(16 * w + 15, nrows - 1)] : -1;
-    auto stage = [&](int j, int buf) {
-        const double* Sg = SigW + (size_t)j * Q * Q;
-        double* Sd = Ss + (size_t)buf * KP * LDS;
-        for (int e = tid; e < Q * Q; e += LF_THREADS) {
-            int a = (int)qdiv.div((unsigned)e), b = e - a * Q;
-            cp_async8(&Sd[a * LDS + b], &Sg[e]);
-        }
-        for (int c = tid; c < Q; c += LF_THREADS) cp_async8(&mus[buf * NP + c], &muW[(size_t)j * Q + c]);
-        for (int r = tid; r < nrows; r += LF_THREADS) cp_async8(&lcol[buf * LF_ROWS + r], &l[(rbase + r) * D + j]);
+    auto stage = [&](int j, int buf) {                    // one thread: whole record by the bulk-copy engine
+        mbar_expect_tx(&mbar[buf], (unsigned)(REC * sizeof(double)));
+        bulk_g2s(Ss + (size_t)buf * REC, rec + (size_t)j * REC, (unsigned)(REC * sizeof(double)), &mbar[buf]);
     };
     double pacc[2][NB][2];
 #pragma unroll
@@ -182,16 +219,24 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
         for (int nb = 0; nb < NB; ++nb) pacc[mb][nb][0] = pacc[mb][nb][1] = 0.0;
     double pen[2] = {0.0, 0.0}, gsum[2] = {0.0, 0.0};
 
-    stage(0, 0);
-    cp_async_commit();
+    if (tid == 0 && jmax >= 0) stage(0, 0);
+    double lnext[2];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) lnext[mb] = (rloc[mb] < nrows) ? __ldg(&l[(rbase + rloc[mb]) * D]) : 0.0;
     for (int j = 0; j <= jmax; ++j) {
         const int buf = j & 1;
-        cp_async_wait<0>();
-        __syncthreads();                                  // buffer `buf` landed; everyone is done with the other one
-        if (j + 1 <= jmax) stage(j + 1, buf ^ 1);
-        cp_async_commit();
+        __syncthreads();                                  // everyone is done with the other buffer (latent j - 1)
+        if (tid == 0 && j + 1 <= jmax) stage(j + 1, buf ^ 1);
         if (warpmaxI < j) continue;                        // warp-uniform: none of this warp's rows uses latent j
-        const double* Sd = Ss + (size_t)buf * KP * LDS;
+        const double lcur[2] = {lnext[0], lnext[1]};
+        if (j + 1 < D) {
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+                lnext[mb] = (rloc[mb] < nrows) ? __ldg(&l[(rbase + rloc[mb]) * D + j + 1]) : 0.0;
+        }
+        mbar_wait(&mbar[buf], (unsigned)((j >> 1) & 1));  // record j landed
+        const double* Sd = Ss + (size_t)buf * REC;
+        const double* mu_b = Sd + KP * LDS;
         double V[2][NB][2];
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb)
@@ -213,7 +258,7 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) {
                 const double2 pv = *reinterpret_cast<const double2*>(&Ps[rl * LDP + 8 * nb + 2 * t]);
-                const double2 mv = *reinterpret_cast<const double2*>(&mus[buf * NP + 8 * nb + 2 * t]);
+                const double2 mv = *reinterpret_cast<const double2*>(&mu_b[8 * nb + 2 * t]);
                 qp = fma(V[mb][nb][0], pv.x, qp);
                 qp1 = fma(V[mb][nb][1], pv.y, qp1);
                 mp = fma(mv.x, pv.x, mp);
@@ -226,7 +271,7 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
             mp += __shfl_xor_sync(0xffffffffu, mp, 1);
             mp += __shfl_xor_sync(0xffffffffu, mp, 2);
             const bool live = (rl < nrows) && (j <= myI[mb]);
-            const double lj = live ? lcol[buf * LF_ROWS + rl] : 0.0;
+            const double lj = live ? lcur[mb] : 0.0;
             const double gq = scale * (0.5 / s2e) * lj * lj;          // cotangent of s2_g[n,j]
             const double gm = -scale * rr[mb] * lj;                    // cotangent of mu_g[n,j]
             const double s2g = omcs[rl] + qp;
@@ -241,12 +286,11 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
             const double g2 = 2.0 * gq;
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) {
-                pacc[mb][nb][0] = fma(g2, V[mb][nb][0], fma(gm, mus[buf * NP + 8 * nb + 2 * t], pacc[mb][nb][0]));
-                pacc[mb][nb][1] = fma(g2, V[mb][nb][1], fma(gm, mus[buf * NP + 8 * nb + 2 * t + 1], pacc[mb][nb][1]));
+                pacc[mb][nb][0] = fma(g2, V[mb][nb][0], fma(gm, mu_b[8 * nb + 2 * t], pacc[mb][nb][0]));
+                pacc[mb][nb][1] = fma(g2, V[mb][nb][1], fma(gm, mu_b[8 * nb + 2 * t + 1], pacc[mb][nb][1]));
             }
         }
     }
-    cp_async_wait<0>();
 
     // ---- outputs ---------------------------------------------------------------------------------------------
 #pragma unroll
@@ -281,12 +325,30 @@ static int launch_latent_fused(const double* PG, const double* cG, const double*
                                const double* SigW, const double* muW, const double* hyp, double scale, double* Rsum,
                                double* ghyp, double* lbar, double* mgbar, double* qgbar, double* cGbar, double* PGbar,
                                int ns, long long B, int Q, int D, cudaStream_t st) {
-    size_t smem = LFShape<NB, KS>::smem_bytes;
+    using SH = LFShape<NB, KS>;
+    size_t smem = SH::smem_bytes;
     if (int r = nmgp_opt_in_smem(k_latent_fused<NB, KS>, smem, "nmgp_latent_fused")) return r;
+    // padded records of (Sigma_W[j], mu_W[j]) in a library-owned scratch buffer (grown on demand, one per process)
+    static double* rec = nullptr;
+    static size_t rec_cap = 0;
+    const size_t need = (size_t)D * SH::REC;
+    if (need > rec_cap) {
+        if (rec) {
+            cudaDeviceSynchronize();
+            cudaFree(rec);
+        }
+        if (cudaMalloc(&rec, need * sizeof(double)) != cudaSuccess) {
+            rec = nullptr;
+            rec_cap = 0;
+            nmgp_set_error("nmgp_latent_fused: cannot allocate %zu bytes of scratch", need * sizeof(double));
+            return -4;
+        }
+        rec_cap = need;
+    }
+    k_pad_records<<<D, 256, 0, st>>>(SigW, muW, rec, Q, SH::KP, SH::LDS, SH::NP);
     dim3 grid((unsigned)((B + LF_ROWS - 1) / LF_ROWS), ns);
-    k_latent_fused<NB, KS><<<grid, LF_THREADS, smem, st>>>(PG, cG, l, y, I, SigW, muW, hyp, scale, Rsum, ghyp, lbar,
-                                                           mgbar, qgbar, cGbar, PGbar, B, Q, D,
-                                                           FastDiv((unsigned)Q));
+    k_latent_fused<NB, KS><<<grid, LF_THREADS, smem, st>>>(PG, cG, l, y, I, rec, muW, hyp, scale, Rsum, ghyp, lbar,
+                                                           mgbar, qgbar, cGbar, PGbar, B, Q, D);
     return nmgp_launch_status("nmgp_latent_fused");
 }
 
