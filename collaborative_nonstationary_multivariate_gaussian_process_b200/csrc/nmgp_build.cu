@@ -69,30 +69,66 @@ __device__ __forceinline__ double gibbs_value(double xn, double zq, double a, do
     return sqrt(2.0 * (a * b) / den) * exp(-r2 / den);
 }
 
+// one warp per GB_ROWS_PER_WARP rows, lanes over q (Q <= 128): the per-column terms (z, b, b^2) are loaded once per
+// warp and every entry costs one reciprocal, one sqrt and one exp
+#define GB_ROWS_PER_WARP 8
 __global__ void k_gibbs_fwd(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ ellx,
                             const double* __restrict__ ellz, double jitter, double* __restrict__ K, long long B, int Q) {
     const int s = blockIdx.y;
-    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= B * Q) return;
-    long long n = gid / Q;
-    int q = (int)(gid - n * Q);
-    double k = gibbs_value(x[n], z[q], ellx[(size_t)s * B + n], ellz[(size_t)s * Q + q]);
-    if (jitter != 0.0 && n == q) k += jitter;
-    K[(size_t)s * B * Q + gid] = k;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const long long row0 = ((long long)blockIdx.x * nw + w) * GB_ROWS_PER_WARP;
+    if (Q > 128) {   // wide case (not on the DSVI path): same arithmetic, column terms re-read per entry
+        for (int rr = 0; rr < GB_ROWS_PER_WARP; ++rr) {
+            const long long n = row0 + rr;
+            if (n >= B) break;
+            const double a = ellx[(size_t)s * B + n], xn = x[n];
+            for (int q = lane; q < Q; q += 32) {
+                const double d = xn - z[q], b = ellz[(size_t)s * Q + q];
+                const double rden = 1.0 / fma(a, a, b * b);
+                double k = sqrt(2.0 * (a * b) * rden) * exp(-(d * d) * rden);
+                if (jitter != 0.0 && n == q) k += jitter;
+                K[((size_t)s * B + n) * Q + q] = k;
+            }
+        }
+        return;
+    }
+    double zq[4], bq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int q = lane + 32 * u;
+        zq[u] = q < Q ? z[q] : 0.0;
+        bq[u] = q < Q ? ellz[(size_t)s * Q + q] : 1.0;
+    }
+    for (int rr = 0; rr < GB_ROWS_PER_WARP; ++rr) {
+        const long long n = row0 + rr;
+        if (n >= B) break;
+        const double a = ellx[(size_t)s * B + n], xn = x[n];
+        double* krow = K + ((size_t)s * B + n) * Q;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = lane + 32 * u;
+            if (q < Q) {
+                const double d = xn - zq[u], b = bq[u];
+                const double rden = 1.0 / fma(a, a, b * b);
+                double k = sqrt(2.0 * (a * b) * rden) * exp(-(d * d) * rden);
+                if (jitter != 0.0 && n == q) k += jitter;
+                krow[q] = k;
+            }
+        }
+    }
 }
 NMGP_API int nmgp_gibbs_build_fwd(const double* x, const double* z, const double* ellx, const double* ellz,
                                   double jitter, double* K, int ns, long long B, int Q, cudaStream_t st) {
     NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && Q > 0, "nmgp_gibbs_build_fwd");
     if (B == 0 || ns == 0) return 0;
-    long long n = B * Q;
-    dim3 grid((unsigned)((n + 255) / 256), ns);
-    k_gibbs_fwd<<<grid, 256, 0, st>>>(x, z, ellx, ellz, jitter, K, B, Q);
+    const int threads = 256, rows_per_block = (threads / 32) * GB_ROWS_PER_WARP;
+    dim3 grid((unsigned)((B + rows_per_block - 1) / rows_per_block), ns);
+    k_gibbs_fwd<<<grid, threads, 0, st>>>(x, z, ellx, ellz, jitter, K, B, Q);
     return nmgp_launch_status("nmgp_gibbs_build_fwd");
 }
 
 // ellxbar[s,n] = sum_q Kbar k dlog k/da ;  ellzbar[s,q] += sum_n Kbar k dlog k/db
 // dlog k/da = 1/(2a) - a/den + 2 a r2/den^2.  One warp per row, lanes over q.
-#define GB_ROWS_PER_WARP 8
 __global__ void k_gibbs_bwd(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ ellx,
                             const double* __restrict__ ellz, const double* __restrict__ Kbar,
                             double* __restrict__ ellxbar, double* __restrict__ ellzbar, long long B, int Q) {
@@ -103,24 +139,31 @@ __global__ void k_gibbs_bwd(const double* __restrict__ x, const double* __restri
     __syncthreads();
     const long long row0 = ((long long)blockIdx.x * nw + w) * GB_ROWS_PER_WARP;
     double cacc[4] = {0.0, 0.0, 0.0, 0.0};  // Q <= 128
+    double zq[4], bq[4], hb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int q = lane + 32 * u;
+        zq[u] = q < Q ? z[q] : 0.0;
+        bq[u] = q < Q ? ellz[(size_t)s * Q + q] : 1.0;
+        hb[u] = 0.5 / bq[u];
+    }
     for (int rr = 0; rr < GB_ROWS_PER_WARP; ++rr) {
         long long n = row0 + rr;
         if (n >= B) break;
-        const double a = ellx[(size_t)s * B + n], xn = x[n];
+        const double a = ellx[(size_t)s * B + n], xn = x[n], ha = 0.5 / a;
         const double* kb = Kbar + ((size_t)s * B + n) * Q;
         double racc = 0.0;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             int q = lane + 32 * u;
             if (q < Q) {
-                double b = ellz[(size_t)s * Q + q];
-                double d = xn - z[q];
-                double r2 = d * d, den = a * a + b * b;
-                double k = sqrt(2.0 * (a * b) / den) * exp(-r2 / den);
-                double g = kb[q] * k;
-                double common = 2.0 * r2 / (den * den) - 1.0 / den;
-                racc = fma(g, 0.5 / a + a * common, racc);
-                cacc[u] = fma(g, 0.5 / b + b * common, cacc[u]);
+                const double b = bq[u], d = xn - zq[u];
+                const double r2 = d * d, rden = 1.0 / fma(a, a, b * b);
+                const double k = sqrt(2.0 * (a * b) * rden) * exp(-r2 * rden);
+                const double g = kb[q] * k;
+                const double common = (2.0 * r2 * rden - 1.0) * rden;
+                racc = fma(g, fma(a, common, ha), racc);
+                cacc[u] = fma(g, fma(b, common, hb[u]), cacc[u]);
             }
         }
         racc = warp_sum(racc);

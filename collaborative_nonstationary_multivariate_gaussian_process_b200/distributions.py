@@ -13,13 +13,14 @@ def multivariate_normal_logpdf(y, mu, logdetSigma, invSigma):
     return (-0.5 * logdetSigma - 0.5 * ops.dot(r, Sr)).reshape(())
 
 
-def multivariate_normal_logpdf0(y, mu, B, K, sigma2):
+def multivariate_normal_logpdf0(y, mu, B, K, sigma2, shard=None):
     """distributions.py:26-52: -1/2 logdet(S) - 1/2 r^T S^-1 r, S = B (x) K + sigma2 I, via the eigen-blocks of B and
-    one blocked Cholesky per block (see kronecker_operation)."""
+    one blocked Cholesky per block (see kronecker_operation).  shard = (rank, world) returns this rank's partial sum
+    over its eigen-blocks (parallel.kron_logpdf0_sharded adds the partials with one all-reduce)."""
     D, T = B.shape[0], K.shape[0]
     r = ops.axpby(y.contiguous(), mu.contiguous(), 1.0, -1.0)
     half_logdet, quad, Rt = None, None, None
-    for m, lam_m, L, hld, V in kronecker_operation._factor_blocks(sigma2, B, K):
+    for m, lam_m, L, hld, V in kronecker_operation._factor_blocks(sigma2, B, K, shard):
         if Rt is None:
             # rows of Rt: (V^T (x) I) r  ->  Rt = V^T R with R = r.view(D, T)
             Rt = ops.gemm_nt(V.t().contiguous(), r.view(D, T).t().contiguous())      # [D, T]
@@ -28,6 +29,8 @@ def multivariate_normal_logpdf0(y, mu, B, K, sigma2):
         q = ops.dot(rm, xm)
         quad = q if quad is None else quad + q
         half_logdet = hld if half_logdet is None else half_logdet + hld
+    if half_logdet is None:                       # a rank that owns no block (world > D)
+        return torch.zeros((), dtype=torch.float64, device=K.device)
     return (-half_logdet - 0.5 * quad).reshape(())
 
 

@@ -20,13 +20,15 @@ def kronecker_product_diag(d1, d2):
     return ops.kron_product(d1.contiguous().view(-1, 1), d2.contiguous().view(-1, 1)).view(-1)
 
 
-def _factor_blocks(sigma2, B, K):
-    """Yields (m, lam_m, L_m, half_logdet_m) with L_m = chol(sigma2 I + lam_m K); V from the Jacobi eigensolver."""
+def _factor_blocks(sigma2, B, K, shard=None):
+    """Yields (m, lam_m, L_m, half_logdet_m, V) with L_m = chol(sigma2 I + lam_m K); V from the Jacobi eigensolver.
+    shard = (rank, world): only the eigen-blocks m = rank, rank + world, ... (the blocks are independent)."""
     lam, V = ops.eigh_small(B.contiguous())
     lam_host = lam.cpu()
     s2 = float(sigma2)
     Kc = K.contiguous()
-    for m in range(B.shape[0]):
+    first, step = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
+    for m in range(first, B.shape[0], step):
         A = ops.scale_add_diag(Kc, float(lam_host[m]), s2)
         L, hld = ops.potrf_big(A)
         yield m, float(lam_host[m]), L, hld, V

@@ -47,3 +47,17 @@ def allreduce_loss_and_grads(loss: torch.Tensor, params: Sequence[torch.nn.Param
         p.grad.copy_(flat[off:off + n].view_as(p.grad))
         off += n
     return flat[0]
+
+
+def kron_logpdf0_sharded(y, mu, B, K, sigma2, group=None):
+    """multivariate_normal_logpdf0 with the D eigen-blocks (sigma2 I + lambda_m K) dealt round-robin to the ranks: every
+    rank factorises its blocks with the blocked Cholesky and the partial log-densities (-1/2 logdet_m - 1/2 quad_m) are
+    summed with one all-reduce of a single double (scale sweep).  A single T x T factorisation is not split."""
+    import torch.distributed as dist
+    from . import distributions
+    if not (dist.is_available() and dist.is_initialized()):
+        return distributions.multivariate_normal_logpdf0(y, mu, B, K, sigma2)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    part = distributions.multivariate_normal_logpdf0(y, mu, B, K, sigma2, shard=(rank, world)).reshape(1).clone()
+    dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+    return part.reshape(())

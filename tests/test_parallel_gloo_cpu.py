@@ -111,3 +111,30 @@ def test_counter_noise_statistics():
     z2 = specs.noise_fill(2, 5000, 7, seed=99, stream_id=(3 << 8) | 2, s0=12, gid=None)
     assert torch.equal(z[2:], z2)                      # sample offset only shifts the counter
     assert float(z.to(torch.float32).to(torch.float64).sub(z).abs().max()) == 0.0   # float32-valued (quirk q2)
+
+
+def _kron_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import kernel_specs as specs
+    from collaborative_nonstationary_multivariate_gaussian_process_b200 import _ops, parallel
+    for n, f in inspect.getmembers(specs, inspect.isfunction):
+        if not n.startswith("_"):
+            setattr(_ops, n, f)
+    g = gu.load("sim_code")
+    val = parallel.kron_logpdf0_sharded(torch.from_numpy(g["y"]), torch.from_numpy(g["mu"]), torch.from_numpy(g["Bf"]),
+                                        torch.from_numpy(g["K_self"]), torch.tensor(float(g["s2"]), dtype=torch.float64))
+    if rank == 0:
+        torch.save({"logpdf0": float(val)}, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_kronecker_logpdf_matches_reference(tmp_path):
+    """eigen-blocks of B dealt to two ranks, one all-reduce: equals the reference's multivariate_normal_logpdf0"""
+    out = str(tmp_path / "kron.pt")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_kron_worker, args=(2, port, out), nprocs=2, join=True)
+    res = torch.load(out, weights_only=False)
+    g = gu.load("sim_code")
+    assert abs(res["logpdf0"] - float(g["logpdf0"])) <= 1e-9 * abs(float(g["logpdf0"]))
