@@ -72,7 +72,8 @@ __device__ __forceinline__ double gibbs_value(double xn, double zq, double a, do
 // one warp per GB_ROWS_PER_WARP rows, lanes over q (Q <= 128): the per-column terms (z, b, b^2) are loaded once per
 // warp and every entry costs one reciprocal, one sqrt and one exp
 #define GB_ROWS_PER_WARP 8
-__global__ void k_gibbs_fwd(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ ellx,
+template <int NU>
+__global__ void __launch_bounds__(256, 4) k_gibbs_fwd(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ ellx,
                             const double* __restrict__ ellz, double jitter, double* __restrict__ K, long long B, int Q) {
     const int s = blockIdx.y;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -92,9 +93,9 @@ __global__ void k_gibbs_fwd(const double* __restrict__ x, const double* __restri
         }
         return;
     }
-    double zq[4], bq[4];
+    double zq[NU], bq[NU];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < NU; ++u) {
         const int q = lane + 32 * u;
         zq[u] = q < Q ? z[q] : 0.0;
         bq[u] = q < Q ? ellz[(size_t)s * Q + q] : 1.0;
@@ -105,7 +106,7 @@ __global__ void k_gibbs_fwd(const double* __restrict__ x, const double* __restri
         const double a = ellx[(size_t)s * B + n], xn = x[n];
         double* krow = K + ((size_t)s * B + n) * Q;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NU; ++u) {
             const int q = lane + 32 * u;
             if (q < Q) {
                 const double d = xn - zq[u], b = bq[u];
@@ -123,13 +124,19 @@ NMGP_API int nmgp_gibbs_build_fwd(const double* x, const double* z, const double
     if (B == 0 || ns == 0) return 0;
     const int threads = 256, rows_per_block = (threads / 32) * GB_ROWS_PER_WARP;
     dim3 grid((unsigned)((B + rows_per_block - 1) / rows_per_block), ns);
-    k_gibbs_fwd<<<grid, threads, 0, st>>>(x, z, ellx, ellz, jitter, K, B, Q);
+    switch (Q > 128 ? 4 : (Q + 31) / 32) {
+        case 1: k_gibbs_fwd<1><<<grid, threads, 0, st>>>(x, z, ellx, ellz, jitter, K, B, Q); break;
+        case 2: k_gibbs_fwd<2><<<grid, threads, 0, st>>>(x, z, ellx, ellz, jitter, K, B, Q); break;
+        case 3: k_gibbs_fwd<3><<<grid, threads, 0, st>>>(x, z, ellx, ellz, jitter, K, B, Q); break;
+        default: k_gibbs_fwd<4><<<grid, threads, 0, st>>>(x, z, ellx, ellz, jitter, K, B, Q); break;
+    }
     return nmgp_launch_status("nmgp_gibbs_build_fwd");
 }
 
 // ellxbar[s,n] = sum_q Kbar k dlog k/da ;  ellzbar[s,q] += sum_n Kbar k dlog k/db
 // dlog k/da = 1/(2a) - a/den + 2 a r2/den^2.  One warp per row, lanes over q.
-__global__ void k_gibbs_bwd(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ ellx,
+template <int NU>
+__global__ void __launch_bounds__(256, 4) k_gibbs_bwd(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ ellx,
                             const double* __restrict__ ellz, const double* __restrict__ Kbar,
                             double* __restrict__ ellxbar, double* __restrict__ ellzbar, long long B, int Q) {
     extern __shared__ double colsum[];  // [Q]
@@ -138,10 +145,12 @@ __global__ void k_gibbs_bwd(const double* __restrict__ x, const double* __restri
     for (int q = threadIdx.x; q < Q; q += blockDim.x) colsum[q] = 0.0;
     __syncthreads();
     const long long row0 = ((long long)blockIdx.x * nw + w) * GB_ROWS_PER_WARP;
-    double cacc[4] = {0.0, 0.0, 0.0, 0.0};  // Q <= 128
-    double zq[4], bq[4], hb[4];
+    double cacc[NU];   // Q <= 32 NU
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < NU; ++u) cacc[u] = 0.0;
+    double zq[NU], bq[NU], hb[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
         const int q = lane + 32 * u;
         zq[u] = q < Q ? z[q] : 0.0;
         bq[u] = q < Q ? ellz[(size_t)s * Q + q] : 1.0;
@@ -154,7 +163,7 @@ __global__ void k_gibbs_bwd(const double* __restrict__ x, const double* __restri
         const double* kb = Kbar + ((size_t)s * B + n) * Q;
         double racc = 0.0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NU; ++u) {
             int q = lane + 32 * u;
             if (q < Q) {
                 const double b = bq[u], d = xn - zq[u];
@@ -170,7 +179,7 @@ __global__ void k_gibbs_bwd(const double* __restrict__ x, const double* __restri
         if (lane == 0) ellxbar[(size_t)s * B + n] = racc;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < NU; ++u) {
         int q = lane + 32 * u;
         if (q < Q && cacc[u] != 0.0) atomicAdd(&colsum[q], cacc[u]);
     }
@@ -185,7 +194,12 @@ NMGP_API int nmgp_gibbs_build_bwd(const double* x, const double* z, const double
     if (B == 0 || ns == 0) return 0;
     const int threads = 256, rows_per_block = (threads / 32) * GB_ROWS_PER_WARP;
     dim3 grid((unsigned)((B + rows_per_block - 1) / rows_per_block), ns);
-    k_gibbs_bwd<<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, ellxbar, ellzbar, B, Q);
+    switch ((Q + 31) / 32) {
+        case 1: k_gibbs_bwd<1><<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, ellxbar, ellzbar, B, Q); break;
+        case 2: k_gibbs_bwd<2><<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, ellxbar, ellzbar, B, Q); break;
+        case 3: k_gibbs_bwd<3><<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, ellxbar, ellzbar, B, Q); break;
+        default: k_gibbs_bwd<4><<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, ellxbar, ellzbar, B, Q); break;
+    }
     return nmgp_launch_status("nmgp_gibbs_build_bwd");
 }
 

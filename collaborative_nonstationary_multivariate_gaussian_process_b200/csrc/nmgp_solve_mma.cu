@@ -28,9 +28,10 @@ __device__ __forceinline__ void c_to_a(double c0, double c1, int t, int lane, do
 
 #define SM_ROWS 128
 #define SM_THREADS 256
+#define SM_TILES 4        // 128-row tiles per CTA: the factor staging / diagonal-block inversion is paid once per 512 rows
 
 template <int NB, bool BWD>
-__global__ void __launch_bounds__(SM_THREADS)
+__global__ void __launch_bounds__(SM_THREADS, 2)
 k_solve_rows_mma(const double* __restrict__ K, const double* __restrict__ R, double* __restrict__ P,
                  double* __restrict__ cout, const double* __restrict__ Pbar, const double* __restrict__ cbar,
                  const double* __restrict__ Pin, double* __restrict__ Kbar, double* __restrict__ Tout, long long B,
@@ -43,7 +44,6 @@ k_solve_rows_mma(const double* __restrict__ K, const double* __restrict__ R, dou
     double* Ri = RTn + QP * LDR;             // [NB][8][8] inv(R_bb)        (Ri[b][r][c])
     double* RiT = Ri + NB * 64;              // [NB][8][8] inv(R_bb)^T
     const int s = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
-    const long long row0 = (long long)blockIdx.x * SM_ROWS;
     const double* Rg = R + (size_t)s * Q * Q;
     for (int e = tid; e < QP * LDR; e += SM_THREADS) {
         int a = e / LDR, b = e - a * LDR;
@@ -81,6 +81,9 @@ k_solve_rows_mma(const double* __restrict__ K, const double* __restrict__ R, dou
     }
     __syncthreads();
 
+  for (int tile = 0; tile < SM_TILES; ++tile) {
+    const long long row0 = ((long long)blockIdx.x * SM_TILES + tile) * SM_ROWS;
+    if (row0 >= B) break;
     const int rl[2] = {16 * w + g, 16 * w + 8 + g};
     const long long gr_[2] = {row0 + rl[0], row0 + rl[1]};
     const bool ok[2] = {gr_[0] < B, gr_[1] < B};
@@ -174,6 +177,7 @@ k_solve_rows_mma(const double* __restrict__ K, const double* __restrict__ R, dou
             if (t == 0 && ok[mb]) cout[(size_t)s * B + gr_[mb]] = v;
         }
     }
+  }
 }
 
 template <int NB, bool BWD>
@@ -183,7 +187,7 @@ static int launch_solve_mma(const double* K, const double* R, double* P, double*
     constexpr int QP = 8 * NB, LDR = ((QP + 3) / 8) * 8 + 4;
     size_t smem = sizeof(double) * (2 * QP * LDR + 2 * NB * 64);
     if (int r = nmgp_opt_in_smem(k_solve_rows_mma<NB, BWD>, smem, what)) return r;
-    dim3 grid((unsigned)((B + SM_ROWS - 1) / SM_ROWS), ns);
+    dim3 grid((unsigned)((B + SM_ROWS * SM_TILES - 1) / (SM_ROWS * SM_TILES)), ns);
     k_solve_rows_mma<NB, BWD><<<grid, SM_THREADS, smem, st>>>(K, R, P, c, Pbar, cbar, Pin, Kbar, Tout, B, Q);
     return nmgp_launch_status(what);
 }
