@@ -15,7 +15,10 @@
  *     `ghyp` accumulates gradients w.r.t. the corresponding *_log parameters;
  *   - rows are sorted by output id I[n]; seg[d] = first row with I >= d, seg[D] = B;
  *   - "+=" marks accumulating outputs (caller zero-initialises), "=" overwriting ones;
- *   - all work is enqueued on `stream` (a cudaStream_t); no internal allocation, no global state;
+ *   - all work is enqueued on `stream` (a cudaStream_t); no per-call allocation.  Two entry points keep a small
+ *     library-owned scratch per process, created on first use and reused: nmgp_latent_fused (padded copies of
+ *     Sigma_W / mu_W, D * ~25 KB) and nmgp_potrf_big (two 128 x 128 inverse blocks, a helper stream and two events for
+ *     the look-ahead); they are therefore not re-entrant from several host threads;
  *   - return value: 0 ok, < 0 argument/launch error, > 0 numerical failure; nmgp_last_error() gives the text
  *     (thread-local).
  */
@@ -171,7 +174,8 @@ int nmgp_pairwise_dist(const double* X1, const double* X2, double* out, long lon
 int nmgp_gemm_nt(const double* A, const double* B, double* C, long long M, long long N, long long K, long long lda,
                  long long ldb, long long ldc, double alpha, double beta, nmgp_stream_t stream);
 /* in-place blocked lower Cholesky, hld = sum log diag L      replaces torch.symeig / torch.logdet / torch.inverse at
- *                                                    kronecker_operation.py:45-47,66-67; distributions.py:37-40,109-110 */
+ *                                                    kronecker_operation.py:45-47,66-67; distributions.py:37-40,109-110
+ * *info = 1 + index of the FIRST non-positive pivot (0 if none); strict upper triangle zeroed on return */
 int nmgp_potrf_big(double* A, long long T, long long lda, double* hld, int* info, nmgp_stream_t stream);
 /* x <- (L L^T)^-1 x */
 int nmgp_potrs_vec(const double* L, long long T, long long lda, double* x, nmgp_stream_t stream);
