@@ -597,7 +597,8 @@ int nmgp_coef_quadform_mma(bool bwd, const double* Pa, const double* Pb, const i
 // Weighted Gram matrices on DMMA.  grid (D outputs, jgroups [+1 for the MODE_U diagonal pair], ns), 128 threads.
 #define GM_NG 4         // latents per CTA
 #define GM_TROWS 32     // rows per staged tile (8 k-steps)
-#define GM_THREADS 128
+#define GM_THREADS 256  // 8 warps: warp w & 3 = block-row role, w >> 2 = which half of the NG latents it accumulates
+#define GM_NGW (GM_NG / 2)
 
 template <int NB>
 struct GMShape {
@@ -607,7 +608,7 @@ struct GMShape {
 };
 
 template <int NB>
-__global__ void __launch_bounds__(GM_THREADS, NB <= 6 ? 3 : 2)
+__global__ void __launch_bounds__(GM_THREADS, 2)
 k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const int* __restrict__ seg,
            const double* __restrict__ qbar, const double* __restrict__ mbar, double* __restrict__ SigBar,
            double* __restrict__ MuBar, long long B, int Q, int D, int mode) {
@@ -631,7 +632,8 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
     }
     const long long rbeg = seg[i], rend = seg[i + 1];
     if (rbeg >= rend) return;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int tid = threadIdx.x, lane = tid & 31, w = (tid >> 5) & 3, ug = tid >> 7, g = lane >> 2, t = lane & 3;
+    const int u0 = ug * GM_NGW;                            // this warp's latents: u0 .. u0 + GM_NGW - 1
     const int a1 = w, a2 = NB - 1 - w;
     const bool active = a1 <= a2;
     const int nslots = !active ? 0 : (a1 == a2 ? a1 + 1 : NB + 1);
@@ -639,10 +641,10 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
     for (int e = tid; e < (int)SH::smem_doubles; e += GM_THREADS) sm[e] = 0.0;
     __syncthreads();
 
-    double acc[GM_NG][NB + 1][2];
+    double acc[GM_NGW][NB + 1][2];
     double accm[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-    for (int u = 0; u < GM_NG; ++u)
+    for (int u = 0; u < GM_NGW; ++u)
 #pragma unroll
         for (int sl = 0; sl <= NB; ++sl) acc[u][sl][0] = acc[u][sl][1] = 0.0;
 
@@ -651,7 +653,7 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
         const long long r0 = rbeg + tile * GM_TROWS;
         const int nr = (int)min((long long)GM_TROWS, rend - r0);
         double* Pd = Pt + (size_t)buf * GM_TROWS * LDP;
-        for (int r = w; r < GM_TROWS; r += GM_THREADS / 32) {
+        for (int r = (tid >> 5); r < GM_TROWS; r += GM_THREADS / 32) {
             if (r < nr) {
                 const double* src = &P[((size_t)s * B + r0 + r) * Q];
                 if ((Q & 1) == 0) {
@@ -692,10 +694,10 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
             const int n = 4 * kk + t;                        // row of the tile this lane feeds as k index
             const double ra1 = Pd[n * LDP + 8 * a1 + g];     // A fragment (a = 8 a1 + g, k = n), unscaled
             const double ra2 = Pd[n * LDP + 8 * a2 + g];
-            double sa1[GM_NG], sa2[GM_NG];
+            double sa1[GM_NGW], sa2[GM_NGW];
 #pragma unroll
-            for (int u = 0; u < GM_NG; ++u) {
-                const double wv = wq[(buf * GM_NG + u) * GM_TROWS + n];
+            for (int u = 0; u < GM_NGW; ++u) {
+                const double wv = wq[(buf * GM_NG + u0 + u) * GM_TROWS + n];
                 sa1[u] = ra1 * wv;
                 sa2[u] = ra2 * wv;
             }
@@ -706,21 +708,24 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
                     const int bb = first ? sl : sl - a1 - 1;
                     const double bf = Pd[n * LDP + 8 * bb + g];   // B fragment (k = n, col = 8 bb + g)
 #pragma unroll
-                    for (int u = 0; u < GM_NG; ++u)
+                    for (int u = 0; u < GM_NGW; ++u)
                         dmma884(acc[u][sl][0], acc[u][sl][1], first ? sa1[u] : sa2[u], bf);
                 }
             }
             // MuBar: (Q x rows)(rows x NG): B fragment column g carries mbar of latent g (< NG), k = n
-            const double bm = (g < GM_NG) ? wm[(buf * GM_NG + g) * GM_TROWS + n] : 0.0;
-            dmma884(accm[0][0], accm[0][1], ra1, bm);
-            if (a2 != a1) dmma884(accm[1][0], accm[1][1], ra2, bm);
+            if (ug == 0) {
+                const double bm = (g < GM_NG) ? wm[(buf * GM_NG + g) * GM_TROWS + n] : 0.0;
+                dmma884(accm[0][0], accm[0][1], ra1, bm);
+                if (a2 != a1) dmma884(accm[1][0], accm[1][1], ra2, bm);
+            }
         }
     }
     cp_async_wait<0>();
     if (!active) return;
     // ---- write-out: block (a, bb) holds rows 8a+g, cols 8bb+2t+e; mirror the strictly-lower blocks ----------
 #pragma unroll
-    for (int u = 0; u < GM_NG; ++u) {
+    for (int uu = 0; uu < GM_NGW; ++uu) {
+        const int u = u0 + uu;
         if (u < nj) {
             const int idx = (mode == MODE_U) ? pair_slot(i, j0 + u, D) : j0 + u;
             double* Sb = SigBar + (size_t)idx * Q * Q;
@@ -734,14 +739,15 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
                     for (int e = 0; e < 2; ++e) {
                         const int c = 8 * bb + 2 * t + e;
                         if (r < Q && c < Q) {
-                            atomicAdd(&Sb[(size_t)r * Q + c], acc[u][sl][e]);
-                            if (a != bb) atomicAdd(&Sb[(size_t)c * Q + r], acc[u][sl][e]);
+                            atomicAdd(&Sb[(size_t)r * Q + c], acc[uu][sl][e]);
+                            if (a != bb) atomicAdd(&Sb[(size_t)c * Q + r], acc[uu][sl][e]);
                         }
                     }
                 }
             }
         }
     }
+    if (ug != 0) return;
 #pragma unroll
     for (int st2 = 0; st2 < 2; ++st2) {
         if (st2 == 1 && a2 == a1) break;
