@@ -37,7 +37,9 @@ _side_streams: Dict[str, "torch.cuda.Stream"] = {}
 def _side_stream(dev):
     key = str(dev)
     if key not in _side_streams:
-        _side_streams[key] = torch.cuda.Stream(device=dev)
+        # highest priority: the few-CTA, latency-bound KL kernels must get SM slots ahead of the queued row-kernel CTAs,
+        # otherwise they only start when a row kernel drains and the overlap is lost
+        _side_streams[key] = torch.cuda.Stream(device=dev, priority=-1)
     return _side_streams[key]
 
 
@@ -125,9 +127,12 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
 
     # ---- the three stationary inducing systems ------------------------------------------------
     sysm = {}
-    for name, is2, ilen in (("ell", H_S2_ELL, H_LEN_ELL), ("L0", H_S2_L0, H_LEN_L0), ("L1", H_S2_L1, H_LEN_L1)):
-        A = ops.rbf_build_fwd(Z, Z, hyp, is2, ilen, EPS).reshape(1, Q, Q)
-        R, hldR = ops.potrf(A, 0.0, info=pd_info)
+    systems = (("ell", H_S2_ELL, H_LEN_ELL), ("L0", H_S2_L0, H_LEN_L0), ("L1", H_S2_L1, H_LEN_L1))
+    # one batched factorisation for the three Q x Q systems (each launch of a single small matrix is pure latency)
+    A3 = torch.stack([ops.rbf_build_fwd(Z, Z, hyp, is2, ilen, EPS) for _, is2, ilen in systems])
+    R3, hldR3 = ops.potrf(A3, 0.0, info=pd_info)
+    for k_sys, (name, is2, ilen) in enumerate(systems):
+        R, hldR = R3[k_sys:k_sys + 1], hldR3[k_sys:k_sys + 1]
         K12 = ops.rbf_build_fwd(x, Z, hyp, is2, ilen, 0.0).reshape(1, B, Q)
         P, c = ops.solve_rows_fwd(K12, R)
         sysm[name] = dict(R=R, hldR=hldR, K12=K12, P=P, c=c, is2=is2, ilen=ilen)
@@ -258,18 +263,24 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
                       MODE_U, SigUbar, muUbar, seg=seg)
     cellbar = ops.ell_sd_bwd(sdellbar, sd_ell, hyp, ghyp)
 
-    for name, Pbar, cbar, Rbar, hldRbar in (("ell", Pellbar.reshape(1, B, Q), cellbar.reshape(1, B), Rellbar, hldRellbar),
-                                            ("L0", PL0bar, cL0bar.reshape(1, B), RL0bar, hldRL0bar),
-                                            ("L1", PL1bar, cL1bar.reshape(1, B), RL1bar, hldRL1bar)):
+    # Cholesky adjoints of the three stationary factors and of C_v in one batched launch
+    chol_adj = ops.potrf_bwd(torch.cat([sysm["ell"]["R"], sysm["L0"]["R"], sysm["L1"]["R"], C_v.reshape(1, Q, Q)]),
+                             torch.cat([Rellbar.reshape(1, Q, Q), RL0bar.reshape(1, Q, Q), RL1bar.reshape(1, Q, Q),
+                                        Cvbar.reshape(1, Q, Q)]),
+                             torch.cat([hldRellbar.reshape(1), hldRL0bar.reshape(1), hldRL1bar.reshape(1),
+                                        hldvbar.reshape(1)]))
+    for k_sys, (name, Pbar, cbar) in enumerate((("ell", Pellbar.reshape(1, B, Q), cellbar.reshape(1, B)),
+                                                ("L0", PL0bar, cL0bar.reshape(1, B)),
+                                                ("L1", PL1bar, cL1bar.reshape(1, B)))):
         sy = sysm[name]
         Abar = zeros(1, Q, Q)
         K12bar = ops.solve_rows_bwd(Pbar, cbar, sy["K12"], sy["P"], sy["R"], Abar)
-        Abar += ops.potrf_bwd(sy["R"], Rbar, hldRbar)
+        Abar += chol_adj[k_sys:k_sys + 1]
         ops.rbf_build_bwd(x, Z, hyp, sy["is2"], sy["ilen"], K12bar[0], ghyp)
         ops.rbf_build_bwd(Z, Z, hyp, sy["is2"], sy["ilen"], Abar[0], ghyp)
 
     # ---- Cholesky / LL^T adjoints back to the sqrt parameters -----------------------------------
-    g_sqrt_v = ops.tril_syrk_bwd(sqrt_v, ops.potrf_bwd(C_v, Cvbar.reshape(1, Q, Q), hldvbar)).reshape(Q, Q)
+    g_sqrt_v = ops.tril_syrk_bwd(sqrt_v, chol_adj[3:4]).reshape(Q, Q)
     SigWbar += SigW_kl
     g_sqrt_W = ops.tril_syrk_bwd(sqrt_W, SigWbar)
     if n1:
