@@ -1,0 +1,46 @@
+"""Golden vectors for the SIM_code predictive functions (code/SIM_code/Utility/prediction.py:337-458), produced by the
+UNMODIFIED reference under the shim of oracle/gen_golden.py.  TEST INFRASTRUCTURE ONLY; run in the build container:
+
+    python oracle/gen_golden_prediction.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from gen_golden import OUT, install_shim  # noqa: E402
+
+
+def main():
+    install_shim()
+    from Utility import prediction, utils as sim_utils
+    torch.manual_seed(11)
+    N, M, G = 60, 3, 7
+    x = torch.sort(torch.rand(N).double())[0]
+    tilde_l = (3 * (x - 1) ** 3 - 1.5) + 0.05 * torch.randn(N).double()        # sim.py:22-26 shape of log-ell
+    tilde_sigma = 0.1 * torch.randn(N).double()
+    Lm = torch.tril(torch.randn(M, M).double()); Lm[range(M), range(M)] = torch.exp(0.3 * torch.randn(M).double())
+    uL_vec = sim_utils.Lvec2uLvec(sim_utils.lowtriangle2vec(Lm, M), M)
+    tilde_s2 = torch.tensor(np.log(1e-2)).double()
+    Y = torch.randn(N, M).double()
+    grids = torch.linspace(0.03, 0.97, G).double()
+    hyp = dict(mu_tilde_l=torch.tensor(-1.0).double(), alpha_tilde_l=torch.tensor(1.5).double(),
+               beta_tilde_l=torch.tensor(0.3).double(), mu_tilde_sigma=torch.tensor(0.0).double(),
+               alpha_tilde_sigma=torch.tensor(0.8).double(), beta_tilde_sigma=torch.tensor(0.4).double())
+    order = ("mu_tilde_l", "alpha_tilde_l", "beta_tilde_l", "mu_tilde_sigma", "alpha_tilde_sigma", "beta_tilde_sigma")
+    args = [hyp[k] for k in order]
+    one = prediction.point_predmap(tilde_l, tilde_sigma, uL_vec, tilde_s2, Y, x, grids[2], *args)
+    allg = prediction.pointwise_predmap(tilde_l, tilde_sigma, uL_vec, tilde_s2, Y, x, grids, *args)
+    tst = prediction.test_predmap(tilde_l, tilde_sigma, uL_vec, tilde_s2, Y, x, x[::9] + 0.004, *args)
+    np.savez_compressed(os.path.join(OUT, "sim_prediction.npz"), x=x.numpy(), tilde_l=tilde_l.numpy(),
+                        tilde_sigma=tilde_sigma.numpy(), uL_vec=uL_vec.numpy(), tilde_s2=float(tilde_s2), Y=Y.numpy(),
+                        grids=grids.numpy(), x_test=(x[::9] + 0.004).numpy(),
+                        **{k: float(v) for k, v in hyp.items()}, point=one.numpy(), pointwise=allg.numpy(),
+                        test=tst.numpy(), L_vec=sim_utils.uLvec2Lvec(uL_vec, M).numpy())
+    print("point_predmap", one.numpy())
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,47 @@
+"""Shared body of the SIM_code prediction parity tests (CPU: kernel specs patched in; GPU: through the C ABI).
+Golden outputs come from the unmodified reference (oracle/gen_golden_prediction.py)."""
+import numpy as np
+import torch
+
+from tests import golden_util as gu
+
+ORDER = ("mu_tilde_l", "alpha_tilde_l", "beta_tilde_l", "mu_tilde_sigma", "alpha_tilde_sigma", "beta_tilde_sigma")
+# The reference solves the two GP-conditional systems Sigma + 1e-6 I (condition number ~1e8 for a smooth RBF on 60
+# points) by LU and eigendecomposes K_x; we use Cholesky factors.  Both are backward stable, so the outputs agree to
+# cond * eps; the bound below is that, not the 1e-9 of the well-conditioned DSVI path.
+RTOL = 2e-8
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def run_all(dev):
+    from collaborative_nonstationary_multivariate_gaussian_process_b200 import prediction
+    g = gu.load("sim_prediction")
+    d = lambda k: torch.from_numpy(np.asarray(g[k], dtype=np.float64)).to(dev)
+    hyp = [torch.tensor(float(g[k]), dtype=torch.float64) for k in ORDER]
+    M = g["Y"].shape[1]
+    # helpers of SIM_code/Utility/utils.py
+    Lv = prediction.uLvec2Lvec(d("uL_vec"), M)
+    assert _rel(Lv.cpu().numpy(), g["L_vec"]) < 1e-15
+    assert _rel(prediction.Lvec2uLvec(Lv, M).cpu().numpy(), g["uL_vec"]) < 1e-14
+    Lm = prediction.vec2lowtriangle(Lv, M)
+    assert float(torch.triu(Lm, 1).abs().max()) == 0.0
+    assert _rel(prediction.lowtriangle2vec(Lm, M).cpu().numpy(), g["L_vec"]) < 1e-15
+    args = (d("tilde_l"), d("tilde_sigma"), d("uL_vec"), torch.tensor(float(g["tilde_s2"]), dtype=torch.float64).to(dev),
+            d("Y"), d("x"))
+    one = prediction.point_predmap(*args, d("grids")[2], *hyp)
+    assert one.shape == (3, M)
+    assert _rel(one.cpu().numpy(), g["point"]) < RTOL, _rel(one.cpu().numpy(), g["point"])
+    allg = prediction.pointwise_predmap(*args, d("grids"), *hyp)
+    assert allg.shape == g["pointwise"].shape
+    assert _rel(allg.cpu().numpy(), g["pointwise"]) < RTOL, _rel(allg.cpu().numpy(), g["pointwise"])
+    tst = prediction.test_predmap(*args, d("x_test"), *hyp)
+    assert _rel(tst.cpu().numpy(), g["test"]) < RTOL, _rel(tst.cpu().numpy(), g["test"])
+    # size-independent property: the band is symmetric around the mean and at least the noise level wide
+    half = (allg[:, 2] - allg[:, 0]) / 2
+    assert torch.allclose(allg[:, 1], (allg[:, 2] + allg[:, 0]) / 2, rtol=0, atol=1e-12)
+    assert bool((half >= 1.96 * np.sqrt(np.exp(float(g["tilde_s2"]))) * (1 - 1e-9)).all())
+    return {"point": _rel(one.cpu().numpy(), g["point"]), "pointwise": _rel(allg.cpu().numpy(), g["pointwise"])}
