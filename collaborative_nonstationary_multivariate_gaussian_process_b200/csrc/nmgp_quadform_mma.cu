@@ -86,10 +86,16 @@ __global__ void k_pad_records(const double* __restrict__ SigW, const double* __r
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// 128-row tiles, 8 warps, one CTA per SM (measured: two 64-row CTAs per SM are 18% slower -- every CTA stages its
-// own copy of Sigma_W[j], profiles/README.md)
+// k_latent_fused: 64-row tiles, 4 warps, TWO CTAs per SM.  The two CTAs of an SM share no barrier, so the epilogue /
+// prologue / output phases of one overlap the DMMA phase of the other (68.1 -> 64.9 ms per step against one 128-row,
+// 8-warp CTA per SM).  This only pays because a latent's record arrives by one bulk copy: with per-thread cp.async
+// staging every CTA paid the staging instructions itself and the same split measured 18% slower (profiles/README.md).
+// k_coef_quadform_mma keeps 128-row tiles (LF_ROWS / LF_THREADS).
 #define LF_ROWS 128
 #define LF_THREADS 256
+#define LFK_ROWS 64       // k_latent_fused: 64-row tiles, 4 warps, two CTAs per SM
+#define LFK_THREADS 128
+#define LFK_CTAS 2
 
 template <int NB, int KS>
 struct LFShape {
@@ -98,12 +104,12 @@ struct LFShape {
     static constexpr int LDP = pad8mod16(NP > KP ? NP : KP);
     static constexpr int LDS = pad4mod8(NP);
     static constexpr int REC = KP * LDS + NP;              // one latent's padded record: Sigma_W[j] then mu_W[j]
-    static constexpr size_t smem_doubles = (size_t)LF_ROWS * LDP + 2 * (size_t)REC + 2 * LF_ROWS + 2;
-    static constexpr size_t smem_bytes = smem_doubles * 8 + LF_ROWS * 4;
+    static constexpr size_t smem_doubles = (size_t)LFK_ROWS * LDP + 2 * (size_t)REC + 2 * LFK_ROWS + 2;
+    static constexpr size_t smem_bytes = smem_doubles * 8 + LFK_ROWS * 4;
 };
 
 template <int NB, int KS>
-__global__ void __launch_bounds__(LF_THREADS, 1)
+__global__ void __launch_bounds__(LFK_THREADS, LFK_CTAS)
 k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, const double* __restrict__ l,
                const double* __restrict__ y, const int* __restrict__ I, const double* __restrict__ rec,
                const double* __restrict__ muW, const double* __restrict__ hyp, double scale,
@@ -113,21 +119,21 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
     using SH = LFShape<NB, KS>;
     constexpr int LDP = SH::LDP, LDS = SH::LDS, KP = SH::KP, REC = SH::REC;
     extern __shared__ __align__(16) double sm[];
-    double* Ps = sm;                                   // [LF_ROWS][LDP]
-    double* Ss = Ps + (size_t)LF_ROWS * LDP;           // [2][REC]: double-buffered records of the latent j
-    double* rrs = Ss + 2 * (size_t)REC;                // [LF_ROWS]
-    double* omcs = rrs + LF_ROWS;                      // [LF_ROWS]
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(omcs + LF_ROWS);   // [2]
-    int* Is = reinterpret_cast<int*>(mbar + 2);        // [LF_ROWS]
+    double* Ps = sm;                                   // [LFK_ROWS][LDP]
+    double* Ss = Ps + (size_t)LFK_ROWS * LDP;           // [2][REC]: double-buffered records of the latent j
+    double* rrs = Ss + 2 * (size_t)REC;                // [LFK_ROWS]
+    double* omcs = rrs + LFK_ROWS;                      // [LFK_ROWS]
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(omcs + LFK_ROWS);   // [2]
+    int* Is = reinterpret_cast<int*>(mbar + 2);        // [LFK_ROWS]
 
     const int s = blockIdx.y;
-    const long long row0 = (long long)blockIdx.x * LF_ROWS;
-    const int nrows = (int)min((long long)LF_ROWS, B - row0);
+    const long long row0 = (long long)blockIdx.x * LFK_ROWS;
+    const int nrows = (int)min((long long)LFK_ROWS, B - row0);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
     const size_t rbase = (size_t)s * B + row0;          // first row of this tile in [ns*B]
     const double s2e = hyp[H_S2_ERR];
 
-    for (int e = tid; e < LF_ROWS * LDP; e += LF_THREADS) {
+    for (int e = tid; e < LFK_ROWS * LDP; e += LFK_THREADS) {
         int r = e / LDP, a = e - r * LDP;
         Ps[e] = (r < nrows && a < Q) ? PG[(rbase + r) * Q + a] : 0.0;
     }
@@ -136,7 +142,7 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    for (int r = tid; r < LF_ROWS; r += LF_THREADS) {
+    for (int r = tid; r < LFK_ROWS; r += LFK_THREADS) {
         Is[r] = r < nrows ? I[row0 + r] : -1;
         omcs[r] = r < nrows ? 1.0 - cG[rbase + r] : 0.0;
     }
@@ -346,8 +352,8 @@ static int launch_latent_fused(const double* PG, const double* cG, const double*
         rec_cap = need;
     }
     k_pad_records<<<D, 256, 0, st>>>(SigW, muW, rec, Q, SH::KP, SH::LDS, SH::NP);
-    dim3 grid((unsigned)((B + LF_ROWS - 1) / LF_ROWS), ns);
-    k_latent_fused<NB, KS><<<grid, LF_THREADS, smem, st>>>(PG, cG, l, y, I, rec, muW, hyp, scale, Rsum, ghyp, lbar,
+    dim3 grid((unsigned)((B + LFK_ROWS - 1) / LFK_ROWS), ns);
+    k_latent_fused<NB, KS><<<grid, LFK_THREADS, smem, st>>>(PG, cG, l, y, I, rec, muW, hyp, scale, Rsum, ghyp, lbar,
                                                            mgbar, qgbar, cGbar, PGbar, B, Q, D);
     return nmgp_launch_status("nmgp_latent_fused");
 }
