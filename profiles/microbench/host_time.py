@@ -1,6 +1,6 @@
 """Diagnostic: host time to enqueue one resident DSVI step (no host sync inside) vs its GPU time."""
 import sys, time, json
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "..", ".."))
 import numpy as np, torch
 import bench
 from collaborative_nonstationary_multivariate_gaussian_process_b200 import _ops, nmgp_dsvi, parallel, dsvi_step

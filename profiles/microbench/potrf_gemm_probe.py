@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "..", ".."))
 from collaborative_nonstationary_multivariate_gaussian_process_b200 import _ops as ops
 def timed(f, n=50):
     for _ in range(5): f()
