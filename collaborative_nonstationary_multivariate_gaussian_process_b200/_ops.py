@@ -163,10 +163,10 @@ def gibbs_build_fwd(x, z, ellx, ellz, jitter=0.0):
     return K
 
 
-def gibbs_build_bwd(x, z, ellx, ellz, Kbar, ellxbar, ellzbar):
+def gibbs_build_bwd(x, z, ellx, ellz, Kbar, ellxbar, ellzbar, Kfwd=None):
     ns, B = ellx.shape
     Q = z.numel()
-    check(lib().nmgp_gibbs_build_bwd(_d(x), _d(z), _d(ellx), _d(ellz), _d(Kbar), _d(ellxbar), _d(ellzbar),
+    check(lib().nmgp_gibbs_build_bwd(_d(x), _d(z), _d(ellx), _d(ellz), _d(Kbar), _optd(Kfwd), _d(ellxbar), _d(ellzbar),
                                      c_int(ns), c_int64(B), c_int(Q), _stream()), "nmgp_gibbs_build_bwd")
 
 

@@ -138,7 +138,8 @@ NMGP_API int nmgp_gibbs_build_fwd(const double* x, const double* z, const double
 template <int NU>
 __global__ void __launch_bounds__(256, 4) k_gibbs_bwd(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ ellx,
                             const double* __restrict__ ellz, const double* __restrict__ Kbar,
-                            double* __restrict__ ellxbar, double* __restrict__ ellzbar, long long B, int Q) {
+                            const double* __restrict__ Kfwd, double* __restrict__ ellxbar, double* __restrict__ ellzbar,
+                            long long B, int Q) {
     extern __shared__ double colsum[];  // [Q]
     const int s = blockIdx.y;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(256, 4) k_gibbs_bwd(const double* __restrict__
         if (n >= B) break;
         const double a = ellx[(size_t)s * B + n], xn = x[n], ha = 0.5 / a;
         const double* kb = Kbar + ((size_t)s * B + n) * Q;
+        const double* kf = Kfwd ? Kfwd + ((size_t)s * B + n) * Q : nullptr;   // forward values (no jitter) if kept
         double racc = 0.0;
 #pragma unroll
         for (int u = 0; u < NU; ++u) {
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(256, 4) k_gibbs_bwd(const double* __restrict__
             if (q < Q) {
                 const double b = bq[u], d = xn - zq[u];
                 const double r2 = d * d, rden = 1.0 / fma(a, a, b * b);
-                const double k = sqrt(2.0 * (a * b) * rden) * exp(-r2 * rden);
+                const double k = kf ? kf[q] : sqrt(2.0 * (a * b) * rden) * exp(-r2 * rden);
                 const double g = kb[q] * k;
                 const double common = (2.0 * r2 * rden - 1.0) * rden;
                 racc = fma(g, fma(a, common, ha), racc);
@@ -188,17 +190,17 @@ __global__ void __launch_bounds__(256, 4) k_gibbs_bwd(const double* __restrict__
         if (colsum[q] != 0.0) atomicAdd(&ellzbar[(size_t)s * Q + q], colsum[q]);
 }
 NMGP_API int nmgp_gibbs_build_bwd(const double* x, const double* z, const double* ellx, const double* ellz,
-                                  const double* Kbar, double* ellxbar, double* ellzbar, int ns, long long B, int Q,
-                                  cudaStream_t st) {
+                                  const double* Kbar, const double* Kfwd, double* ellxbar, double* ellzbar, int ns,
+                                  long long B, int Q, cudaStream_t st) {
     NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && Q > 0 && Q <= 128, "nmgp_gibbs_build_bwd");
     if (B == 0 || ns == 0) return 0;
     const int threads = 256, rows_per_block = (threads / 32) * GB_ROWS_PER_WARP;
     dim3 grid((unsigned)((B + rows_per_block - 1) / rows_per_block), ns);
     switch ((Q + 31) / 32) {
-        case 1: k_gibbs_bwd<1><<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, ellxbar, ellzbar, B, Q); break;
-        case 2: k_gibbs_bwd<2><<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, ellxbar, ellzbar, B, Q); break;
-        case 3: k_gibbs_bwd<3><<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, ellxbar, ellzbar, B, Q); break;
-        default: k_gibbs_bwd<4><<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, ellxbar, ellzbar, B, Q); break;
+        case 1: k_gibbs_bwd<1><<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, Kfwd, ellxbar, ellzbar, B, Q); break;
+        case 2: k_gibbs_bwd<2><<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, Kfwd, ellxbar, ellzbar, B, Q); break;
+        case 3: k_gibbs_bwd<3><<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, Kfwd, ellxbar, ellzbar, B, Q); break;
+        default: k_gibbs_bwd<4><<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, Kfwd, ellxbar, ellzbar, B, Q); break;
     }
     return nmgp_launch_status("nmgp_gibbs_build_bwd");
 }

@@ -224,7 +224,7 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
         ops.weighted_gram(PG, PG, I, qgbar, mgbar, MODE_W, SigWbar, muWrows, seg=seg)
         KGbar = ops.solve_rows_bwd(PGbar, cGbar, KG, PG, R_G[sl], AGbar[sl])
         ellxbar = torch.empty_like(ellx)
-        ops.gibbs_build_bwd(x, Z, ellx, ellZ[sl], KGbar, ellxbar, ellZbar[sl])
+        ops.gibbs_build_bwd(x, Z, ellx, ellZ[sl], KGbar, ellxbar, ellZbar[sl], Kfwd=KG)
         ops.ell_rows_bwd(ellxbar, ellx, P_ell, v[sl], z_ell[sl], vbar[sl], Pellbar, sdellbar)
         ops.coef_sample_bwd(lbar, l, zl_, I, mUbar, sdUbar, noise=nz_)
 

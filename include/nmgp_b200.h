@@ -68,9 +68,10 @@ int nmgp_rbf_build_bwd(const double* x, const double* z, const double* hyp, int 
 /* K[s,n,q] = sqrt(2ab/(a^2+b^2)) exp(-(x_n-z_q)^2/(a^2+b^2)), a = ellx[s,n], b = ellz[s,q]   utils.py:97-103 create_Gibbs */
 int nmgp_gibbs_build_fwd(const double* x, const double* z, const double* ellx, const double* ellz, double jitter,
                          double* K, int ns, long long B, int Q, nmgp_stream_t stream);
+/* Kfwd: the forward values K (built with jitter 0) if the caller still holds them, else NULL (they are recomputed) */
 int nmgp_gibbs_build_bwd(const double* x, const double* z, const double* ellx, const double* ellz, const double* Kbar,
-                         double* ellxbar /* = */, double* ellzbar /* += */, int ns, long long B, int Q,
-                         nmgp_stream_t stream);
+                         const double* Kfwd, double* ellxbar /* = */, double* ellzbar /* += */, int ns, long long B,
+                         int Q, nmgp_stream_t stream);
 
 /* P = K (R R^T)^-1, c = rowsum(P o K)                                      utils.py:117-122 (torch.solve of K22 + eps I) */
 int nmgp_solve_rows_fwd(const double* K, const double* R, double* P, double* c, int ns, long long B, int Q,

@@ -128,8 +128,9 @@ def gibbs_build_fwd(x, z, ellx, ellz, jitter=0.0):
     return K
 
 
-def gibbs_build_bwd(x, z, ellx, ellz, Kbar, ellxbar, ellzbar):
-    """ellxbar[ns,B] = ; ellzbar[ns,Q] += (cotangents w.r.t. ell itself, not its log)."""
+def gibbs_build_bwd(x, z, ellx, ellz, Kbar, ellxbar, ellzbar, Kfwd=None):
+    """ellxbar[ns,B] = ; ellzbar[ns,Q] += (cotangents w.r.t. ell itself, not its log).  Kfwd: the forward values
+    (jitter 0) when the caller kept them -- the kernel then skips their recomputation; same result."""
     r2 = (x.view(1, -1, 1) - z.view(1, 1, -1)) ** 2
     a = ellx.unsqueeze(2); b = ellz.unsqueeze(1)
     den = a * a + b * b

@@ -116,10 +116,14 @@ def test_builds(Q, D, B):
     check(KGzz, specs.gibbs_build_fwd(z, z, ellz, ellz, 1e-4), 1e-14, "gibbs zz")
     Kb = torch.randn(ns, B, Q, generator=gen, dtype=torch.float64)
     exb = torch.zeros(ns, B, dtype=torch.float64); ezb = torch.randn(ns, Q, generator=gen, dtype=torch.float64)
+    ezb0 = ezb.clone()
     exd = g(torch.full_like(exb, 7.0)); ezd = g(ezb.clone())
     specs.gibbs_build_bwd(x, z, ellx, ellz, Kb, exb, ezb)
     ops.gibbs_build_bwd(g(x), g(z), g(ellx), g(ellz), g(Kb), exd, ezd)
     check(exd, exb, 1e-12, "gibbs bwd x"); check(ezd, ezb, 1e-11, "gibbs bwd z")
+    exd2 = g(torch.full_like(exb, -3.0)); ezd2 = g(ezb0.clone())          # same with the forward values handed in
+    ops.gibbs_build_bwd(g(x), g(z), g(ellx), g(ellz), g(Kb), exd2, ezd2, Kfwd=KG)
+    check(exd2, exb, 1e-12, "gibbs bwd x (kept K)"); check(ezd2, ezb, 1e-11, "gibbs bwd z (kept K)")
 
 
 @pytest.mark.parametrize("Q,D,B", CASES)
