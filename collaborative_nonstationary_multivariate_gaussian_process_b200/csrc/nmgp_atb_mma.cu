@@ -22,11 +22,11 @@ __device__ __forceinline__ void cpa_wait0() { asm volatile("cp.async.wait_group 
 // C[s] += sign * sum_n A[s,n,:]^T B[s,n,:]   (Q x Q, rows n of one chunk per CTA), DMMA.
 #define ATB_TROWS 32
 #define ATB_CHUNK 2048
-#define ATB_THREADS 128
+#define ATB_THREADS 256   // 8 warps: warp & 3 = strips of C it owns, warp >> 2 = which half of a tile's rows it sums
 __host__ __device__ constexpr int atb_pad(int n) { return ((n + 3) / 8) * 8 + 4; }
 
 template <int NB>
-__global__ void __launch_bounds__(ATB_THREADS)
+__global__ void __launch_bounds__(ATB_THREADS, 3)
 k_atb_mma(const double* __restrict__ A, const double* __restrict__ Bm, double* __restrict__ C, double sign,
           long long B, int Q, long long chunk, const double* __restrict__ cbar, double* __restrict__ Kbar) {
     constexpr int LDP = atb_pad(8 * NB);
@@ -34,11 +34,12 @@ k_atb_mma(const double* __restrict__ A, const double* __restrict__ Bm, double* _
     double* At = sm;                                   // [2][ATB_TROWS][LDP]
     double* Bt = At + 2 * ATB_TROWS * LDP;             // [2][ATB_TROWS][LDP]
     const int s = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int wr = w & 3, half = w >> 2;
     const long long rbeg = (long long)blockIdx.x * chunk, rend = min(B, rbeg + chunk);
     if (rbeg >= rend) return;
     for (int e = tid; e < 4 * ATB_TROWS * LDP; e += ATB_THREADS) sm[e] = 0.0;
     __syncthreads();
-    const int a1 = w, a2 = w + 4;                      // strips of 8 rows of C handled by this warp
+    const int a1 = wr, a2 = wr + 4;                    // strips of 8 rows of C handled by this warp
     const bool on1 = a1 < NB, on2 = a2 < NB;
     double acc[2][NB][2];
 #pragma unroll
@@ -94,8 +95,8 @@ k_atb_mma(const double* __restrict__ A, const double* __restrict__ Bm, double* _
         }
         if (!on1) continue;
 #pragma unroll
-        for (int kk = 0; kk < ATB_TROWS / 4; ++kk) {
-            const int n = 4 * kk + t;
+        for (int kq = 0; kq < ATB_TROWS / 8; ++kq) {
+            const int n = 4 * (kq + half * (ATB_TROWS / 8)) + t;
             const double fa1 = Ad[n * LDP + 8 * a1 + g];
             const double fa2 = on2 ? Ad[n * LDP + 8 * a2 + g] : 0.0;
 #pragma unroll
