@@ -485,32 +485,60 @@ NMGP_API int nmgp_potrf_big(double* A, long long T, long long lda, double* hld, 
 // ------------------------------------------------------------------------------------------------------------
 // x <- (L L^T)^-1 x for one vector: blocked forward then backward substitution (PB-wide diagonal solves in one CTA,
 // the remaining update as a memory-bound matrix-vector product).
+// One CTA (4 warps): 32-wide chunks are solved by warp 0 with the running right-hand side in registers (one row per
+// lane, solved entries broadcast by shuffle: no block-wide barrier per pivot), the other rows of the block are then
+// updated by all threads.  Indices >= nb are padded with an identity so every chunk is full.
 __global__ void __launch_bounds__(PB)
 k_trsv_diag(const double* __restrict__ L, long long lda, double* __restrict__ x, int nb, int transposed) {
     extern __shared__ double sm[];
-    double* Ls = sm;            // [nb][nb|1]
-    double* xs = Ls + nb * (nb | 1);
-    const int ld = nb | 1, tid = threadIdx.x;
-    for (int e = tid; e < nb * nb; e += blockDim.x) {
-        int a = e / nb, b = e - a * nb;
-        Ls[a * ld + b] = L[(long long)a * lda + b];
+    constexpr int LD = PB + 1;
+    double* Ls = sm;            // [PB][PB+1]
+    double* xs = Ls + PB * LD;  // [PB]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int e = tid; e < PB * PB; e += blockDim.x) {
+        const int a = e / PB, b = e - a * PB;
+        Ls[a * LD + b] = (a < nb && b < nb) ? L[(long long)a * lda + b] : (a == b ? 1.0 : 0.0);
     }
-    if (tid < nb) xs[tid] = x[tid];
+    xs[tid] = tid < nb ? x[tid] : 0.0;
     __syncthreads();
-    if (!transposed) {
-        for (int a = 0; a < nb; ++a) {
-            if (tid == a) xs[a] /= Ls[a * ld + a];
-            __syncthreads();
-            if (tid > a && tid < nb) xs[tid] = fma(-Ls[tid * ld + a], xs[a], xs[tid]);
-            __syncthreads();
+    const int nchunk = (nb + 31) / 32;
+    for (int ci = 0; ci < nchunk; ++ci) {
+        const int c0 = 32 * (transposed ? nchunk - 1 - ci : ci);
+        if (w == 0) {
+            double r = xs[c0 + lane];
+            const double rinv = 1.0 / Ls[(c0 + lane) * LD + c0 + lane];
+            if (!transposed) {
+#pragma unroll 8
+                for (int c = 0; c < 32; ++c) {
+                    const double xv = __shfl_sync(0xffffffffu, r * rinv, c);
+                    if (lane == c) r = xv;
+                    else if (lane > c) r = fma(-Ls[(c0 + lane) * LD + c0 + c], xv, r);
+                }
+            } else {
+#pragma unroll 8
+                for (int c = 31; c >= 0; --c) {
+                    const double xv = __shfl_sync(0xffffffffu, r * rinv, c);
+                    if (lane == c) r = xv;
+                    else if (lane < c) r = fma(-Ls[(c0 + c) * LD + c0 + lane], xv, r);
+                }
+            }
+            xs[c0 + lane] = r;
         }
-    } else {
-        for (int a = nb - 1; a >= 0; --a) {
-            if (tid == a) xs[a] /= Ls[a * ld + a];
-            __syncthreads();
-            if (tid < a) xs[tid] = fma(-Ls[a * ld + tid], xs[a], xs[tid]);
-            __syncthreads();
+        __syncthreads();
+        // rows of the block still to be solved: below the chunk (forward) / above it (transposed)
+        const bool mine = transposed ? (tid < c0) : (tid >= c0 + 32);
+        if (mine) {
+            double acc = xs[tid];
+            if (!transposed) {
+#pragma unroll 8
+                for (int c = 0; c < 32; ++c) acc = fma(-Ls[tid * LD + c0 + c], xs[c0 + c], acc);
+            } else {
+#pragma unroll 8
+                for (int c = 0; c < 32; ++c) acc = fma(-Ls[(c0 + c) * LD + tid], xs[c0 + c], acc);
+            }
+            xs[tid] = acc;
         }
+        __syncthreads();
     }
     if (tid < nb) x[tid] = xs[tid];
 }
@@ -537,18 +565,18 @@ __global__ void k_gemv_t_sub(const double* __restrict__ Mx, long long lda, const
 }
 NMGP_API int nmgp_potrs_vec(const double* L, long long T, long long lda, double* x, cudaStream_t st) {
     NMGP_REQUIRE(T > 0 && lda >= T, "nmgp_potrs_vec");
-    const size_t smem = sizeof(double) * (PB * (PB | 1) + PB);
+    const size_t smem = sizeof(double) * (PB * (PB + 1) + PB);
     if (int r = nmgp_opt_in_smem(k_trsv_diag, smem, "nmgp_potrs_vec")) return r;
     for (long long k = 0; k < T; k += PB) {                       // L y = b
         const int nb = (int)min((long long)PB, T - k);
-        k_trsv_diag<<<1, PB, sizeof(double) * (nb * (nb | 1) + nb), st>>>(L + k * lda + k, lda, x + k, nb, 0);
+        k_trsv_diag<<<1, PB, smem, st>>>(L + k * lda + k, lda, x + k, nb, 0);
         const long long rest = T - k - nb;
         if (rest > 0)
             k_gemv_sub<<<(unsigned)((rest + 7) / 8), 256, 0, st>>>(L + (k + nb) * lda + k, lda, x + k, x + k + nb, rest, nb);
     }
     for (long long k = ((T - 1) / PB) * PB; k >= 0; k -= PB) {    // L^T x = y
         const int nb = (int)min((long long)PB, T - k);
-        k_trsv_diag<<<1, PB, sizeof(double) * (nb * (nb | 1) + nb), st>>>(L + k * lda + k, lda, x + k, nb, 1);
+        k_trsv_diag<<<1, PB, smem, st>>>(L + k * lda + k, lda, x + k, nb, 1);
         if (k > 0)   // x[0:k] -= L[k:k+nb, 0:k]^T x[k:k+nb]
             k_gemv_t_sub<<<(unsigned)((k + 127) / 128), 128, 0, st>>>(L + k * lda, lda, x + k, x, nb, k);
     }
