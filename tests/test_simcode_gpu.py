@@ -110,7 +110,7 @@ def test_potrf_big_raises_on_non_pd():
         ops.potrf_big(d(A))
 
 
-@pytest.mark.parametrize("n", [2, 3, 16, 64])
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 16, 64, 127, 128])
 def test_eigh_small(n):
     gen = torch.Generator().manual_seed(n)
     L = torch.tril(torch.randn(n, n, generator=gen, dtype=torch.float64)); A = L @ L.t()
