@@ -177,7 +177,10 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
                     const int j = 8 * jb + 2 * t + e;
                     if (j < D) {
                         const size_t o = (rbase + rloc[mb]) * D + j;
-                        if (j <= myI[mb]) Fp[mb] = fma(l[o], acc[mb][e], Fp[mb]);
+                        if (j <= myI[mb]) {
+                            Fp[mb] = fma(l[o], acc[mb][e], Fp[mb]);
+                            mgbar[o] = acc[mb][e];        // m[n,j] parked in the slot its cotangent overwrites at latent j
+                        }
                     }
                 }
             }
@@ -226,19 +229,24 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
     double pen[2] = {0.0, 0.0}, gsum[2] = {0.0, 0.0};
 
     if (tid == 0 && jmax >= 0) stage(0, 0);
-    double lnext[2];
+    double lnext[2], mnext[2];
 #pragma unroll
-    for (int mb = 0; mb < 2; ++mb) lnext[mb] = (rloc[mb] < nrows) ? __ldg(&l[(rbase + rloc[mb]) * D]) : 0.0;
+    for (int mb = 0; mb < 2; ++mb) {
+        lnext[mb] = (rloc[mb] < nrows) ? __ldg(&l[(rbase + rloc[mb]) * D]) : 0.0;
+        mnext[mb] = (rloc[mb] < nrows && 0 <= myI[mb]) ? __ldcg(&mgbar[(rbase + rloc[mb]) * D]) : 0.0;
+    }
     for (int j = 0; j <= jmax; ++j) {
         const int buf = j & 1;
         __syncthreads();                                  // everyone is done with the other buffer (latent j - 1)
         if (tid == 0 && j + 1 <= jmax) stage(j + 1, buf ^ 1);
         if (warpmaxI < j) continue;                        // warp-uniform: none of this warp's rows uses latent j
-        const double lcur[2] = {lnext[0], lnext[1]};
+        const double lcur[2] = {lnext[0], lnext[1]}, mcur[2] = {mnext[0], mnext[1]};
         if (j + 1 < D) {
 #pragma unroll
-            for (int mb = 0; mb < 2; ++mb)
+            for (int mb = 0; mb < 2; ++mb) {
                 lnext[mb] = (rloc[mb] < nrows) ? __ldg(&l[(rbase + rloc[mb]) * D + j + 1]) : 0.0;
+                mnext[mb] = (rloc[mb] < nrows && j + 1 <= myI[mb]) ? __ldcg(&mgbar[(rbase + rloc[mb]) * D + j + 1]) : 0.0;
+            }
         }
         mbar_wait(&mbar[buf], (unsigned)((j >> 1) & 1));  // record j landed
         const double* Sd = Ss + (size_t)buf * REC;
@@ -260,22 +268,17 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {
             const int rl = rloc[mb];
-            double qp = 0.0, qp1 = 0.0, mp = 0.0, mp1 = 0.0;
+            double qp = 0.0, qp1 = 0.0;
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) {
                 const double2 pv = *reinterpret_cast<const double2*>(&Ps[rl * LDP + 8 * nb + 2 * t]);
-                const double2 mv = *reinterpret_cast<const double2*>(&mu_b[8 * nb + 2 * t]);
                 qp = fma(V[mb][nb][0], pv.x, qp);
                 qp1 = fma(V[mb][nb][1], pv.y, qp1);
-                mp = fma(mv.x, pv.x, mp);
-                mp1 = fma(mv.y, pv.y, mp1);
             }
             qp += qp1;
-            mp += mp1;
             qp += __shfl_xor_sync(0xffffffffu, qp, 1);
             qp += __shfl_xor_sync(0xffffffffu, qp, 2);
-            mp += __shfl_xor_sync(0xffffffffu, mp, 1);
-            mp += __shfl_xor_sync(0xffffffffu, mp, 2);
+            const double mp = mcur[mb];                                // p_n . mu_W[j], computed by phase 1
             const bool live = (rl < nrows) && (j <= myI[mb]);
             const double lj = live ? lcur[mb] : 0.0;
             const double gq = scale * (0.5 / s2e) * lj * lj;          // cotangent of s2_g[n,j]
@@ -292,9 +295,26 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
             const double g2 = 2.0 * gq;
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) {
-                pacc[mb][nb][0] = fma(g2, V[mb][nb][0], fma(gm, mu_b[8 * nb + 2 * t], pacc[mb][nb][0]));
-                pacc[mb][nb][1] = fma(g2, V[mb][nb][1], fma(gm, mu_b[8 * nb + 2 * t + 1], pacc[mb][nb][1]));
+                pacc[mb][nb][0] = fma(g2, V[mb][nb][0], pacc[mb][nb][0]);
+                pacc[mb][nb][1] = fma(g2, V[mb][nb][1], pacc[mb][nb][1]);
             }
+        }
+    }
+    // Pbar += mbar mu_W (the mean-path part of the adjoint) as one DMMA product over the latents: A = mbar rows of this
+    // warp (just written to mgbar; zeros beyond I[n]), B = mu_W.  Replaces 28 FMAs per thread and latent in the loop.
+    __syncthreads();
+    for (int ks = 0; 4 * ks < D; ++ks) {
+        const int jj = 4 * ks + t;
+        double av[2];
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+            av[mb] = (rloc[mb] < nrows && jj < D) ? __ldcg(&mgbar[(rbase + rloc[mb]) * D + jj]) : 0.0;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+            const int c = 8 * nb + g;
+            const double b = (jj < D && c < Q) ? __ldg(&muW[(size_t)jj * Q + c]) : 0.0;
+            dmma884(pacc[0][nb][0], pacc[0][nb][1], av[0], b);
+            dmma884(pacc[1][nb][0], pacc[1][nb][1], av[1], b);
         }
     }
 
