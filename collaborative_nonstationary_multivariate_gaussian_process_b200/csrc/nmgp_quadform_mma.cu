@@ -250,7 +250,6 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
         }
         mbar_wait(&mbar[buf], (unsigned)((j >> 1) & 1));  // record j landed
         const double* Sd = Ss + (size_t)buf * REC;
-        const double* mu_b = Sd + KP * LDS;
         double V[2][NB][2];
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb)
