@@ -117,7 +117,7 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
                double* __restrict__ mgbar, double* __restrict__ qgbar, double* __restrict__ cGbar,
                double* __restrict__ PGbar, long long B, int Q, int D) {
     using SH = LFShape<NB, KS>;
-    constexpr int LDP = SH::LDP, LDS = SH::LDS, KP = SH::KP, REC = SH::REC;
+    constexpr int LDP = SH::LDP, LDS = SH::LDS, REC = SH::REC;
     extern __shared__ __align__(16) double sm[];
     double* Ps = sm;                                   // [LFK_ROWS][LDP]
     double* Ss = Ps + (size_t)LFK_ROWS * LDP;           // [2][REC]: double-buffered records of the latent j
