@@ -57,30 +57,40 @@ def lowtriangle2vec(L, N=None):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-class KroneckerPosterior:
-    """Everything of point_predmap that does not depend on x_star (prediction.py:350-381)."""
+class _ConditionalGP:
+    """GP conditional of a log-hyper-function (log-ell or log-sigma) at a new input (prediction.py:52-57, 353-358):
+    Sigma = RBF_cov(x) (+1e-6 I) is factorised once; it depends only on (x, alpha, beta)."""
 
-    def __init__(self, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, mu_tilde_l, alpha_tilde_l, beta_tilde_l,
-                 mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma):
+    def __init__(self, x, mu, alpha, beta):
+        self.x, self.mu, self.alpha, self.beta = x, float(mu), float(alpha), float(beta)
+        self.Lc, _ = ops.potrf_big(kernels.RBF_cov(x, alpha=self.alpha, beta=self.beta))
+
+    def weights(self, tilde):
+        """Sigma^-1 (tilde - mu): enough for the conditional mean."""
+        return ops.potrs_vec(self.Lc, (tilde - self.mu).contiguous())
+
+    def projection(self, xs):
+        """(k, Sigma^-1 k, k** - k . Sigma^-1 k) for the single input xs [1,1]."""
+        k = kernels.RBF_cov(self.x, xs, alpha=self.alpha, beta=self.beta).view(-1).contiguous()
+        proj = ops.potrs_vec(self.Lc, k)
+        kss = kernels.RBF_cov(xs, alpha=self.alpha, beta=self.beta).view(())
+        return k, proj, kss - ops.dot(proj, k).reshape(())
+
+
+class _KronState:
+    """sigma2 I + B_f (x) K_x factorised through the eigen-blocks of B_f for ONE parameter sample
+    (prediction.py:60-77 / 360-381), plus alpha_k = A_k^-1 (V^T Y^T)_k."""
+
+    def __init__(self, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x):
         N, M = Y.shape
-        self.N, self.M = N, M
         dev = Y.device
-        self.x = x.contiguous().view(-1, 1)
-        f = lambda v: float(v)
-        self.hyp_l = (f(mu_tilde_l), f(alpha_tilde_l), f(beta_tilde_l))
-        self.hyp_s = (f(mu_tilde_sigma), f(alpha_tilde_sigma), f(beta_tilde_sigma))
-        # GP conditionals of log-ell and log-sigma: mu + k^T Sigma^-1 (tilde - mu); Sigma^-1 (tilde - mu) is hoisted
-        self.beta = []
-        for tilde, (mu, alpha, beta) in ((tilde_l, self.hyp_l), (tilde_sigma, self.hyp_s)):
-            Sigma = kernels.RBF_cov(self.x, alpha=alpha, beta=beta)
-            Lc, _ = ops.potrf_big(Sigma)
-            self.beta.append(ops.potrs_vec(Lc, (tilde - mu).contiguous()))
+        self.x = x
         self.sigma2_err = torch.exp(tilde_sigma2_err)
         self.l = torch.exp(tilde_l).contiguous()
         self.sigma = torch.exp(tilde_sigma).contiguous()
         L = vec2lowtriangle(uLvec2Lvec(uL_vec, M), M)
         self.B_f = ops.gemm_nt(L.contiguous(), L.contiguous())
-        K_x = kernels.Nonstationary_RBF_cov(self.x, sigma1=self.sigma, ell1=self.l)
+        K_x = kernels.Nonstationary_RBF_cov(x, sigma1=self.sigma, ell1=self.l)
         y = Y.t().contiguous().view(-1)
         self.blocks = []          # (lambda_k, chol(sigma2 I + lambda_k K_x), alpha_k)
         Rt = None
@@ -91,14 +101,8 @@ class KroneckerPosterior:
             self.blocks.append((lam_k, Lk, ops.potrs_vec(Lk, Rt[k].contiguous())))
         self.lam = torch.tensor([b[0] for b in self.blocks], dtype=torch.float64, device=dev)
 
-    def point(self, x_star):
-        """prediction.py:353-408 for one test input: [3, M] = (mean - 1.96 sd, mean, mean + 1.96 sd)."""
-        xs = x_star.reshape(1, 1).to(self.x.dtype)
-        est = []
-        for b, (mu, alpha, beta) in zip(self.beta, (self.hyp_l, self.hyp_s)):
-            k = kernels.RBF_cov(self.x, xs, alpha=alpha, beta=beta).view(-1)
-            est.append(mu + ops.dot(k.contiguous(), b).reshape(()))
-        l_star, sigma_star = torch.exp(est[0]).view(1), torch.exp(est[1]).view(1)
+    def predict(self, xs, l_star, sigma_star):
+        """Predictive mean and variance of y at xs given (ell, sigma) there (prediction.py:78-93 / 382-402)."""
         k_x = kernels.Nonstationary_RBF_cov(X1=self.x, sigma1=self.sigma, ell1=self.l, X2=xs, sigma2=sigma_star,
                                             ell2=l_star).view(-1).contiguous()
         k_ss = kernels.Nonstationary_RBF_cov(X1=xs, sigma1=sigma_star, ell1=l_star).view(())      # incl. the 1e-6 jitter
@@ -110,6 +114,28 @@ class KroneckerPosterior:
         sigma2_f = torch.diagonal(self.B_f) * k_ss - (c * c) @ dots[:, 1]
         sigma2_y = sigma2_f + self.sigma2_err
         sigma2_y = torch.where(sigma2_y <= 0, torch.full_like(sigma2_y, settings.precision), sigma2_y)
+        return mu_f, sigma2_y
+
+
+class KroneckerPosterior:
+    """Everything of point_predmap that does not depend on x_star (prediction.py:350-381)."""
+
+    def __init__(self, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, mu_tilde_l, alpha_tilde_l, beta_tilde_l,
+                 mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma):
+        self.x = x.contiguous().view(-1, 1)
+        self.gp_l = _ConditionalGP(self.x, mu_tilde_l, alpha_tilde_l, beta_tilde_l)
+        self.gp_s = _ConditionalGP(self.x, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma)
+        self.w_l, self.w_s = self.gp_l.weights(tilde_l), self.gp_s.weights(tilde_sigma)
+        self.state = _KronState(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, self.x)
+
+    def point(self, x_star):
+        """prediction.py:353-408 for one test input: [3, M] = (mean - 1.96 sd, mean, mean + 1.96 sd)."""
+        xs = x_star.reshape(1, 1).to(self.x.dtype)
+        est = []
+        for gp, wts in ((self.gp_l, self.w_l), (self.gp_s, self.w_s)):
+            k = kernels.RBF_cov(self.x, xs, alpha=gp.alpha, beta=gp.beta).view(-1).contiguous()
+            est.append(gp.mu + ops.dot(k, wts).reshape(()))
+        mu_f, sigma2_y = self.state.predict(xs, torch.exp(est[0]).view(1), torch.exp(est[1]).view(1))
         sd = torch.sqrt(sigma2_y)
         return torch.stack([mu_f - 1.96 * sd, mu_f, mu_f + 1.96 * sd])
 
@@ -137,4 +163,69 @@ def test_predmap(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, x_test, m
                              beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma)
 
 
-test_predmap.__test__ = False      # not a pytest test
+
+
+
+# ---- sampling predictors (prediction.py:34-184) -----------------------------------------------------------------------
+def _draw(loc, scale):
+    """torch.distributions.Normal(loc, scale).sample() of the reference: the same torch.normal call on the CPU generator,
+    so a seeded run consumes the random stream exactly as the reference does."""
+    return torch.normal(loc.detach().cpu(), scale.detach().cpu()).to(loc.device)
+
+
+def _predsample(hist, Y, x, points, hyp_l, hyp_s, N_sample):
+    tl_h, ts_h, uL_h, s2_h = (h[-N_sample:] for h in hist)
+    xcol = x.contiguous().view(-1, 1)
+    gp_l, gp_s = _ConditionalGP(xcol, *hyp_l), _ConditionalGP(xcol, *hyp_s)
+    # one factorisation per parameter sample, shared by all test inputs (the reference redoes it per input)
+    states = [_KronState(tl, ts, uL, s2, Y, xcol) for tl, ts, uL, s2 in zip(tl_h, ts_h, uL_h, s2_h)]
+    floor = torch.tensor(settings.precision, dtype=torch.float64, device=Y.device)
+    out = []
+    for x_star in points:                                   # draw order of the reference: inputs outer, samples inner
+        xs = x_star.reshape(1, 1).to(xcol.dtype)
+        _, proj_l, var_l = gp_l.projection(xs)
+        _, proj_s, var_s = gp_s.projection(xs)
+        var_l = torch.where(var_l < 0, floor, var_l)
+        var_s = torch.where(var_s < 0, floor, var_s)
+        rows = []
+        for st, tl, ts in zip(states, tl_h, ts_h):
+            mu_l = gp_l.mu + ops.dot(proj_l, (tl - gp_l.mu).contiguous()).reshape(())
+            l_star = torch.exp(_draw(mu_l, torch.sqrt(var_l))).view(1)
+            mu_s = gp_s.mu + ops.dot(proj_s, (ts - gp_s.mu).contiguous()).reshape(())
+            sigma_star = torch.exp(_draw(mu_s, torch.sqrt(var_s))).view(1)
+            mu_f, sigma2_y = st.predict(xs, l_star, sigma_star)
+            rows.append(_draw(mu_f, torch.sqrt(sigma2_y)))
+        out.append(torch.stack(rows))
+    return out
+
+
+def point_predsample(tilde_l_hist, tilde_sigma_hist, uL_vec_hist, tilde_sigma2_err_hist, Y, x, x_star, mu_tilde_l,
+                     alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, N_sample,
+                     *args, **kwargs):
+    """prediction.py:34-131: one posterior draw of y(x_star) per retained parameter sample, [N_sample, M]."""
+    return _predsample((tilde_l_hist, tilde_sigma_hist, uL_vec_hist, tilde_sigma2_err_hist), Y, x, [x_star],
+                       (mu_tilde_l, alpha_tilde_l, beta_tilde_l), (mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma),
+                       N_sample)[0]
+
+
+def pointwise_predsample(tilde_l_hist, tilde_sigma_hist, uL_vec_hist, tilde_sigma2_err_hist, Y, x, grids, mu_tilde_l,
+                         alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, N_sample,
+                         *args, **kwargs):
+    """prediction.py:133-156: numpy array [N_grid, N_sample, M] (the reference returns numpy here)."""
+    res = _predsample((tilde_l_hist, tilde_sigma_hist, uL_vec_hist, tilde_sigma2_err_hist), Y, x, list(grids),
+                      (mu_tilde_l, alpha_tilde_l, beta_tilde_l), (mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma),
+                      N_sample)
+    return torch.stack(res).cpu().numpy()
+
+
+def test_predsample(tilde_l_hist, tilde_sigma_hist, uL_vec_hist, tilde_sigma2_err_hist, Y, x, x_test, mu_tilde_l,
+                    alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, N_sample,
+                    *args, **kwargs):
+    """prediction.py:158-184: the same loop over held-out inputs."""
+    return pointwise_predsample(tilde_l_hist, tilde_sigma_hist, uL_vec_hist, tilde_sigma2_err_hist, Y, x, x_test,
+                                mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma,
+                                beta_tilde_sigma, N_sample)
+
+
+test_predmap.__test__ = False      # not pytest tests
+test_predsample.__test__ = False

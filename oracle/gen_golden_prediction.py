@@ -34,7 +34,21 @@ def main():
     one = prediction.point_predmap(tilde_l, tilde_sigma, uL_vec, tilde_s2, Y, x, grids[2], *args)
     allg = prediction.pointwise_predmap(tilde_l, tilde_sigma, uL_vec, tilde_s2, Y, x, grids, *args)
     tst = prediction.test_predmap(tilde_l, tilde_sigma, uL_vec, tilde_s2, Y, x, x[::9] + 0.004, *args)
+    # sampling predictors: a short parameter history (N_hist = 4, the last N_sample = 3 are used), seeded global RNG
+    H = 4
+    tl_h = torch.stack([tilde_l + 0.03 * torch.randn(N).double() for _ in range(H)])
+    ts_h = torch.stack([tilde_sigma + 0.03 * torch.randn(N).double() for _ in range(H)])
+    uL_h = torch.stack([uL_vec + 0.05 * torch.randn(uL_vec.numel()).double() for _ in range(H)])
+    s2_h = tilde_s2 + 0.05 * torch.randn(H).double()
+    import contextlib, io
+    torch.manual_seed(123)
+    ps_one = prediction.point_predsample(tl_h, ts_h, uL_h, s2_h, Y, x, grids[4], *args, 3)
+    torch.manual_seed(321)
+    with contextlib.redirect_stdout(io.StringIO()):          # the reference prints every grid point
+        ps_grid = prediction.pointwise_predsample(tl_h, ts_h, uL_h, s2_h, Y, x, grids[:3], *args, 3)
     np.savez_compressed(os.path.join(OUT, "sim_prediction.npz"), x=x.numpy(), tilde_l=tilde_l.numpy(),
+                        tl_hist=tl_h.numpy(), ts_hist=ts_h.numpy(), uL_hist=uL_h.numpy(), s2_hist=s2_h.numpy(),
+                        predsample_point=ps_one.numpy(), predsample_grid=np.asarray(ps_grid),
                         tilde_sigma=tilde_sigma.numpy(), uL_vec=uL_vec.numpy(), tilde_s2=float(tilde_s2), Y=Y.numpy(),
                         grids=grids.numpy(), x_test=(x[::9] + 0.004).numpy(),
                         **{k: float(v) for k, v in hyp.items()}, point=one.numpy(), pointwise=allg.numpy(),

@@ -44,4 +44,16 @@ def run_all(dev):
     half = (allg[:, 2] - allg[:, 0]) / 2
     assert torch.allclose(allg[:, 1], (allg[:, 2] + allg[:, 0]) / 2, rtol=0, atol=1e-12)
     assert bool((half >= 1.96 * np.sqrt(np.exp(float(g["tilde_s2"]))) * (1 - 1e-9)).all())
-    return {"point": _rel(one.cpu().numpy(), g["point"]), "pointwise": _rel(allg.cpu().numpy(), g["pointwise"])}
+    # sampling predictors: the global CPU generator is consumed exactly as by the reference (same seeds as the generator
+    # script), so the draws themselves are reproduced
+    hist = (d("tl_hist"), d("ts_hist"), d("uL_hist"), d("s2_hist"))
+    torch.manual_seed(123)
+    ps = prediction.point_predsample(*hist, d("Y"), d("x"), d("grids")[4], *hyp, 3)
+    assert ps.shape == g["predsample_point"].shape
+    assert _rel(ps.cpu().numpy(), g["predsample_point"]) < RTOL, _rel(ps.cpu().numpy(), g["predsample_point"])
+    torch.manual_seed(321)
+    pg = prediction.pointwise_predsample(*hist, d("Y"), d("x"), d("grids")[:3], *hyp, 3)
+    assert isinstance(pg, np.ndarray) and pg.shape == g["predsample_grid"].shape
+    assert _rel(pg, g["predsample_grid"]) < RTOL, _rel(pg, g["predsample_grid"])
+    return {"point": _rel(one.cpu().numpy(), g["point"]), "pointwise": _rel(allg.cpu().numpy(), g["pointwise"]),
+            "predsample": _rel(ps.cpu().numpy(), g["predsample_point"]), "predsample_grid": _rel(pg, g["predsample_grid"])}
