@@ -101,11 +101,16 @@ class _KronState:
             self.blocks.append((lam_k, Lk, ops.potrs_vec(Lk, Rt[k].contiguous())))
         self.lam = torch.tensor([b[0] for b in self.blocks], dtype=torch.float64, device=dev)
 
-    def predict(self, xs, l_star, sigma_star):
-        """Predictive mean and variance of y at xs given (ell, sigma) there (prediction.py:78-93 / 382-402)."""
+    def predict(self, xs, l_star, sigma_star, self_jitter=True):
+        """Predictive mean and variance of y at xs given (ell, sigma) there (prediction.py:78-93 / 382-402).
+        self_jitter=False: prior variance sigma_star^2 B_f[m,m] without the 1e-6 of the self-covariance, as
+        point_predmap_sampling writes it (prediction.py:262)."""
         k_x = kernels.Nonstationary_RBF_cov(X1=self.x, sigma1=self.sigma, ell1=self.l, X2=xs, sigma2=sigma_star,
                                             ell2=l_star).view(-1).contiguous()
-        k_ss = kernels.Nonstationary_RBF_cov(X1=xs, sigma1=sigma_star, ell1=l_star).view(())      # incl. the 1e-6 jitter
+        if self_jitter:
+            k_ss = kernels.Nonstationary_RBF_cov(X1=xs, sigma1=sigma_star, ell1=l_star).view(())  # incl. the 1e-6 jitter
+        else:
+            k_ss = (sigma_star * sigma_star).view(())
         dots = torch.stack([torch.stack((ops.dot(k_x, a_k).reshape(()),
                                          ops.dot(k_x, ops.potrs_vec(Lk, k_x)).reshape(())))
                             for _, Lk, a_k in self.blocks])                                        # [D, 2]
@@ -227,5 +232,60 @@ def test_predsample(tilde_l_hist, tilde_sigma_hist, uL_vec_hist, tilde_sigma2_er
                                 beta_tilde_sigma, N_sample)
 
 
+def _predmap_sampling(n_sample, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, points, hyp_l, hyp_s):
+    xcol = x.contiguous().view(-1, 1)
+    gp_l, gp_s = _ConditionalGP(xcol, *hyp_l), _ConditionalGP(xcol, *hyp_s)
+    state = _KronState(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, xcol)
+    floor = torch.tensor(settings.precision, dtype=torch.float64, device=Y.device)
+    dl, ds = (tilde_l - gp_l.mu).contiguous(), (tilde_sigma - gp_s.mu).contiguous()
+    out = []
+    for x_star in points:
+        xs = x_star.reshape(1, 1).to(xcol.dtype)
+        _, proj_l, var_l = gp_l.projection(xs)
+        _, proj_s, var_s = gp_s.projection(xs)
+        var_l = torch.where(var_l < 0, floor, var_l)
+        var_s = torch.where(var_s < 0, floor, var_s)
+        mu_l = gp_l.mu + ops.dot(proj_l, dl).reshape(())
+        mu_s = gp_s.mu + ops.dot(proj_s, ds).reshape(())
+        draws = []
+        for _ in range(n_sample):                           # draw order of the reference: ell*, sigma*, y per sample
+            l_star = torch.exp(_draw(mu_l, torch.sqrt(var_l))).view(1)
+            sigma_star = torch.exp(_draw(mu_s, torch.sqrt(var_s))).view(1)
+            mu_f, sigma2_y = state.predict(xs, l_star, sigma_star, self_jitter=False)
+            draws.append(_draw(mu_f, torch.sqrt(sigma2_y)))
+        ys = torch.stack(draws).cpu().numpy()
+        out.append((np.percentile(ys, q=[2.5, 97.5], axis=0), np.mean(ys, axis=0), np.std(ys, axis=0)))
+    return out
+
+
+def point_predmap_sampling(n_sample, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, x_star, mu_tilde_l,
+                           alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma,
+                           *args, **kwargs):
+    """prediction.py:189-277: (2.5 % / 97.5 % quantiles [2, M], mean [M], std [M]) of n_sample predictive draws."""
+    return _predmap_sampling(n_sample, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, [x_star],
+                             (mu_tilde_l, alpha_tilde_l, beta_tilde_l),
+                             (mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma))[0]
+
+
+def pointwise_predmap_sampling(n_sample, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, grids, mu_tilde_l,
+                               alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma,
+                               *args, **kwargs):
+    """prediction.py:279-306: stacked over the grid: ([G, 2, M], [G, M], [G, M])."""
+    res = _predmap_sampling(n_sample, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, list(grids),
+                            (mu_tilde_l, alpha_tilde_l, beta_tilde_l),
+                            (mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma))
+    return (np.stack([r[0] for r in res]), np.stack([r[1] for r in res]), np.stack([r[2] for r in res]))
+
+
+def test_predmap_sampling(n_sample, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, x_test, mu_tilde_l,
+                          alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma,
+                          *args, **kwargs):
+    """prediction.py:308-335."""
+    return pointwise_predmap_sampling(n_sample, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, x_test,
+                                      mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma,
+                                      beta_tilde_sigma)
+
+
 test_predmap.__test__ = False      # not pytest tests
+test_predmap_sampling.__test__ = False
 test_predsample.__test__ = False

@@ -46,7 +46,11 @@ def main():
     torch.manual_seed(321)
     with contextlib.redirect_stdout(io.StringIO()):          # the reference prints every grid point
         ps_grid = prediction.pointwise_predsample(tl_h, ts_h, uL_h, s2_h, Y, x, grids[:3], *args, 3)
+    torch.manual_seed(77)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mq, mm, ms = prediction.pointwise_predmap_sampling(6, tilde_l, tilde_sigma, uL_vec, tilde_s2, Y, x, grids[1:3], *args)
     np.savez_compressed(os.path.join(OUT, "sim_prediction.npz"), x=x.numpy(), tilde_l=tilde_l.numpy(),
+                        mapsamp_q=mq, mapsamp_mean=mm, mapsamp_std=ms,
                         tl_hist=tl_h.numpy(), ts_hist=ts_h.numpy(), uL_hist=uL_h.numpy(), s2_hist=s2_h.numpy(),
                         predsample_point=ps_one.numpy(), predsample_grid=np.asarray(ps_grid),
                         tilde_sigma=tilde_sigma.numpy(), uL_vec=uL_vec.numpy(), tilde_s2=float(tilde_s2), Y=Y.numpy(),

@@ -55,5 +55,11 @@ def run_all(dev):
     pg = prediction.pointwise_predsample(*hist, d("Y"), d("x"), d("grids")[:3], *hyp, 3)
     assert isinstance(pg, np.ndarray) and pg.shape == g["predsample_grid"].shape
     assert _rel(pg, g["predsample_grid"]) < RTOL, _rel(pg, g["predsample_grid"])
+    torch.manual_seed(77)
+    mq, mm, ms = prediction.pointwise_predmap_sampling(6, *args, d("grids")[1:3], *hyp)
+    assert mq.shape == g["mapsamp_q"].shape and mm.shape == g["mapsamp_mean"].shape
+    for got, key in ((mq, "mapsamp_q"), (mm, "mapsamp_mean"), (ms, "mapsamp_std")):
+        assert _rel(got, g[key]) < 10 * RTOL, (key, _rel(got, g[key]))        # std of 6 draws: difference of close numbers
     return {"point": _rel(one.cpu().numpy(), g["point"]), "pointwise": _rel(allg.cpu().numpy(), g["pointwise"]),
+            "mapsamp_mean": _rel(mm, g["mapsamp_mean"]), "mapsamp_std": _rel(ms, g["mapsamp_std"]),
             "predsample": _rel(ps.cpu().numpy(), g["predsample_point"]), "predsample_grid": _rel(pg, g["predsample_grid"])}
