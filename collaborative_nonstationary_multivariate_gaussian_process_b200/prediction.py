@@ -81,16 +81,22 @@ class _KronState:
     """sigma2 I + B_f (x) K_x factorised through the eigen-blocks of B_f for ONE parameter sample
     (prediction.py:60-77 / 360-381), plus alpha_k = A_k^-1 (V^T Y^T)_k."""
 
-    def __init__(self, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x):
+    def __init__(self, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, stationary=False):
         N, M = Y.shape
-        dev = Y.device
         self.x = x
         self.sigma2_err = torch.exp(tilde_sigma2_err)
         self.l = torch.exp(tilde_l).contiguous()
         self.sigma = torch.exp(tilde_sigma).contiguous()
         L = vec2lowtriangle(uLvec2Lvec(uL_vec, M), M)
         self.B_f = ops.gemm_nt(L.contiguous(), L.contiguous())
-        K_x = kernels.Nonstationary_RBF_cov(x, sigma1=self.sigma, ell1=self.l)
+        if stationary:                                     # the *_S variants: scalar sigma, ell (prediction.py:1547)
+            K_x = kernels.RBF_cov(x, alpha=float(self.sigma), beta=float(self.l))
+        else:
+            K_x = kernels.Nonstationary_RBF_cov(x, sigma1=self.sigma, ell1=self.l)
+        self._factor(K_x, Y)
+
+    def _factor(self, K_x, Y):
+        N, M = Y.shape
         y = Y.t().contiguous().view(-1)
         self.blocks = []          # (lambda_k, chol(sigma2 I + lambda_k K_x), alpha_k)
         Rt = None
@@ -99,7 +105,17 @@ class _KronState:
                 self.V = V
                 Rt = ops.gemm_nt(V.t().contiguous(), y.view(M, N).t().contiguous())        # rows: (V^T (x) I) y
             self.blocks.append((lam_k, Lk, ops.potrs_vec(Lk, Rt[k].contiguous())))
-        self.lam = torch.tensor([b[0] for b in self.blocks], dtype=torch.float64, device=dev)
+        self.lam = torch.tensor([b[0] for b in self.blocks], dtype=torch.float64, device=Y.device)
+
+    def predict_with(self, k_x, k_ss):
+        """Mean and variance of y for a cross-covariance vector k_x [N] and prior variance factor k_ss (scalar)."""
+        dots = torch.stack([torch.stack((ops.dot(k_x, a_k).reshape(()),
+                                         ops.dot(k_x, ops.potrs_vec(Lk, k_x)).reshape(())))
+                            for _, Lk, a_k in self.blocks])                                        # [D, 2]
+        c = self.V * self.lam.view(1, -1)                       # c[m, k] = lambda_k V[m, k]
+        mu_f = c @ dots[:, 0]
+        sigma2_f = torch.diagonal(self.B_f) * k_ss - (c * c) @ dots[:, 1]
+        return mu_f, sigma2_f + self.sigma2_err
 
     def predict(self, xs, l_star, sigma_star, self_jitter=True):
         """Predictive mean and variance of y at xs given (ell, sigma) there (prediction.py:78-93 / 382-402).
@@ -111,14 +127,16 @@ class _KronState:
             k_ss = kernels.Nonstationary_RBF_cov(X1=xs, sigma1=sigma_star, ell1=l_star).view(())  # incl. the 1e-6 jitter
         else:
             k_ss = (sigma_star * sigma_star).view(())
-        dots = torch.stack([torch.stack((ops.dot(k_x, a_k).reshape(()),
-                                         ops.dot(k_x, ops.potrs_vec(Lk, k_x)).reshape(())))
-                            for _, Lk, a_k in self.blocks])                                        # [D, 2]
-        c = self.V * self.lam.view(1, -1)                       # c[m, k] = lambda_k V[m, k]
-        mu_f = c @ dots[:, 0]
-        sigma2_f = torch.diagonal(self.B_f) * k_ss - (c * c) @ dots[:, 1]
-        sigma2_y = sigma2_f + self.sigma2_err
+        mu_f, sigma2_y = self.predict_with(k_x, k_ss)
         sigma2_y = torch.where(sigma2_y <= 0, torch.full_like(sigma2_y, settings.precision), sigma2_y)
+        return mu_f, sigma2_y
+
+    def predict_stationary(self, xs):
+        """The *_S variants (prediction.py:1550-1556): k_x = RBF_cov(x, xs; sigma, ell), prior variance sigma^2 B_f[m,m],
+        variances clipped where < 0 (strictly, as the reference writes it)."""
+        k_x = kernels.RBF_cov(self.x, xs, alpha=float(self.sigma), beta=float(self.l)).view(-1).contiguous()
+        mu_f, sigma2_y = self.predict_with(k_x, (self.sigma * self.sigma).view(()))
+        sigma2_y = torch.where(sigma2_y < 0, torch.full_like(sigma2_y, settings.precision), sigma2_y)
         return mu_f, sigma2_y
 
 
@@ -286,6 +304,47 @@ def test_predmap_sampling(n_sample, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_e
                                       beta_tilde_sigma)
 
 
+# ---- stationary variants (prediction.py:1532-1658): dense inverse of B_f (x) K_x + sigma2 I -> eigen-block factors ---------
+def pointwise_predmap_S(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, grids, *args, **kwargs):
+    """prediction.py:1532-1565: [N_grid, 3, M]."""
+    st = _KronState(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x.contiguous().view(-1, 1), stationary=True)
+    res = []
+    for grid in grids:
+        mu_f, s2 = st.predict_stationary(grid.reshape(1, 1).to(torch.float64))
+        sd = torch.sqrt(s2)
+        res.append(torch.stack([mu_f - 1.96 * sd, mu_f, mu_f + 1.96 * sd]))
+    return torch.stack(res)
+
+
+def test_predmap_S(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, test_x, *args, **kwargs):
+    """prediction.py:1567-1604: (mean [N_test, M], std [N_test, M])."""
+    st = _KronState(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x.contiguous().view(-1, 1), stationary=True)
+    out = [st.predict_stationary(xs.reshape(1, 1).to(torch.float64)) for xs in test_x]
+    return torch.stack([o[0] for o in out]), torch.stack([torch.sqrt(o[1]) for o in out])
+
+
+def pointwise_predsample_S(tilde_ls, tilde_sigmas, uL_vecs, tilde_sigma2_errs, Y, x, grids, *args, **kwargs):
+    """prediction.py:1606-1631: numpy [N_sample, N_grid, M]; ONE np.random.randn() scalar per (sample, grid point), shared
+    by the M outputs, drawn from numpy's global generator in the reference's order."""
+    xcol = x.contiguous().view(-1, 1)
+    samples = []
+    for tl, ts, uL, s2 in zip(tilde_ls, tilde_sigmas, uL_vecs, tilde_sigma2_errs):
+        st = _KronState(tl, ts, uL, s2, Y, xcol, stationary=True)
+        res = []
+        for grid in grids:
+            mu_f, var = st.predict_stationary(grid.reshape(1, 1).to(torch.float64))
+            res.append(mu_f + np.random.randn() * torch.sqrt(var))
+        samples.append(torch.stack(res))
+    return torch.stack(samples).cpu().numpy()
+
+
+def test_predsample_S(tilde_ls, tilde_sigmas, uL_vecs, tilde_sigma2_errs, Y, x, test_x, *args, **kwargs):
+    """prediction.py:1633-1658."""
+    return pointwise_predsample_S(tilde_ls, tilde_sigmas, uL_vecs, tilde_sigma2_errs, Y, x, test_x)
+
+
 test_predmap.__test__ = False      # not pytest tests
+test_predmap_S.__test__ = False
+test_predsample_S.__test__ = False
 test_predmap_sampling.__test__ = False
 test_predsample.__test__ = False

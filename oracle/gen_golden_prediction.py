@@ -49,7 +49,16 @@ def main():
     torch.manual_seed(77)
     with contextlib.redirect_stdout(io.StringIO()):
         mq, mm, ms = prediction.pointwise_predmap_sampling(6, tilde_l, tilde_sigma, uL_vec, tilde_s2, Y, x, grids[1:3], *args)
+    # stationary (_S) variants: scalar log-ell / log-sigma
+    tl_S, ts_S = torch.tensor(-1.8).double(), torch.tensor(0.2).double()
+    S_grid = prediction.pointwise_predmap_S(tl_S, ts_S, uL_vec, tilde_s2, Y, x, grids)
+    S_mean, S_std = prediction.test_predmap_S(tl_S, ts_S, uL_vec, tilde_s2, Y, x, x[::9] + 0.004)
+    tls_S = tl_S + 0.05 * torch.randn(3).double(); tss_S = ts_S + 0.05 * torch.randn(3).double()
+    np.random.seed(5)
+    S_samp = prediction.pointwise_predsample_S(tls_S, tss_S, uL_h[:3], s2_h[:3], Y, x, grids[:4])
     np.savez_compressed(os.path.join(OUT, "sim_prediction.npz"), x=x.numpy(), tilde_l=tilde_l.numpy(),
+                        tl_S=float(tl_S), ts_S=float(ts_S), S_grid=S_grid.numpy(), S_mean=S_mean.numpy(), S_std=S_std.numpy(),
+                        tls_S=tls_S.numpy(), tss_S=tss_S.numpy(), S_samp=S_samp,
                         mapsamp_q=mq, mapsamp_mean=mm, mapsamp_std=ms,
                         tl_hist=tl_h.numpy(), ts_hist=ts_h.numpy(), uL_hist=uL_h.numpy(), s2_hist=s2_h.numpy(),
                         predsample_point=ps_one.numpy(), predsample_grid=np.asarray(ps_grid),

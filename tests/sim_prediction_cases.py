@@ -60,6 +60,18 @@ def run_all(dev):
     assert mq.shape == g["mapsamp_q"].shape and mm.shape == g["mapsamp_mean"].shape
     for got, key in ((mq, "mapsamp_q"), (mm, "mapsamp_mean"), (ms, "mapsamp_std")):
         assert _rel(got, g[key]) < 10 * RTOL, (key, _rel(got, g[key]))        # std of 6 draws: difference of close numbers
+    # stationary (_S) variants: the reference inverts the dense (N M) x (N M) matrix; here the eigen-block factors
+    sc = lambda k: torch.tensor(float(g[k]), dtype=torch.float64).to(dev)
+    s2t = torch.tensor(float(g["tilde_s2"]), dtype=torch.float64).to(dev)
+    Sg = prediction.pointwise_predmap_S(sc("tl_S"), sc("ts_S"), d("uL_vec"), s2t, d("Y"), d("x"), d("grids"))
+    assert _rel(Sg.cpu().numpy(), g["S_grid"]) < RTOL, _rel(Sg.cpu().numpy(), g["S_grid"])
+    Sm, Ss = prediction.test_predmap_S(sc("tl_S"), sc("ts_S"), d("uL_vec"), s2t, d("Y"), d("x"), d("x_test"))
+    assert _rel(Sm.cpu().numpy(), g["S_mean"]) < RTOL and _rel(Ss.cpu().numpy(), g["S_std"]) < RTOL
+    np.random.seed(5)
+    Sp = prediction.pointwise_predsample_S(d("tls_S"), d("tss_S"), d("uL_hist")[:3], d("s2_hist")[:3], d("Y"), d("x"),
+                                           d("grids")[:4])
+    assert Sp.shape == g["S_samp"].shape and _rel(Sp, g["S_samp"]) < RTOL, _rel(Sp, g["S_samp"])
     return {"point": _rel(one.cpu().numpy(), g["point"]), "pointwise": _rel(allg.cpu().numpy(), g["pointwise"]),
+            "S_grid": _rel(Sg.cpu().numpy(), g["S_grid"]), "S_samp": _rel(Sp, g["S_samp"]),
             "mapsamp_mean": _rel(mm, g["mapsamp_mean"]), "mapsamp_std": _rel(ms, g["mapsamp_std"]),
             "predsample": _rel(ps.cpu().numpy(), g["predsample_point"]), "predsample_grid": _rel(pg, g["predsample_grid"])}
