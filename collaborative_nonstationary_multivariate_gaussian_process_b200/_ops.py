@@ -408,6 +408,14 @@ def nonstationary_cov(X1, sigma1, ell1, X2, sigma2, ell2, jitter):
     return K
 
 
+def hadamard_index_cov(Kx, Bf, indx1, indx2, diag=0.0):
+    N1, N2 = Kx.shape
+    out = _empty(Kx, N1, N2)
+    check(lib().nmgp_hadamard_index_cov(_d(Kx), _d(Bf), _i(indx1), _i(indx2), c_double(diag), _d(out), c_int64(N1),
+                                        c_int64(N2), c_int(Bf.shape[0]), _stream()), "nmgp_hadamard_index_cov")
+    return out
+
+
 def sim_rbf_cov(X1, X2, alpha, beta, jitter):
     T1, dx = X1.shape
     T2 = X2.shape[0]

@@ -270,3 +270,25 @@ NMGP_API int nmgp_sim_rbf_cov(const double* X1, const double* X2, double alpha, 
     k_sim_rbf_cov<<<grid, 256, 0, st>>>(X1, X2, alpha, beta, jitter, K, T1, T2, dx);
     return nmgp_launch_status("nmgp_sim_rbf_cov");
 }
+
+// Hadamard (irregular-observation) covariance of the SIM_code line: out[i,j] = Kx[i,j] * Bf[indx1[i], indx2[j]]
+// (+ diag on i == j)   -- logpos.generate_K_index (logpos.py:87-98) fused with the elementwise product K_x * K_i
+// (prediction.py:746-748) and the sigma2_err I of the observation covariance.
+__global__ void k_hadamard_index_cov(const double* __restrict__ Kx, const double* __restrict__ Bf,
+                                     const int* __restrict__ indx1, const int* __restrict__ indx2, double diag,
+                                     double* __restrict__ out, long long N1, long long N2, int M) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = blockIdx.y + (long long)blockIdx.z * 65535;
+    if (i >= N1 || j >= N2) return;
+    double v = Kx[i * N2 + j] * Bf[(size_t)indx1[i] * M + indx2[j]];
+    if (i == j) v += diag;
+    out[i * N2 + j] = v;
+}
+NMGP_API int nmgp_hadamard_index_cov(const double* Kx, const double* Bf, const int* indx1, const int* indx2, double diag,
+                                     double* out, long long N1, long long N2, int M, cudaStream_t st) {
+    NMGP_REQUIRE(N1 >= 0 && N2 >= 0 && M > 0, "nmgp_hadamard_index_cov");
+    if (N1 == 0 || N2 == 0) return 0;
+    dim3 grid((unsigned)((N2 + 255) / 256), (unsigned)min(N1, 65535LL), (unsigned)((N1 + 65534) / 65535));
+    k_hadamard_index_cov<<<grid, 256, 0, st>>>(Kx, Bf, indx1, indx2, diag, out, N1, N2, M);
+    return nmgp_launch_status("nmgp_hadamard_index_cov");
+}

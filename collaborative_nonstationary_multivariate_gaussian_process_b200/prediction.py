@@ -343,7 +343,100 @@ def test_predsample_S(tilde_ls, tilde_sigmas, uL_vecs, tilde_sigma2_errs, Y, x, 
     return pointwise_predsample_S(tilde_ls, tilde_sigmas, uL_vecs, tilde_sigma2_errs, Y, x, test_x)
 
 
+# ---- Hadamard (irregular observations) MAP predictors (prediction.py:710-910) ------------------------------------------
+class _HadamardState:
+    """S = K_x * K_i + sigma2 I for observations (x_n, indx_n, y_n) (prediction.py:742-750): one dense blocked Cholesky
+    instead of symeig(K) and an explicit inverse; alpha = S^-1 y."""
+
+    def __init__(self, tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, M):
+        self.x = x.contiguous().view(-1, 1)
+        self.indx = indx.to(torch.int32).contiguous()
+        self.sigma2_err = torch.exp(tilde_sigma2_err)
+        self.l = torch.exp(tilde_l).contiguous()
+        self.sigma = torch.exp(tilde_sigma).contiguous()
+        Lm = vec2lowtriangle(L_vec, M)
+        self.B_f = ops.gemm_nt(Lm.contiguous(), Lm.contiguous())
+        K_x = kernels.Nonstationary_RBF_cov(self.x, sigma1=self.sigma, ell1=self.l)
+        S = ops.hadamard_index_cov(K_x, self.B_f, self.indx, self.indx, float(self.sigma2_err))
+        self.Lc, _ = ops.potrf_big(S)
+        self.alpha = ops.potrs_vec(self.Lc, y.contiguous())
+        self.M = M
+
+    def cross(self, xs, l_star, sigma_star):
+        return kernels.Nonstationary_RBF_cov(X1=self.x, sigma1=self.sigma, ell1=self.l, X2=xs, sigma2=sigma_star,
+                                             ell2=l_star).contiguous()                            # [N, 1]
+
+    def output(self, k_x, m, k_ss):
+        """mean and variance of output m at the test input with cross-covariance column k_x."""
+        mi = torch.full((1,), int(m), dtype=torch.int32, device=k_x.device)
+        kf = ops.hadamard_index_cov(k_x, self.B_f, self.indx, mi, 0.0).view(-1).contiguous()      # B_f[indx_n, m] k_x[n]
+        mu = ops.dot(kf, self.alpha).reshape(())
+        var = self.B_f[int(m), int(m)] * k_ss - ops.dot(kf, ops.potrs_vec(self.Lc, kf)).reshape(()) + self.sigma2_err
+        return mu, var
+
+
+def _hadamard_setup(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, hyp_l, hyp_s):
+    M = int(torch.unique(indx).numel())
+    xcol = x.contiguous().view(-1, 1)
+    gp_l, gp_s = _ConditionalGP(xcol, *hyp_l), _ConditionalGP(xcol, *hyp_s)
+    return (M, gp_l, gp_s, gp_l.weights(tilde_l), gp_s.weights(tilde_sigma),
+            _HadamardState(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, M))
+
+
+def _hadamard_point(setup, x_star, outputs):
+    M, gp_l, gp_s, w_l, w_s, st = setup
+    xs = x_star.reshape(1, 1).to(torch.float64)
+    est = []
+    for gp, wts in ((gp_l, w_l), (gp_s, w_s)):
+        k = kernels.RBF_cov(st.x, xs, alpha=gp.alpha, beta=gp.beta).view(-1).contiguous()
+        est.append(gp.mu + ops.dot(k, wts).reshape(()))
+    l_star, sigma_star = torch.exp(est[0]).view(1), torch.exp(est[1]).view(1)
+    k_x = st.cross(xs, l_star, sigma_star)
+    k_ss = kernels.Nonstationary_RBF_cov(X1=xs, sigma1=sigma_star, ell1=l_star).view(())          # incl. the 1e-6 jitter
+    mus, vs = zip(*[st.output(k_x, m, k_ss) for m in outputs])
+    mu_f, s2 = torch.stack(mus), torch.stack(vs)
+    s2 = torch.where(s2 <= 0, torch.full_like(s2, settings.precision), s2)
+    sd = torch.sqrt(s2)
+    return torch.stack([mu_f - 1.96 * sd, mu_f, mu_f + 1.96 * sd])
+
+
+def point_predmap_hadamard(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, x_star, mu_tilde_l, alpha_tilde_l,
+                           beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, *args, **kwargs):
+    """prediction.py:710-785: [3, M] band of all outputs at x_star."""
+    setup = _hadamard_setup(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y,
+                            (mu_tilde_l, alpha_tilde_l, beta_tilde_l), (mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma))
+    return _hadamard_point(setup, x_star, range(setup[0]))
+
+
+def pointwise_predmap_hadmard(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, grids, mu_tilde_l,
+                              alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma,
+                              *args, **kwargs):
+    """prediction.py:787-808 (the reference's spelling): [N_grid, 3, M], one factorisation for all grid points."""
+    setup = _hadamard_setup(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y,
+                            (mu_tilde_l, alpha_tilde_l, beta_tilde_l), (mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma))
+    return torch.stack([_hadamard_point(setup, g, range(setup[0])) for g in grids])
+
+
+def indexedpoint_predmap_hadamard(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, x_star, indx_star,
+                                  mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma,
+                                  beta_tilde_sigma, *args, **kwargs):
+    """prediction.py:810-885: [3] band of output indx_star at x_star."""
+    setup = _hadamard_setup(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y,
+                            (mu_tilde_l, alpha_tilde_l, beta_tilde_l), (mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma))
+    return _hadamard_point(setup, x_star, [int(indx_star)]).view(3)
+
+
+def test_predmap_harmard(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, x_test, indx_test, mu_tilde_l,
+                         alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma,
+                         *args, **kwargs):
+    """prediction.py:887-909 (the reference's spelling): [N_test, 3]."""
+    setup = _hadamard_setup(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y,
+                            (mu_tilde_l, alpha_tilde_l, beta_tilde_l), (mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma))
+    return torch.stack([_hadamard_point(setup, xs, [int(ii)]).view(3) for xs, ii in zip(x_test, indx_test)])
+
+
 test_predmap.__test__ = False      # not pytest tests
+test_predmap_harmard.__test__ = False
 test_predmap_S.__test__ = False
 test_predsample_S.__test__ = False
 test_predmap_sampling.__test__ = False

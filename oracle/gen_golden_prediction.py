@@ -56,7 +56,25 @@ def main():
     tls_S = tl_S + 0.05 * torch.randn(3).double(); tss_S = ts_S + 0.05 * torch.randn(3).double()
     np.random.seed(5)
     S_samp = prediction.pointwise_predsample_S(tls_S, tss_S, uL_h[:3], s2_h[:3], Y, x, grids[:4])
+    # Hadamard (irregular observations): each output observed at its own subset of the inputs
+    gen = torch.Generator().manual_seed(5)
+    keep = torch.rand(N, M, generator=gen) < 0.6
+    xh = torch.cat([x[keep[:, m]] for m in range(M)])
+    ih = torch.cat([torch.full((int(keep[:, m].sum()),), m, dtype=torch.long) for m in range(M)])
+    yh = torch.cat([Y[keep[:, m], m] for m in range(M)])
+    tlh = (3 * (xh - 1) ** 3 - 1.5) + 0.05 * torch.randn(xh.numel()).double()
+    tsh = 0.1 * torch.randn(xh.numel()).double()
+    L_vec_h = sim_utils.uLvec2Lvec(uL_vec, M)
+    H_point = prediction.point_predmap_hadamard(tlh, tsh, L_vec_h, tilde_s2, xh, ih, yh, grids[3], *args)
+    with contextlib.redirect_stdout(io.StringIO()):
+        H_grid = prediction.pointwise_predmap_hadmard(tlh, tsh, L_vec_h, tilde_s2, xh, ih, yh, grids[:3], *args)
+    H_idx = prediction.indexedpoint_predmap_hadamard(tlh, tsh, L_vec_h, tilde_s2, xh, ih, yh, grids[5], torch.tensor(1), *args)
+    xt_h = x[::9][:5] + 0.004; it_h = torch.tensor([0, 2, 1, 1, 0])
+    H_test = prediction.test_predmap_harmard(tlh, tsh, L_vec_h, tilde_s2, xh, ih, yh, xt_h, it_h, *args)
     np.savez_compressed(os.path.join(OUT, "sim_prediction.npz"), x=x.numpy(), tilde_l=tilde_l.numpy(),
+                        xh=xh.numpy(), ih=ih.numpy(), yh=yh.numpy(), tlh=tlh.numpy(), tsh=tsh.numpy(), L_vec_h=L_vec_h.numpy(),
+                        H_point=H_point.numpy(), H_grid=H_grid.numpy(), H_idx=H_idx.numpy(), H_test=H_test.numpy(),
+                        xt_h=xt_h.numpy(), it_h=it_h.numpy(),
                         tl_S=float(tl_S), ts_S=float(ts_S), S_grid=S_grid.numpy(), S_mean=S_mean.numpy(), S_std=S_std.numpy(),
                         tls_S=tls_S.numpy(), tss_S=tss_S.numpy(), S_samp=S_samp,
                         mapsamp_q=mq, mapsamp_mean=mm, mapsamp_std=ms,

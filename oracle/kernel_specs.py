@@ -415,6 +415,12 @@ def nonstationary_cov(X1, sigma1, ell1, X2, sigma2, ell2, jitter):
     return K + jitter * torch.eye(n1, n2, dtype=F64)
 
 
+def hadamard_index_cov(Kx, Bf, indx1, indx2, diag=0.0):
+    """out[i,j] = Kx[i,j] Bf[indx1[i], indx2[j]] (+ diag on i == j)."""
+    Ki = Bf[indx1.long().view(-1, 1), indx2.long().view(1, -1)]
+    return Kx * Ki + diag * torch.eye(Kx.shape[0], Kx.shape[1], dtype=F64)
+
+
 def sim_rbf_cov(X1, X2, alpha, beta, jitter):
     d = pairwise_dist(X1 / beta, X2 / beta)
     return torch.exp(-0.5 * d) * alpha ** 2 + jitter * torch.eye(X1.shape[0], X2.shape[0], dtype=F64)

@@ -10,6 +10,7 @@ ORDER = ("mu_tilde_l", "alpha_tilde_l", "beta_tilde_l", "mu_tilde_sigma", "alpha
 # points) by LU and eigendecomposes K_x; we use Cholesky factors.  Both are backward stable, so the outputs agree to
 # cond * eps; the bound below is that, not the 1e-9 of the well-conditioned DSVI path.
 RTOL = 2e-8
+HTOL = RTOL      # Hadamard layout (the reference goes through symeig(K) and an explicit inverse): measured 3e-10
 
 
 def _rel(a, b):
@@ -71,7 +72,20 @@ def run_all(dev):
     Sp = prediction.pointwise_predsample_S(d("tls_S"), d("tss_S"), d("uL_hist")[:3], d("s2_hist")[:3], d("Y"), d("x"),
                                            d("grids")[:4])
     assert Sp.shape == g["S_samp"].shape and _rel(Sp, g["S_samp"]) < RTOL, _rel(Sp, g["S_samp"])
+    # Hadamard (irregular observations) MAP predictors: dense Cholesky of K_x * K_i + sigma2 I instead of symeig + inverse
+    ih = torch.from_numpy(g["ih"]).to(dev)
+    hargs = (d("tlh"), d("tsh"), d("L_vec_h"), s2t, d("xh"), ih, d("yh"))
+    Hp = prediction.point_predmap_hadamard(*hargs, d("grids")[3], *hyp)
+    assert _rel(Hp.cpu().numpy(), g["H_point"]) < HTOL, _rel(Hp.cpu().numpy(), g["H_point"])
+    Hg = prediction.pointwise_predmap_hadmard(*hargs, d("grids")[:3], *hyp)
+    assert _rel(Hg.cpu().numpy(), g["H_grid"]) < HTOL, _rel(Hg.cpu().numpy(), g["H_grid"])
+    Hi = prediction.indexedpoint_predmap_hadamard(*hargs, d("grids")[5], torch.tensor(1), *hyp)
+    assert Hi.shape == (3,) and _rel(Hi.cpu().numpy(), g["H_idx"]) < HTOL, _rel(Hi.cpu().numpy(), g["H_idx"])
+    Ht = prediction.test_predmap_harmard(*hargs, d("xt_h"), torch.from_numpy(g["it_h"]), *hyp)
+    assert _rel(Ht.cpu().numpy(), g["H_test"]) < HTOL, _rel(Ht.cpu().numpy(), g["H_test"])
     return {"point": _rel(one.cpu().numpy(), g["point"]), "pointwise": _rel(allg.cpu().numpy(), g["pointwise"]),
+            "H_point": _rel(Hp.cpu().numpy(), g["H_point"]), "H_grid": _rel(Hg.cpu().numpy(), g["H_grid"]),
+            "H_test": _rel(Ht.cpu().numpy(), g["H_test"]),
             "S_grid": _rel(Sg.cpu().numpy(), g["S_grid"]), "S_samp": _rel(Sp, g["S_samp"]),
             "mapsamp_mean": _rel(mm, g["mapsamp_mean"]), "mapsamp_std": _rel(ms, g["mapsamp_std"]),
             "predsample": _rel(ps.cpu().numpy(), g["predsample_point"]), "predsample_grid": _rel(pg, g["predsample_grid"])}

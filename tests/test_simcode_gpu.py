@@ -120,3 +120,15 @@ def test_eigh_small(n):
     Vc = V.cpu()
     assert rel(Vc @ torch.diag(w.cpu()) @ Vc.t(), A) < 1e-12
     assert rel(Vc.t() @ Vc, torch.eye(n, dtype=torch.float64)) < 1e-12
+
+
+def test_hadamard_index_cov():
+    """out[i,j] = Kx[i,j] Bf[indx1[i], indx2[j]] (+ diag): logpos.generate_K_index fused with the Hadamard product."""
+    from oracle import kernel_specs as specs
+    gen = torch.Generator().manual_seed(8)
+    for (n1, n2, M) in ((37, 37, 3), (300, 1, 5), (5, 70, 2)):
+        Kx = torch.randn(n1, n2, generator=gen, dtype=torch.float64)
+        L = torch.randn(M, M, generator=gen, dtype=torch.float64); Bf = L @ L.t()
+        i1 = torch.randint(0, M, (n1,), generator=gen).to(torch.int32); i2 = torch.randint(0, M, (n2,), generator=gen).to(torch.int32)
+        got = ops.hadamard_index_cov(d(Kx), d(Bf), i1.cuda(), i2.cuda(), 0.25)
+        assert rel(got, specs.hadamard_index_cov(Kx, Bf, i1, i2, 0.25)) < 1e-15
