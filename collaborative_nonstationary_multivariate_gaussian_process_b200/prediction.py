@@ -435,7 +435,81 @@ def test_predmap_harmard(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx,
     return torch.stack([_hadamard_point(setup, xs, [int(ii)]).view(3) for xs, ii in zip(x_test, indx_test)])
 
 
+# ---- Hadamard sampling predictors (prediction.py:461-708) ---------------------------------------------------------------
+def _hadamard_predsample(hist, x, indx, y, points, outputs_of, hyp_l, hyp_s):
+    tl_h, ts_h, L_h, s2_h = hist
+    M = int(torch.unique(indx).numel())
+    xcol = x.contiguous().view(-1, 1)
+    gp_l, gp_s = _ConditionalGP(xcol, *hyp_l), _ConditionalGP(xcol, *hyp_s)
+    states = [_HadamardState(tl, ts, Lv, s2, x, indx, y, M) for tl, ts, Lv, s2 in zip(tl_h, ts_h, L_h, s2_h)]
+    floor = torch.tensor(settings.precision, dtype=torch.float64, device=y.device)
+    out = []
+    for ip, x_star in enumerate(points):                    # draw order of the reference: inputs outer, samples inner
+        xs = x_star.reshape(1, 1).to(torch.float64)
+        _, proj_l, var_l = gp_l.projection(xs)
+        _, proj_s, var_s = gp_s.projection(xs)
+        var_l = torch.where(var_l < 0, floor, var_l)
+        var_s = torch.where(var_s < 0, floor, var_s)
+        outputs = outputs_of(ip, M)
+        rows = []
+        for st, tl, ts in zip(states, tl_h, ts_h):
+            mu_l = gp_l.mu + ops.dot(proj_l, (tl - gp_l.mu).contiguous()).reshape(())
+            l_star = torch.exp(_draw(mu_l, torch.sqrt(var_l))).view(1)
+            mu_s = gp_s.mu + ops.dot(proj_s, (ts - gp_s.mu).contiguous()).reshape(())
+            sigma_star = torch.exp(_draw(mu_s, torch.sqrt(var_s))).view(1)
+            k_x = st.cross(xs, l_star, sigma_star)
+            k_ss = kernels.Nonstationary_RBF_cov(X1=xs, sigma1=sigma_star, ell1=l_star).view(())
+            mus, vs = zip(*[st.output(k_x, m, k_ss) for m in outputs])
+            mu_f, s2 = torch.stack(mus), torch.stack(vs)
+            s2 = torch.where(s2 <= 0, torch.full_like(s2, settings.precision), s2)
+            rows.append(_draw(mu_f, torch.sqrt(s2)))
+        out.append(rows)
+    return out
+
+
+def point_predsample_hadamard(tilde_l_hist, tilde_sigma_hist, L_vec_hist, tilde_sigma2_err_hist, x, indx, y, x_star,
+                              mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma,
+                              beta_tilde_sigma, *args, **kwargs):
+    """prediction.py:461-553: [N_hist, M]."""
+    res = _hadamard_predsample((tilde_l_hist, tilde_sigma_hist, L_vec_hist, tilde_sigma2_err_hist), x, indx, y, [x_star],
+                               lambda ip, M: range(M), (mu_tilde_l, alpha_tilde_l, beta_tilde_l),
+                               (mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma))
+    return torch.stack(res[0])
+
+
+def pointwise_predsample_hadamard(tilde_l_hist, tilde_sigma_hist, L_vec_hist, tilde_sigma2_err_hist, x, indx, y, grids,
+                                  mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma,
+                                  beta_tilde_sigma, *args, **kwargs):
+    """prediction.py:555-583: [N_grid, N_hist, M]."""
+    res = _hadamard_predsample((tilde_l_hist, tilde_sigma_hist, L_vec_hist, tilde_sigma2_err_hist), x, indx, y,
+                               list(grids), lambda ip, M: range(M), (mu_tilde_l, alpha_tilde_l, beta_tilde_l),
+                               (mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma))
+    return torch.stack([torch.stack(r) for r in res])
+
+
+def indexedpoint_predsample_hadamard(tilde_l_hist, tilde_sigma_hist, L_vec_hist, tilde_sigma2_err_hist, x, indx, y,
+                                     x_star, indx_star, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_tilde_sigma,
+                                     alpha_tilde_sigma, beta_tilde_sigma, *args, **kwargs):
+    """prediction.py:585-676: [N_hist] draws of output indx_star at x_star."""
+    res = _hadamard_predsample((tilde_l_hist, tilde_sigma_hist, L_vec_hist, tilde_sigma2_err_hist), x, indx, y, [x_star],
+                               lambda ip, M: [int(indx_star)], (mu_tilde_l, alpha_tilde_l, beta_tilde_l),
+                               (mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma))
+    return torch.cat(res[0])
+
+
+def test_predsample_hadamard(tilde_l_hist, tilde_sigma_hist, L_vec_hist, tilde_sigma2_err_hist, x, indx, y, x_test,
+                             indx_test, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma,
+                             beta_tilde_sigma, *args, **kwargs):
+    """prediction.py:678-708: [N_test, N_hist]."""
+    idx = [int(i) for i in indx_test]
+    res = _hadamard_predsample((tilde_l_hist, tilde_sigma_hist, L_vec_hist, tilde_sigma2_err_hist), x, indx, y,
+                               list(x_test), lambda ip, M: [idx[ip]], (mu_tilde_l, alpha_tilde_l, beta_tilde_l),
+                               (mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma))
+    return torch.stack([torch.cat(r) for r in res])
+
+
 test_predmap.__test__ = False      # not pytest tests
+test_predsample_hadamard.__test__ = False
 test_predmap_harmard.__test__ = False
 test_predmap_S.__test__ = False
 test_predsample_S.__test__ = False

@@ -71,7 +71,20 @@ def main():
     H_idx = prediction.indexedpoint_predmap_hadamard(tlh, tsh, L_vec_h, tilde_s2, xh, ih, yh, grids[5], torch.tensor(1), *args)
     xt_h = x[::9][:5] + 0.004; it_h = torch.tensor([0, 2, 1, 1, 0])
     H_test = prediction.test_predmap_harmard(tlh, tsh, L_vec_h, tilde_s2, xh, ih, yh, xt_h, it_h, *args)
+    Hh = 3
+    tlh_h = torch.stack([tlh + 0.03 * torch.randn(xh.numel()).double() for _ in range(Hh)])
+    tsh_h = torch.stack([tsh + 0.03 * torch.randn(xh.numel()).double() for _ in range(Hh)])
+    Lh_h = torch.stack([L_vec_h + 0.05 * torch.randn(L_vec_h.numel()).double() for _ in range(Hh)])
+    s2h_h = tilde_s2 + 0.05 * torch.randn(Hh).double()
+    torch.manual_seed(41)
+    with contextlib.redirect_stdout(io.StringIO()):
+        HS_grid = prediction.pointwise_predsample_hadamard(tlh_h, tsh_h, Lh_h, s2h_h, xh, ih, yh, grids[2:4], *args)
+    torch.manual_seed(42)
+    with contextlib.redirect_stdout(io.StringIO()):
+        HS_test = prediction.test_predsample_hadamard(tlh_h, tsh_h, Lh_h, s2h_h, xh, ih, yh, xt_h[:3], it_h[:3], *args)
     np.savez_compressed(os.path.join(OUT, "sim_prediction.npz"), x=x.numpy(), tilde_l=tilde_l.numpy(),
+                        tlh_h=tlh_h.numpy(), tsh_h=tsh_h.numpy(), Lh_h=Lh_h.numpy(), s2h_h=s2h_h.numpy(),
+                        HS_grid=HS_grid.numpy(), HS_test=HS_test.numpy(),
                         xh=xh.numpy(), ih=ih.numpy(), yh=yh.numpy(), tlh=tlh.numpy(), tsh=tsh.numpy(), L_vec_h=L_vec_h.numpy(),
                         H_point=H_point.numpy(), H_grid=H_grid.numpy(), H_idx=H_idx.numpy(), H_test=H_test.numpy(),
                         xt_h=xt_h.numpy(), it_h=it_h.numpy(),

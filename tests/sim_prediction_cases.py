@@ -83,7 +83,15 @@ def run_all(dev):
     assert Hi.shape == (3,) and _rel(Hi.cpu().numpy(), g["H_idx"]) < HTOL, _rel(Hi.cpu().numpy(), g["H_idx"])
     Ht = prediction.test_predmap_harmard(*hargs, d("xt_h"), torch.from_numpy(g["it_h"]), *hyp)
     assert _rel(Ht.cpu().numpy(), g["H_test"]) < HTOL, _rel(Ht.cpu().numpy(), g["H_test"])
+    hh = (d("tlh_h"), d("tsh_h"), d("Lh_h"), d("s2h_h"), d("xh"), ih, d("yh"))
+    torch.manual_seed(41)
+    HSg = prediction.pointwise_predsample_hadamard(*hh, d("grids")[2:4], *hyp)
+    assert HSg.shape == g["HS_grid"].shape and _rel(HSg.cpu().numpy(), g["HS_grid"]) < HTOL, _rel(HSg.cpu().numpy(), g["HS_grid"])
+    torch.manual_seed(42)
+    HSt = prediction.test_predsample_hadamard(*hh, d("xt_h")[:3], torch.from_numpy(g["it_h"])[:3], *hyp)
+    assert HSt.shape == g["HS_test"].shape and _rel(HSt.cpu().numpy(), g["HS_test"]) < HTOL, _rel(HSt.cpu().numpy(), g["HS_test"])
     return {"point": _rel(one.cpu().numpy(), g["point"]), "pointwise": _rel(allg.cpu().numpy(), g["pointwise"]),
+            "HS_grid": _rel(HSg.cpu().numpy(), g["HS_grid"]), "HS_test": _rel(HSt.cpu().numpy(), g["HS_test"]),
             "H_point": _rel(Hp.cpu().numpy(), g["H_point"]), "H_grid": _rel(Hg.cpu().numpy(), g["H_grid"]),
             "H_test": _rel(Ht.cpu().numpy(), g["H_test"]),
             "S_grid": _rel(Sg.cpu().numpy(), g["S_grid"]), "S_samp": _rel(Sp, g["S_samp"]),
