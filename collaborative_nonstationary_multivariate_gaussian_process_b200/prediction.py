@@ -348,7 +348,8 @@ class _HadamardState:
     """S = K_x * K_i + sigma2 I for observations (x_n, indx_n, y_n) (prediction.py:742-750): one dense blocked Cholesky
     instead of symeig(K) and an explicit inverse; alpha = S^-1 y."""
 
-    def __init__(self, tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, M):
+    def __init__(self, tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, M, stationary=False):
+        self.stationary = stationary
         self.x = x.contiguous().view(-1, 1)
         self.indx = indx.to(torch.int32).contiguous()
         self.sigma2_err = torch.exp(tilde_sigma2_err)
@@ -356,7 +357,10 @@ class _HadamardState:
         self.sigma = torch.exp(tilde_sigma).contiguous()
         Lm = vec2lowtriangle(L_vec, M)
         self.B_f = ops.gemm_nt(Lm.contiguous(), Lm.contiguous())
-        K_x = kernels.Nonstationary_RBF_cov(self.x, sigma1=self.sigma, ell1=self.l)
+        if stationary:                                     # scalar sigma, ell (prediction.py:1669)
+            K_x = kernels.RBF_cov(self.x, alpha=float(self.sigma), beta=float(self.l))
+        else:
+            K_x = kernels.Nonstationary_RBF_cov(self.x, sigma1=self.sigma, ell1=self.l)
         S = ops.hadamard_index_cov(K_x, self.B_f, self.indx, self.indx, float(self.sigma2_err))
         self.Lc, _ = ops.potrf_big(S)
         self.alpha = ops.potrs_vec(self.Lc, y.contiguous())
@@ -366,13 +370,24 @@ class _HadamardState:
         return kernels.Nonstationary_RBF_cov(X1=self.x, sigma1=self.sigma, ell1=self.l, X2=xs, sigma2=sigma_star,
                                              ell2=l_star).contiguous()                            # [N, 1]
 
-    def output(self, k_x, m, k_ss):
-        """mean and variance of output m at the test input with cross-covariance column k_x."""
+    def output(self, k_x, m, k_ss, prior_index=None):
+        """mean and variance of output m at the test input with cross-covariance column k_x (prior variance taken from
+        output `prior_index`, default m)."""
         mi = torch.full((1,), int(m), dtype=torch.int32, device=k_x.device)
         kf = ops.hadamard_index_cov(k_x, self.B_f, self.indx, mi, 0.0).view(-1).contiguous()      # B_f[indx_n, m] k_x[n]
         mu = ops.dot(kf, self.alpha).reshape(())
-        var = self.B_f[int(m), int(m)] * k_ss - ops.dot(kf, ops.potrs_vec(self.Lc, kf)).reshape(()) + self.sigma2_err
+        pi = int(m) if prior_index is None else int(prior_index)
+        var = self.B_f[pi, pi] * k_ss - ops.dot(kf, ops.potrs_vec(self.Lc, kf)).reshape(()) + self.sigma2_err
         return mu, var
+
+    def stationary_point(self, x_star, outputs, prior_index=None):
+        xs = x_star.reshape(1, 1).to(torch.float64)
+        a, b = float(self.sigma), float(self.l)
+        k_x = kernels.RBF_cov(self.x, xs, alpha=a, beta=b).contiguous()
+        k_ss = kernels.RBF_cov(xs, alpha=a, beta=b).view(())                                       # sigma^2 + 1e-6
+        mus, vs = zip(*[self.output(k_x, m, k_ss, prior_index) for m in outputs])
+        mu_f, s2 = torch.stack(mus), torch.stack(vs)
+        return mu_f, torch.where(s2 <= 0, torch.full_like(s2, settings.precision), s2)
 
 
 def _hadamard_setup(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, hyp_l, hyp_s):
@@ -508,7 +523,54 @@ def test_predsample_hadamard(tilde_l_hist, tilde_sigma_hist, L_vec_hist, tilde_s
     return torch.stack([torch.cat(r) for r in res])
 
 
+# ---- stationary Hadamard MAP predictors (prediction.py:1661-1762) -------------------------------------------------------
+def _S_hadamard_state(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y):
+    return _HadamardState(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, int(torch.unique(indx).numel()),
+                          stationary=True)
+
+
+def point_predmap_S_hadamard(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, x_star, *args, **kwargs):
+    """prediction.py:1661-1694: [3, M]."""
+    st = _S_hadamard_state(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y)
+    mu_f, s2 = st.stationary_point(x_star, range(st.M))
+    sd = torch.sqrt(s2)
+    return torch.stack([mu_f - 1.96 * sd, mu_f, mu_f + 1.96 * sd])
+
+
+def pointwise_predmap_S_hadamard(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, grids, *args, **kwargs):
+    """prediction.py:1696-1706: [N_grid, 3, M]."""
+    st = _S_hadamard_state(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y)
+    res = []
+    for grid in grids:
+        mu_f, s2 = st.stationary_point(grid, range(st.M))
+        sd = torch.sqrt(s2)
+        res.append(torch.stack([mu_f - 1.96 * sd, mu_f, mu_f + 1.96 * sd]))
+    return torch.stack(res)
+
+
+def _S_indexed(st, x_star, indx_star):
+    # the reference takes (A - B)[0, 0] with A = B_f (x) k**: the prior variance of output 0 whatever indx_star is
+    # (prediction.py:1738-1740); reproduced
+    mu_f, s2 = st.stationary_point(x_star, [int(indx_star)], prior_index=0)
+    return torch.stack([mu_f.view(()), torch.sqrt(s2).view(())])
+
+
+def indexedpoint_predmap_S_hadamard(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, x_star, indx_star,
+                                    *args, **kwargs):
+    """prediction.py:1708-1744: tensor [mean, std] of output indx_star at x_star."""
+    return _S_indexed(_S_hadamard_state(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y), x_star, indx_star)
+
+
+def test_predmap_S_hadamard(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, x_test, indx_test,
+                            *args, **kwargs):
+    """prediction.py:1746-1762: (means [N_test], stds [N_test])."""
+    st = _S_hadamard_state(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y)
+    res = torch.stack([_S_indexed(st, xs, ii) for xs, ii in zip(x_test, indx_test)])
+    return res[:, 0], res[:, 1]
+
+
 test_predmap.__test__ = False      # not pytest tests
+test_predmap_S_hadamard.__test__ = False
 test_predsample_hadamard.__test__ = False
 test_predmap_harmard.__test__ = False
 test_predmap_S.__test__ = False

@@ -65,12 +65,15 @@ def main():
     tlh = (3 * (xh - 1) ** 3 - 1.5) + 0.05 * torch.randn(xh.numel()).double()
     tsh = 0.1 * torch.randn(xh.numel()).double()
     L_vec_h = sim_utils.uLvec2Lvec(uL_vec, M)
+    tl_S0, ts_S0 = torch.tensor(-1.8).double(), torch.tensor(0.2).double()
     H_point = prediction.point_predmap_hadamard(tlh, tsh, L_vec_h, tilde_s2, xh, ih, yh, grids[3], *args)
     with contextlib.redirect_stdout(io.StringIO()):
         H_grid = prediction.pointwise_predmap_hadmard(tlh, tsh, L_vec_h, tilde_s2, xh, ih, yh, grids[:3], *args)
     H_idx = prediction.indexedpoint_predmap_hadamard(tlh, tsh, L_vec_h, tilde_s2, xh, ih, yh, grids[5], torch.tensor(1), *args)
     xt_h = x[::9][:5] + 0.004; it_h = torch.tensor([0, 2, 1, 1, 0])
     H_test = prediction.test_predmap_harmard(tlh, tsh, L_vec_h, tilde_s2, xh, ih, yh, xt_h, it_h, *args)
+    SH_grid = prediction.pointwise_predmap_S_hadamard(tl_S0, ts_S0, L_vec_h, tilde_s2, xh, ih, yh, grids[:3])
+    SH_mean, SH_std = prediction.test_predmap_S_hadamard(tl_S0, ts_S0, L_vec_h, tilde_s2, xh, ih, yh, xt_h, it_h)
     Hh = 3
     tlh_h = torch.stack([tlh + 0.03 * torch.randn(xh.numel()).double() for _ in range(Hh)])
     tsh_h = torch.stack([tsh + 0.03 * torch.randn(xh.numel()).double() for _ in range(Hh)])
@@ -85,6 +88,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "sim_prediction.npz"), x=x.numpy(), tilde_l=tilde_l.numpy(),
                         tlh_h=tlh_h.numpy(), tsh_h=tsh_h.numpy(), Lh_h=Lh_h.numpy(), s2h_h=s2h_h.numpy(),
                         HS_grid=HS_grid.numpy(), HS_test=HS_test.numpy(),
+                        SH_grid=SH_grid.numpy(), SH_mean=SH_mean.numpy(), SH_std=SH_std.numpy(),
                         xh=xh.numpy(), ih=ih.numpy(), yh=yh.numpy(), tlh=tlh.numpy(), tsh=tsh.numpy(), L_vec_h=L_vec_h.numpy(),
                         H_point=H_point.numpy(), H_grid=H_grid.numpy(), H_idx=H_idx.numpy(), H_test=H_test.numpy(),
                         xt_h=xt_h.numpy(), it_h=it_h.numpy(),

@@ -87,6 +87,12 @@ def run_all(dev):
     assert Hi.shape == (3,) and _rel(Hi.cpu().numpy(), g["H_idx"]) < HTOL, _rel(Hi.cpu().numpy(), g["H_idx"])
     Ht = prediction.test_predmap_harmard(*hargs, d("xt_h"), torch.from_numpy(g["it_h"]), *hyp)
     assert _rel(Ht.cpu().numpy(), g["H_test"]) < HTOL, _rel(Ht.cpu().numpy(), g["H_test"])
+    # stationary Hadamard (incl. the reference's quirk: the indexed variants take the prior variance of output 0)
+    SHg = prediction.pointwise_predmap_S_hadamard(sc("tl_S"), sc("ts_S"), d("L_vec_h"), s2t, d("xh"), ih, d("yh"), d("grids")[:3])
+    assert _rel(SHg.cpu().numpy(), g["SH_grid"]) < HTOL, _rel(SHg.cpu().numpy(), g["SH_grid"])
+    SHm, SHs = prediction.test_predmap_S_hadamard(sc("tl_S"), sc("ts_S"), d("L_vec_h"), s2t, d("xh"), ih, d("yh"), d("xt_h"),
+                                                  torch.from_numpy(g["it_h"]))
+    assert _rel(SHm.cpu().numpy(), g["SH_mean"]) < HTOL and _rel(SHs.cpu().numpy(), g["SH_std"]) < HTOL
     hh = (d("tlh_h"), d("tsh_h"), d("Lh_h"), d("s2h_h"), d("xh"), ih, d("yh"))
     torch.manual_seed(41)
     HSg = prediction.pointwise_predsample_hadamard(*hh, d("grids")[2:4], *hyp)
