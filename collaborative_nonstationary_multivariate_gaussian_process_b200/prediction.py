@@ -40,6 +40,15 @@ def Lvec2uLvec(L_vec, M):
     return uL_vec
 
 
+def uLvecs2Lvecs(uL_vecs, N, M):
+    """utils.py:38-46: uLvec2Lvec applied to each of the N consecutive packed triangles."""
+    P = M * (M + 1) // 2
+    on = _diag_positions(M)
+    U = uL_vecs.reshape(N, P).clone()
+    U[:, on] = torch.exp(U[:, on])
+    return U.reshape(-1)
+
+
 def vec2lowtriangle(x, N=None):
     """utils.py:56-74."""
     if N * (N + 1) / 2 != x.shape[0]:
@@ -569,7 +578,90 @@ def test_predmap_S_hadamard(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, in
     return res[:, 0], res[:, 1]
 
 
+# ---- spatially varying coregionalisation ("inhomogeneous") MAP predictors (prediction.py:912-1036) -------------------
+class _InhomogeneousState:
+    """K[(m,n),(m',n')] = K_x[n,n'] (L_n L_n'^T)[m,m'] + sigma2 I in the output-major order of y = Y^T.view(-1)
+    (prediction.py:944-953): built as (L_row L_row^T) * K_x[n,n'] and factorised once by the blocked Cholesky; the GP
+    conditionals of log-ell and of the P = M(M+1)/2 entries of the packed triangle are hoisted as well."""
+
+    def __init__(self, tilde_l, uL_vecs, tilde_sigma2_err, Y, x, hyp_l, hyp_L):
+        N, M = Y.shape
+        P = M * (M + 1) // 2
+        dev = Y.device
+        self.N, self.M, self.P = N, M, P
+        self.x = x.contiguous().view(-1, 1)
+        self.gp_l, self.gp_L = _ConditionalGP(self.x, *hyp_l), _ConditionalGP(self.x, *hyp_L)
+        self.w_l = self.gp_l.weights(tilde_l)
+        U = uL_vecs.reshape(N, P)
+        self.W_L = torch.stack([self.gp_L.weights(U[:, p_].contiguous()) for p_ in range(P)])       # [P, N]
+        self.sigma2_err = torch.exp(tilde_sigma2_err)
+        self.l = torch.exp(tilde_l).contiguous()
+        Lmat = torch.zeros(N, M, M, dtype=torch.float64, device=dev)
+        idx = torch.tril_indices(M, M, device=dev)
+        Lmat[:, idx[0], idx[1]] = uLvecs2Lvecs(uL_vecs, N, M).reshape(N, P)
+        self.Lrow = Lmat.permute(1, 0, 2).reshape(M * N, M).contiguous()          # row (m, n) = L_n[m, :]
+        self.nidx = torch.arange(N, dtype=torch.int32, device=dev).repeat(M).contiguous()
+        self.zero_idx = torch.zeros(M, dtype=torch.int32, device=dev)
+        K_i = ops.gemm_nt(self.Lrow, self.Lrow)
+        K_x = kernels.Nonstationary_RBF_cov(self.x, ell1=self.l)
+        S = ops.hadamard_index_cov(K_i, K_x, self.nidx, self.nidx, float(self.sigma2_err))
+        self.Lc, _ = ops.potrf_big(S)
+        self.alpha = ops.potrs_vec(self.Lc, Y.t().contiguous().view(-1))
+
+    def point(self, x_star):
+        N, M = self.N, self.M
+        dev = self.x.device
+        xs = x_star.reshape(1, 1).to(torch.float64)
+        k = kernels.RBF_cov(self.x, xs, alpha=self.gp_l.alpha, beta=self.gp_l.beta).view(-1).contiguous()
+        l_star = torch.exp(self.gp_l.mu + ops.dot(k, self.w_l).reshape(())).view(1)
+        kL = kernels.RBF_cov(self.x, xs, alpha=self.gp_L.alpha, beta=self.gp_L.beta).view(1, -1).contiguous()
+        uL_star = self.gp_L.mu + ops.gemm_nt(self.W_L.contiguous(), kL).view(-1)                  # [P]
+        L_vec_star = uLvec2Lvec(uL_star, M)
+        L_star = vec2lowtriangle(L_vec_star, M).contiguous()
+        one = torch.ones(1, dtype=torch.float64, device=dev)
+        k_x = kernels.Nonstationary_RBF_cov(X1=self.x, sigma1=torch.ones(N, dtype=torch.float64, device=dev), ell1=self.l,
+                                            X2=xs, sigma2=one, ell2=l_star).contiguous()           # [N, 1]
+        A_f = ops.hadamard_index_cov(self.Lrow, k_x, self.nidx, self.zero_idx, 0.0)                # row (m,n): k_x[n] L_n[m,:]
+        k_fT = ops.gemm_nt(L_star, A_f)                                                            # [M, M N]
+        k_ss = kernels.Nonstationary_RBF_cov(X1=xs, sigma1=one, ell1=l_star).view(())             # 1 + 1e-6
+        prior = ops.gemm_nt(L_star, L_star)
+        mus, vs = [], []
+        for m in range(M):
+            kf = k_fT[m].contiguous()
+            mus.append(ops.dot(kf, self.alpha).reshape(()))
+            vs.append(prior[m, m] * k_ss - ops.dot(kf, ops.potrs_vec(self.Lc, kf)).reshape(()) + self.sigma2_err)
+        mu_f, s2 = torch.stack(mus), torch.stack(vs)
+        s2 = torch.where(s2 <= 0, torch.full_like(s2, settings.precision), s2)
+        sd = torch.sqrt(s2)
+        return torch.stack([mu_f - 1.96 * sd, mu_f, mu_f + 1.96 * sd]), L_vec_star
+
+
+def point_predmap_inhomogeneous(tilde_l, uL_vecs, tilde_sigma2_err, Y, x, x_star, mu_tilde_l, alpha_tilde_l,
+                                beta_tilde_l, mu_L, alpha_L, beta_L, *args, **kwargs):
+    """prediction.py:912-988: ([3, M] band, estimated packed triangle L_vec at x_star)."""
+    st = _InhomogeneousState(tilde_l, uL_vecs, tilde_sigma2_err, Y, x, (mu_tilde_l, alpha_tilde_l, beta_tilde_l),
+                             (mu_L, alpha_L, beta_L))
+    return st.point(x_star)
+
+
+def pointwise_predmap_inhomogeneous(tilde_l, uL_vecs, tilde_sigma2_err, Y, x, grids, mu_tilde_l, alpha_tilde_l,
+                                    beta_tilde_l, mu_L, alpha_L, beta_L, *args, **kwargs):
+    """prediction.py:990-1012: ([N_grid, 3, M], [N_grid, P]); one factorisation for all grid points."""
+    st = _InhomogeneousState(tilde_l, uL_vecs, tilde_sigma2_err, Y, x, (mu_tilde_l, alpha_tilde_l, beta_tilde_l),
+                             (mu_L, alpha_L, beta_L))
+    res = [st.point(g) for g in grids]
+    return torch.stack([r[0] for r in res]), torch.stack([r[1] for r in res])
+
+
+def test_predmap_inhomogeneous(tilde_l, L_vecs, tilde_sigma2_err, Y, x, x_test, mu_tilde_l, alpha_tilde_l, beta_tilde_l,
+                               mu_L, alpha_L, beta_L, *args, **kwargs):
+    """prediction.py:1014-1036 (its `L_vecs` argument is passed on as the unconstrained uL_vecs, as in the reference)."""
+    return pointwise_predmap_inhomogeneous(tilde_l, L_vecs, tilde_sigma2_err, Y, x, x_test, mu_tilde_l, alpha_tilde_l,
+                                           beta_tilde_l, mu_L, alpha_L, beta_L)
+
+
 test_predmap.__test__ = False      # not pytest tests
+test_predmap_inhomogeneous.__test__ = False
 test_predmap_S_hadamard.__test__ = False
 test_predsample_hadamard.__test__ = False
 test_predmap_harmard.__test__ = False

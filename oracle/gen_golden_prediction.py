@@ -74,6 +74,17 @@ def main():
     H_test = prediction.test_predmap_harmard(tlh, tsh, L_vec_h, tilde_s2, xh, ih, yh, xt_h, it_h, *args)
     SH_grid = prediction.pointwise_predmap_S_hadamard(tl_S0, ts_S0, L_vec_h, tilde_s2, xh, ih, yh, grids[:3])
     SH_mean, SH_std = prediction.test_predmap_S_hadamard(tl_S0, ts_S0, L_vec_h, tilde_s2, xh, ih, yh, xt_h, it_h)
+    # spatially varying coregionalisation ("inhomogeneous"): a packed triangle per input
+    Ni, Mi = 24, 2
+    Pi = Mi * (Mi + 1) // 2
+    gi = torch.Generator().manual_seed(17)
+    xi = torch.sort(torch.rand(Ni, generator=gi).double())[0]
+    tli = (3 * (xi - 1) ** 3 - 1.5) + 0.05 * torch.randn(Ni, generator=gi).double()
+    uLi = (0.3 * torch.randn(Ni * Pi, generator=gi).double())
+    Yi = torch.randn(Ni, Mi, generator=gi).double()
+    hyp_i = [torch.tensor(v).double() for v in (-1.0, 1.5, 0.3, 0.1, 0.7, 0.35)]
+    with contextlib.redirect_stdout(io.StringIO()):
+        IN_y, IN_L = prediction.pointwise_predmap_inhomogeneous(tli, uLi, tilde_s2, Yi, xi, grids[1:4], *hyp_i)
     Hh = 3
     tlh_h = torch.stack([tlh + 0.03 * torch.randn(xh.numel()).double() for _ in range(Hh)])
     tsh_h = torch.stack([tsh + 0.03 * torch.randn(xh.numel()).double() for _ in range(Hh)])
@@ -88,6 +99,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "sim_prediction.npz"), x=x.numpy(), tilde_l=tilde_l.numpy(),
                         tlh_h=tlh_h.numpy(), tsh_h=tsh_h.numpy(), Lh_h=Lh_h.numpy(), s2h_h=s2h_h.numpy(),
                         HS_grid=HS_grid.numpy(), HS_test=HS_test.numpy(),
+                        xi=xi.numpy(), tli=tli.numpy(), uLi=uLi.numpy(), Yi=Yi.numpy(), hyp_i=np.array([float(v) for v in hyp_i]),
+                        IN_y=IN_y.numpy(), IN_L=IN_L.numpy(),
                         SH_grid=SH_grid.numpy(), SH_mean=SH_mean.numpy(), SH_std=SH_std.numpy(),
                         xh=xh.numpy(), ih=ih.numpy(), yh=yh.numpy(), tlh=tlh.numpy(), tsh=tsh.numpy(), L_vec_h=L_vec_h.numpy(),
                         H_point=H_point.numpy(), H_grid=H_grid.numpy(), H_idx=H_idx.numpy(), H_test=H_test.numpy(),

@@ -93,6 +93,12 @@ def run_all(dev):
     SHm, SHs = prediction.test_predmap_S_hadamard(sc("tl_S"), sc("ts_S"), d("L_vec_h"), s2t, d("xh"), ih, d("yh"), d("xt_h"),
                                                   torch.from_numpy(g["it_h"]))
     assert _rel(SHm.cpu().numpy(), g["SH_mean"]) < HTOL and _rel(SHs.cpu().numpy(), g["SH_std"]) < HTOL
+    # spatially varying coregionalisation: dense (N M) x (N M) system, one Cholesky for all grid points
+    hyp_i = [torch.tensor(float(v), dtype=torch.float64) for v in g["hyp_i"]]
+    INy, INL = prediction.pointwise_predmap_inhomogeneous(d("tli"), d("uLi"), s2t, d("Yi"), d("xi"), d("grids")[1:4], *hyp_i)
+    assert INy.shape == g["IN_y"].shape and INL.shape == g["IN_L"].shape
+    assert _rel(INy.cpu().numpy(), g["IN_y"]) < HTOL, _rel(INy.cpu().numpy(), g["IN_y"])
+    assert _rel(INL.cpu().numpy(), g["IN_L"]) < HTOL, _rel(INL.cpu().numpy(), g["IN_L"])
     hh = (d("tlh_h"), d("tsh_h"), d("Lh_h"), d("s2h_h"), d("xh"), ih, d("yh"))
     torch.manual_seed(41)
     HSg = prediction.pointwise_predsample_hadamard(*hh, d("grids")[2:4], *hyp)
@@ -101,6 +107,7 @@ def run_all(dev):
     HSt = prediction.test_predsample_hadamard(*hh, d("xt_h")[:3], torch.from_numpy(g["it_h"])[:3], *hyp)
     assert HSt.shape == g["HS_test"].shape and _rel(HSt.cpu().numpy(), g["HS_test"]) < HTOL, _rel(HSt.cpu().numpy(), g["HS_test"])
     return {"point": _rel(one.cpu().numpy(), g["point"]), "pointwise": _rel(allg.cpu().numpy(), g["pointwise"]),
+            "IN_y": _rel(INy.cpu().numpy(), g["IN_y"]), "IN_L": _rel(INL.cpu().numpy(), g["IN_L"]),
             "HS_grid": _rel(HSg.cpu().numpy(), g["HS_grid"]), "HS_test": _rel(HSt.cpu().numpy(), g["HS_test"]),
             "H_point": _rel(Hp.cpu().numpy(), g["H_point"]), "H_grid": _rel(Hg.cpu().numpy(), g["H_grid"]),
             "H_test": _rel(Ht.cpu().numpy(), g["H_test"]),
