@@ -412,7 +412,7 @@ def hadamard_index_cov(Kx, Bf, indx1, indx2, diag=0.0):
     N1, N2 = Kx.shape
     out = _empty(Kx, N1, N2)
     check(lib().nmgp_hadamard_index_cov(_d(Kx), _d(Bf), _i(indx1), _i(indx2), c_double(diag), _d(out), c_int64(N1),
-                                        c_int64(N2), c_int(Bf.shape[0]), _stream()), "nmgp_hadamard_index_cov")
+                                        c_int64(N2), c_int(Bf.shape[1]), _stream()), "nmgp_hadamard_index_cov")
     return out
 
 

@@ -168,7 +168,8 @@ int nmgp_sim_rbf_cov(const double* X1, const double* X2, double alpha, double be
                      long long T1, long long T2, int dx, nmgp_stream_t stream);
 
 /* out[i,j] = Kx[i,j] * Bf[indx1[i], indx2[j]] (+ diag on i == j): logpos.py:87-98 generate_K_index fused with the
- * Hadamard product K_x * K_i and the sigma2_err I of prediction.py:746-750 (irregular observations); indices int32 in [0, M) */
+ * Hadamard product K_x * K_i and the sigma2_err I of prediction.py:746-750 (irregular observations); Bf is row-major
+ * with M columns (square M x M on the reference's call sites), indices int32 */
 int nmgp_hadamard_index_cov(const double* Kx, const double* Bf, const int* indx1, const int* indx2, double diag,
                             double* out, long long N1, long long N2, int M, nmgp_stream_t stream);
 

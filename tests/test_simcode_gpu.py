@@ -132,3 +132,7 @@ def test_hadamard_index_cov():
         i1 = torch.randint(0, M, (n1,), generator=gen).to(torch.int32); i2 = torch.randint(0, M, (n2,), generator=gen).to(torch.int32)
         got = ops.hadamard_index_cov(d(Kx), d(Bf), i1.cuda(), i2.cuda(), 0.25)
         assert rel(got, specs.hadamard_index_cov(Kx, Bf, i1, i2, 0.25)) < 1e-15
+    # non-square weight table (rows scaled by a per-row factor: Bf is [R, 1], all column indices 0)
+    Kx = torch.randn(40, 3, generator=gen, dtype=torch.float64); Bf = torch.randn(8, 1, generator=gen, dtype=torch.float64)
+    i1 = torch.randint(0, 8, (40,), generator=gen).to(torch.int32); i2 = torch.zeros(3, dtype=torch.int32)
+    assert rel(ops.hadamard_index_cov(d(Kx), d(Bf), i1.cuda(), i2.cuda(), 0.0), specs.hadamard_index_cov(Kx, Bf, i1, i2, 0.0)) < 1e-15
