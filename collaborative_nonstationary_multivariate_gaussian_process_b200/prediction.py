@@ -660,7 +660,109 @@ def test_predmap_inhomogeneous(tilde_l, L_vecs, tilde_sigma2_err, Y, x, x_test, 
                                            beta_tilde_l, mu_L, alpha_L, beta_L)
 
 
+# ---- SVC Hadamard MAP predictors (prediction.py:1367-1530): irregular observations, a triangle per observation -------
+class _SVCHadamardState:
+    """K[n,n'] = K_x[n,n'] (L_n[indx_n,:] . L_n'[indx_n',:]) + sigma2 I (prediction.py:1391-1397), factorised once."""
+
+    def __init__(self, tilde_l, L_vecs, tilde_sigma2_err, x, indx, y, hyp_l, hyp_L):
+        N = y.shape[0]
+        M = int(torch.unique(indx).numel())
+        P = M * (M + 1) // 2
+        dev = y.device
+        self.N, self.M, self.P = N, M, P
+        self.x = x.contiguous().view(-1, 1)
+        self.gp_l, self.gp_L = _ConditionalGP(self.x, *hyp_l), _ConditionalGP(self.x, *hyp_L)
+        self.w_l = self.gp_l.weights(tilde_l)
+        Lv = L_vecs.reshape(N, P)                            # used as given (no exp of the diagonal, prediction.py:1385)
+        self.W_L = torch.stack([self.gp_L.weights(Lv[:, p_].contiguous()) for p_ in range(P)])    # [P, N]
+        self.sigma2_err = torch.exp(tilde_sigma2_err)
+        self.l = torch.exp(tilde_l).contiguous()
+        Lmat = torch.zeros(N, M, M, dtype=torch.float64, device=dev)
+        idx = torch.tril_indices(M, M, device=dev)
+        Lmat[:, idx[0], idx[1]] = Lv
+        self.Lsel = Lmat[torch.arange(N, device=dev), indx.long().to(dev)].contiguous()            # row n = L_n[indx_n, :]
+        self.ident = torch.arange(N, dtype=torch.int32, device=dev)
+        self.zero_idx = torch.zeros(M, dtype=torch.int32, device=dev)
+        K_i = ops.gemm_nt(self.Lsel, self.Lsel)
+        K_x = kernels.Nonstationary_RBF_cov(self.x, ell1=self.l)
+        S = ops.hadamard_index_cov(K_i, K_x, self.ident, self.ident, float(self.sigma2_err))
+        self.Lc, _ = ops.potrf_big(S)
+        self.alpha = ops.potrs_vec(self.Lc, y.contiguous())
+
+    def _common(self, x_star):
+        N, M = self.N, self.M
+        dev = self.x.device
+        xs = x_star.reshape(1, 1).to(torch.float64)
+        k = kernels.RBF_cov(self.x, xs, alpha=self.gp_l.alpha, beta=self.gp_l.beta).view(-1).contiguous()
+        l_star = torch.exp(self.gp_l.mu + ops.dot(k, self.w_l).reshape(())).view(1)
+        kL = kernels.RBF_cov(self.x, xs, alpha=self.gp_L.alpha, beta=self.gp_L.beta).view(1, -1).contiguous()
+        L_star = vec2lowtriangle(self.gp_L.mu + ops.gemm_nt(self.W_L.contiguous(), kL).view(-1), M).contiguous()
+        one = torch.ones(1, dtype=torch.float64, device=dev)
+        k_x = kernels.Nonstationary_RBF_cov(X1=self.x, sigma1=torch.ones(N, dtype=torch.float64, device=dev), ell1=self.l,
+                                            X2=xs, sigma2=one, ell2=l_star).contiguous()           # [N, 1]
+        k_ss = kernels.Nonstationary_RBF_cov(X1=xs, ell1=l_star).view(())                          # 1 + 1e-6
+        prior = torch.diagonal(ops.gemm_nt(L_star, L_star)) * k_ss                                 # diag of A
+        k_i = ops.gemm_nt(self.Lsel, L_star)                                                       # [N, M]
+        k_f = ops.hadamard_index_cov(k_i, k_x, self.ident, self.zero_idx, 0.0)                     # rows scaled by k_x[n]
+        return prior, k_f.t().contiguous()                                                         # [M], [M, N]
+
+    def _quad(self, kf):
+        return ops.dot(kf, self.alpha).reshape(()), ops.dot(kf, ops.potrs_vec(self.Lc, kf)).reshape(())
+
+    def point(self, x_star):
+        prior, k_fT = self._common(x_star)
+        mq = [self._quad(k_fT[m].contiguous()) for m in range(self.M)]
+        mu_f = torch.stack([a for a, _ in mq])
+        s2 = prior - torch.stack([b for _, b in mq]) + self.sigma2_err
+        s2 = torch.where(s2 <= 0, torch.full_like(s2, settings.precision), s2)
+        sd = torch.sqrt(s2)
+        return torch.stack([mu_f - 1.96 * sd, mu_f, mu_f + 1.96 * sd])
+
+    def indexed(self, x_star, indx_star):
+        """[mean, A[0,0]-b+s2, ..., A[M-1,M-1]-b+s2]: the reference subtracts the 1x1 explained variance of the requested
+        output from the whole prior diagonal and returns VARIANCES (prediction.py:1505-1512); reproduced."""
+        prior, k_fT = self._common(x_star)
+        mu, b = self._quad(k_fT[int(indx_star)].contiguous())
+        s2 = prior - b + self.sigma2_err
+        s2 = torch.where(s2 <= 0, torch.full_like(s2, settings.precision), s2)
+        return torch.cat([mu.view(1), s2.view(-1)])
+
+
+def _svc_state(tilde_l, L_vecs, tilde_sigma2_err, x, indx, y, hyper):
+    mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L = hyper[:6]
+    return _SVCHadamardState(tilde_l, L_vecs, tilde_sigma2_err, x, indx, y, (mu_tilde_l, alpha_tilde_l, beta_tilde_l),
+                             (mu_L, alpha_L, beta_L))
+
+
+def point_predmap_SVC_hadamard(tilde_l, L_vecs, tilde_sigma2_err, x, indx, y, x_star, mu_tilde_l, alpha_tilde_l,
+                               beta_tilde_l, mu_L, alpha_L, beta_L, *args, **kwargs):
+    """prediction.py:1367-1431: [3, M]."""
+    return _svc_state(tilde_l, L_vecs, tilde_sigma2_err, x, indx, y,
+                      (mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L)).point(x_star)
+
+
+def pointwise_predmap_SVC_hadamard(tilde_l, L_vecs, tilde_sigma2_err, x, indx, y, grids, *args, **kwargs):
+    """prediction.py:1433-1444: [N_grid, 3, M]; the six hyper-parameters travel in *args as in the reference."""
+    st = _svc_state(tilde_l, L_vecs, tilde_sigma2_err, x, indx, y, args)
+    return torch.stack([st.point(g) for g in grids])
+
+
+def indexedpoint_predmap_SVC_hadamard(tilde_l, L_vecs, tilde_sigma2_err, x, indx, y, x_star, indx_star, mu_tilde_l,
+                                      alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L, *args, **kwargs):
+    """prediction.py:1446-1513: tensor of length 1 + M (see _SVCHadamardState.indexed)."""
+    return _svc_state(tilde_l, L_vecs, tilde_sigma2_err, x, indx, y,
+                      (mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L)).indexed(x_star, indx_star)
+
+
+def test_predmap_SVC_hadamard(tilde_l, L_vecs, tilde_sigma2_err, x, indx, y, x_test, indx_test, *args, **kwargs):
+    """prediction.py:1515-1530: (res[:, 0], res[:, 1]) of the stacked indexed results."""
+    st = _svc_state(tilde_l, L_vecs, tilde_sigma2_err, x, indx, y, args)
+    res = torch.stack([st.indexed(xs, ii) for xs, ii in zip(x_test, indx_test)])
+    return res[:, 0], res[:, 1]
+
+
 test_predmap.__test__ = False      # not pytest tests
+test_predmap_SVC_hadamard.__test__ = False
 test_predmap_inhomogeneous.__test__ = False
 test_predmap_S_hadamard.__test__ = False
 test_predsample_hadamard.__test__ = False

@@ -85,6 +85,13 @@ def main():
     hyp_i = [torch.tensor(v).double() for v in (-1.0, 1.5, 0.3, 0.1, 0.7, 0.35)]
     with contextlib.redirect_stdout(io.StringIO()):
         IN_y, IN_L = prediction.pointwise_predmap_inhomogeneous(tli, uLi, tilde_s2, Yi, xi, grids[1:4], *hyp_i)
+    # SVC Hadamard: irregular observations with a packed triangle per observation (used raw, no exp)
+    Nh = xh.numel()
+    Lv_svc = 0.4 * torch.randn(Nh * (M * (M + 1) // 2), generator=gi).double() + 0.3
+    with contextlib.redirect_stdout(io.StringIO()):
+        SVC_grid = prediction.pointwise_predmap_SVC_hadamard(tlh, Lv_svc, tilde_s2, xh, ih, yh, grids[2:5], *hyp_i)
+        SVC_m, SVC_v = prediction.test_predmap_SVC_hadamard(tlh, Lv_svc, tilde_s2, xh, ih, yh, xt_h, it_h, *hyp_i)
+    SVC_idx = prediction.indexedpoint_predmap_SVC_hadamard(tlh, Lv_svc, tilde_s2, xh, ih, yh, grids[1], torch.tensor(2), *hyp_i)
     Hh = 3
     tlh_h = torch.stack([tlh + 0.03 * torch.randn(xh.numel()).double() for _ in range(Hh)])
     tsh_h = torch.stack([tsh + 0.03 * torch.randn(xh.numel()).double() for _ in range(Hh)])
@@ -98,7 +105,8 @@ def main():
         HS_test = prediction.test_predsample_hadamard(tlh_h, tsh_h, Lh_h, s2h_h, xh, ih, yh, xt_h[:3], it_h[:3], *args)
     np.savez_compressed(os.path.join(OUT, "sim_prediction.npz"), x=x.numpy(), tilde_l=tilde_l.numpy(),
                         tlh_h=tlh_h.numpy(), tsh_h=tsh_h.numpy(), Lh_h=Lh_h.numpy(), s2h_h=s2h_h.numpy(),
-                        HS_grid=HS_grid.numpy(), HS_test=HS_test.numpy(),
+                        HS_grid=HS_grid.numpy(), HS_test=HS_test.numpy(), Lv_svc=Lv_svc.numpy(),
+                        SVC_grid=SVC_grid.numpy(), SVC_m=SVC_m.numpy(), SVC_v=SVC_v.numpy(), SVC_idx=SVC_idx.numpy(),
                         xi=xi.numpy(), tli=tli.numpy(), uLi=uLi.numpy(), Yi=Yi.numpy(), hyp_i=np.array([float(v) for v in hyp_i]),
                         IN_y=IN_y.numpy(), IN_L=IN_L.numpy(),
                         SH_grid=SH_grid.numpy(), SH_mean=SH_mean.numpy(), SH_std=SH_std.numpy(),

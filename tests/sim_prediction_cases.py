@@ -99,6 +99,14 @@ def run_all(dev):
     assert INy.shape == g["IN_y"].shape and INL.shape == g["IN_L"].shape
     assert _rel(INy.cpu().numpy(), g["IN_y"]) < HTOL, _rel(INy.cpu().numpy(), g["IN_y"])
     assert _rel(INL.cpu().numpy(), g["IN_L"]) < HTOL, _rel(INL.cpu().numpy(), g["IN_L"])
+    # SVC Hadamard (incl. the reference's return conventions for the indexed variants)
+    svc = (d("tlh"), d("Lv_svc"), s2t, d("xh"), ih, d("yh"))
+    SVg = prediction.pointwise_predmap_SVC_hadamard(*svc, d("grids")[2:5], *hyp_i)
+    assert SVg.shape == g["SVC_grid"].shape and _rel(SVg.cpu().numpy(), g["SVC_grid"]) < HTOL, _rel(SVg.cpu().numpy(), g["SVC_grid"])
+    SVm, SVv = prediction.test_predmap_SVC_hadamard(*svc, d("xt_h"), torch.from_numpy(g["it_h"]), *hyp_i)
+    assert _rel(SVm.cpu().numpy(), g["SVC_m"]) < HTOL and _rel(SVv.cpu().numpy(), g["SVC_v"]) < HTOL
+    SVi = prediction.indexedpoint_predmap_SVC_hadamard(*svc, d("grids")[1], torch.tensor(2), *hyp_i)
+    assert SVi.shape == g["SVC_idx"].shape and _rel(SVi.cpu().numpy(), g["SVC_idx"]) < HTOL, _rel(SVi.cpu().numpy(), g["SVC_idx"])
     hh = (d("tlh_h"), d("tsh_h"), d("Lh_h"), d("s2h_h"), d("xh"), ih, d("yh"))
     torch.manual_seed(41)
     HSg = prediction.pointwise_predsample_hadamard(*hh, d("grids")[2:4], *hyp)
@@ -107,6 +115,7 @@ def run_all(dev):
     HSt = prediction.test_predsample_hadamard(*hh, d("xt_h")[:3], torch.from_numpy(g["it_h"])[:3], *hyp)
     assert HSt.shape == g["HS_test"].shape and _rel(HSt.cpu().numpy(), g["HS_test"]) < HTOL, _rel(HSt.cpu().numpy(), g["HS_test"])
     return {"point": _rel(one.cpu().numpy(), g["point"]), "pointwise": _rel(allg.cpu().numpy(), g["pointwise"]),
+            "SVC_grid": _rel(SVg.cpu().numpy(), g["SVC_grid"]), "SVC_idx": _rel(SVi.cpu().numpy(), g["SVC_idx"]),
             "IN_y": _rel(INy.cpu().numpy(), g["IN_y"]), "IN_L": _rel(INL.cpu().numpy(), g["IN_L"]),
             "HS_grid": _rel(HSg.cpu().numpy(), g["HS_grid"]), "HS_test": _rel(HSt.cpu().numpy(), g["HS_test"]),
             "H_point": _rel(Hp.cpu().numpy(), g["H_point"]), "H_grid": _rel(Hg.cpu().numpy(), g["H_grid"]),
