@@ -19,6 +19,18 @@ from . import _ops as ops
 from . import kernels, kronecker_operation, settings
 
 
+def vec2pars(pars_hist, N, M):
+    """prediction.py:14-24: split a history of flat parameter vectors (slicing only)."""
+    P = M * (M + 1) // 2
+    return pars_hist[:, :N], pars_hist[:, N:2 * N], pars_hist[:, 2 * N:2 * N + P], pars_hist[:, -1]
+
+
+def vec2list(y_vec, indx):
+    """prediction.py:26-30: observations of each output as a list (indexing only)."""
+    M = int(np.unique(np.asarray(indx.cpu() if torch.is_tensor(indx) else indx)).shape[0])
+    return [y_vec[indx == i] for i in range(M)]
+
+
 # ---- code/SIM_code/Utility/utils.py:10-88 (index plumbing on tiny vectors) -------------------------------------------
 def _diag_positions(M):
     return list(np.cumsum(np.arange(1, M + 1)) - 1)
@@ -584,7 +596,7 @@ class _InhomogeneousState:
     (prediction.py:944-953): built as (L_row L_row^T) * K_x[n,n'] and factorised once by the blocked Cholesky; the GP
     conditionals of log-ell and of the P = M(M+1)/2 entries of the packed triangle are hoisted as well."""
 
-    def __init__(self, tilde_l, uL_vecs, tilde_sigma2_err, Y, x, hyp_l, hyp_L):
+    def __init__(self, tilde_l, uL_vecs, tilde_sigma2_err, Y, x, hyp_l, hyp_L, constrained_conditional=False):
         N, M = Y.shape
         P = M * (M + 1) // 2
         dev = Y.device
@@ -592,7 +604,9 @@ class _InhomogeneousState:
         self.x = x.contiguous().view(-1, 1)
         self.gp_l, self.gp_L = _ConditionalGP(self.x, *hyp_l), _ConditionalGP(self.x, *hyp_L)
         self.w_l = self.gp_l.weights(tilde_l)
-        U = uL_vecs.reshape(N, P)
+        # the MAP predictors condition the GP on the unconstrained entries (prediction.py:931-934); the history-based
+        # sampler conditions it on the constrained ones, diagonals already exponentiated (prediction.py:1259-1266)
+        U = (uLvecs2Lvecs(uL_vecs, N, M) if constrained_conditional else uL_vecs).reshape(N, P)
         self.W_L = torch.stack([self.gp_L.weights(U[:, p_].contiguous()) for p_ in range(P)])       # [P, N]
         self.sigma2_err = torch.exp(tilde_sigma2_err)
         self.l = torch.exp(tilde_l).contiguous()
@@ -608,15 +622,22 @@ class _InhomogeneousState:
         self.Lc, _ = ops.potrf_big(S)
         self.alpha = ops.potrs_vec(self.Lc, Y.t().contiguous().view(-1))
 
-    def point(self, x_star):
+    def cond_l(self, xs, with_var=False):
+        """conditional mean (and variance) of log-ell at xs"""
+        k = kernels.RBF_cov(self.x, xs, alpha=self.gp_l.alpha, beta=self.gp_l.beta).view(-1).contiguous()
+        mu = self.gp_l.mu + ops.dot(k, self.w_l).reshape(())
+        return (mu, self.gp_l.projection(xs)[2]) if with_var else mu
+
+    def cond_uL(self, xs, with_var=False):
+        """conditional means of the P packed-triangle entries at xs (and their common variance)"""
+        kL = kernels.RBF_cov(self.x, xs, alpha=self.gp_L.alpha, beta=self.gp_L.beta).view(1, -1).contiguous()
+        mu = self.gp_L.mu + ops.gemm_nt(self.W_L.contiguous(), kL).view(-1)                        # [P]
+        return (mu, self.gp_L.projection(xs)[2]) if with_var else mu
+
+    def predict(self, xs, l_star, L_vec_star):
+        """mean and variance of y(xs) given ell and the (constrained) packed triangle there"""
         N, M = self.N, self.M
         dev = self.x.device
-        xs = x_star.reshape(1, 1).to(torch.float64)
-        k = kernels.RBF_cov(self.x, xs, alpha=self.gp_l.alpha, beta=self.gp_l.beta).view(-1).contiguous()
-        l_star = torch.exp(self.gp_l.mu + ops.dot(k, self.w_l).reshape(())).view(1)
-        kL = kernels.RBF_cov(self.x, xs, alpha=self.gp_L.alpha, beta=self.gp_L.beta).view(1, -1).contiguous()
-        uL_star = self.gp_L.mu + ops.gemm_nt(self.W_L.contiguous(), kL).view(-1)                  # [P]
-        L_vec_star = uLvec2Lvec(uL_star, M)
         L_star = vec2lowtriangle(L_vec_star, M).contiguous()
         one = torch.ones(1, dtype=torch.float64, device=dev)
         k_x = kernels.Nonstationary_RBF_cov(X1=self.x, sigma1=torch.ones(N, dtype=torch.float64, device=dev), ell1=self.l,
@@ -631,9 +652,44 @@ class _InhomogeneousState:
             mus.append(ops.dot(kf, self.alpha).reshape(()))
             vs.append(prior[m, m] * k_ss - ops.dot(kf, ops.potrs_vec(self.Lc, kf)).reshape(()) + self.sigma2_err)
         mu_f, s2 = torch.stack(mus), torch.stack(vs)
-        s2 = torch.where(s2 <= 0, torch.full_like(s2, settings.precision), s2)
+        return mu_f, torch.where(s2 <= 0, torch.full_like(s2, settings.precision), s2)
+
+    def point(self, x_star):
+        xs = x_star.reshape(1, 1).to(torch.float64)
+        l_star = torch.exp(self.cond_l(xs)).view(1)
+        L_vec_star = uLvec2Lvec(self.cond_uL(xs), self.M)
+        mu_f, s2 = self.predict(xs, l_star, L_vec_star)
         sd = torch.sqrt(s2)
         return torch.stack([mu_f - 1.96 * sd, mu_f, mu_f + 1.96 * sd]), L_vec_star
+
+    def sample_point(self, x_star, n_sample, pred_smoothness=False, pred_cov=False):
+        """prediction.py:1056-1158: n_sample draws at one input; the three modes of the reference and its draw order."""
+        xs = x_star.reshape(1, 1).to(torch.float64)
+        floor = torch.tensor(settings.precision, dtype=torch.float64, device=self.x.device)
+        ls, Ls, ys = [], [], []
+        if not pred_cov:
+            mu_l, var_l = self.cond_l(xs, with_var=True)
+            var_l = torch.where(var_l < 0, floor, var_l)
+        if pred_cov or not pred_smoothness:
+            mu_u, var_u = self.cond_uL(xs, with_var=True)
+            sd_u = torch.sqrt(torch.where(var_u < 0, floor, var_u)).expand(self.P).contiguous()
+        for _ in range(n_sample):
+            if pred_smoothness:
+                ls.append(_draw(mu_l, torch.sqrt(var_l)))
+                continue
+            if pred_cov:
+                Ls.append(vec2lowtriangle(uLvec2Lvec(_draw(mu_u, sd_u), self.M), self.M))
+                continue
+            tl = _draw(mu_l, torch.sqrt(var_l))
+            L_vec_star = uLvec2Lvec(_draw(mu_u, sd_u), self.M)
+            mu_f, s2 = self.predict(xs, torch.exp(tl).view(1), L_vec_star)
+            ys.append(_draw(mu_f, torch.sqrt(s2)))
+        if pred_smoothness:
+            return torch.stack(ls).cpu().numpy()
+        if pred_cov:
+            return torch.stack(Ls).cpu().numpy()
+        ys = torch.stack(ys).cpu().numpy()
+        return np.percentile(ys, q=[2.5, 97.5], axis=0), np.mean(ys, axis=0), np.std(ys, axis=0)
 
 
 def point_predmap_inhomogeneous(tilde_l, uL_vecs, tilde_sigma2_err, Y, x, x_star, mu_tilde_l, alpha_tilde_l,
@@ -761,7 +817,88 @@ def test_predmap_SVC_hadamard(tilde_l, L_vecs, tilde_sigma2_err, x, indx, y, x_t
     return res[:, 0], res[:, 1]
 
 
+def _inhomogeneous_sampling(n_sample, tilde_l, uL_vecs, tilde_sigma2_err, Y, x, points, hyper, pred_smoothness, pred_cov):
+    st = _InhomogeneousState(tilde_l, uL_vecs, tilde_sigma2_err, Y, x, hyper[:3], hyper[3:6])
+    res = [st.sample_point(p_, n_sample, pred_smoothness, pred_cov) for p_ in points]
+    if pred_smoothness or pred_cov:
+        return res
+    return [r[0] for r in res], [r[1] for r in res], [r[2] for r in res]
+
+
+def point_predmap_inhomogeneous_sampling(n_sample, tilde_l, uL_vecs, tilde_sigma2_err, Y, x, x_star, mu_tilde_l,
+                                         alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L, pred_smoothness=False,
+                                         pred_cov=False, *args, **kwargs):
+    """prediction.py:1038-1158: (quantiles [2, M], mean [M], std [M]); or the n_sample draws of log-ell (pred_smoothness)
+    / of the coregionalisation triangle [n_sample, M, M] (pred_cov) at x_star."""
+    res = _inhomogeneous_sampling(n_sample, tilde_l, uL_vecs, tilde_sigma2_err, Y, x, [x_star],
+                                  (mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L), pred_smoothness, pred_cov)
+    return res[0] if (pred_smoothness or pred_cov) else (res[0][0], res[1][0], res[2][0])
+
+
+def pointwise_predmap_inhomogeneous_sampling(n_sample, tilde_l, uL_vecs, tilde_sigma2_err, Y, x, grids, mu_tilde_l,
+                                             alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L, pred_smoothness=False,
+                                             pred_cov=False, *args, **kwargs):
+    """prediction.py:1160-1201: the same stacked over the grid (numpy)."""
+    res = _inhomogeneous_sampling(n_sample, tilde_l, uL_vecs, tilde_sigma2_err, Y, x, list(grids),
+                                  (mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L), pred_smoothness, pred_cov)
+    if pred_smoothness or pred_cov:
+        return np.stack(res)
+    return np.stack(res[0]), np.stack(res[1]), np.stack(res[2])
+
+
+def test_predmap_inhomogeneous_sampling(n_sample, tilde_l, uL_vecs, tilde_sigma2_err, Y, x, x_test, mu_tilde_l,
+                                        alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L, *args, **kwargs):
+    """prediction.py:1203-1229."""
+    return pointwise_predmap_inhomogeneous_sampling(n_sample, tilde_l, uL_vecs, tilde_sigma2_err, Y, x, x_test, mu_tilde_l,
+                                                    alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L)
+
+
+def _predsample_inhomogeneous(hist, Y, x, points, hyper, N_sample):
+    tl_h, uL_h, s2_h = (h[-N_sample:] for h in hist)
+    states = [_InhomogeneousState(tl, uL, s2, Y, x, hyper[:3], hyper[3:6], constrained_conditional=True)
+              for tl, uL, s2 in zip(tl_h, uL_h, s2_h)]
+    floor = torch.tensor(settings.precision, dtype=torch.float64, device=Y.device)
+    out = []
+    for x_star in points:                                   # draw order of the reference: inputs outer, samples inner
+        xs = x_star.reshape(1, 1).to(torch.float64)
+        rows = []
+        for st in states:
+            mu_l, var_l = st.cond_l(xs, with_var=True)
+            tl = _draw(mu_l, torch.sqrt(torch.where(var_l < 0, floor, var_l)))
+            mu_L, var_L = st.cond_uL(xs, with_var=True)
+            sd_L = torch.sqrt(torch.where(var_L < 0, floor, var_L)).expand(st.P).contiguous()
+            L_vec_star = _draw(mu_L, sd_L)                  # used as the triangle itself (no exp), prediction.py:1267-1268
+            mu_f, s2 = st.predict(xs, torch.exp(tl).view(1), L_vec_star)
+            rows.append(_draw(mu_f, torch.sqrt(s2)))
+        out.append(torch.stack(rows))
+    return out
+
+
+def point_predsample_inhomogeneous(tilde_l_hist, uL_vecs_hist, tilde_sigma2_err_hist, Y, x, x_star, mu_tilde_l,
+                                   alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L, N_sample, *args, **kwargs):
+    """prediction.py:1231-1323: [N_sample, M]."""
+    return _predsample_inhomogeneous((tilde_l_hist, uL_vecs_hist, tilde_sigma2_err_hist), Y, x, [x_star],
+                                     (mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L), N_sample)[0]
+
+
+def pointwise_predsample_inhomogeneous(tilde_l_hist, uL_vecs_hist, tilde_sigma2_err_hist, Y, x, grids, mu_tilde_l,
+                                       alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L, N_sample, *args, **kwargs):
+    """prediction.py:1325-1344: numpy [N_grid, N_sample, M]."""
+    res = _predsample_inhomogeneous((tilde_l_hist, uL_vecs_hist, tilde_sigma2_err_hist), Y, x, list(grids),
+                                    (mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L), N_sample)
+    return torch.stack(res).cpu().numpy()
+
+
+def test_predsample_inhomogeneous(tilde_l_hist, uL_vecs_hist, tilde_sigma2_err_hist, Y, x, x_test, mu_tilde_l,
+                                  alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L, N_sample, *args, **kwargs):
+    """prediction.py:1346-1365."""
+    return pointwise_predsample_inhomogeneous(tilde_l_hist, uL_vecs_hist, tilde_sigma2_err_hist, Y, x, x_test, mu_tilde_l,
+                                              alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L, N_sample)
+
+
 test_predmap.__test__ = False      # not pytest tests
+test_predsample_inhomogeneous.__test__ = False
+test_predmap_inhomogeneous_sampling.__test__ = False
 test_predmap_SVC_hadamard.__test__ = False
 test_predmap_inhomogeneous.__test__ = False
 test_predmap_S_hadamard.__test__ = False

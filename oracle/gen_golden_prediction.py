@@ -85,6 +85,21 @@ def main():
     hyp_i = [torch.tensor(v).double() for v in (-1.0, 1.5, 0.3, 0.1, 0.7, 0.35)]
     with contextlib.redirect_stdout(io.StringIO()):
         IN_y, IN_L = prediction.pointwise_predmap_inhomogeneous(tli, uLi, tilde_s2, Yi, xi, grids[1:4], *hyp_i)
+    torch.manual_seed(91)
+    with contextlib.redirect_stdout(io.StringIO()):
+        INS_q, INS_m, INS_s = prediction.pointwise_predmap_inhomogeneous_sampling(5, tli, uLi, tilde_s2, Yi, xi, grids[1:3], *hyp_i)
+    torch.manual_seed(92)
+    with contextlib.redirect_stdout(io.StringIO()):
+        INS_l = prediction.pointwise_predmap_inhomogeneous_sampling(4, tli, uLi, tilde_s2, Yi, xi, grids[1:3], *hyp_i, pred_smoothness=True)
+    torch.manual_seed(93)
+    with contextlib.redirect_stdout(io.StringIO()):
+        INS_L = prediction.pointwise_predmap_inhomogeneous_sampling(4, tli, uLi, tilde_s2, Yi, xi, grids[1:3], *hyp_i, pred_cov=True)
+    tli_h = torch.stack([tli + 0.03 * torch.randn(Ni, generator=gi).double() for _ in range(3)])
+    uLi_h = torch.stack([uLi + 0.05 * torch.randn(Ni * Pi, generator=gi).double() for _ in range(3)])
+    s2i_h = tilde_s2 + 0.05 * torch.randn(3, generator=gi).double()
+    torch.manual_seed(94)
+    with contextlib.redirect_stdout(io.StringIO()):
+        INP = prediction.pointwise_predsample_inhomogeneous(tli_h, uLi_h, s2i_h, Yi, xi, grids[1:3], *hyp_i, 2)
     # SVC Hadamard: irregular observations with a packed triangle per observation (used raw, no exp)
     Nh = xh.numel()
     Lv_svc = 0.4 * torch.randn(Nh * (M * (M + 1) // 2), generator=gi).double() + 0.3
@@ -108,7 +123,8 @@ def main():
                         HS_grid=HS_grid.numpy(), HS_test=HS_test.numpy(), Lv_svc=Lv_svc.numpy(),
                         SVC_grid=SVC_grid.numpy(), SVC_m=SVC_m.numpy(), SVC_v=SVC_v.numpy(), SVC_idx=SVC_idx.numpy(),
                         xi=xi.numpy(), tli=tli.numpy(), uLi=uLi.numpy(), Yi=Yi.numpy(), hyp_i=np.array([float(v) for v in hyp_i]),
-                        IN_y=IN_y.numpy(), IN_L=IN_L.numpy(),
+                        IN_y=IN_y.numpy(), IN_L=IN_L.numpy(), INS_q=INS_q, INS_m=INS_m, INS_s=INS_s, INS_l=INS_l, INS_L=INS_L,
+                        tli_h=tli_h.numpy(), uLi_h=uLi_h.numpy(), s2i_h=s2i_h.numpy(), INP=INP,
                         SH_grid=SH_grid.numpy(), SH_mean=SH_mean.numpy(), SH_std=SH_std.numpy(),
                         xh=xh.numpy(), ih=ih.numpy(), yh=yh.numpy(), tlh=tlh.numpy(), tsh=tsh.numpy(), L_vec_h=L_vec_h.numpy(),
                         H_point=H_point.numpy(), H_grid=H_grid.numpy(), H_idx=H_idx.numpy(), H_test=H_test.numpy(),

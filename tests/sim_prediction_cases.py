@@ -35,6 +35,11 @@ def run_all(dev):
     Lm = prediction.vec2lowtriangle(Lv, M)
     assert float(torch.triu(Lm, 1).abs().max()) == 0.0
     assert _rel(prediction.lowtriangle2vec(Lm, M).cpu().numpy(), g["L_vec"]) < 1e-15
+    ph = torch.arange(2 * (2 * 5 + 3 + 1), dtype=torch.float64).reshape(2, -1)
+    a_, b_, c_, e_ = prediction.vec2pars(ph, 5, 2)
+    assert a_.shape == (2, 5) and b_.shape == (2, 5) and c_.shape == (2, 3) and float(e_[1]) == float(ph[1, -1])
+    yl = prediction.vec2list(torch.tensor([1., 2., 3., 4.]), torch.tensor([0, 1, 0, 1]))
+    assert [t.tolist() for t in yl] == [[1., 3.], [2., 4.]]
     args = (d("tilde_l"), d("tilde_sigma"), d("uL_vec"), torch.tensor(float(g["tilde_s2"]), dtype=torch.float64).to(dev),
             d("Y"), d("x"))
     one = prediction.point_predmap(*args, d("grids")[2], *hyp)
@@ -99,6 +104,21 @@ def run_all(dev):
     assert INy.shape == g["IN_y"].shape and INL.shape == g["IN_L"].shape
     assert _rel(INy.cpu().numpy(), g["IN_y"]) < HTOL, _rel(INy.cpu().numpy(), g["IN_y"])
     assert _rel(INL.cpu().numpy(), g["IN_L"]) < HTOL, _rel(INL.cpu().numpy(), g["IN_L"])
+    inh = (d("tli"), d("uLi"), s2t, d("Yi"), d("xi"), d("grids")[1:3])
+    torch.manual_seed(91)
+    q_, m_, s_ = prediction.pointwise_predmap_inhomogeneous_sampling(5, *inh, *hyp_i)
+    for got, key in ((q_, "INS_q"), (m_, "INS_m"), (s_, "INS_s")):
+        assert got.shape == g[key].shape and _rel(got, g[key]) < 10 * HTOL, (key, _rel(got, g[key]))
+    torch.manual_seed(92)
+    l_ = prediction.pointwise_predmap_inhomogeneous_sampling(4, *inh, *hyp_i, pred_smoothness=True)
+    assert l_.shape == g["INS_l"].shape and _rel(l_, g["INS_l"]) < HTOL, _rel(l_, g["INS_l"])
+    torch.manual_seed(93)
+    L_ = prediction.pointwise_predmap_inhomogeneous_sampling(4, *inh, *hyp_i, pred_cov=True)
+    assert L_.shape == g["INS_L"].shape and _rel(L_, g["INS_L"]) < HTOL, _rel(L_, g["INS_L"])
+    torch.manual_seed(94)
+    INP = prediction.pointwise_predsample_inhomogeneous(d("tli_h"), d("uLi_h"), d("s2i_h"), d("Yi"), d("xi"), d("grids")[1:3],
+                                                        *hyp_i, 2)
+    assert INP.shape == g["INP"].shape and _rel(INP, g["INP"]) < HTOL, _rel(INP, g["INP"])
     # SVC Hadamard (incl. the reference's return conventions for the indexed variants)
     svc = (d("tlh"), d("Lv_svc"), s2t, d("xh"), ih, d("yh"))
     SVg = prediction.pointwise_predmap_SVC_hadamard(*svc, d("grids")[2:5], *hyp_i)
@@ -116,6 +136,7 @@ def run_all(dev):
     assert HSt.shape == g["HS_test"].shape and _rel(HSt.cpu().numpy(), g["HS_test"]) < HTOL, _rel(HSt.cpu().numpy(), g["HS_test"])
     return {"point": _rel(one.cpu().numpy(), g["point"]), "pointwise": _rel(allg.cpu().numpy(), g["pointwise"]),
             "SVC_grid": _rel(SVg.cpu().numpy(), g["SVC_grid"]), "SVC_idx": _rel(SVi.cpu().numpy(), g["SVC_idx"]),
+            "INP": _rel(INP, g["INP"]), "INS_m": _rel(m_, g["INS_m"]), "INS_l": _rel(l_, g["INS_l"]), "INS_L": _rel(L_, g["INS_L"]),
             "IN_y": _rel(INy.cpu().numpy(), g["IN_y"]), "IN_L": _rel(INL.cpu().numpy(), g["IN_L"]),
             "HS_grid": _rel(HSg.cpu().numpy(), g["HS_grid"]), "HS_test": _rel(HSt.cpu().numpy(), g["HS_test"]),
             "H_point": _rel(Hp.cpu().numpy(), g["H_point"]), "H_grid": _rel(Hg.cpu().numpy(), g["H_grid"]),
