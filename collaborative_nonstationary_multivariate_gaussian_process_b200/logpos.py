@@ -1,0 +1,212 @@
+"""Forward values of the log joint posteriors of code/SIM_code/Utility/logpos.py (Kronecker NMGP, its stationary variant,
+and the Hadamard / irregular-observation variants), the deviance, and the index helpers next to them.
+
+Values only: the reference differentiates these objectives with autograd (scipy / HMC drivers); the adjoints of the
+SIM_code kernels are not built yet, so `nlogpos_obj*` here return plain values.  Every heavy step runs on
+the C-ABI kernels: covariance builds, the eigen-block Kronecker log-density (no symeig of K_x), dense blocked Cholesky
+in place of torch.inverse + torch.logdet and of MultivariateNormal's own factorisation.
+"""
+import math
+
+import torch
+
+from . import _ops as ops
+from . import distributions, kernels, kronecker_operation
+from .prediction import uLvec2Lvec, vec2lowtriangle
+
+
+# ---- parameter-vector helpers (logpos.py:17-72): slicing only ---------------------------------------------------------
+def vec2pars(pars, N, M):
+    P = M * (M + 1) // 2
+    return pars[:N], pars[N:2 * N], pars[2 * N:2 * N + P], pars[-1]
+
+
+def vec2pars_SVC(pars, N, M):
+    P = M * (M + 1) // 2
+    return pars[:N], pars[N:N + N * P], pars[-1]
+
+
+def vec2pars_S(pars, M):
+    P = M * (M + 1) // 2
+    return pars[0], pars[1], pars[2:2 + P], pars[-1]
+
+
+def vec2pars_hadamard_SVC(pars, N, M):
+    return vec2pars_SVC(pars, N, M)
+
+
+def generate_vectorized_indexes(indx1, indx2):
+    """logpos.py:74-84."""
+    N1, N2 = indx1.shape[0], indx2.shape[0]
+    return indx1.view(-1, 1).repeat(1, N2).view(-1).long(), indx2.repeat(N1).long()
+
+
+def generate_K_index(B_f, indx):
+    """logpos.py:87-98: K_i[n, n'] = B_f[indx_n, indx_n'] (a gather)."""
+    i = indx.long()
+    return B_f[i.view(-1, 1), i.view(1, -1)]
+
+
+# ---- shared pieces -----------------------------------------------------------------------------------------------------
+def _mvn_logprob(value, mean, Sigma):
+    """torch.distributions.MultivariateNormal(mean 1, covariance_matrix=Sigma).log_prob(value) through one blocked Cholesky."""
+    r = (value - mean).contiguous()
+    L, hld = ops.potrf_big(Sigma)
+    quad = ops.dot(r, ops.potrs_vec(L, r)).reshape(())
+    return -0.5 * quad - hld.reshape(()) - 0.5 * r.numel() * math.log(2.0 * math.pi)
+
+
+def _normal_logprob_sum(v, loc, scale):
+    """sum torch.distributions.Normal(loc, scale).log_prob(v), including its dtype behaviour: python numbers become
+    tensors of the default dtype (float32), so Normal(0, c) carries float32 roundings of c^2 and log(c) -- reproduced."""
+    def as_param(p_, like):
+        if torch.is_tensor(p_):
+            return p_.detach().cpu()
+        return torch.tensor(float(p_), dtype=like.dtype if like is not None else torch.get_default_dtype())
+    first = next((t for t in (loc, scale) if torch.is_tensor(t)), None)
+    loc_t, scale_t = as_param(loc, first), as_param(scale, first)
+    var = float(scale_t ** 2)
+    log_scale = float(scale_t.log())
+    v = v.contiguous().view(-1)
+    s_eff = math.sqrt(var)
+    base = ops.normal_logprob_sum(torch.full_like(v, float(loc_t)), torch.full((1,), s_eff, dtype=v.dtype, device=v.device),
+                                  v).reshape(())
+    return base + v.numel() * (math.log(s_eff) - log_scale)
+
+
+def _coregionalisation(L_vec, M):
+    L = vec2lowtriangle(L_vec, M).contiguous()
+    return ops.gemm_nt(L, L)
+
+
+def _dense_loglik(K_x, B_f, indx, sigma2_err, y):
+    """-1/2 logdet(S) - 1/2 y^T S^-1 y for S = K_x * K_i + sigma2 I (logpos.py:521-526), dense Cholesky."""
+    ii = indx.to(torch.int32).contiguous()
+    L, hld = ops.potrf_big(ops.hadamard_index_cov(K_x, B_f, ii, ii, float(sigma2_err)))
+    yc = y.contiguous()
+    return (-hld - 0.5 * ops.dot(yc, ops.potrs_vec(L, yc))).reshape(())
+
+
+# ---- deviance (logpos.py:176-213) --------------------------------------------------------------------------------------
+def deviance(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, Y, x):
+    """-2 log-likelihood of the Kronecker model (same value as the reference's dense-inverse route)."""
+    N, M = Y.shape
+    y = Y.t().contiguous().view(-1)
+    B_f = _coregionalisation(L_vec, M)
+    K_x = kernels.Nonstationary_RBF_cov(x.view(-1, 1), sigma1=torch.exp(tilde_sigma), ell1=torch.exp(tilde_l))
+    return -2.0 * distributions.multivariate_normal_logpdf0(y, torch.zeros_like(y), B_f, K_x, torch.exp(tilde_sigma2_err))
+
+
+def deviance_obj(pars, Y, x):
+    N, M = Y.shape
+    return deviance(*vec2pars(pars, N, M), Y, x)
+
+
+# ---- Kronecker NMGP posterior (logpos.py:216-296) ----------------------------------------------------------------------
+def logpos(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_tilde_sigma,
+           alpha_tilde_sigma, beta_tilde_sigma, a, b, c, verbose=False, Prior=True):
+    N, M = Y.shape
+    y = Y.t().contiguous().view(-1)
+    B_f = _coregionalisation(uLvec2Lvec(uL_vec, M), M)
+    sigma2_err = torch.exp(tilde_sigma2_err)
+    xc = x.contiguous().view(-1, 1)
+    K_x = kernels.Nonstationary_RBF_cov(xc, sigma1=torch.exp(tilde_sigma), ell1=torch.exp(tilde_l))
+    loglik = distributions.multivariate_normal_logpdf0(y, torch.zeros_like(y), B_f, K_x, sigma2_err)
+    while bool(loglik != loglik):                         # the reference's NaN retry with the jittered variant
+        loglik = distributions.multivariate_normal_logpdf1(y, torch.zeros_like(y), B_f, K_x, sigma2_err)
+    lp_l = _mvn_logprob(tilde_l, float(mu_tilde_l), kernels.RBF_cov(xc, alpha=float(alpha_tilde_l), beta=float(beta_tilde_l)))
+    lp_s = _mvn_logprob(tilde_sigma, float(mu_tilde_sigma),
+                        kernels.RBF_cov(xc, alpha=float(alpha_tilde_sigma), beta=float(beta_tilde_sigma)))
+    lp_L = _normal_logprob_sum(uL_vec, 0.0, c)
+    lp_e = distributions.inverse_gamma_logpdf(sigma2_err, alpha=a, beta=b)
+    res = loglik
+    if Prior:
+        res = res + lp_l + lp_s + lp_L + lp_e + tilde_sigma2_err
+    return (res, loglik, lp_l, lp_s, lp_L, lp_e) if verbose else res
+
+
+def nlogpos_obj(pars, Y, x, mu_tilde_l=0., alpha_tilde_l=1., beta_tilde_l=1., mu_tilde_sigma=0., alpha_tilde_sigma=1.,
+                beta_tilde_sigma=1., a=1, b=1, c=10, verbose=False, Prior=True):
+    N, M = Y.shape
+    out = logpos(*vec2pars(pars, N, M), Y, x, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma,
+                 beta_tilde_sigma, a, b, c, verbose, Prior)
+    return (-out[0],) + tuple(out[1:]) if verbose else -out
+
+
+# ---- stationary variant (logpos.py:383-462) ----------------------------------------------------------------------------
+def logpos_S(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, mu_tilde_l, sigma_tilde_l, a, b, c, verbose=False,
+             Prior=True):
+    N, M = Y.shape
+    y = Y.t().contiguous().view(-1)
+    B_f = _coregionalisation(uLvec2Lvec(uL_vec, M), M)
+    sigma2_err = torch.exp(tilde_sigma2_err)
+    one = torch.ones(N, dtype=torch.float64, device=Y.device)
+    K_x = kernels.Nonstationary_RBF_cov(x.contiguous().view(-1, 1), sigma1=torch.exp(tilde_sigma * one),
+                                        ell1=torch.exp(tilde_l * one))
+    loglik = distributions.multivariate_normal_logpdf0(y, torch.zeros_like(y), B_f, K_x, sigma2_err)
+    while bool(loglik != loglik):
+        loglik = distributions.multivariate_normal_logpdf1(y, torch.zeros_like(y), B_f, K_x, sigma2_err)
+    lp_l = _normal_logprob_sum(tilde_l.reshape(1), mu_tilde_l, sigma_tilde_l)
+    lp_L = _normal_logprob_sum(uL_vec, 0.0, c)
+    lp_e = distributions.inverse_gamma_logpdf(sigma2_err, alpha=a, beta=b)
+    res = loglik
+    if Prior:
+        res = res + lp_l + lp_L + lp_e + tilde_sigma2_err
+    return (res, loglik, lp_l, lp_L, lp_e) if verbose else res
+
+
+def nlogpos_obj_S(pars, Y, x, mu_tilde_l, sigma_tilde_l, a=1, b=1, c=10, verbose=False, Prior=True):
+    M = Y.shape[1]
+    out = logpos_S(*vec2pars_S(pars, M), Y, x, mu_tilde_l, sigma_tilde_l, a, b, c, verbose, Prior)
+    return (-out[0],) + tuple(out[1:]) if verbose else -out
+
+
+# ---- Hadamard (irregular observations) variants (logpos.py:465-563, 662-716) ------------------------------------------
+def logpos_hadamard(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, mu_tilde_l, alpha_tilde_l, beta_tilde_l,
+                    mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, a, b, c, verbose=False, Prior=True):
+    M = int(torch.unique(indx).numel())
+    B_f = _coregionalisation(L_vec, M)
+    sigma2_err = torch.exp(tilde_sigma2_err)
+    xc = x.contiguous().view(-1, 1)
+    K_x = kernels.Nonstationary_RBF_cov(xc, sigma1=torch.exp(tilde_sigma), ell1=torch.exp(tilde_l))
+    loglik = _dense_loglik(K_x, B_f, indx, sigma2_err, y)
+    lp_l = _mvn_logprob(tilde_l, float(mu_tilde_l), kernels.RBF_cov(xc, alpha=float(alpha_tilde_l), beta=float(beta_tilde_l)))
+    lp_s = _mvn_logprob(tilde_sigma, float(mu_tilde_sigma),
+                        kernels.RBF_cov(xc, alpha=float(alpha_tilde_sigma), beta=float(beta_tilde_sigma)))
+    lp_L = _normal_logprob_sum(L_vec, 0.0, c)
+    lp_e = distributions.inverse_gamma_logpdf_u(sigma2_err, alpha=a, beta=b)
+    res = loglik
+    if Prior:
+        res = res + lp_l + lp_s + lp_L + lp_e + tilde_sigma2_err
+    return (res, loglik, lp_l, lp_s, lp_L, lp_e) if verbose else res
+
+
+def nlogpos_obj_hadamard(pars, x, indx, y, mu_tilde_l=0., alpha_tilde_l=1., beta_tilde_l=1., mu_tilde_sigma=0.,
+                         alpha_tilde_sigma=1., beta_tilde_sigma=1., a=1, b=1, c=10, verbose=False, Prior=True):
+    N = y.shape[0]
+    M = int(torch.unique(indx).numel())
+    out = logpos_hadamard(*vec2pars(pars, N, M), x, indx, y, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_tilde_sigma,
+                          alpha_tilde_sigma, beta_tilde_sigma, a, b, c, verbose, Prior)
+    return (-out[0],) + tuple(out[1:]) if verbose else -out
+
+
+def logpos_hadamard_S(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, mu_tilde_l, sigma_tilde_l, a, b, c,
+                      verbose=False, Prior=True):
+    M = int(torch.unique(indx).numel())
+    B_f = _coregionalisation(L_vec, M)
+    sigma2_err = torch.exp(tilde_sigma2_err)
+    K_x = kernels.RBF_cov(x.contiguous().view(-1, 1), alpha=float(torch.exp(tilde_sigma)), beta=float(torch.exp(tilde_l)))
+    loglik = _dense_loglik(K_x, B_f, indx, sigma2_err, y)
+    lp_l = _normal_logprob_sum(tilde_l.reshape(1), mu_tilde_l, sigma_tilde_l)
+    lp_L = _normal_logprob_sum(L_vec, 0.0, c)
+    lp_e = distributions.inverse_gamma_logpdf_u(sigma2_err, alpha=a, beta=b)
+    res = loglik
+    if Prior:
+        res = res + lp_l + lp_L + lp_e + tilde_sigma2_err
+    return (res, loglik, lp_l, lp_L, lp_e) if verbose else res
+
+
+def nlogpos_obj_hadamard_S(pars, x, indx, y, mu_tilde_l, sigma_tilde_l, a=1, b=1, c=10, verbose=False, Prior=True):
+    M = int(torch.unique(indx).numel())
+    out = logpos_hadamard_S(*vec2pars_S(pars, M), x, indx, y, mu_tilde_l, sigma_tilde_l, a, b, c, verbose, Prior)
+    return (-out[0],) + tuple(out[1:]) if verbose else -out
