@@ -12,7 +12,7 @@ import torch
 
 from . import _ops as ops
 from . import distributions, kernels, kronecker_operation
-from .prediction import uLvec2Lvec, vec2lowtriangle
+from .prediction import uLvec2Lvec, uLvecs2Lvecs, vec2lowtriangle
 
 
 # ---- parameter-vector helpers (logpos.py:17-72): slicing only ---------------------------------------------------------
@@ -210,3 +210,123 @@ def nlogpos_obj_hadamard_S(pars, x, indx, y, mu_tilde_l, sigma_tilde_l, a=1, b=1
     M = int(torch.unique(indx).numel())
     out = logpos_hadamard_S(*vec2pars_S(pars, M), x, indx, y, mu_tilde_l, sigma_tilde_l, a, b, c, verbose, Prior)
     return (-out[0],) + tuple(out[1:]) if verbose else -out
+
+
+# ---- spatially varying coregionalisation posteriors (logpos.py:299-380, 566-660) ---------------------------------------
+def generate_K_index_SVC(L_f_list):
+    """logpos.py:111-118 (row-indexed (n, m) order, as the reference)."""
+    L = torch.cat(list(L_f_list), dim=0).contiguous()
+    return ops.gemm_nt(L, L)
+
+
+def generate_K_index_SVC_hadamard0(L_f_list, indexes):
+    """logpos.py:121-124."""
+    L = torch.stack([L_f[int(i), :] for L_f, i in zip(L_f_list, indexes)]).contiguous()
+    return ops.gemm_nt(L, L)
+
+
+def generate_K_index_SVC_hadamard(L_f_list, indexes):
+    """logpos.py:127-137: the same N x N table as generate_K_index_SVC_hadamard0 (the reference builds it entry by entry)."""
+    return generate_K_index_SVC_hadamard0(L_f_list, indexes)
+
+
+def show_covs(pars, Y, x):
+    """logpos.py:140-157: prints the coregionalisation matrix, the time kernel and the noise variance."""
+    N, M = Y.shape
+    tilde_l, tilde_sigma, L_vec, tilde_sigma2_err = vec2pars(pars, N, M)
+    print("B_f: {}".format(_coregionalisation(L_vec, M)))
+    print("K_x: {}".format(kernels.Nonstationary_RBF_cov(x.view(-1, 1), sigma1=torch.exp(tilde_sigma), ell1=torch.exp(tilde_l))))
+    print("sigma2_err: {}".format(torch.exp(tilde_sigma2_err)))
+
+
+def show_covs_hadamard(pars, x, indx):
+    """logpos.py:160-173."""
+    N = x.shape[0]
+    M = int(torch.unique(indx).numel())
+    _, _, L_vec, tilde_sigma2_err = vec2pars(pars, N, M)
+    print("B_f: {}".format(_coregionalisation(L_vec, M)))
+    print("sigma2_err: {}".format(torch.exp(tilde_sigma2_err)))
+
+
+def _triangles(L_vecs, N, M):
+    P = M * (M + 1) // 2
+    Lmat = torch.zeros(N, M, M, dtype=torch.float64, device=L_vecs.device)
+    idx = torch.tril_indices(M, M, device=L_vecs.device)
+    Lmat[:, idx[0], idx[1]] = L_vecs.reshape(N, P)
+    return Lmat
+
+
+def _gp_prior_entries(V, mu, Sigma):
+    """sum over the columns of V [N, P] of MultivariateNormal(mu 1, Sigma).log_prob(V[:, p]): one factorisation, P solves."""
+    L, hld = ops.potrf_big(Sigma)
+    N, P = V.shape
+    total = -P * (hld.reshape(()) + 0.5 * N * math.log(2.0 * math.pi))
+    for p_ in range(P):
+        r = (V[:, p_] - mu).contiguous()
+        total = total - 0.5 * ops.dot(r, ops.potrs_vec(L, r)).reshape(())
+    return total
+
+
+def logpos_SVC(tilde_l, uL_vecs, tilde_sigma2_err, Y, x, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L, a, b,
+               verbose=False, Prior=True):
+    N, M = Y.shape
+    P = M * (M + 1) // 2
+    y = Y.t().contiguous().view(-1)                         # output-major
+    Lmat = _triangles(uLvecs2Lvecs(uL_vecs, N, M), N, M)
+    Lrow = Lmat.permute(1, 0, 2).reshape(M * N, M).contiguous()                 # row (m, n) = L_n[m, :]
+    nidx = torch.arange(N, dtype=torch.int32, device=Y.device).repeat(M).contiguous()
+    sigma2_err = torch.exp(tilde_sigma2_err)
+    xc = x.contiguous().view(-1, 1)
+    K_x = kernels.Nonstationary_RBF_cov(xc, ell1=torch.exp(tilde_l))
+    S = ops.hadamard_index_cov(ops.gemm_nt(Lrow, Lrow), K_x, nidx, nidx, float(sigma2_err))
+    Lc, hld = ops.potrf_big(S)
+    loglik = (-hld - 0.5 * ops.dot(y, ops.potrs_vec(Lc, y))).reshape(())
+    lp_l = _mvn_logprob(tilde_l, float(mu_tilde_l), kernels.RBF_cov(xc, alpha=float(alpha_tilde_l), beta=float(beta_tilde_l)))
+    lp_L = _gp_prior_entries(uL_vecs.reshape(N, P), float(mu_L), kernels.RBF_cov(xc, alpha=float(alpha_L), beta=float(beta_L)))
+    lp_e = distributions.inverse_gamma_logpdf(sigma2_err, alpha=a, beta=b)
+    res = loglik
+    if Prior:
+        res = res + lp_l + lp_L + lp_e + tilde_sigma2_err
+    return (res, loglik, lp_l, lp_L, lp_e) if verbose else res
+
+
+def nlogpos_obj_SVC(pars, Y, x, mu_tilde_l=0., alpha_tilde_l=5., beta_tilde_l=1., mu_L=0., alpha_L=5., beta_L=1., a=1, b=1,
+                    verbose=False, Prior=True):
+    N, M = Y.shape
+    out = logpos_SVC(*vec2pars_SVC(pars, N, M), Y, x, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L, a, b,
+                     verbose, Prior)
+    return (-out[0],) + tuple(out[1:]) if verbose else -out
+
+
+def logpos_hadamard_SVC(tilde_l, L_vecs, tilde_sigma2_err, x, indx, y, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L,
+                        beta_L, a, b, verbose=False, Prior=True):
+    N = y.shape[0]
+    M = int(torch.unique(indx).numel())
+    P = M * (M + 1) // 2
+    Lmat = _triangles(L_vecs, N, M)                         # used as given (no exp of the diagonals)
+    Lsel = Lmat[torch.arange(N, device=y.device), indx.long().to(y.device)].contiguous()
+    ident = torch.arange(N, dtype=torch.int32, device=y.device)
+    sigma2_err = torch.exp(tilde_sigma2_err)
+    xc = x.contiguous().view(-1, 1)
+    K_x = kernels.Nonstationary_RBF_cov(xc, ell1=torch.exp(tilde_l))
+    S = ops.hadamard_index_cov(ops.gemm_nt(Lsel, Lsel), K_x, ident, ident, float(sigma2_err))
+    Lc, hld = ops.potrf_big(S)
+    yc = y.contiguous()
+    loglik = (-hld - 0.5 * ops.dot(yc, ops.potrs_vec(Lc, yc))).reshape(())
+    lp_l = _mvn_logprob(tilde_l, float(mu_tilde_l), kernels.RBF_cov(xc, alpha=float(alpha_tilde_l), beta=float(beta_tilde_l)))
+    lp_L = _gp_prior_entries(L_vecs.reshape(N, P), float(mu_L), kernels.RBF_cov(xc, alpha=float(alpha_L), beta=float(beta_L)))
+    lp_e = distributions.inverse_gamma_logpdf_u(sigma2_err, alpha=a, beta=b)
+    res = loglik
+    if Prior:
+        res = res + lp_l + lp_L + lp_e + tilde_sigma2_err
+    return (res, loglik, lp_l, lp_L, lp_e) if verbose else res
+
+
+def nlogpos_obj_hadamard_SVC(pars, x, indx, y, mu_tilde_l=0., alpha_tilde_l=1., beta_tilde_l=1., mu_L=0., alpha_L=1., beta_L=1.,
+                             a=1, b=1, verbose=False, Prior=True):
+    N = y.shape[0]
+    M = int(torch.unique(indx).numel())
+    out = logpos_hadamard_SVC(*vec2pars_hadamard_SVC(pars, N, M), x, indx, y, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L,
+                              alpha_L, beta_L, a, b, verbose, Prior)
+    return (-out[0],) + tuple(out[1:]) if verbose else -out
+

@@ -48,7 +48,23 @@ def main():
     out["logpos_hadamard_S_verbose"] = np.array([float(t) for t in vHS])
     parsH = torch.cat([tlh, tsh, L_vec, ts2.view(1)])
     out["nlogpos_obj_hadamard"] = float(logpos.nlogpos_obj_hadamard(parsH, xh, ih, yh, *[float(h) for h in hyp], a, b, c))
-    np.savez_compressed(os.path.join(OUT, "sim_logpos.npz"), x=x.numpy(), tilde_l=tilde_l.numpy(), tilde_sigma=tilde_sigma.numpy(),
+    # spatially varying coregionalisation
+    Ni, Mi = 20, 2
+    Pi = Mi * (Mi + 1) // 2
+    xi = torch.sort(torch.rand(Ni, generator=g).double())[0]
+    tli = (3 * (xi - 1) ** 3 - 1.5) + 0.05 * torch.randn(Ni, generator=g).double()
+    uLi = 0.3 * torch.randn(Ni * Pi, generator=g).double()
+    Yi = torch.randn(Ni, Mi, generator=g).double()
+    hyp_i = [torch.tensor(v_).double() for v_ in (-1.0, 1.5, 0.3, 0.1, 0.7, 0.35)]
+    vSVC = logpos.logpos_SVC(tli, uLi, ts2, Yi, xi, *hyp_i, a, b, verbose=True)
+    out["logpos_SVC_verbose"] = np.array([float(t) for t in vSVC])
+    out["nlogpos_obj_SVC"] = float(logpos.nlogpos_obj_SVC(torch.cat([tli, uLi, ts2.view(1)]), Yi, xi, *[float(h) for h in hyp_i], a, b))
+    Nh = xh.numel()
+    Lv_h = 0.4 * torch.randn(Nh * P, generator=g).double() + 0.3
+    vHSVC = logpos.logpos_hadamard_SVC(tlh, Lv_h, ts2, xh, ih, yh, *hyp_i, a, b, verbose=True)
+    out["logpos_hadamard_SVC_verbose"] = np.array([float(t) for t in vHSVC])
+    np.savez_compressed(os.path.join(OUT, "sim_logpos.npz"), xi=xi.numpy(), tli=tli.numpy(), uLi=uLi.numpy(), Yi=Yi.numpy(),
+                        hyp_i=np.array([float(h) for h in hyp_i]), Lv_h=Lv_h.numpy(), x=x.numpy(), tilde_l=tilde_l.numpy(), tilde_sigma=tilde_sigma.numpy(),
                         uL_vec=uL_vec.numpy(), L_vec=L_vec.numpy(), ts2=float(ts2), Y=Y.numpy(), hyp=np.array([float(h) for h in hyp]),
                         abc=np.array([a, b, c]), tlS=float(tlS), tsS=float(tsS), xh=xh.numpy(), ih=ih.numpy(), yh=yh.numpy(),
                         tlh=tlh.numpy(), tsh=tsh.numpy(), **out)

@@ -54,6 +54,18 @@ def test_logpos_values_match_reference():
     parsH = torch.cat([d("tlh"), d("tsh"), d("L_vec"), ts2.view(1)])
     _close(logpos.nlogpos_obj_hadamard(parsH, d("xh"), ih, d("yh"), *[float(h) for h in hyp], a, b, c),
            g["nlogpos_obj_hadamard"], TOL)
+    # spatially varying coregionalisation posteriors
+    hyp_i = [sc(v) for v in g["hyp_i"]]
+    _close(logpos.logpos_SVC(d("tli"), d("uLi"), ts2, d("Yi"), d("xi"), *hyp_i, a, b, verbose=True), g["logpos_SVC_verbose"], TOL)
+    _close(logpos.nlogpos_obj_SVC(torch.cat([d("tli"), d("uLi"), ts2.view(1)]), d("Yi"), d("xi"), *[float(h) for h in hyp_i], a, b),
+           g["nlogpos_obj_SVC"], TOL)
+    _close(logpos.logpos_hadamard_SVC(d("tlh"), d("Lv_h"), ts2, d("xh"), ih, d("yh"), *hyp_i, a, b, verbose=True),
+           g["logpos_hadamard_SVC_verbose"], TOL)
+    Lf = [torch.tril(torch.arange(1., 5.).view(2, 2) + k) for k in range(3)]
+    Kh = logpos.generate_K_index_SVC_hadamard(Lf, torch.tensor([0, 1, 1]))
+    Lsel = torch.stack([Lf[0][0], Lf[1][1], Lf[2][1]])
+    assert torch.allclose(Kh, Lsel @ Lsel.t(), rtol=0, atol=1e-12)
+    assert logpos.generate_K_index_SVC(Lf).shape == (6, 6)
     # helpers
     i1, i2 = logpos.generate_vectorized_indexes(torch.tensor([0, 2]), torch.tensor([1, 0, 2]))
     assert i1.tolist() == [0, 0, 0, 2, 2, 2] and i2.tolist() == [1, 0, 2, 1, 0, 2]
