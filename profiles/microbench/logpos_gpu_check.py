@@ -14,3 +14,6 @@ print("hadamard", rel(logpos.logpos_hadamard(d("tlh"), d("tsh"), d("L_vec"), ts2
 print("hadamard_S", rel(logpos.logpos_hadamard_S(sc(g["tlS"]), sc(g["tsS"]), d("L_vec"), ts2, d("xh"), ih, d("yh"), sc(-1.0), sc(0.7), a, b, c, verbose=True), g["logpos_hadamard_S_verbose"]))
 parsH = torch.cat([d("tlh"), d("tsh"), d("L_vec"), ts2.view(1)])
 print("nlogpos_obj_hadamard", rel([logpos.nlogpos_obj_hadamard(parsH, d("xh"), ih, d("yh"), *[float(h) for h in hyp], a, b, c)], g["nlogpos_obj_hadamard"]))
+hyp_i = [sc(v) for v in g["hyp_i"]]
+print("logpos_SVC", rel(logpos.logpos_SVC(d("tli"), d("uLi"), ts2, d("Yi"), d("xi"), *hyp_i, a, b, verbose=True), g["logpos_SVC_verbose"]))
+print("logpos_hadamard_SVC", rel(logpos.logpos_hadamard_SVC(d("tlh"), d("Lv_h"), ts2, d("xh"), ih, d("yh"), *hyp_i, a, b, verbose=True), g["logpos_hadamard_SVC_verbose"]))
