@@ -20,16 +20,27 @@ MODE_W, MODE_U = 0, 1
 MAX_Q = 112
 
 
+def _same_device(t: torch.Tensor) -> None:
+    """Kernels are enqueued on the CURRENT device's current stream (and the library-owned scratch lives there), so a
+    tensor of another device would be dereferenced on the wrong GPU: refuse it.  Use ``torch.cuda.device(model.device)``
+    (``nmgp_dsvi`` does) when a model lives on a GPU that is not the current one."""
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError("tensor on %s but the current CUDA device is cuda:%d; wrap the call in "
+                           "torch.cuda.device(...)" % (t.device, torch.cuda.current_device()))
+
+
 def _d(t: torch.Tensor) -> c_void_p:
     if not (t.is_cuda and t.dtype == F64 and t.is_contiguous()):
         raise TypeError("expected a contiguous CUDA float64 tensor, got %s %s contiguous=%s (no CPU fallback)"
                         % (t.device, t.dtype, t.is_contiguous()))
+    _same_device(t)
     return c_void_p(t.data_ptr())
 
 
 def _i(t: torch.Tensor) -> c_void_p:
     if not (t.is_cuda and t.dtype == torch.int32 and t.is_contiguous()):
         raise TypeError("expected a contiguous CUDA int32 tensor, got %s %s" % (t.device, t.dtype))
+    _same_device(t)
     return c_void_p(t.data_ptr())
 
 
@@ -127,6 +138,8 @@ def kl_fwd(CS, hldS, mu, R, hldR, exact=False):
 
 
 def kl_bwd(klbar, CS, mu, R, t, exact=False):
+    if exact:
+        raise NotImplementedError("exact KL (flagged variant of quirk q10) is not built yet")
     nb, Q, _ = CS.shape
     np_ = R.shape[0]
     CSbar = torch.empty_like(CS)
@@ -183,7 +196,8 @@ def solve_rows_fwd(K, R):
 def solve_rows_bwd(Pbar, cbar, K, P, R, Abar):
     ns, B, Q = K.shape
     Kbar = torch.empty_like(K)
-    work = _d(torch.empty_like(K)) if Q <= 64 else c_void_p(0)
+    work_t = torch.empty_like(K) if Q <= 64 else None      # kept alive until the launch below has been enqueued
+    work = _optd(work_t)
     check(lib().nmgp_solve_rows_bwd(_d(Pbar), _d(cbar), _d(K), _d(P), _d(R), _d(Kbar), _d(Abar), work,
                                     c_int(ns), c_int64(B), c_int(Q), _stream()), "nmgp_solve_rows_bwd")
     return Kbar
@@ -321,13 +335,23 @@ def noise_fill(ns, B, C, seed, stream_id, s0, gid, device):
     return out
 
 
+def _ystride(y, ns, B):
+    """y [B]: one target vector shared by the samples of the chunk; y [ns, B]: one per sample (subjects)."""
+    if y.dim() == 1:
+        return 0
+    if y.shape[0] != ns or y.shape[1] != B:
+        raise ValueError("per-sample targets must be [ns, B] = [%d, %d], got %s" % (ns, B, tuple(y.shape)))
+    return B
+
+
 def lik_rows(l, mg, qg, cG, y, I, hyp, scale, Rsum, ghyp):
     ns, B, D = l.shape
     lbar = torch.empty_like(l); mgbar = torch.empty_like(l); qgbar = torch.empty_like(l)
     cGbar = _empty(l, ns, B)
     Rsum.zero_()
     check(lib().nmgp_lik_rows(_d(l), _d(mg), _d(qg), _d(cG), _d(y), _i(I), _d(hyp), c_double(scale), _d(Rsum), _d(ghyp),
-                              _d(lbar), _d(mgbar), _d(qgbar), _d(cGbar), c_int(ns), c_int64(B), c_int(D), _stream()),
+                              _d(lbar), _d(mgbar), _d(qgbar), _d(cGbar), c_int(ns), c_int64(B), c_int(D),
+                              c_int64(_ystride(y, ns, B)), _stream()),
           "nmgp_lik_rows")
     return lbar, mgbar, qgbar, cGbar
 
@@ -365,7 +389,8 @@ def latent_fused(PG, cG, l, y, I, SigW, muW, hyp, scale, Rsum, ghyp, seg=None):
         pq = pm = c_void_p(0)
     check(lib().nmgp_latent_fused(_d(PG), _d(cG), _d(l), _d(y), _i(I), _i(seg), _d(SigW), _d(muW), _d(hyp),
                                   c_double(scale), _d(Rsum), _d(ghyp), _d(lbar), _d(mgbar), _d(qgbar), _d(cGbar),
-                                  _d(PGbar), pq, pm, c_int(ns), c_int64(B), c_int(Q), c_int(D), _stream()),
+                                  _d(PGbar), pq, pm, c_int(ns), c_int64(B), c_int(Q), c_int(D),
+                                  c_int64(_ystride(y, ns, B)), _stream()),
           "nmgp_latent_fused")
     return lbar, mgbar, qgbar, cGbar, PGbar
 
@@ -506,6 +531,15 @@ _PROFILE = None
 _CALLS = [0]
 
 
+def launch_count() -> int:
+    """Kernel launches issued by libnmgp_b200.so since it was loaded (+ launches replayed from captured CUDA graphs)."""
+    lib().nmgp_launch_count.restype = ctypes.c_uint64
+    return int(lib().nmgp_launch_count()) + _GRAPH_LAUNCHES[0]
+
+
+_GRAPH_LAUNCHES = [0]
+
+
 def _profile_begin():
     global _PROFILE
     _PROFILE = []
@@ -541,7 +575,7 @@ def _instrument(fn):
 
 for _name, _fn in list(globals().items()):
     if callable(_fn) and not _name.startswith("_") and getattr(_fn, "__module__", None) == __name__ \
-            and _name not in ("check", "lib"):
+            and _name not in ("check", "lib", "launch_count"):
         globals()[_name] = _instrument(_fn)
 
 

@@ -13,6 +13,10 @@ enum { H_S2_ELL = 0, H_LEN_ELL, H_S2_L0, H_LEN_L0, H_S2_L1, H_LEN_L1, H_S2_ERR, 
 enum { MODE_W = 0, MODE_U = 1 };
 
 void nmgp_set_error(const char* fmt, ...);
+// every kernel launch of the library is counted (bench.py reports the count as gpu_launches): the first launch-
+// configuration argument is wrapped as <<<NMGP_L(grid), ...>>>
+extern unsigned long long g_nmgp_launches;
+#define NMGP_L(grid) (++g_nmgp_launches, (grid))
 int nmgp_launch_status(const char* what);
 
 #define NMGP_REQUIRE(cond, what)                                  \

@@ -134,7 +134,7 @@ static int launch_atb(const double* A, const double* Bm, double* C, double sign,
     long long chunk = ((B + nchunks - 1) / nchunks + ATB_TROWS - 1) / ATB_TROWS * ATB_TROWS;
     if (chunk < 4 * ATB_TROWS) chunk = 4 * ATB_TROWS;
     dim3 grid((unsigned)((B + chunk - 1) / chunk), ns);
-    k_atb_mma<NB><<<grid, ATB_THREADS, smem, st>>>(A, Bm, C, sign, B, Q, chunk, cbar, Kbar);
+    k_atb_mma<NB><<<NMGP_L(grid), ATB_THREADS, smem, st>>>(A, Bm, C, sign, B, Q, chunk, cbar, Kbar);
     return nmgp_launch_status("nmgp_atb");
 }
 int nmgp_atb_mma(const double* A, const double* Bm, double* C, double sign, int ns, long long B, int Q,

@@ -22,7 +22,7 @@ NMGP_API int nmgp_rbf_build_fwd(const double* x, const double* z, const double* 
     NMGP_REQUIRE(B >= 0 && Q > 0 && is2 >= 0 && is2 < H_COUNT && ilen >= 0 && ilen < H_COUNT, "nmgp_rbf_build_fwd");
     if (B == 0) return 0;
     long long n = B * Q;
-    k_rbf_fwd<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, z, hyp, is2, ilen, jitter, K, B, Q);
+    k_rbf_fwd<<<NMGP_L((unsigned)((n + 255) / 256)), 256, 0, st>>>(x, z, hyp, is2, ilen, jitter, K, B, Q);
     return nmgp_launch_status("nmgp_rbf_build_fwd");
 }
 
@@ -57,7 +57,7 @@ NMGP_API int nmgp_rbf_build_bwd(const double* x, const double* z, const double* 
     long long n = B * Q;
     long long blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_rbf_bwd<<<(unsigned)blocks, 256, 0, st>>>(x, z, hyp, is2, ilen, Kbar, ghyp, B, Q);
+    k_rbf_bwd<<<NMGP_L((unsigned)blocks), 256, 0, st>>>(x, z, hyp, is2, ilen, Kbar, ghyp, B, Q);
     return nmgp_launch_status("nmgp_rbf_build_bwd");
 }
 
@@ -125,10 +125,10 @@ NMGP_API int nmgp_gibbs_build_fwd(const double* x, const double* z, const double
     const int threads = 256, rows_per_block = (threads / 32) * GB_ROWS_PER_WARP;
     dim3 grid((unsigned)((B + rows_per_block - 1) / rows_per_block), ns);
     switch (Q > 128 ? 4 : (Q + 31) / 32) {
-        case 1: k_gibbs_fwd<1><<<grid, threads, 0, st>>>(x, z, ellx, ellz, jitter, K, B, Q); break;
-        case 2: k_gibbs_fwd<2><<<grid, threads, 0, st>>>(x, z, ellx, ellz, jitter, K, B, Q); break;
-        case 3: k_gibbs_fwd<3><<<grid, threads, 0, st>>>(x, z, ellx, ellz, jitter, K, B, Q); break;
-        default: k_gibbs_fwd<4><<<grid, threads, 0, st>>>(x, z, ellx, ellz, jitter, K, B, Q); break;
+        case 1: k_gibbs_fwd<1><<<NMGP_L(grid), threads, 0, st>>>(x, z, ellx, ellz, jitter, K, B, Q); break;
+        case 2: k_gibbs_fwd<2><<<NMGP_L(grid), threads, 0, st>>>(x, z, ellx, ellz, jitter, K, B, Q); break;
+        case 3: k_gibbs_fwd<3><<<NMGP_L(grid), threads, 0, st>>>(x, z, ellx, ellz, jitter, K, B, Q); break;
+        default: k_gibbs_fwd<4><<<NMGP_L(grid), threads, 0, st>>>(x, z, ellx, ellz, jitter, K, B, Q); break;
     }
     return nmgp_launch_status("nmgp_gibbs_build_fwd");
 }
@@ -197,10 +197,10 @@ NMGP_API int nmgp_gibbs_build_bwd(const double* x, const double* z, const double
     const int threads = 256, rows_per_block = (threads / 32) * GB_ROWS_PER_WARP;
     dim3 grid((unsigned)((B + rows_per_block - 1) / rows_per_block), ns);
     switch ((Q + 31) / 32) {
-        case 1: k_gibbs_bwd<1><<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, Kfwd, ellxbar, ellzbar, B, Q); break;
-        case 2: k_gibbs_bwd<2><<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, Kfwd, ellxbar, ellzbar, B, Q); break;
-        case 3: k_gibbs_bwd<3><<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, Kfwd, ellxbar, ellzbar, B, Q); break;
-        default: k_gibbs_bwd<4><<<grid, threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, Kfwd, ellxbar, ellzbar, B, Q); break;
+        case 1: k_gibbs_bwd<1><<<NMGP_L(grid), threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, Kfwd, ellxbar, ellzbar, B, Q); break;
+        case 2: k_gibbs_bwd<2><<<NMGP_L(grid), threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, Kfwd, ellxbar, ellzbar, B, Q); break;
+        case 3: k_gibbs_bwd<3><<<NMGP_L(grid), threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, Kfwd, ellxbar, ellzbar, B, Q); break;
+        default: k_gibbs_bwd<4><<<NMGP_L(grid), threads, Q * sizeof(double), st>>>(x, z, ellx, ellz, Kbar, Kfwd, ellxbar, ellzbar, B, Q); break;
     }
     return nmgp_launch_status("nmgp_gibbs_build_bwd");
 }
@@ -240,7 +240,7 @@ NMGP_API int nmgp_nonstationary_cov(const double* X1, const double* sigma1, cons
     for (long long r0 = 0; r0 < T1; r0 += 65535) {  // grid.y is limited to 65535
         long long rows = T1 - r0 < 65535 ? T1 - r0 : 65535;
         dim3 grid((unsigned)((T2 + 255) / 256), (unsigned)rows);
-        k_nonstat_cov<<<grid, 256, 0, st>>>(X1, sigma1, ell1, X2, sigma2, ell2, jitter, K, r0, T2, dx);
+        k_nonstat_cov<<<NMGP_L(grid), 256, 0, st>>>(X1, sigma1, ell1, X2, sigma2, ell2, jitter, K, r0, T2, dx);
     }
     return nmgp_launch_status("nmgp_nonstationary_cov");
 }
@@ -267,7 +267,7 @@ NMGP_API int nmgp_sim_rbf_cov(const double* X1, const double* X2, double alpha, 
     NMGP_REQUIRE(T1 >= 0 && T2 >= 0 && dx > 0 && T1 <= 65535, "nmgp_sim_rbf_cov");
     if (T1 == 0 || T2 == 0) return 0;
     dim3 grid((unsigned)((T2 + 255) / 256), (unsigned)T1);
-    k_sim_rbf_cov<<<grid, 256, 0, st>>>(X1, X2, alpha, beta, jitter, K, T1, T2, dx);
+    k_sim_rbf_cov<<<NMGP_L(grid), 256, 0, st>>>(X1, X2, alpha, beta, jitter, K, T1, T2, dx);
     return nmgp_launch_status("nmgp_sim_rbf_cov");
 }
 
@@ -289,6 +289,6 @@ NMGP_API int nmgp_hadamard_index_cov(const double* Kx, const double* Bf, const i
     NMGP_REQUIRE(N1 >= 0 && N2 >= 0 && M > 0, "nmgp_hadamard_index_cov");
     if (N1 == 0 || N2 == 0) return 0;
     dim3 grid((unsigned)((N2 + 255) / 256), (unsigned)min(N1, 65535LL), (unsigned)((N1 + 65534) / 65535));
-    k_hadamard_index_cov<<<grid, 256, 0, st>>>(Kx, Bf, indx1, indx2, diag, out, N1, N2, M);
+    k_hadamard_index_cov<<<NMGP_L(grid), 256, 0, st>>>(Kx, Bf, indx1, indx2, diag, out, N1, N2, M);
     return nmgp_launch_status("nmgp_hadamard_index_cov");
 }

@@ -176,12 +176,12 @@ static int gemm_nt_launch(const double* A, const double* Bm, double* C, long lon
         size_t smem = sizeof(double) * 2 * (GT_M + 64) * GT_LD;
         if (int r = nmgp_opt_in_smem(k_gemm_nt<1>, smem, "nmgp_gemm_nt")) return r;
         dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + GT_M - 1) / GT_M));
-        k_gemm_nt<1><<<grid, 128, smem, st>>>(A, Bm, C, M, N, K, lda, ldb, ldc, alpha, beta, lower_only);
+        k_gemm_nt<1><<<NMGP_L(grid), 128, smem, st>>>(A, Bm, C, M, N, K, lda, ldb, ldc, alpha, beta, lower_only);
     } else {
         size_t smem = sizeof(double) * 2 * (GT_M + GT_N) * GT_LD;
         if (int r = nmgp_opt_in_smem(k_gemm_nt<2>, smem, "nmgp_gemm_nt")) return r;
         dim3 grid((unsigned)((N + GT_N - 1) / GT_N), (unsigned)((M + GT_M - 1) / GT_M));
-        k_gemm_nt<2><<<grid, 256, smem, st>>>(A, Bm, C, M, N, K, lda, ldb, ldc, alpha, beta, lower_only);
+        k_gemm_nt<2><<<NMGP_L(grid), 256, smem, st>>>(A, Bm, C, M, N, K, lda, ldb, ldc, alpha, beta, lower_only);
     }
     return nmgp_launch_status("nmgp_gemm_nt");
 }
@@ -394,7 +394,7 @@ static int factor_panel(double* Akk, long long lda, int nb, long long rest, doub
             if (int r = gemm_nt_launch(Akk + (long long)c0 * lda, Akk + (long long)c0 * lda, Dcc, rows, h, c0, lda, lda, lda,
                                        -1.0, 1.0, 0, st))
                 return r;
-        k_potrf_diag_inv<<<1, DI_THREADS, DI_SMEM, st>>>(Dcc, lda, h, linv, info, pivot_base + c0);
+        k_potrf_diag_inv<<<NMGP_L(1), DI_THREADS, DI_SMEM, st>>>(Dcc, lda, h, linv, info, pivot_base + c0);
         const long long below = rows - h;
         if (below > 0) {
             // in place: the 128-wide tile variant gives every row block to one CTA, which reads all of its K columns
@@ -477,8 +477,8 @@ NMGP_API int nmgp_potrf_big(double* A, long long T, long long lda, double* hld, 
         if (int r = factor_panel(A, lda, (int)T, 0, g_linv, info, 0, st)) return r;
     }
     dim3 gz((unsigned)((T + 255) / 256), (unsigned)min(T, 65535LL));
-    if (T <= 65535) k_zero_upper<<<gz, 256, 0, st>>>(A, T, lda);
-    if (hld) k_logdiag_sum<<<1, 1024, 0, st>>>(A, T, lda, hld);
+    if (T <= 65535) k_zero_upper<<<NMGP_L(gz), 256, 0, st>>>(A, T, lda);
+    if (hld) k_logdiag_sum<<<NMGP_L(1), 1024, 0, st>>>(A, T, lda, hld);
     return nmgp_launch_status("nmgp_potrf_big");
 }
 
@@ -569,16 +569,16 @@ NMGP_API int nmgp_potrs_vec(const double* L, long long T, long long lda, double*
     if (int r = nmgp_opt_in_smem(k_trsv_diag, smem, "nmgp_potrs_vec")) return r;
     for (long long k = 0; k < T; k += PB) {                       // L y = b
         const int nb = (int)min((long long)PB, T - k);
-        k_trsv_diag<<<1, PB, smem, st>>>(L + k * lda + k, lda, x + k, nb, 0);
+        k_trsv_diag<<<NMGP_L(1), PB, smem, st>>>(L + k * lda + k, lda, x + k, nb, 0);
         const long long rest = T - k - nb;
         if (rest > 0)
-            k_gemv_sub<<<(unsigned)((rest + 7) / 8), 256, 0, st>>>(L + (k + nb) * lda + k, lda, x + k, x + k + nb, rest, nb);
+            k_gemv_sub<<<NMGP_L((unsigned)((rest + 7) / 8)), 256, 0, st>>>(L + (k + nb) * lda + k, lda, x + k, x + k + nb, rest, nb);
     }
     for (long long k = ((T - 1) / PB) * PB; k >= 0; k -= PB) {    // L^T x = y
         const int nb = (int)min((long long)PB, T - k);
-        k_trsv_diag<<<1, PB, smem, st>>>(L + k * lda + k, lda, x + k, nb, 1);
+        k_trsv_diag<<<NMGP_L(1), PB, smem, st>>>(L + k * lda + k, lda, x + k, nb, 1);
         if (k > 0)   // x[0:k] -= L[k:k+nb, 0:k]^T x[k:k+nb]
-            k_gemv_t_sub<<<(unsigned)((k + 127) / 128), 128, 0, st>>>(L + k * lda, lda, x + k, x, nb, k);
+            k_gemv_t_sub<<<NMGP_L((unsigned)((k + 127) / 128)), 128, 0, st>>>(L + k * lda, lda, x + k, x, nb, k);
     }
     return nmgp_launch_status("nmgp_potrs_vec");
 }
@@ -594,7 +594,7 @@ NMGP_API int nmgp_scale_add_diag(const double* K, double* A, long long T, double
                                  cudaStream_t st) {
     NMGP_REQUIRE(T > 0, "nmgp_scale_add_diag");
     dim3 grid((unsigned)((T + 255) / 256), (unsigned)min(T, 65535LL), (unsigned)((T + 65534) / 65535));
-    k_scale_add_diag<<<grid, 256, 0, st>>>(K, A, T, alpha, sigma2);
+    k_scale_add_diag<<<NMGP_L(grid), 256, 0, st>>>(K, A, T, alpha, sigma2);
     return nmgp_launch_status("nmgp_scale_add_diag");
 }
 // out[(i1*h2+i2), (j1*w2+j2)] = t1[i1,j1] * t2[i2,j2]     (kronecker_operation.py:5-22)
@@ -613,7 +613,7 @@ NMGP_API int nmgp_kron_product(const double* t1, const double* t2, double* out, 
     long long total = (long long)h1 * h2 * w1 * w2;
     NMGP_REQUIRE(total >= 0 && total < (1LL << 40), "nmgp_kron_product");
     if (total == 0) return 0;
-    k_kron<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t1, t2, out, h1, w1, h2, w2);
+    k_kron<<<NMGP_L((unsigned)((total + 255) / 256)), 256, 0, st>>>(t1, t2, out, h1, w1, h2, w2);
     return nmgp_launch_status("nmgp_kron_product");
 }
 
@@ -721,7 +721,7 @@ NMGP_API int nmgp_eigh_small(const double* A, double* w, double* V, double* work
     NMGP_REQUIRE(n > 0 && n <= 128 && work != nullptr, "nmgp_eigh_small");
     size_t smem = sizeof(double) * n * n;
     if (int r = nmgp_opt_in_smem(k_eigh_jacobi, smem, "nmgp_eigh_small")) return r;
-    k_eigh_jacobi<<<1, EJ_THREADS, smem, st>>>(A, w, V, work, n);
+    k_eigh_jacobi<<<NMGP_L(1), EJ_THREADS, smem, st>>>(A, w, V, work, n);
     return nmgp_launch_status("nmgp_eigh_small");
 }
 
@@ -735,7 +735,7 @@ __global__ void k_axpby(const double* __restrict__ x, const double* __restrict__
 NMGP_API int nmgp_axpby(const double* x, const double* y, double* out, long long n, double a, double b,
                         cudaStream_t st) {
     if (n <= 0) return 0;
-    k_axpby<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, out, n, a, b);
+    k_axpby<<<NMGP_L((unsigned)((n + 255) / 256)), 256, 0, st>>>(x, y, out, n, a, b);
     return nmgp_launch_status("nmgp_axpby");
 }
 __global__ void k_dot(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out,
@@ -750,7 +750,7 @@ NMGP_API int nmgp_dot(const double* x, const double* y, double* out /* += */, lo
     if (n <= 0) return 0;
     long long blocks = (n + 255) / 256;
     if (blocks > 592) blocks = 592;
-    k_dot<<<(unsigned)blocks, 256, 0, st>>>(x, y, out, n);
+    k_dot<<<NMGP_L((unsigned)blocks), 256, 0, st>>>(x, y, out, n);
     return nmgp_launch_status("nmgp_dot");
 }
 // dist[i,j] = |x_i|^2 + |y_j|^2 - 2 x_i.y_j   (kernels.py:5-21)
@@ -772,6 +772,6 @@ NMGP_API int nmgp_pairwise_dist(const double* X1, const double* X2, double* out,
     NMGP_REQUIRE(T1 >= 0 && T2 >= 0 && dx > 0, "nmgp_pairwise_dist");
     if (T1 == 0 || T2 == 0) return 0;
     dim3 grid((unsigned)((T2 + 255) / 256), (unsigned)min(T1, 65535LL), (unsigned)((T1 + 65534) / 65535));
-    k_pairwise<<<grid, 256, 0, st>>>(X1, X2, out, T1, T2, dx);
+    k_pairwise<<<NMGP_L(grid), 256, 0, st>>>(X1, X2, out, T1, T2, dx);
     return nmgp_launch_status("nmgp_pairwise_dist");
 }

@@ -148,7 +148,7 @@ NMGP_API int nmgp_quadform_fwd(const double* Pa, const double* Pb, const int* I,
     size_t smem = quadform_smem(Q, mode, false, TR);
     if (int r = nmgp_opt_in_smem(k_quadform<false>, smem, "nmgp_quadform_fwd")) return r;
     dim3 grid((unsigned)((B + TR - 1) / TR), ns);
-    k_quadform<false><<<grid, TR * QF_SUB, smem, st>>>(Pa, Pb, I, Sig, Mu, q, m, nullptr, nullptr, nullptr, nullptr, B,
+    k_quadform<false><<<NMGP_L(grid), TR * QF_SUB, smem, st>>>(Pa, Pb, I, Sig, Mu, q, m, nullptr, nullptr, nullptr, nullptr, B,
                                                        Q, D, mode);
     return nmgp_launch_status("nmgp_quadform_fwd");
 }
@@ -167,7 +167,7 @@ NMGP_API int nmgp_quadform_bwd(const double* Pa, const double* Pb, const int* I,
     size_t smem = quadform_smem(Q, mode, true, TR);
     if (int r = nmgp_opt_in_smem(k_quadform<true>, smem, "nmgp_quadform_bwd")) return r;
     dim3 grid((unsigned)((B + TR - 1) / TR), ns);
-    k_quadform<true><<<grid, TR * QF_SUB, smem, st>>>(Pa, Pb, I, Sig, Mu, nullptr, nullptr, qbar, mbar, Pabar, Pbbar, B,
+    k_quadform<true><<<NMGP_L(grid), TR * QF_SUB, smem, st>>>(Pa, Pb, I, Sig, Mu, nullptr, nullptr, qbar, mbar, Pabar, Pbbar, B,
                                                       Q, D, mode);
     return nmgp_launch_status("nmgp_quadform_bwd");
 }
@@ -253,6 +253,6 @@ NMGP_API int nmgp_weighted_gram(const double* Pa, const double* Pb, const int* I
     size_t smem = sizeof(double) * ((size_t)Q * Q + Q + (size_t)WG_SUB * (Q + 1) + 2 * WG_SUB);
     if (int r = nmgp_opt_in_smem(k_weighted_gram, smem, "nmgp_weighted_gram")) return r;
     dim3 grid((unsigned)((B + WG_CHUNK - 1) / WG_CHUNK), ntasks, ns);
-    k_weighted_gram<<<grid, 256, smem, st>>>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, B, Q, D, mode);
+    k_weighted_gram<<<NMGP_L(grid), 256, smem, st>>>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, B, Q, D, mode);
     return nmgp_launch_status("nmgp_weighted_gram");
 }

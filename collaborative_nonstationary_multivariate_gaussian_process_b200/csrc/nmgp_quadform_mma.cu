@@ -115,7 +115,7 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
                const double* __restrict__ muW, const double* __restrict__ hyp, double scale,
                double* __restrict__ Rsum, double* __restrict__ ghyp, double* __restrict__ lbar,
                double* __restrict__ mgbar, double* __restrict__ qgbar, double* __restrict__ cGbar,
-               double* __restrict__ PGbar, long long B, int Q, int D) {
+               double* __restrict__ PGbar, long long B, int Q, int D, long long ystride) {
     using SH = LFShape<NB, KS>;
     constexpr int LDP = SH::LDP, LDS = SH::LDS, REC = SH::REC;
     extern __shared__ __align__(16) double sm[];
@@ -195,7 +195,7 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
         F += __shfl_xor_sync(0xffffffffu, F, 1);
         F += __shfl_xor_sync(0xffffffffu, F, 2);
         double r = 0.0;
-        if (rloc[mb] < nrows) r = y[row0 + rloc[mb]] - F;
+        if (rloc[mb] < nrows) r = y[(size_t)s * ystride + row0 + rloc[mb]] - F;
         rr[mb] = r / s2e;
         if (t == 0 && rloc[mb] < nrows) {
             rrs[rloc[mb]] = rr[mb];
@@ -349,7 +349,7 @@ template <int NB, int KS>
 static int launch_latent_fused(const double* PG, const double* cG, const double* l, const double* y, const int* I,
                                const double* SigW, const double* muW, const double* hyp, double scale, double* Rsum,
                                double* ghyp, double* lbar, double* mgbar, double* qgbar, double* cGbar, double* PGbar,
-                               int ns, long long B, int Q, int D, cudaStream_t st) {
+                               int ns, long long B, int Q, int D, long long ystride, cudaStream_t st) {
     using SH = LFShape<NB, KS>;
     size_t smem = SH::smem_bytes;
     if (int r = nmgp_opt_in_smem(k_latent_fused<NB, KS>, smem, "nmgp_latent_fused")) return r;
@@ -370,10 +370,10 @@ static int launch_latent_fused(const double* PG, const double* cG, const double*
         }
         rec_cap = need;
     }
-    k_pad_records<<<D, 256, 0, st>>>(SigW, muW, rec, Q, SH::KP, SH::LDS, SH::NP);
+    k_pad_records<<<NMGP_L(D), 256, 0, st>>>(SigW, muW, rec, Q, SH::KP, SH::LDS, SH::NP);
     dim3 grid((unsigned)((B + LFK_ROWS - 1) / LFK_ROWS), ns);
-    k_latent_fused<NB, KS><<<grid, LFK_THREADS, smem, st>>>(PG, cG, l, y, I, rec, muW, hyp, scale, Rsum, ghyp, lbar,
-                                                           mgbar, qgbar, cGbar, PGbar, B, Q, D);
+    k_latent_fused<NB, KS><<<NMGP_L(grid), LFK_THREADS, smem, st>>>(PG, cG, l, y, I, rec, muW, hyp, scale, Rsum, ghyp, lbar,
+                                                           mgbar, qgbar, cGbar, PGbar, B, Q, D, ystride);
     return nmgp_launch_status("nmgp_latent_fused");
 }
 
@@ -385,12 +385,12 @@ extern "C" int nmgp_quadform_bwd(const double*, const double*, const int*, const
                                  cudaStream_t);
 extern "C" int nmgp_lik_rows(const double*, const double*, const double*, const double*, const double*, const int*,
                              const double*, double, double*, double*, double*, double*, double*, double*, int,
-                             long long, int, cudaStream_t);
+                             long long, int, long long, cudaStream_t);
 
 #define LF_CASE(nb, ks)                                                                                              \
     if (NBr == nb && KSr == ks)                                                                                      \
         return launch_latent_fused<nb, ks>(PG, cG, l, y, I, SigW, muW, hyp, scale, Rsum, ghyp, lbar, mgbar, qgbar,   \
-                                           cGbar, PGbar, ns, B, Q, D, st);
+                                           cGbar, PGbar, ns, B, Q, D, ystride, st);
 
 // Fused latent-function statistics + expected log-likelihood + cotangents.  `work_q`, `work_m` ([ns,B,D] each) are
 // only used on the generic-Q path (they receive q and m).
@@ -398,7 +398,7 @@ NMGP_API int nmgp_latent_fused(const double* PG, const double* cG, const double*
                                const int* seg, const double* SigW, const double* muW, const double* hyp, double scale,
                                double* Rsum, double* ghyp, double* lbar, double* mgbar, double* qgbar, double* cGbar,
                                double* PGbar, double* work_q, double* work_m, int ns, long long B, int Q, int D,
-                               cudaStream_t st) {
+                               long long ystride, cudaStream_t st) {
     NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && Q > 0 && Q <= 128 && D > 0, "nmgp_latent_fused");
     if (ns == 0 || B == 0) return 0;
     const int NBr = (Q + 7) / 8, KSr = (Q + 3) / 4;
@@ -410,7 +410,7 @@ NMGP_API int nmgp_latent_fused(const double* PG, const double* cG, const double*
     // Q > 64: three-kernel path
     if (int r = nmgp_quadform_fwd(PG, PG, I, seg, SigW, muW, work_q, work_m, ns, B, Q, D, MODE_W, st)) return r;
     if (int r = nmgp_lik_rows(l, work_m, work_q, cG, y, I, hyp, scale, Rsum, ghyp, lbar, mgbar, qgbar, cGbar, ns, B, D,
-                              st))
+                              ystride, st))
         return r;
     return nmgp_quadform_bwd(PG, PG, I, seg, SigW, muW, qgbar, mgbar, PGbar, PGbar, ns, B, Q, D, MODE_W, st);
 }
@@ -594,7 +594,7 @@ static int launch_coef_quadform(const double* Pa, const double* Pb, const int* I
     size_t smem = 8 * (2 * (size_t)LF_ROWS * SH::LDP + 2 * (size_t)SH::KP * SH::LDS + 2 * SH::NP + 4 * LF_ROWS) + LF_ROWS * 4;
     if (int r = nmgp_opt_in_smem(k_coef_quadform_mma<NB, KS, BWD>, smem, "nmgp_quadform(mma)")) return r;
     dim3 grid((unsigned)((B + LF_ROWS - 1) / LF_ROWS), ns);
-    k_coef_quadform_mma<NB, KS, BWD><<<grid, LF_THREADS, smem, st>>>(Pa, Pb, I, Sig, Mu, q, m, qbar, mbar, Pabar, Pbbar,
+    k_coef_quadform_mma<NB, KS, BWD><<<NMGP_L(grid), LF_THREADS, smem, st>>>(Pa, Pb, I, Sig, Mu, q, m, qbar, mbar, Pabar, Pbbar,
                                                                      B, Q, D, FastDiv((unsigned)Q));
     return nmgp_launch_status("nmgp_quadform(mma)");
 }
@@ -796,7 +796,7 @@ static int launch_gram(const double* Pa, const double* Pb, const int* seg, const
     if (int r = nmgp_opt_in_smem(k_gram_mma<NB>, smem, "nmgp_weighted_gram")) return r;
     const int ngroups = (D + GM_NG - 1) / GM_NG;
     dim3 grid(D, ngroups + (mode == MODE_U ? 1 : 0), ns);
-    k_gram_mma<NB><<<grid, GM_THREADS, smem, st>>>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, B, Q, D, mode);
+    k_gram_mma<NB><<<NMGP_L(grid), GM_THREADS, smem, st>>>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, B, Q, D, mode);
     return nmgp_launch_status("nmgp_weighted_gram(mma)");
 }
 

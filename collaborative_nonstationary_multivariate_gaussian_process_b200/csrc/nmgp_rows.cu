@@ -112,7 +112,7 @@ NMGP_API int nmgp_solve_rows_fwd(const double* K, const double* R, double* P, do
     size_t smem = sizeof(double) * ((size_t)Q * Q + (size_t)Q * (TR + 1));
     if (int r = nmgp_opt_in_smem(k_solve_rows<false>, smem, "nmgp_solve_rows_fwd")) return r;
     dim3 grid((unsigned)((B + TR - 1) / TR), ns);
-    k_solve_rows<false><<<grid, TR, smem, st>>>(K, R, P, c, nullptr, nullptr, nullptr, nullptr, nullptr, B, Q);
+    k_solve_rows<false><<<NMGP_L(grid), TR, smem, st>>>(K, R, P, c, nullptr, nullptr, nullptr, nullptr, nullptr, B, Q);
     return nmgp_launch_status("nmgp_solve_rows_fwd");
 }
 NMGP_API int nmgp_solve_rows_bwd(const double* Pbar, const double* cbar, const double* K, const double* P,
@@ -129,7 +129,7 @@ NMGP_API int nmgp_solve_rows_bwd(const double* Pbar, const double* cbar, const d
     size_t smem = sizeof(double) * ((size_t)Q * Q + 2 * (size_t)Q * (TR + 1));
     if (int r = nmgp_opt_in_smem(k_solve_rows<true>, smem, "nmgp_solve_rows_bwd")) return r;
     dim3 grid((unsigned)((B + TR - 1) / TR), ns);
-    k_solve_rows<true><<<grid, TR, smem, st>>>(K, R, nullptr, nullptr, Pbar, cbar, P, Kbar, Abar, B, Q);
+    k_solve_rows<true><<<NMGP_L(grid), TR, smem, st>>>(K, R, nullptr, nullptr, Pbar, cbar, P, Kbar, Abar, B, Q);
     return nmgp_launch_status("nmgp_solve_rows_bwd");
 }
 
@@ -142,7 +142,7 @@ __global__ void k_ell_sd_fwd(const double* __restrict__ c, const double* __restr
 }
 NMGP_API int nmgp_ell_sd_fwd(const double* c, const double* hyp, double* sd, long long B, cudaStream_t st) {
     if (B == 0) return 0;
-    k_ell_sd_fwd<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(c, hyp, sd, B);
+    k_ell_sd_fwd<<<NMGP_L((unsigned)((B + 255) / 256)), 256, 0, st>>>(c, hyp, sd, B);
     return nmgp_launch_status("nmgp_ell_sd_fwd");
 }
 __global__ void k_ell_sd_bwd(const double* __restrict__ sdbar, const double* __restrict__ sd,
@@ -162,7 +162,7 @@ NMGP_API int nmgp_ell_sd_bwd(const double* sdbar, const double* sd, const double
     if (B == 0) return 0;
     long long blocks = (B + 255) / 256;
     if (blocks > 592) blocks = 592;
-    k_ell_sd_bwd<<<(unsigned)blocks, 256, 0, st>>>(sdbar, sd, hyp, ghyp, cbar, B);
+    k_ell_sd_bwd<<<NMGP_L((unsigned)blocks), 256, 0, st>>>(sdbar, sd, hyp, ghyp, cbar, B);
     return nmgp_launch_status("nmgp_ell_sd_bwd");
 }
 
@@ -201,7 +201,7 @@ NMGP_API int nmgp_ell_rows_fwd(const double* Pell, const double* v, const double
     if (B == 0) return 0;
     size_t smem = (size_t)ns * Q * sizeof(double);
     if (int r = nmgp_opt_in_smem(k_ell_rows_fwd, smem, "nmgp_ell_rows_fwd")) return r;
-    k_ell_rows_fwd<<<(unsigned)((B + 7) / 8), 256, smem, st>>>(Pell, v, zell, sd, ellx, ns, B, Q);
+    k_ell_rows_fwd<<<NMGP_L((unsigned)((B + 7) / 8)), 256, smem, st>>>(Pell, v, zell, sd, ellx, ns, B, Q);
     return nmgp_launch_status("nmgp_ell_rows_fwd");
 }
 // tb = ellxbar*ellx;  vbar[s,q] += sum_n tb P[n,q];  Pellbar[n,q] += sum_s tb v[s,q];  sdbar[n] += sum_s tb z
@@ -248,7 +248,7 @@ NMGP_API int nmgp_ell_rows_bwd(const double* ellxbar, const double* ellx, const 
     if (B == 0) return 0;
     size_t smem = sizeof(double) * ((size_t)ns * Q + (size_t)ns * ER_TILE + (size_t)ER_TILE * Q);
     if (int r = nmgp_opt_in_smem(k_ell_rows_bwd, smem, "nmgp_ell_rows_bwd")) return r;
-    k_ell_rows_bwd<<<(unsigned)((B + ER_TILE - 1) / ER_TILE), 256, smem, st>>>(ellxbar, ellx, Pell, v, zell, vbar,
+    k_ell_rows_bwd<<<NMGP_L((unsigned)((B + ER_TILE - 1) / ER_TILE)), 256, smem, st>>>(ellxbar, ellx, Pell, v, zell, vbar,
                                                                                Pellbar, sdbar, ns, B, Q);
     return nmgp_launch_status("nmgp_ell_rows_bwd");
 }
@@ -273,7 +273,7 @@ NMGP_API int nmgp_coef_sd_fwd(const double* q, const double* cL0, const double* 
                               double* sd, long long B, int D, cudaStream_t st) {
     if (B == 0) return 0;
     long long n = B * D;
-    k_coef_sd_fwd<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, cL0, cL1, I, hyp, sd, B, D);
+    k_coef_sd_fwd<<<NMGP_L((unsigned)((n + 255) / 256)), 256, 0, st>>>(q, cL0, cL1, I, hyp, sd, B, D);
     return nmgp_launch_status("nmgp_coef_sd_fwd");
 }
 // qbar = sdbar/(2 sd); cL0bar[n] = -sum_{j<i} qbar; cL1bar[n] = -qbar[n,i]; ghyp += s2 * sums.  Warp per row.
@@ -315,7 +315,7 @@ NMGP_API int nmgp_coef_sd_bwd(const double* sdbar, const double* sd, const int* 
     if (B == 0) return 0;
     long long blocks = (B + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_coef_sd_bwd<<<(unsigned)blocks, 256, 0, st>>>(sdbar, sd, I, hyp, ghyp, qbar, cL0bar, cL1bar, B, D);
+    k_coef_sd_bwd<<<NMGP_L((unsigned)blocks), 256, 0, st>>>(sdbar, sd, I, hyp, ghyp, qbar, cL0bar, cL1bar, B, D);
     return nmgp_launch_status("nmgp_coef_sd_bwd");
 }
 
@@ -369,7 +369,7 @@ NMGP_API int nmgp_coef_sample_fwd(const double* m, const double* sd, const doubl
     long long n = B * ((D + 3) / 4);
     dim3 grid((unsigned)((n + 255) / 256), ns);
     NoiseKey key{seed, stream_id};
-    k_coef_sample_fwd<<<grid, 256, 0, st>>>(m, sd, zL, I, l, B, D, key, s0, gid);
+    k_coef_sample_fwd<<<NMGP_L(grid), 256, 0, st>>>(m, sd, zL, I, l, B, D, key, s0, gid);
     return nmgp_launch_status("nmgp_coef_sample_fwd");
 }
 __global__ void k_coef_sample_bwd(const double* __restrict__ lbar, const double* __restrict__ l,
@@ -414,7 +414,7 @@ NMGP_API int nmgp_coef_sample_bwd(const double* lbar, const double* l, const dou
     if (B == 0 || ns == 0) return 0;
     long long n = B * ((D + 3) / 4);
     NoiseKey key{seed, stream_id};
-    k_coef_sample_bwd<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(lbar, l, zL, I, mbar, sdbar, ns, B, D, key, s0, gid);
+    k_coef_sample_bwd<<<NMGP_L((unsigned)((n + 255) / 256)), 256, 0, st>>>(lbar, l, zL, I, mbar, sdbar, ns, B, D, key, s0, gid);
     return nmgp_launch_status("nmgp_coef_sample_bwd");
 }
 
@@ -442,7 +442,7 @@ NMGP_API int nmgp_noise_fill(double* out, int ns, long long B, int C, unsigned l
     long long n = B * ((C + 3) / 4);
     dim3 grid((unsigned)((n + 255) / 256), ns);
     NoiseKey key{seed, stream_id};
-    k_noise_fill<<<grid, 256, 0, st>>>(out, B, C, key, s0, gid);
+    k_noise_fill<<<NMGP_L(grid), 256, 0, st>>>(out, B, C, key, s0, gid);
     return nmgp_launch_status("nmgp_noise_fill");
 }
 
@@ -453,7 +453,7 @@ __global__ void k_lik_rows(const double* __restrict__ l, const double* __restric
                            const double* __restrict__ cG, const double* __restrict__ y, const int* __restrict__ I,
                            const double* __restrict__ hyp, double scale, double* __restrict__ Rsum,
                            double* __restrict__ ghyp, double* __restrict__ lbar, double* __restrict__ mgbar,
-                           double* __restrict__ qgbar, double* __restrict__ cGbar, long long B, int D) {
+                           double* __restrict__ qgbar, double* __restrict__ cGbar, long long B, int D, long long ystride) {
     const int s = blockIdx.y;
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const double s2e = hyp[H_S2_ERR];
@@ -471,7 +471,7 @@ __global__ void k_lik_rows(const double* __restrict__ l, const double* __restric
         }
         F = warp_sum(F);
         pen = warp_sum(pen);
-        const double r = y[n] - F;
+        const double r = y[(size_t)s * ystride + n] - F;
         const double rr = r / s2e;
         double qsum = 0.0;
         for (int j = lane; j < D; j += 32) {
@@ -504,13 +504,13 @@ __global__ void k_lik_rows(const double* __restrict__ l, const double* __restric
 NMGP_API int nmgp_lik_rows(const double* l, const double* mg, const double* qg, const double* cG, const double* y,
                            const int* I, const double* hyp, double scale, double* Rsum /* pre-zeroed */, double* ghyp,
                            double* lbar, double* mgbar, double* qgbar, double* cGbar, int ns, long long B, int D,
-                           cudaStream_t st) {
-    NMGP_REQUIRE(ns >= 0 && ns <= 65535, "nmgp_lik_rows");
+                           long long ystride, cudaStream_t st) {
+    NMGP_REQUIRE(ns >= 0 && ns <= 65535 && (ystride == 0 || ystride >= B), "nmgp_lik_rows");
     if (B == 0 || ns == 0) return 0;
     long long blocks = (B + 7) / 8;
     if (blocks > 148 * 4) blocks = 148 * 4;
     dim3 grid((unsigned)blocks, ns);
-    k_lik_rows<<<grid, 256, 0, st>>>(l, mg, qg, cG, y, I, hyp, scale, Rsum, ghyp, lbar, mgbar, qgbar, cGbar, B, D);
+    k_lik_rows<<<NMGP_L(grid), 256, 0, st>>>(l, mg, qg, cG, y, I, hyp, scale, Rsum, ghyp, lbar, mgbar, qgbar, cGbar, B, D, ystride);
     return nmgp_launch_status("nmgp_lik_rows");
 }
 
@@ -554,7 +554,7 @@ NMGP_API int nmgp_pair_means(const double* Pa, const double* Pb, const int* I, c
     NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && Q > 0 && Q <= 128 && D > 0, "nmgp_pair_means");
     if (ns == 0 || B == 0) return 0;
     dim3 grid((unsigned)((B + 7) / 8), ns);
-    k_pair_means<<<grid, 256, 0, st>>>(Pa, Pb, I, Mu, m, B, Q, D, mode);
+    k_pair_means<<<NMGP_L(grid), 256, 0, st>>>(Pa, Pb, I, Mu, m, B, Q, D, mode);
     return nmgp_launch_status("nmgp_pair_means");
 }
 
@@ -577,7 +577,7 @@ NMGP_API int nmgp_rowdot_live(const double* l, const double* g, const int* I, do
     NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && D > 0, "nmgp_rowdot_live");
     if (ns == 0 || B == 0) return 0;
     dim3 grid((unsigned)((B + 7) / 8), ns);
-    k_rowdot_live<<<grid, 256, 0, st>>>(l, g, I, F, B, D);
+    k_rowdot_live<<<NMGP_L(grid), 256, 0, st>>>(l, g, I, F, B, D);
     return nmgp_launch_status("nmgp_rowdot_live");
 }
 
@@ -592,7 +592,7 @@ __global__ void k_reparam_diag(const double* __restrict__ mean, const double* __
 NMGP_API int nmgp_reparam_diag(const double* mean, const double* var, const double* z, double* out, long long n,
                                cudaStream_t st) {
     if (n <= 0) return 0;
-    k_reparam_diag<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mean, var, z, out, n);
+    k_reparam_diag<<<NMGP_L((unsigned)((n + 255) / 256)), 256, 0, st>>>(mean, var, z, out, n);
     return nmgp_launch_status("nmgp_reparam_diag");
 }
 // out += sum_i [ -(y-loc)^2/(2 scale^2) - log(scale) - log(sqrt(2 pi)) ]   (scale: scalar on device)
@@ -613,7 +613,7 @@ NMGP_API int nmgp_normal_logprob_sum(const double* loc, const double* scale, con
     if (n <= 0) return 0;
     long long blocks = (n + 255) / 256;
     if (blocks > 592) blocks = 592;
-    k_normal_logprob<<<(unsigned)blocks, 256, 0, st>>>(loc, scale, y, out, n);
+    k_normal_logprob<<<NMGP_L((unsigned)blocks), 256, 0, st>>>(loc, scale, y, out, n);
     return nmgp_launch_status("nmgp_normal_logprob_sum");
 }
 // out[r] = sum_k x[r,k]^2   (warp per row)
@@ -631,7 +631,7 @@ __global__ void k_sumsq_rows(const double* __restrict__ x, double* __restrict__ 
 }
 NMGP_API int nmgp_sumsq_rows(const double* x, double* out, long long rows, long long cols, cudaStream_t st) {
     if (rows <= 0) return 0;
-    k_sumsq_rows<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, out, rows, cols);
+    k_sumsq_rows<<<NMGP_L((unsigned)((rows + 7) / 8)), 256, 0, st>>>(x, out, rows, cols);
     return nmgp_launch_status("nmgp_sumsq_rows");
 }
 
@@ -656,6 +656,6 @@ NMGP_API int nmgp_lcorr(const double* L, double* corr, long long nmat, int D, cu
     NMGP_REQUIRE(nmat >= 0 && D > 0, "nmgp_lcorr");
     if (nmat == 0) return 0;
     long long n = nmat * D * D;
-    k_lcorr<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, corr, nmat, D);
+    k_lcorr<<<NMGP_L((unsigned)((n + 255) / 256)), 256, 0, st>>>(L, corr, nmat, D);
     return nmgp_launch_status("nmgp_lcorr");
 }

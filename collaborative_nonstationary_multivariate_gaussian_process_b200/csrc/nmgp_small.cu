@@ -26,7 +26,11 @@ int nmgp_launch_status(const char* what) {
     return 0;
 }
 NMGP_API const char* nmgp_last_error(void) { return g_err; }
-NMGP_API int nmgp_version(void) { return 100; }
+NMGP_API int nmgp_version(void) { return 200; }
+// kernel launches issued by this library since it was loaded (host-side counter; CUDA-graph replays are added by the
+// host code that replays them)
+unsigned long long g_nmgp_launches = 0;
+NMGP_API unsigned long long nmgp_launch_count(void) { return g_nmgp_launches; }
 
 // ------------------------------------------------------------------------------------------
 __global__ void k_hyper_exp(const double* __restrict__ logs, double* __restrict__ out, int n) {
@@ -35,7 +39,7 @@ __global__ void k_hyper_exp(const double* __restrict__ logs, double* __restrict_
 }
 NMGP_API int nmgp_hyper_exp(const double* logs, double* hyp, int n, cudaStream_t st) {
     NMGP_REQUIRE(n > 0, "nmgp_hyper_exp");
-    k_hyper_exp<<<(n + 63) / 64, 64, 0, st>>>(logs, hyp, n);
+    k_hyper_exp<<<NMGP_L((n + 63) / 64), 64, 0, st>>>(logs, hyp, n);
     return nmgp_launch_status("nmgp_hyper_exp");
 }
 
@@ -52,7 +56,7 @@ __global__ void k_segment_offsets(const int* __restrict__ I, int* __restrict__ s
 }
 NMGP_API int nmgp_segment_offsets(const int* I, int* seg, long long B, int D, cudaStream_t st) {
     NMGP_REQUIRE(B >= 0 && D > 0 && B < 2147483647LL, "nmgp_segment_offsets");
-    k_segment_offsets<<<(D + 1 + 127) / 128, 128, 0, st>>>(I, seg, B, D);
+    k_segment_offsets<<<NMGP_L((D + 1 + 127) / 128), 128, 0, st>>>(I, seg, B, D);
     return nmgp_launch_status("nmgp_segment_offsets");
 }
 
@@ -81,7 +85,7 @@ NMGP_API int nmgp_tril_syrk_fwd(const double* S, double* Sigma, int nb, int Q, c
     if (nb == 0) return 0;
     size_t smem = (size_t)Q * (Q | 1) * sizeof(double);
     if (int r = nmgp_opt_in_smem(k_tril_syrk_fwd, smem, "nmgp_tril_syrk_fwd")) return r;
-    k_tril_syrk_fwd<<<nb, 256, smem, st>>>(S, Sigma, Q);
+    k_tril_syrk_fwd<<<NMGP_L(nb), 256, smem, st>>>(S, Sigma, Q);
     return nmgp_launch_status("nmgp_tril_syrk_fwd");
 }
 
@@ -112,7 +116,7 @@ NMGP_API int nmgp_tril_syrk_bwd(const double* S, const double* SigBar, double* S
     if (nb == 0) return 0;
     size_t smem = 2 * (size_t)Q * (Q | 1) * sizeof(double);
     if (int r = nmgp_opt_in_smem(k_tril_syrk_bwd, smem, "nmgp_tril_syrk_bwd")) return r;
-    k_tril_syrk_bwd<<<nb, 256, smem, st>>>(S, SigBar, Sbar, Q);
+    k_tril_syrk_bwd<<<NMGP_L(nb), 256, smem, st>>>(S, SigBar, Sbar, Q);
     return nmgp_launch_status("nmgp_tril_syrk_bwd");
 }
 
@@ -164,7 +168,7 @@ NMGP_API int nmgp_potrf_batched(const double* A, double jitter, double* C, doubl
     if (nb == 0) return 0;
     size_t smem = (size_t)Q * (Q | 1) * sizeof(double);
     if (int r = nmgp_opt_in_smem(k_potrf, smem, "nmgp_potrf_batched")) return r;
-    k_potrf<<<nb, 128, smem, st>>>(A, jitter, C, hld, info, Q);
+    k_potrf<<<NMGP_L(nb), 128, smem, st>>>(A, jitter, C, hld, info, Q);
     return nmgp_launch_status("nmgp_potrf_batched");
 }
 
@@ -245,7 +249,7 @@ NMGP_API int nmgp_potrf_bwd_batched(const double* C, const double* Cbar, const d
     if (nb == 0) return 0;
     size_t smem = 2 * (size_t)Q * (Q | 1) * sizeof(double);
     if (int r = nmgp_opt_in_smem(k_potrf_bwd, smem, "nmgp_potrf_bwd_batched")) return r;
-    k_potrf_bwd<<<nb, 128, smem, st>>>(C, Cbar, hldbar, Abar, Q);
+    k_potrf_bwd<<<NMGP_L(nb), 128, smem, st>>>(C, Cbar, hldbar, Abar, Q);
     return nmgp_launch_status("nmgp_potrf_bwd_batched");
 }
 
@@ -289,7 +293,7 @@ NMGP_API int nmgp_kl_fwd(const double* CS, const double* hldS, const double* mu,
     size_t smem = (size_t)Q * Q * sizeof(double);
     if (int r = nmgp_opt_in_smem(k_kl_fwd, smem, "nmgp_kl_fwd")) return r;
     dim3 grid((nb + 127) / 128, np_);
-    k_kl_fwd<<<grid, 128, smem, st>>>(CS, hldS, mu, R, hldR, kl, t, np_, nb, Q);
+    k_kl_fwd<<<NMGP_L(grid), 128, smem, st>>>(CS, hldS, mu, R, hldR, kl, t, np_, nb, Q);
     return nmgp_launch_status("nmgp_kl_fwd");
 }
 
@@ -377,13 +381,13 @@ NMGP_API int nmgp_kl_bwd(const double* klbar, const double* CS, const double* mu
     size_t smem = (size_t)Q * Q * sizeof(double);
     if (int r = nmgp_opt_in_smem(k_kl_bwd_solve, smem, "nmgp_kl_bwd")) return r;
     dim3 g1((nb + 127) / 128, np_);
-    k_kl_bwd_solve<<<g1, 128, smem, st>>>(klbar, R, t, work, np_, nb, Q);
+    k_kl_bwd_solve<<<NMGP_L(g1), 128, smem, st>>>(klbar, R, t, work, np_, nb, Q);
     const int chunk = 32;
     dim3 g2((nb + chunk - 1) / chunk, np_);
-    k_kl_bwd_R<<<g2, 256, 0, st>>>(klbar, CS, R, t, work, Rbar, np_, nb, Q, chunk);
+    k_kl_bwd_R<<<NMGP_L(g2), 256, 0, st>>>(klbar, CS, R, t, work, Rbar, np_, nb, Q, chunk);
     long long n3 = (long long)nb * Q;
-    k_kl_bwd_S<<<(unsigned)((n3 + 127) / 128), 128, 0, st>>>(klbar, CS, R, work, CSbar, hldSbar, mubar, np_, nb, Q);
-    k_kl_bwd_hldR<<<np_, 128, 0, st>>>(klbar, hldRbar, np_, nb);
+    k_kl_bwd_S<<<NMGP_L((unsigned)((n3 + 127) / 128)), 128, 0, st>>>(klbar, CS, R, work, CSbar, hldSbar, mubar, np_, nb, Q);
+    k_kl_bwd_hldR<<<NMGP_L(np_), 128, 0, st>>>(klbar, hldRbar, np_, nb);
     return nmgp_launch_status("nmgp_kl_bwd");
 }
 
@@ -403,7 +407,7 @@ __global__ void k_sample_v_fwd(const double* __restrict__ mu, const double* __re
 NMGP_API int nmgp_sample_v_fwd(const double* mu_v, const double* Cv, const double* zv, double* v, double* ellz, int S,
                                int Q, cudaStream_t st) {
     NMGP_REQUIRE(S > 0 && Q > 0, "nmgp_sample_v_fwd");
-    k_sample_v_fwd<<<(S * Q + 127) / 128, 128, 0, st>>>(mu_v, Cv, zv, v, ellz, S, Q);
+    k_sample_v_fwd<<<NMGP_L((S * Q + 127) / 128), 128, 0, st>>>(mu_v, Cv, zv, v, ellz, S, Q);
     return nmgp_launch_status("nmgp_sample_v_fwd");
 }
 // vb = vbar + ellzbar*ellz;  mu_v_bar[a] += sum_s vb[s,a];  Cvbar[a,c] += sum_s vb[s,a] z[s,c] (c<=a)
@@ -426,6 +430,6 @@ __global__ void k_sample_v_bwd(const double* __restrict__ ellzbar, const double*
 NMGP_API int nmgp_sample_v_bwd(const double* ellzbar, const double* vbar, const double* ellz, const double* zv,
                                double* mu_v_bar, double* Cvbar, int S, int Q, cudaStream_t st) {
     NMGP_REQUIRE(S > 0 && Q > 0, "nmgp_sample_v_bwd");
-    k_sample_v_bwd<<<(Q * Q + 127) / 128, 128, 0, st>>>(ellzbar, vbar, ellz, zv, mu_v_bar, Cvbar, S, Q);
+    k_sample_v_bwd<<<NMGP_L((Q * Q + 127) / 128), 128, 0, st>>>(ellzbar, vbar, ellz, zv, mu_v_bar, Cvbar, S, Q);
     return nmgp_launch_status("nmgp_sample_v_bwd");
 }

@@ -188,7 +188,7 @@ static int launch_solve_mma(const double* K, const double* R, double* P, double*
     size_t smem = sizeof(double) * (2 * QP * LDR + 2 * NB * 64);
     if (int r = nmgp_opt_in_smem(k_solve_rows_mma<NB, BWD>, smem, what)) return r;
     dim3 grid((unsigned)((B + SM_ROWS * SM_TILES - 1) / (SM_ROWS * SM_TILES)), ns);
-    k_solve_rows_mma<NB, BWD><<<grid, SM_THREADS, smem, st>>>(K, R, P, c, Pbar, cbar, Pin, Kbar, Tout, B, Q);
+    k_solve_rows_mma<NB, BWD><<<NMGP_L(grid), SM_THREADS, smem, st>>>(K, R, P, c, Pbar, cbar, Pin, Kbar, Tout, B, Q);
     return nmgp_launch_status(what);
 }
 #define SMM_DISPATCH(BWDFLAG, ...)                                           \

@@ -67,7 +67,8 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
               sample_chunk: Optional[int] = None, want_grads: bool = True, pair_index: Optional[torch.Tensor] = None,
               latent_order: Optional[torch.Tensor] = None, aux: Optional[dict] = None,
               kl_shard: Optional[tuple] = None, noise_key: Optional[tuple] = None,
-              row_gid: Optional[torch.Tensor] = None):
+              row_gid: Optional[torch.Tensor] = None, defer_pd_check: bool = False,
+              S_total: Optional[int] = None, sample_offset: int = 0):
     """Returns (loss, grads) for rows (x, y, I) -- I sorted ascending, int32 -- and noise
     z_v [S,Q], z_ell [S,B], z_L [S,B,D] (z_L[s,n,j] is the draw for pair (I[n], j)).
 
@@ -82,6 +83,17 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
     P coefficient covariances, KL forward/backward) over the ranks instead of replicating it: each KL_U pair and each
     sample's KL_W is then evaluated by exactly one rank with weight 1 (KL_v stays replicated with ``kl_weight``).
 
+    ``y`` may be [S, B]: one target vector per sample -- the S "samples" are then S subjects observed on the same rows
+    (HCP-shaped step: the mean over subjects of the reference's one-draw forward on that subject's data).
+
+    ``S_total`` / ``sample_offset`` (sample sharding: each rank holds ALL rows but only samples sample_offset ..
+    sample_offset + S - 1 of S_total): the estimate is scaled by 1/S_total, every local sample's KL_W is evaluated
+    here, and the counter-based noise is keyed by the global sample index.
+
+    ``defer_pd_check`` (set under multi-rank sharding): a failed Cholesky is not raised here -- a rank that raised alone
+    would leave the others waiting in the gradient all-reduce -- but returned as ``aux["pd_info"]`` (int32 device scalar,
+    1 + index of the failing matrix); ``parallel.allreduce_loss_and_grads`` reduces it and raises on every rank.
+
     ``pair_index`` (flat i*D+j per packed pair slot) and ``latent_order`` (permutation of the D latent functions)
     override the default packing; compute_ELBO uses them to evaluate the reference's transposed coefficient gather
     (quirk q5) with the same kernels.  ``aux`` (a dict) receives the per-sample pieces of the estimate.
@@ -89,9 +101,12 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
     D, Q = p["mu_W"].shape
     B = x.shape[0]
     S = z_v.shape[0]
+    if y.dim() == 2 and tuple(y.shape) != (S, B):
+        raise ValueError("per-sample targets must be [S, B] = [%d, %d], got %s" % (S, B, tuple(y.shape)))
     dev = x.device
     f64 = torch.float64
-    scale = float(N) / float((B if B_total is None else B_total) * S)
+    S_tot = S if S_total is None else int(S_total)
+    scale = float(N) / float((B if B_total is None else B_total) * S_tot)
     zeros = lambda *s: torch.zeros(*s, dtype=f64, device=dev)
     ns_max = sample_chunk or default_sample_chunk(S, B, Q, D)
 
@@ -121,7 +136,7 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
     part = lambda n: slice((n * rank_) // world_, (n * (rank_ + 1)) // world_)
     sl1 = part(D)                                             # diagonal pairs handled here
     sl0 = slice(D + part(npair - D).start, D + part(npair - D).stop)   # strictly-lower pairs handled here
-    slS = part(S)                                             # samples whose KL_W is evaluated here
+    slS = part(S) if S_total is None else slice(0, S)         # samples whose KL_W is evaluated here
     w_sh = kl_weight if kl_shard is None else 1.0
     n1, n0, nS = sl1.stop - sl1.start, sl0.stop - sl0.start, slS.stop - slS.start
 
@@ -163,7 +178,7 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
         kl_W = None
         if nS:
             kl_W, t_W = ops.kl_fwd(C_W, hld_W, mu_W, R_G[slS], hld_G[slS])
-            loss_kl = loss_kl + w_sh * kl_W.sum() / S
+            loss_kl = loss_kl + w_sh * kl_W.sum() / S_tot
         klU_sum = zeros(())
         if n1:
             kl_U1, t_U1 = ops.kl_fwd(C_U1, hld_U1, muU[sl1], sysm["L1"]["R"], sysm["L1"]["hldR"])
@@ -178,7 +193,7 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
             CWbar = zeros(D, Q, Q); hldWbar = zeros(D); muWbar = zeros(D, Q)
             RGbar = zeros(S, Q, Q); hldGbar = zeros(S)
             if nS:
-                a, b, c_, rg, hg = ops.kl_bwd(full((nS, D), w_sh / S), C_W, mu_W, R_G[slS], t_W)
+                a, b, c_, rg, hg = ops.kl_bwd(full((nS, D), w_sh / S_tot), C_W, mu_W, R_G[slS], t_W)
                 CWbar, hldWbar, muWbar = a, b, c_
                 RGbar[slS] = rg; hldGbar[slS] = hg
             Cvbar, hldvbar, muvbar, Rellbar, hldRellbar = ops.kl_bwd(full((1, 1), kl_weight), C_v, mu_v.reshape(1, Q),
@@ -213,12 +228,12 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
         if z_L is not None:
             zl_, nz_ = z_L[sl], None
         else:
-            zl_, nz_ = None, (int(noise_key[0]), int(noise_key[1]), sl.start, sl.stop - sl.start, row_gid)
+            zl_, nz_ = None, (int(noise_key[0]), int(noise_key[1]), sl.start + int(sample_offset), sl.stop - sl.start, row_gid)
         l = ops.coef_sample_fwd(mU[0], sdU, zl_, I, noise=nz_)
         KG = ops.gibbs_build_fwd(x, Z, ellx, ellZ[sl], 0.0)
         PG, cG = ops.solve_rows_fwd(KG, R_G[sl])
-        lbar, mgbar, qgbar, cGbar, PGbar = ops.latent_fused(PG, cG, l, y, I, Sig_W, mu_W, hyp, scale, Rsum[sl], ghyp,
-                                                            seg=seg)
+        lbar, mgbar, qgbar, cGbar, PGbar = ops.latent_fused(PG, cG, l, y if y.dim() == 1 else y[sl], I, Sig_W, mu_W, hyp,
+                                                            scale, Rsum[sl], ghyp, seg=seg)
         if not want_grads:
             continue
         ops.weighted_gram(PG, PG, I, qgbar, mgbar, MODE_W, SigWbar, muWrows, seg=seg)
@@ -237,7 +252,10 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
     if aux is not None:
         aux.update(Rsum=Rsum, kl_W=kl_W, kl_v=kl_v.sum(), kl_U=klU_sum)
     if not want_grads:
-        ops.raise_if_not_pd(pd_info)
+        if defer_pd_check and aux is not None:
+            aux["pd_info"] = pd_info
+        else:
+            ops.raise_if_not_pd(pd_info)
         return loss, None
 
     # ---- backward of the per-sample small stage ------------------------------------------------
@@ -296,5 +314,8 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
     for i, k in enumerate(HYPER_ORDER):
         grads[k] = ghyp[i]
     # the only host synchronisation of the step, after everything is enqueued (torch.cholesky's RuntimeError)
-    ops.raise_if_not_pd(pd_info)
+    if defer_pd_check and aux is not None:
+        aux["pd_info"] = pd_info
+    else:
+        ops.raise_if_not_pd(pd_info)
     return loss, grads

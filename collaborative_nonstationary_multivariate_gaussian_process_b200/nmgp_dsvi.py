@@ -67,7 +67,14 @@ class _DSVILoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, x, y, I, N, z_v, z_ell, z_L, step_kw, *params):
         p = dict(zip(_step.PARAM_NAMES, params))
+        aux = None
+        if step_kw.get("defer_pd_check"):
+            aux = step_kw.get("aux")
+            if aux is None:
+                aux = {}
+                step_kw = dict(step_kw, aux=aux)
         loss, grads = _step.dsvi_step(p, model.Z.reshape(-1), x, y, I, N, z_v, z_ell, z_L, **step_kw)
+        model._last_pd_info = aux.get("pd_info") if aux is not None else None
         ctx.grads = [grads[k].reshape(p[k].shape) for k in _step.PARAM_NAMES]
         return loss
 
@@ -155,7 +162,7 @@ class NMGP(torch.nn.Module):
                         zL[s, sel[i], j] = zs[sel[i]]
         return zv, zell, zL
 
-    def _device_noise(self, B, n_mc, row_gid=None):
+    def _device_noise(self, B, n_mc, row_gid=None, sample_offset=0):
         """Counter-based device noise (csrc/philox.cuh): float32 normals widened to float64 like the reference's
         (quirk q2), a pure function of (noise_seed, step, sample, global row id, column) -- identical however the rows
         are sharded over ranks.  z_v and z_ell are materialised (small); the B*D coefficient draws are generated inside
@@ -164,8 +171,9 @@ class NMGP(torch.nn.Module):
         step = self._noise_step
         self._noise_step += 1
         seed = int(self.noise_seed)
-        zv = ops.noise_fill(1, n_mc, self.M, seed, (step << 8) | 0, 0, None, dev)[0]
-        zell = ops.noise_fill(n_mc, B, 1, seed, (step << 8) | 1, 0, row_gid, dev).reshape(n_mc, B)
+        sid = None if not sample_offset else torch.arange(sample_offset, sample_offset + n_mc, dtype=torch.int64, device=dev)
+        zv = ops.noise_fill(1, n_mc, self.M, seed, (step << 8) | 0, 0, sid, dev)[0]
+        zell = ops.noise_fill(n_mc, B, 1, seed, (step << 8) | 1, int(sample_offset), row_gid, dev).reshape(n_mc, B)
         return zv, zell, None, (seed, (step << 8) | 2)
 
     def forward_rows(self, x, y, I, n_mc=1, explicit_noise=None, row_gid=None):
@@ -175,7 +183,7 @@ class NMGP(torch.nn.Module):
         if explicit_noise is not None:
             zv, zell, zL = explicit_noise
         else:
-            zv, zell, zL, key = self._device_noise(x.shape[0], n_mc, row_gid)
+            zv, zell, zL, key = self._device_noise(x.shape[0], n_mc, row_gid, int(kw.get("sample_offset", 0)))
             kw.update(noise_key=key, row_gid=row_gid)
         return _DSVILoss.apply(self, x, y, I, self.N, zv, zell, zL, kw, *self._param_list())
 
@@ -196,7 +204,7 @@ class NMGP(torch.nn.Module):
         elif noise == "reference":
             zv, zell, zL = self._reference_noise(B, I, perm, n_mc)
         elif noise == "device":
-            zv, zell, zL, key = self._device_noise(B, n_mc, row_gid)
+            zv, zell, zL, key = self._device_noise(B, n_mc, row_gid, int(kw.get("sample_offset", 0)))
             kw.update(noise_key=key, row_gid=row_gid)
         else:
             raise ValueError("noise must be 'reference' or 'device'")

@@ -21,11 +21,26 @@ def shard_rows_per_output(counts: Sequence[int], rank: int, world: int) -> List[
     return [np.arange(rank, int(c), world) for c in counts]
 
 
-def configure_model_for_sharding(model, total_rows: int, rank: int, world: int):
-    """Row sharding: global row count for the N/B scaling, KL terms split over the ranks.  The device noise is
-    counter-based and keyed by global row ids (pass ``row_gid`` to ``forward_rows``), so no per-rank generator state."""
+def shard_samples(n_samples: int, rank: int, world: int):
+    """Contiguous block of samples (MC draws, or the subjects of an HCP-style step) owned by ``rank``."""
+    return (n_samples * rank) // world, (n_samples * (rank + 1)) // world
+
+
+def configure_model_for_sharding(model, total_rows: int, rank: int, world: int, shard: str = "rows",
+                                 n_samples_total: int = None):
+    """shard="rows" (default): rows of the minibatch are dealt to the ranks -- global row count for the N/B scaling, KL
+    terms split over the ranks.  shard="samples": every rank keeps all rows but only its block of the ``n_samples_total``
+    samples / subjects (``shard_samples``); the sample-independent coefficient statistics are then replicated (1/S_local
+    of a rank's work).  Either way the device noise is counter-based and keyed by global row and sample ids, so the
+    estimate does not depend on the number of ranks."""
     model.step_options = dict(B_total=int(total_rows), kl_weight=1.0 / world,
-                              kl_shard=(rank, world) if world > 1 else None)
+                              kl_shard=(rank, world) if world > 1 else None,
+                              defer_pd_check=world > 1)      # a Cholesky failure is raised collectively, after the all-reduce
+    if shard == "samples":
+        lo, hi = shard_samples(int(n_samples_total), rank, world)
+        model.step_options.update(S_total=int(n_samples_total), sample_offset=lo)
+    elif shard != "rows":
+        raise ValueError("shard must be 'rows' or 'samples'")
     for name in ("mu_U", "sqrt_U"):      # [D, D, ...] with exact-zero gradient blocks for j > i: reduced in packed form
         prm = getattr(model, name, None)
         if prm is not None and prm.dim() >= 2 and prm.shape[0] == prm.shape[1]:
@@ -38,8 +53,27 @@ def global_row_ids(counts: Sequence[int], rows_per_output: Sequence[np.ndarray])
     return np.concatenate([starts[d] + np.asarray(r, dtype=np.int64) for d, r in enumerate(rows_per_output)]).astype(np.int64)
 
 
-def allreduce_loss_and_grads(loss: torch.Tensor, params: Sequence[torch.nn.Parameter], group=None) -> torch.Tensor:
+_pending_pd = []          # reduced PD flags not yet looked at (check="defer")
+
+
+def raise_if_pending_not_pd():
+    """Host check of the PD flags that ``allreduce_loss_and_grads(..., check="defer")`` left on the device."""
+    flags, _pending_pd[:] = list(_pending_pd), []
+    for f in flags:
+        if float(f) != 0.0:
+            raise RuntimeError("cholesky: a matrix of the step is not positive-definite on %d rank(s)" % int(round(float(f))))
+
+
+def allreduce_loss_and_grads(loss: torch.Tensor, params: Sequence[torch.nn.Parameter], group=None,
+                             pd_info=None, check: str = "sync") -> torch.Tensor:
     """Sum loss and all gradients over ranks with a single collective on one flat float64 buffer.
+
+    ``pd_info`` (the step's deferred positive-definiteness flag, ``model._last_pd_info``) rides in the same buffer:
+    under ``kl_shard`` every rank factorises only its slice of the coefficient covariances, so a failure is seen by
+    one rank only; raising it there before the collective would leave the other ranks hanging in the all-reduce.
+    After the reduction every rank sees a non-zero slot and raises the same RuntimeError the reference's
+    torch.cholesky would.  ``check="defer"`` skips the host read (one synchronisation per step) and keeps the reduced
+    flag for ``raise_if_pending_not_pd()``.
 
     Parameters tagged by `configure_model_for_sharding` as coefficient-pair tensors (`mu_U`, `sqrt_U`: [D, D, ...]) only
     travel as their live (i, j <= i) blocks -- the other blocks are exact zeros on every rank (reference quirk q8) --
@@ -48,7 +82,8 @@ def allreduce_loss_and_grads(loss: torch.Tensor, params: Sequence[torch.nn.Param
         return loss.detach()
     from .dsvi_step import packed_pair_index
     live = [p for p in params if p.grad is not None]
-    chunks, plan = [loss.detach().reshape(1)], []
+    pd_slot = (pd_info != 0).to(loss.dtype).reshape(1) if pd_info is not None else torch.zeros_like(loss.detach().reshape(1))
+    chunks, plan = [loss.detach().reshape(1), pd_slot], []
     for p in live:
         Dp = getattr(p, "_nmgp_pair_D", None)
         if Dp is not None and p.grad.dim() >= 2 and p.grad.shape[0] == Dp and p.grad.shape[1] == Dp:
@@ -61,7 +96,7 @@ def allreduce_loss_and_grads(loss: torch.Tensor, params: Sequence[torch.nn.Param
             chunks.append(p.grad.reshape(-1))
     flat = torch.cat(chunks)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    off = 1
+    off = 2
     for p, idx, shp in plan:
         if idx is None:
             n = p.grad.numel()
@@ -70,6 +105,10 @@ def allreduce_loss_and_grads(loss: torch.Tensor, params: Sequence[torch.nn.Param
             n = shp[0] * shp[1]
             p.grad.view(p.grad.shape[0] * p.grad.shape[1], -1).index_copy_(0, idx, flat[off:off + n].view(shp))
         off += n
+    if pd_info is not None:
+        _pending_pd.append(flat[1])
+        if check == "sync":                                   # same decision on every rank (host read after the collective)
+            raise_if_pending_not_pd()
     return flat[0]
 
 

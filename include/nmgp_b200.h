@@ -33,6 +33,8 @@ typedef void* nmgp_stream_t; /* cudaStream_t */
 
 const char* nmgp_last_error(void);
 int nmgp_version(void);
+/* number of kernel launches this library has issued since it was loaded (host-side counter; measurement aid) */
+unsigned long long nmgp_launch_count(void);
 
 /* hyp[i] = exp(logs[i])                                                    code/nmgp_dsvi.py:180-188 */
 int nmgp_hyper_exp(const double* logs, double* hyp, int n, nmgp_stream_t stream);
@@ -99,6 +101,8 @@ int nmgp_latent_fused(const double* PG, const double* cG, const double* l, const
                       const int* seg, const double* SigW, const double* muW, const double* hyp, double scale,
                       double* Rsum /* += */, double* ghyp /* += */, double* lbar, double* mgbar, double* qgbar,
                       double* cGbar, double* PGbar, double* work_q, double* work_m, int ns, long long B, int Q, int D,
+                      long long y_stride /* 0: y[B] shared by the samples; >= B: y[ns, y_stride], one target vector
+                                            per sample (the subjects of an HCP-style step) */,
                       nmgp_stream_t stream);
 
 /* v = mu_v + C_v z, ellz = exp(v)                                          utils.py:225-227, nmgp_dsvi.py:215 */
@@ -140,7 +144,8 @@ int nmgp_noise_fill(double* out, int ns, long long B, int C, unsigned long long 
 /* expected log-likelihood of a sample chunk and its cotangents             nmgp_dsvi.py:255-258, utils.py:268-272 */
 int nmgp_lik_rows(const double* l, const double* mg, const double* qg, const double* cG, const double* y, const int* I,
                   const double* hyp, double scale, double* Rsum /* += */, double* ghyp /* += */, double* lbar,
-                  double* mgbar, double* qgbar, double* cGbar, int ns, long long B, int D, nmgp_stream_t stream);
+                  double* mgbar, double* qgbar, double* cGbar, int ns, long long B, int D, long long y_stride,
+                  nmgp_stream_t stream);
 
 /* means only: m[s,n,j] = p . Mu[idx], j <= I[n]                            utils.py:149-157 MGP_mu (predict_Y) */
 int nmgp_pair_means(const double* Pa, const double* Pb, const int* I, const double* Mu, double* m, int ns, long long B,

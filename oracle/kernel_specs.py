@@ -47,8 +47,16 @@ def raise_if_not_pd(info):
 
 
 def potrf(A, jitter=0.0, info=None):
+    """Same protocol as _ops.potrf: raises like torch.cholesky, or -- with ``info`` -- records 1 + index of the first
+    failing matrix there and returns (deferred check, dsvi_step)."""
     n = A.shape[-1]
-    C = torch.linalg.cholesky(A + jitter * torch.eye(n, dtype=F64))
+    C, bad = torch.linalg.cholesky_ex(A + jitter * torch.eye(n, dtype=F64))
+    if bool((bad != 0).any()):
+        first = int(torch.nonzero(bad.reshape(-1) != 0)[0])
+        if info is None:
+            raise RuntimeError("cholesky: matrix %d of a batch is not positive-definite" % first)
+        if int(info) == 0:
+            info.fill_(1 + first)
     return C, C.diagonal(dim1=-2, dim2=-1).log().sum(-1)
 
 
@@ -358,7 +366,7 @@ def lik_rows(l, mg, qg, cG, y, I, hyp, scale, Rsum, ghyp):
     s2e = hyp[H_S2_ERR]
     s2g = (1.0 - cG.unsqueeze(-1) + qg) * live
     F = (l * mg * live).sum(-1)
-    r = y.view(1, -1) - F
+    r = (y.view(1, -1) if y.dim() == 1 else y) - F          # y [B] shared, or [ns, B] one target vector per sample
     pen = (l * l * s2g).sum(-1)
     import math
     Rsum.copy_((-(r * r) / (2 * s2e) - 0.5 * torch.log(s2e) - math.log(math.sqrt(2 * math.pi))).sum(1) - 0.5 / s2e * pen.sum(1))
@@ -486,3 +494,8 @@ def lcorr(L):
     cov = L @ L.transpose(-1, -2)
     inv = torch.sqrt(torch.diag_embed(1.0 / torch.diagonal(cov, dim1=-2, dim2=-1)))
     return inv @ cov @ inv
+
+
+def launch_count():
+    """CPU specifications launch no kernels."""
+    return 0

@@ -57,6 +57,51 @@ def test_two_rank_row_sharding_matches_reference(tmp_path):
         gu.check_grad(k, res[k], g, 1e-9)
 
 
+def _nonpd_worker(rank, world, port, outdir):
+    """One coefficient covariance that only rank 1 factorises (kl_shard) is poisoned: BOTH ranks must raise after the
+    all-reduce (a rank raising alone before it would leave the other one hanging in the collective)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import datetime
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=60))
+    from oracle import kernel_specs as specs
+    from collaborative_nonstationary_multivariate_gaussian_process_b200 import _ops, nmgp_dsvi, parallel
+    for n, f in inspect.getmembers(specs, inspect.isfunction):
+        if not n.startswith("_"):
+            setattr(_ops, n, f)
+    g = gu.load("dsvi_ragged")
+    D = int(g["D"])
+    model = nmgp_dsvi.NMGP(int(g["N"]), D, torch.from_numpy(g["Z"]).view(-1, 1), device="cpu")
+    model.load_state_dict(gu.case_params(g))
+    with torch.no_grad():
+        model.sqrt_U[D - 1, D - 2].fill_(float("nan"))        # last strictly-lower pair: rank 1's slice
+    counts = [int((g["I"] == d).sum()) for d in range(D)]
+    rows = parallel.shard_rows_per_output(counts, rank, world)
+    starts = np.cumsum([0] + counts[:-1])
+    sel = np.concatenate([starts[d] + rows[d] for d in range(D)]).astype(np.int64)
+    parallel.configure_model_for_sharding(model, g["x"].shape[0], rank, world)
+    noise = (torch.from_numpy(g["z_v"]), torch.from_numpy(g["z_ell"][:, sel]), torch.from_numpy(g["z_L"][:, sel]))
+    loss = model.forward_rows(torch.from_numpy(g["x"][sel]), torch.from_numpy(g["y"][sel]),
+                              torch.from_numpy(g["I"][sel].astype(np.int32)), explicit_noise=noise)
+    local_flag = int(model._last_pd_info)
+    loss.backward()
+    raised = False
+    try:
+        parallel.allreduce_loss_and_grads(loss, list(model.parameters()), pd_info=model._last_pd_info)
+    except RuntimeError as e:
+        raised = "positive-definite" in str(e)
+    torch.save({"raised": raised, "local_flag": local_flag}, os.path.join(outdir, "r%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_two_rank_nonpd_is_raised_on_every_rank(tmp_path):
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_nonpd_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    res = [torch.load(str(tmp_path / ("r%d.pt" % r)), weights_only=False) for r in range(2)]
+    assert res[0]["raised"] and res[1]["raised"]
+    assert res[0]["local_flag"] == 0 and res[1]["local_flag"] != 0      # only one rank saw it locally
+
+
 def test_shard_rows_cover_every_row_once():
     from collaborative_nonstationary_multivariate_gaussian_process_b200 import parallel
     counts = [5, 0, 13, 1]

@@ -55,3 +55,59 @@ def test_every_wrapper_has_a_spec():
              if not n.startswith("_") and f.__module__ == _ops.__name__]
     missing = [n for n in names if not hasattr(specs, n)]
     assert not missing, missing
+
+
+def _subject_case(S=3):
+    """dsvi_ragged rows with S different target vectors (subjects) and the case's first noise draw repeated."""
+    g = gu.load("dsvi_ragged")
+    rng = np.random.default_rng(5)
+    ys = np.stack([g["y"]] + [g["y"] + 0.3 * rng.standard_normal(g["y"].shape) for _ in range(S - 1)])
+    reps = lambda a: np.concatenate([a[:1]] * S)
+    return g, ys, reps(g["z_v"]), reps(g["z_ell"]), reps(g["z_L"])
+
+
+def test_per_subject_targets_match_the_mean_of_reference_forwards(spec_ops):
+    """y [S, B] (HCP-style step): loss and gradients equal the mean over subjects of one-draw oracle forwards."""
+    g, ys, zv, zell, zL = _subject_case()
+    S = ys.shape[0]
+    p = gu.case_params(g)
+    I = torch.from_numpy(g["I"]).to(torch.int32)
+    loss, grads = dsvi_step.dsvi_step(p, torch.from_numpy(g["Z"]), torch.from_numpy(g["x"]), torch.from_numpy(ys), I,
+                                      int(g["N"]), torch.from_numpy(zv), torch.from_numpy(zell), torch.from_numpy(zL))
+    Xl, _ = gu.case_lists(g)
+    D = int(g["D"])
+    ref_loss, ref_grads = 0.0, None
+    for s in range(S):
+        Yl = [torch.from_numpy(ys[s][g["I"] == d]).view(-1, 1) for d in range(D)]
+        l_s, g_s = orc.step_loss_and_grads(p, torch.from_numpy(g["Z"]).view(-1, 1), int(g["N"]), Xl, Yl,
+                                           draws=gu.replay_draws(g)[:1])
+        ref_loss += float(l_s) / S
+        ref_grads = {k: (v / S if v is not None else None) for k, v in g_s.items()} if ref_grads is None else \
+            {k: (ref_grads[k] + v / S if v is not None else None) for k, v in g_s.items()}
+    assert abs(float(loss) - ref_loss) <= 1e-10 * abs(ref_loss)
+    for k, gr in ref_grads.items():
+        if gr is None:
+            continue
+        den = max(float(torch.linalg.norm(gr)), 1e-300)
+        assert float(torch.linalg.norm(grads[k].reshape(-1) - gr.reshape(-1))) / den <= 1e-9, k
+
+
+def test_sample_sharding_sums_to_the_unsharded_step(spec_ops):
+    """Two ranks each holding all rows and half of the subjects (S_total / sample_offset, KL pairs split by kl_shard):
+    the sum of (loss, gradients) over the ranks equals the single-rank step."""
+    g, ys, zv, zell, zL = _subject_case(S=4)
+    p = gu.case_params(g)
+    I = torch.from_numpy(g["I"]).to(torch.int32)
+    args = lambda sl: (p, torch.from_numpy(g["Z"]), torch.from_numpy(g["x"]), torch.from_numpy(ys[sl]), I, int(g["N"]),
+                       torch.from_numpy(zv[sl]), torch.from_numpy(zell[sl]), torch.from_numpy(zL[sl]))
+    full_loss, full_grads = dsvi_step.dsvi_step(*args(slice(0, 4)))
+    tot, acc = 0.0, None
+    for rank in range(2):
+        l_r, g_r = dsvi_step.dsvi_step(*args(slice(2 * rank, 2 * rank + 2)), kl_weight=0.5, kl_shard=(rank, 2),
+                                       S_total=4, sample_offset=2 * rank)
+        tot += float(l_r)
+        acc = g_r if acc is None else {k: acc[k] + g_r[k] for k in g_r}
+    assert abs(tot - float(full_loss)) <= 1e-12 * abs(float(full_loss))
+    for k in full_grads:
+        den = max(float(torch.linalg.norm(full_grads[k])), 1e-300)
+        assert float(torch.linalg.norm(acc[k] - full_grads[k])) / den <= 1e-10, k
