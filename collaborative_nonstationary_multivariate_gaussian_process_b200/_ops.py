@@ -17,7 +17,7 @@ from ._lib import check, lib
 
 F64 = torch.float64
 MODE_W, MODE_U = 0, 1
-MAX_Q = 112
+MAX_Q = 128
 
 
 def _same_device(t: torch.Tensor) -> None:
@@ -196,29 +196,57 @@ def solve_rows_fwd(K, R):
 def solve_rows_bwd(Pbar, cbar, K, P, R, Abar):
     ns, B, Q = K.shape
     Kbar = torch.empty_like(K)
-    work_t = torch.empty_like(K) if Q <= 64 else None      # kept alive until the launch below has been enqueued
+    work_t = torch.empty_like(K)                           # kept alive until the launch below has been enqueued
     work = _optd(work_t)
     check(lib().nmgp_solve_rows_bwd(_d(Pbar), _d(cbar), _d(K), _d(P), _d(R), _d(Kbar), _d(Abar), work,
                                     c_int(ns), c_int64(B), c_int(Q), _stream()), "nmgp_solve_rows_bwd")
     return Kbar
 
 
-def quadform_fwd(Pa, Pb, I, Sig, Mu, D, mode, seg=None):
+def lq_pad_records(Sig):
+    """Padded, half-split copies of a batch of Q x Q covariances (64 < Q <= 128) in the order the large-Q DMMA kernels
+    stream them (csrc/nmgp_quadform_lq.cu); build once per step and pass as ``rec``."""
+    n, Q, _ = Sig.shape
+    lib().nmgp_lq_record_doubles.restype = ctypes.c_longlong
+    per = int(lib().nmgp_lq_record_doubles(c_int(Q)))
+    if per <= 0:
+        raise ValueError("lq_pad_records: Q=%d outside 65..128" % Q)
+    rec = torch.empty(n * per, dtype=F64, device=Sig.device)
+    check(lib().nmgp_lq_pad_records(_d(Sig), _d(rec), c_int(n), c_int(Q), _stream()), "nmgp_lq_pad_records")
+    return rec
+
+
+LQ_MIN_Q = 65          # the register-resident DMMA kernels cover Q <= 64, the ring-pipelined ones 65..128
+
+
+def quadform_fwd(Pa, Pb, I, Sig, Mu, D, mode, seg=None, rec=None):
     ns, B, Q = Pa.shape
     seg = segment_offsets(I, D) if seg is None else seg
     q = _zeros(Pa, ns, B, D)
     m = _zeros(Pa, ns, B, D)
+    if mode == MODE_U and Q >= LQ_MIN_Q:
+        rec = lq_pad_records(Sig) if rec is None else rec
+        check(lib().nmgp_lq_coef_quadform(c_int(0), _d(Pa), _d(Pb), _i(I), _d(rec), _d(Mu), _d(q), _d(m), c_void_p(0),
+                                          c_void_p(0), c_void_p(0), c_void_p(0), c_int(ns), c_int64(B), c_int(Q),
+                                          c_int(D), _stream()), "nmgp_lq_coef_quadform")
+        return q, m
     check(lib().nmgp_quadform_fwd(_d(Pa), _d(Pb), _i(I), _i(seg), _d(Sig), _d(Mu), _d(q), _d(m),
                                   c_int(ns), c_int64(B), c_int(Q), c_int(D), c_int(mode), _stream()), "nmgp_quadform_fwd")
     return q, m
 
 
-def quadform_bwd(Pa, Pb, I, Sig, Mu, qbar, mbar, mode, seg=None):
+def quadform_bwd(Pa, Pb, I, Sig, Mu, qbar, mbar, mode, seg=None, rec=None):
     ns, B, Q = Pa.shape
     D = qbar.shape[-1]
     seg = segment_offsets(I, D) if seg is None else seg
     Pabar = torch.empty_like(Pa)
     Pbbar = torch.empty_like(Pa) if mode == MODE_U else Pabar
+    if mode == MODE_U and Q >= LQ_MIN_Q:
+        rec = lq_pad_records(Sig) if rec is None else rec
+        check(lib().nmgp_lq_coef_quadform(c_int(1), _d(Pa), _d(Pb), _i(I), _d(rec), _d(Mu), c_void_p(0), c_void_p(0),
+                                          _d(qbar), _d(mbar), _d(Pabar), _d(Pbbar), c_int(ns), c_int64(B), c_int(Q),
+                                          c_int(D), _stream()), "nmgp_lq_coef_quadform")
+        return Pabar, Pbbar
     check(lib().nmgp_quadform_bwd(_d(Pa), _d(Pb), _i(I), _i(seg), _d(Sig), _d(Mu), _d(qbar), _d(mbar),
                                   _d(Pabar), _d(Pbbar), c_int(ns), c_int64(B), c_int(Q), c_int(D), c_int(mode),
                                   _stream()), "nmgp_quadform_bwd")
@@ -372,21 +400,26 @@ def rowdot_live(l, g, I):
     return F
 
 
-def latent_fused(PG, cG, l, y, I, SigW, muW, hyp, scale, Rsum, ghyp, seg=None):
+def latent_fused(PG, cG, l, y, I, SigW, muW, hyp, scale, Rsum, ghyp, seg=None, rec=None):
     """Latent-function statistics, expected log-likelihood and every row cotangent of one sample chunk in a
-    single DMMA kernel (Q <= 64).  Returns (lbar, mgbar, qgbar, cGbar, PGbar); Rsum (=) and ghyp (+=) in place."""
+    single DMMA kernel (register-resident for Q <= 64, ring-pipelined for 64 < Q <= 128; ``rec`` = lq_pad_records(SigW)
+    may be passed to reuse the padded records over the sample chunks of a step).
+    Returns (lbar, mgbar, qgbar, cGbar, PGbar); Rsum (=) and ghyp (+=) in place."""
     ns, B, Q = PG.shape
     D = l.shape[-1]
-    seg = segment_offsets(I, D) if seg is None else seg
     lbar = torch.empty_like(l); mgbar = torch.empty_like(l); qgbar = torch.empty_like(l)
     cGbar = _empty(l, ns, B)
     PGbar = torch.empty_like(PG)
     Rsum.zero_()
-    if Q > 64:
-        wq_, wm_ = _zeros(l, ns, B, D), _zeros(l, ns, B, D)
-        pq, pm = _d(wq_), _d(wm_)
-    else:
-        pq = pm = c_void_p(0)
+    if Q >= LQ_MIN_Q:
+        rec = lq_pad_records(SigW) if rec is None else rec
+        check(lib().nmgp_lq_latent_fused(_d(PG), _d(cG), _d(l), _d(y), _i(I), _d(rec), _d(muW), _d(hyp), c_double(scale),
+                                         _d(Rsum), _d(ghyp), _d(lbar), _d(mgbar), _d(qgbar), _d(cGbar), _d(PGbar),
+                                         c_int(ns), c_int64(B), c_int(Q), c_int(D), c_int64(_ystride(y, ns, B)),
+                                         _stream()), "nmgp_lq_latent_fused")
+        return lbar, mgbar, qgbar, cGbar, PGbar
+    seg = segment_offsets(I, D) if seg is None else seg
+    pq = pm = c_void_p(0)
     check(lib().nmgp_latent_fused(_d(PG), _d(cG), _d(l), _d(y), _i(I), _i(seg), _d(SigW), _d(muW), _d(hyp),
                                   c_double(scale), _d(Rsum), _d(ghyp), _d(lbar), _d(mgbar), _d(qgbar), _d(cGbar),
                                   _d(PGbar), pq, pm, c_int(ns), c_int64(B), c_int(Q), c_int(D),

@@ -25,8 +25,10 @@ __device__ __forceinline__ void cpa_wait0() { asm volatile("cp.async.wait_group 
 #define ATB_THREADS 256   // 8 warps: warp & 3 = strips of C it owns, warp >> 2 = which half of a tile's rows it sums
 __host__ __device__ constexpr int atb_pad(int n) { return ((n + 3) / 8) * 8 + 4; }
 
-template <int NB>
-__global__ void __launch_bounds__(ATB_THREADS, 3)
+// WIDE (8 < NB <= 16): the 8 warps are 8 strip roles (strips w and w + 8 of C) and every warp sums all rows of a tile;
+// otherwise 4 strip roles x 2 row halves.
+template <int NB, bool WIDE>
+__global__ void __launch_bounds__(ATB_THREADS, WIDE ? 1 : 3)
 k_atb_mma(const double* __restrict__ A, const double* __restrict__ Bm, double* __restrict__ C, double sign,
           long long B, int Q, long long chunk, const double* __restrict__ cbar, double* __restrict__ Kbar) {
     constexpr int LDP = atb_pad(8 * NB);
@@ -34,12 +36,13 @@ k_atb_mma(const double* __restrict__ A, const double* __restrict__ Bm, double* _
     double* At = sm;                                   // [2][ATB_TROWS][LDP]
     double* Bt = At + 2 * ATB_TROWS * LDP;             // [2][ATB_TROWS][LDP]
     const int s = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
-    const int wr = w & 3, half = w >> 2;
+    const int wr = WIDE ? w : (w & 3), half = WIDE ? 0 : (w >> 2);
+    constexpr int NSTRIP = WIDE ? 8 : 4, KQ = WIDE ? ATB_TROWS / 4 : ATB_TROWS / 8;
     const long long rbeg = (long long)blockIdx.x * chunk, rend = min(B, rbeg + chunk);
     if (rbeg >= rend) return;
     for (int e = tid; e < 4 * ATB_TROWS * LDP; e += ATB_THREADS) sm[e] = 0.0;
     __syncthreads();
-    const int a1 = wr, a2 = wr + 4;                    // strips of 8 rows of C handled by this warp
+    const int a1 = wr, a2 = wr + NSTRIP;               // strips of 8 rows of C handled by this warp
     const bool on1 = a1 < NB, on2 = a2 < NB;
     double acc[2][NB][2];
 #pragma unroll
@@ -95,8 +98,8 @@ k_atb_mma(const double* __restrict__ A, const double* __restrict__ Bm, double* _
         }
         if (!on1) continue;
 #pragma unroll
-        for (int kq = 0; kq < ATB_TROWS / 8; ++kq) {
-            const int n = 4 * (kq + half * (ATB_TROWS / 8)) + t;
+        for (int kq = 0; kq < KQ; ++kq) {
+            const int n = 4 * (kq + half * KQ) + t;
             const double fa1 = Ad[n * LDP + 8 * a1 + g];
             const double fa2 = on2 ? Ad[n * LDP + 8 * a2 + g] : 0.0;
 #pragma unroll
@@ -124,17 +127,17 @@ k_atb_mma(const double* __restrict__ A, const double* __restrict__ Bm, double* _
     }
 }
 
-template <int NB>
+template <int NB, bool WIDE = (NB > 8)>
 static int launch_atb(const double* A, const double* Bm, double* C, double sign, int ns, long long B, int Q,
                       const double* cbar, double* Kbar, cudaStream_t st) {
     size_t smem = sizeof(double) * 4 * ATB_TROWS * atb_pad(8 * NB);
-    if (int r = nmgp_opt_in_smem(k_atb_mma<NB>, smem, "nmgp_atb")) return r;
+    if (int r = nmgp_opt_in_smem(k_atb_mma<NB, WIDE>, smem, "nmgp_atb")) return r;
     // one wave: 148 SMs x 3 resident CTAs (61 KB of shared memory each), split evenly over the ns samples
-    long long nchunks = (444 + ns - 1) / ns;
+    long long nchunks = ((WIDE ? 296 : 444) + ns - 1) / ns;
     long long chunk = ((B + nchunks - 1) / nchunks + ATB_TROWS - 1) / ATB_TROWS * ATB_TROWS;
     if (chunk < 4 * ATB_TROWS) chunk = 4 * ATB_TROWS;
     dim3 grid((unsigned)((B + chunk - 1) / chunk), ns);
-    k_atb_mma<NB><<<NMGP_L(grid), ATB_THREADS, smem, st>>>(A, Bm, C, sign, B, Q, chunk, cbar, Kbar);
+    k_atb_mma<NB, WIDE><<<NMGP_L(grid), ATB_THREADS, smem, st>>>(A, Bm, C, sign, B, Q, chunk, cbar, Kbar);
     return nmgp_launch_status("nmgp_atb");
 }
 int nmgp_atb_mma(const double* A, const double* Bm, double* C, double sign, int ns, long long B, int Q,
@@ -148,6 +151,14 @@ int nmgp_atb_mma(const double* A, const double* Bm, double* C, double sign, int 
         case 6: return launch_atb<6>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
         case 7: return launch_atb<7>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
         case 8: return launch_atb<8>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
+        case 9: return launch_atb<9>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
+        case 10: return launch_atb<10>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
+        case 11: return launch_atb<11>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
+        case 12: return launch_atb<12>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
+        case 13: return launch_atb<13>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
+        case 14: return launch_atb<14>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
+        case 15: return launch_atb<15>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
+        case 16: return launch_atb<16>(A, Bm, C, sign, ns, B, Q, cbar, Kbar, st);
         default: return 1;
     }
 }

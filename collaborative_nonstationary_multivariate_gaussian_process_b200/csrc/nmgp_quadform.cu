@@ -247,7 +247,7 @@ NMGP_API int nmgp_weighted_gram(const double* Pa, const double* Pb, const int* I
     NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && Q > 0 && Q <= 128 && D > 0 && (mode == MODE_W || mode == MODE_U),
                  "nmgp_weighted_gram");
     if (ns == 0 || B == 0) return 0;
-    if (Q <= 64) return nmgp_weighted_gram_mma(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+    if (Q <= 128) return nmgp_weighted_gram_mma(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
     const int ntasks = (mode == MODE_W) ? D : D * (D + 1) / 2;
     NMGP_REQUIRE(ntasks <= 65535, "nmgp_weighted_gram");
     size_t smem = sizeof(double) * ((size_t)Q * Q + Q + (size_t)WG_SUB * (Q + 1) + 2 * WG_SUB);

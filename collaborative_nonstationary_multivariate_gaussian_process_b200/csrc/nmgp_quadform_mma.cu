@@ -620,25 +620,28 @@ int nmgp_coef_quadform_mma(bool bwd, const double* Pa, const double* Pb, const i
 
 // ------------------------------------------------------------------------------------------------------------
 // Weighted Gram matrices on DMMA.  grid (D outputs, jgroups [+1 for the MODE_U diagonal pair], ns), 128 threads.
-#define GM_NG 4         // latents per CTA
 #define GM_TROWS 32     // rows per staged tile (8 k-steps)
-#define GM_THREADS 256  // 8 warps: warp w & 3 = block-row role, w >> 2 = which half of the NG latents it accumulates
-#define GM_NGW (GM_NG / 2)
+#define GM_THREADS 256  // 8 warps.  NB <= 8: warp w & 3 = block-row role, w >> 2 = which half of the 4 latents of the CTA
+                        // it accumulates.  8 < NB <= 16 (WIDE): 8 block-row roles, 2 latents per CTA, both in every warp
+#define GM_NGW 2        // latents accumulated per warp
 
 template <int NB>
 struct GMShape {
+    static constexpr bool WIDE = NB > 8;
+    static constexpr int NG = WIDE ? 2 : 4;                // latents per CTA
     static constexpr int NP = 8 * NB;
     static constexpr int LDP = pad4mod8(NP);
-    static constexpr size_t smem_doubles = 2 * (size_t)GM_TROWS * LDP + 2 * 2 * GM_NG * GM_TROWS;
+    static constexpr size_t smem_doubles = 2 * (size_t)GM_TROWS * LDP + 2 * 2 * NG * GM_TROWS;
 };
 
 template <int NB>
-__global__ void __launch_bounds__(GM_THREADS, 2)
+__global__ void __launch_bounds__(GM_THREADS, NB > 8 ? 1 : 2)
 k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const int* __restrict__ seg,
            const double* __restrict__ qbar, const double* __restrict__ mbar, double* __restrict__ SigBar,
            double* __restrict__ MuBar, long long B, int Q, int D, int mode) {
     using SH = GMShape<NB>;
-    constexpr int LDP = SH::LDP;
+    constexpr int LDP = SH::LDP, GM_NG = SH::NG;
+    constexpr bool WIDE = SH::WIDE;
     extern __shared__ __align__(16) double sm[];
     double* Pt = sm;                                        // [2][GM_TROWS][LDP]
     double* wq = Pt + 2 * (size_t)GM_TROWS * LDP;           // [2][GM_NG][GM_TROWS]
@@ -657,7 +660,8 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
     }
     const long long rbeg = seg[i], rend = seg[i + 1];
     if (rbeg >= rend) return;
-    const int tid = threadIdx.x, lane = tid & 31, w = (tid >> 5) & 3, ug = tid >> 7, g = lane >> 2, t = lane & 3;
+    const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int w = WIDE ? (tid >> 5) : ((tid >> 5) & 3), ug = WIDE ? 0 : (tid >> 7);
     const int u0 = ug * GM_NGW;                            // this warp's latents: u0 .. u0 + GM_NGW - 1
     const int a1 = w, a2 = NB - 1 - w;
     const bool active = a1 <= a2;
@@ -794,6 +798,7 @@ static int launch_gram(const double* Pa, const double* Pb, const int* seg, const
                        double* SigBar, double* MuBar, int ns, long long B, int Q, int D, int mode, cudaStream_t st) {
     size_t smem = GMShape<NB>::smem_doubles * sizeof(double);
     if (int r = nmgp_opt_in_smem(k_gram_mma<NB>, smem, "nmgp_weighted_gram")) return r;
+    constexpr int GM_NG = GMShape<NB>::NG;
     const int ngroups = (D + GM_NG - 1) / GM_NG;
     dim3 grid(D, ngroups + (mode == MODE_U ? 1 : 0), ns);
     k_gram_mma<NB><<<NMGP_L(grid), GM_THREADS, smem, st>>>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, B, Q, D, mode);
@@ -813,6 +818,14 @@ int nmgp_weighted_gram_mma(const double* Pa, const double* Pb, const int* seg, c
         case 6: return launch_gram<6>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
         case 7: return launch_gram<7>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
         case 8: return launch_gram<8>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+        case 9: return launch_gram<9>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+        case 10: return launch_gram<10>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+        case 11: return launch_gram<11>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+        case 12: return launch_gram<12>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+        case 13: return launch_gram<13>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+        case 14: return launch_gram<14>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+        case 15: return launch_gram<15>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+        case 16: return launch_gram<16>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
         default: return 1;
     }
 }

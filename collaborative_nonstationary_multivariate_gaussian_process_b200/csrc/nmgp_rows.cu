@@ -107,7 +107,7 @@ NMGP_API int nmgp_solve_rows_fwd(const double* K, const double* R, double* P, do
                                  cudaStream_t st) {
     NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && Q > 0 && Q <= 128, "nmgp_solve_rows_fwd");
     if (ns == 0 || B == 0) return 0;
-    if (Q <= 64) return nmgp_solve_rows_fwd_mma(K, R, P, c, ns, B, Q, st);
+    if (Q <= 128) return nmgp_solve_rows_fwd_mma(K, R, P, c, ns, B, Q, st);
     const int TR = solve_rows_tile(Q, false);
     size_t smem = sizeof(double) * ((size_t)Q * Q + (size_t)Q * (TR + 1));
     if (int r = nmgp_opt_in_smem(k_solve_rows<false>, smem, "nmgp_solve_rows_fwd")) return r;
@@ -120,7 +120,7 @@ NMGP_API int nmgp_solve_rows_bwd(const double* Pbar, const double* cbar, const d
                                  int ns, long long B, int Q, cudaStream_t st) {
     NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && Q > 0 && Q <= 128, "nmgp_solve_rows_bwd");
     if (ns == 0 || B == 0) return 0;
-    if (Q <= 64) {
+    if (Q <= 128) {
         NMGP_REQUIRE(work != nullptr, "nmgp_solve_rows_bwd");
         if (int r = nmgp_solve_rows_bwd_mma(Pbar, cbar, K, P, R, Kbar, work, ns, B, Q, st)) return r;
         return nmgp_atb_mma(work, P, Abar, -1.0, ns, B, Q, cbar, Kbar, st);      // Abar -= T^T P ; Kbar = T + cbar P

@@ -153,7 +153,10 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
         sysm[name] = dict(R=R, hldR=hldR, K12=K12, P=P, c=c, is2=is2, ilen=ilen)
     sd_ell = ops.ell_sd_fwd(sysm["ell"]["c"][0], hyp)
     seg = ops.segment_offsets(I, D)
-    qU, mU = ops.quadform_fwd(sysm["L0"]["P"], sysm["L1"]["P"], I, Sig_U, muU, D, MODE_U, seg=seg)
+    # 64 < Q <= 128: padded records of the covariances for the ring-pipelined DMMA kernels, built once per step
+    recU = ops.lq_pad_records(Sig_U) if Q >= ops.LQ_MIN_Q else None
+    recW = ops.lq_pad_records(Sig_W) if Q >= ops.LQ_MIN_Q else None
+    qU, mU = ops.quadform_fwd(sysm["L0"]["P"], sysm["L1"]["P"], I, Sig_U, muU, D, MODE_U, seg=seg, rec=recU)
     sdU = ops.coef_sd_fwd(qU[0], sysm["L0"]["c"][0], sysm["L1"]["c"][0], I, hyp)
 
     # ---- per-sample inducing draws, Gibbs K22 factor -----------------------------------------
@@ -233,7 +236,7 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
         KG = ops.gibbs_build_fwd(x, Z, ellx, ellZ[sl], 0.0)
         PG, cG = ops.solve_rows_fwd(KG, R_G[sl])
         lbar, mgbar, qgbar, cGbar, PGbar = ops.latent_fused(PG, cG, l, y if y.dim() == 1 else y[sl], I, Sig_W, mu_W, hyp,
-                                                            scale, Rsum[sl], ghyp, seg=seg)
+                                                            scale, Rsum[sl], ghyp, seg=seg, rec=recW)
         if not want_grads:
             continue
         ops.weighted_gram(PG, PG, I, qgbar, mgbar, MODE_W, SigWbar, muWrows, seg=seg)
@@ -275,7 +278,7 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
     # ---- backward of the sample-independent coefficient statistics ------------------------------
     qUbar, cL0bar, cL1bar = ops.coef_sd_bwd(sdUbar, sdU, I, hyp, ghyp)
     PL0bar, PL1bar = ops.quadform_bwd(sysm["L0"]["P"], sysm["L1"]["P"], I, Sig_U, muU,
-                                      qUbar.reshape(1, B, D), mUbar.reshape(1, B, D), MODE_U, seg=seg)
+                                      qUbar.reshape(1, B, D), mUbar.reshape(1, B, D), MODE_U, seg=seg, rec=recU)
     SigUbar = zeros(npair, Q, Q)
     ops.weighted_gram(sysm["L0"]["P"], sysm["L1"]["P"], I, qUbar.reshape(1, B, D), mUbar.reshape(1, B, D),
                       MODE_U, SigUbar, muUbar, seg=seg)

@@ -141,6 +141,24 @@ int nmgp_coef_sample_bwd(const double* lbar, const double* l, const double* zL, 
 int nmgp_noise_fill(double* out, int ns, long long B, int C, unsigned long long seed, unsigned long long stream_id,
                     int s0, const long long* gid, nmgp_stream_t stream);
 
+/* ---- 64 < Q <= 128 (the PM2.5 / HCP drivers use Q = 100): ring-pipelined DMMA kernels, csrc/nmgp_quadform_lq.cu ----
+ * The Q x Q covariances are first copied into padded, half-split records (the order the kernels stream them through
+ * shared memory with cp.async.bulk); nmgp_lq_record_doubles(Q) doubles per record, 0 if Q is outside 65..128. */
+long long nmgp_lq_record_doubles(int Q);
+int nmgp_lq_pad_records(const double* Sig /* [n,Q,Q] */, double* rec /* [n, record_doubles] */, int n, int Q,
+                        nmgp_stream_t stream);
+/* = nmgp_latent_fused with recW = padded Sigma_W                           utils.py:143-144 + nmgp_dsvi.py:255-258 */
+int nmgp_lq_latent_fused(const double* PG, const double* cG, const double* l, const double* y, const int* I,
+                         const double* recW, const double* muW, const double* hyp, double scale, double* Rsum /* += */,
+                         double* ghyp /* += */, double* lbar, double* mgbar, double* qgbar, double* cGbar, double* PGbar,
+                         int ns, long long B, int Q, int D, long long y_stride, nmgp_stream_t stream);
+/* = nmgp_quadform_fwd (bwd == 0: q, m; entries of pairs a row does not consume stay as the caller initialised them)
+ * / nmgp_quadform_bwd (bwd != 0: Pabar, Pbbar) in coefficient mode, recU = padded Sigma_U[packed pairs]
+ *                                                                          utils.py:120-122 in the loop nmgp_dsvi.py:228-237 */
+int nmgp_lq_coef_quadform(int bwd, const double* Pa, const double* Pb, const int* I, const double* recU,
+                          const double* Mu, double* q, double* m, const double* qbar, const double* mbar,
+                          double* Pabar, double* Pbbar, int ns, long long B, int Q, int D, nmgp_stream_t stream);
+
 /* expected log-likelihood of a sample chunk and its cotangents             nmgp_dsvi.py:255-258, utils.py:268-272 */
 int nmgp_lik_rows(const double* l, const double* mg, const double* qg, const double* cG, const double* y, const int* I,
                   const double* hyp, double scale, double* Rsum /* += */, double* ghyp /* += */, double* lbar,

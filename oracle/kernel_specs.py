@@ -177,7 +177,7 @@ def _pair_index(I, j, mode, D):
     return torch.where(Il == j, Il, D + (Il * (Il - 1)) // 2 + j)
 
 
-def quadform_fwd(Pa, Pb, I, Sig, Mu, D, mode, seg=None):
+def quadform_fwd(Pa, Pb, I, Sig, Mu, D, mode, seg=None, rec=None):
     ns, B, Q = Pa.shape
     q = torch.zeros(ns, B, D, dtype=F64); m = torch.zeros(ns, B, D, dtype=F64)
     Il = I.long()
@@ -197,7 +197,7 @@ def quadform_fwd(Pa, Pb, I, Sig, Mu, D, mode, seg=None):
     return q, m
 
 
-def quadform_bwd(Pa, Pb, I, Sig, Mu, qbar, mbar, mode, seg=None):
+def quadform_bwd(Pa, Pb, I, Sig, Mu, qbar, mbar, mode, seg=None, rec=None):
     ns, B, Q = Pa.shape
     D = qbar.shape[-1]
     Pabar = torch.zeros_like(Pa)
@@ -401,7 +401,7 @@ def rowdot_live(l, g, I):
     return (l * g * live).sum(-1)
 
 
-def latent_fused(PG, cG, l, y, I, SigW, muW, hyp, scale, Rsum, ghyp, seg=None):
+def latent_fused(PG, cG, l, y, I, SigW, muW, hyp, scale, Rsum, ghyp, seg=None, rec=None):
     """= quadform_fwd(MODE_W) -> lik_rows -> quadform_bwd(MODE_W)."""
     D = l.shape[-1]
     qg, mg = quadform_fwd(PG, PG, I, SigW, muW, D, MODE_W)
@@ -499,3 +499,8 @@ def lcorr(L):
 def launch_count():
     """CPU specifications launch no kernels."""
     return 0
+
+
+def lq_pad_records(Sig):
+    """The CPU specifications read the covariances directly; the padded records are a device-side staging format."""
+    return None

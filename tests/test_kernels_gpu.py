@@ -46,6 +46,8 @@ def make_I(gen, B, D, empty=()):
 
 
 CASES = [(20, 3, 37), (50, 8, 300), (100, 5, 131), (112, 2, 70)]
+# 64 < Q <= 128: ring-pipelined DMMA quadratic forms, right-looking row solves, wide Gram / A^T B kernels
+LQ_CASES = [(72, 6, 300), (100, 9, 700), (104, 3, 129), (128, 3, 200), (65, 12, 1030)]
 
 
 @pytest.mark.parametrize("Q,nb", [(20, 5), (50, 70), (100, 3), (112, 2)])
@@ -126,7 +128,7 @@ def test_builds(Q, D, B):
     check(exd2, exb, 1e-12, "gibbs bwd x (kept K)"); check(ezd2, ezb, 1e-11, "gibbs bwd z (kept K)")
 
 
-@pytest.mark.parametrize("Q,D,B", CASES)
+@pytest.mark.parametrize("Q,D,B", CASES + LQ_CASES)
 def test_solve_rows(Q, D, B):
     gen = torch.Generator().manual_seed(B + 1)
     ns = 2
@@ -143,7 +145,7 @@ def test_solve_rows(Q, D, B):
     check(Kbd, Kbr, 1e-11, "solve bwd K"); check(Abd, Ab, 1e-11, "solve bwd A")
 
 
-@pytest.mark.parametrize("Q,D,B", CASES + [(50, 9, 64), (50, 4, 1)])
+@pytest.mark.parametrize("Q,D,B", CASES + [(50, 9, 64), (50, 4, 1)] + LQ_CASES + [(100, 4, 1)])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_quadform_family(Q, D, B, mode):
     gen = torch.Generator().manual_seed(B * 3 + mode)
@@ -222,7 +224,7 @@ def test_row_elementwise(Q, D, B):
     check(mbd, mb, 1e-12); check(sbd, sb2, 1e-12)
     # likelihood rows
     mg = rn(ns, B, D); qg = torch.rand(ns, B, D, generator=gen, dtype=torch.float64); cG = torch.rand(ns, B, generator=gen, dtype=torch.float64)
-    y = rn(B)
+    y = rn(ns, B) if per_sample_y else rn(B)
     Rs = torch.zeros(ns, dtype=torch.float64); gh = torch.zeros(7, dtype=torch.float64)
     Rsd, ghd = g(Rs.clone()), g(gh.clone())
     ref = specs.lik_rows(lr, mg, qg, cG, y, I, hyp, 0.37, Rs, gh)
@@ -237,9 +239,12 @@ def test_cpu_tensors_are_rejected():
         ops.tril_syrk_fwd(torch.zeros(1, 4, 4, dtype=torch.float64))
 
 
-@pytest.mark.parametrize("Q,D,B", [(20, 3, 37), (50, 8, 300), (50, 70, 517), (64, 5, 131), (100, 4, 90), (8, 2, 129)])
-def test_latent_fused(Q, D, B):
-    """DMMA fused kernel (Q <= 64) and the three-kernel path (Q > 64) against the composed specification."""
+@pytest.mark.parametrize("Q,D,B", [(20, 3, 37), (50, 8, 300), (50, 70, 517), (64, 5, 131), (100, 4, 90), (8, 2, 129)]
+                         + LQ_CASES + [(100, 40, 517), (100, 2, 1)])
+@pytest.mark.parametrize("per_sample_y", [False, True])
+def test_latent_fused(Q, D, B, per_sample_y):
+    """DMMA fused kernels (register-resident for Q <= 64, ring-pipelined for 64 < Q <= 128) against the composed
+    specification; with one target vector shared by the samples or one per sample (subjects)."""
     gen = torch.Generator().manual_seed(B + 11)
     ns = 2
     rn = lambda *s: torch.randn(*s, generator=gen, dtype=torch.float64)
@@ -249,7 +254,7 @@ def test_latent_fused(Q, D, B):
     PG = rn(ns, B, Q) * 0.3; cG = torch.rand(ns, B, generator=gen, dtype=torch.float64)
     j = torch.arange(D).view(1, 1, -1)
     l = rn(ns, B, D) * (j <= I.long().view(1, -1, 1))
-    y = rn(B)
+    y = rn(ns, B) if per_sample_y else rn(B)
     Rs = torch.zeros(ns, dtype=torch.float64); gh = torch.zeros(7, dtype=torch.float64)
     Rsd, ghd = g(Rs.clone()), g(gh.clone())
     ref = specs.latent_fused(PG, cG, l, y, I, SigW, muW, hyp, 0.37, Rs, gh)
