@@ -125,31 +125,74 @@ def potrf_bwd(C, Cbar, hldbar):
     return out
 
 
-def kl_fwd(CS, hldS, mu, R, hldR, exact=False):
-    if exact:
-        raise NotImplementedError("exact KL (flagged variant of quirk q10) is not built yet")
+def atb(A, Bm, C, sign=1.0):
+    """C[s] += sign * A[s]^T Bm[s]  (A, Bm [ns,B,Q], C [ns,Q,Q]) on the FP64 tensor cores."""
+    ns, B, Q = A.shape
+    check(lib().nmgp_atb(_d(A), _d(Bm), _d(C), c_double(sign), c_int(ns), c_int64(B), c_int(Q), _stream()), "nmgp_atb")
+    return C
+
+
+def kl_rbar(R, G, Rbar):
+    """Rbar[p] += -tril(G[p] R[p])."""
+    np_, Q, _ = R.shape
+    check(lib().nmgp_kl_rbar(_d(R), _d(G), _d(Rbar), c_int(np_), c_int(Q), _stream()), "nmgp_kl_rbar")
+    return Rbar
+
+
+def _kl_exact_rows(CS, mu, np_):
+    """[np, nb (Q+1), Q]: per b the row mu_b followed by the Q columns of CS_b (as rows), repeated for every prior p."""
     nb, Q, _ = CS.shape
+    rows = torch.cat([mu.reshape(nb, 1, Q), CS.transpose(1, 2)], dim=1).reshape(1, nb * (Q + 1), Q)
+    return rows.expand(np_, nb * (Q + 1), Q).contiguous()
+
+
+def kl_fwd(CS, hldS, mu, R, hldR, exact=False):
+    """kl[p,b] = KL(N(mu_b, CS_b CS_b^T) || N(0, R_p R_p^T)).  Default: the reference's form (quirk q10: the trace term
+    only sees diag(R_p), code/utils.py:349).  ``exact=True``: the true trace term tr((R_p R_p^T)^-1 CS_b CS_b^T),
+    obtained from the same DMMA row solve with the columns of CS_b as extra rows.
+    Returns (kl [np,nb], saved); ``saved`` is what kl_bwd needs."""
+    nb, Q, _ = CS.shape
+    _checkQ(Q)
     np_ = R.shape[0]
+    if exact:
+        K = _kl_exact_rows(CS, mu, np_)
+        P, c = solve_rows_fwd(K, R)
+        kl = hldR.reshape(np_, 1) - hldS.reshape(1, nb) + 0.5 * (c.reshape(np_, nb, Q + 1).sum(-1) - Q)
+        return kl, (P,)
     kl = _empty(CS, np_, nb)
     t = _empty(CS, np_, nb, Q)
-    check(lib().nmgp_kl_fwd(_d(CS), _d(hldS), _d(mu), _d(R), _d(hldR), _d(kl), _d(t),
+    rs = _empty(CS, nb, Q)
+    work = _empty(CS, np_, nb, Q)
+    check(lib().nmgp_kl_fwd(_d(CS), _d(hldS), _d(mu), _d(R), _d(hldR), _d(kl), _d(t), _d(rs), _d(work),
                             c_int(np_), c_int(nb), c_int(Q), _stream()), "nmgp_kl_fwd")
-    return kl, t
+    return kl, (t, rs)
 
 
-def kl_bwd(klbar, CS, mu, R, t, exact=False):
-    if exact:
-        raise NotImplementedError("exact KL (flagged variant of quirk q10) is not built yet")
+def kl_bwd(klbar, CS, mu, R, saved, exact=False):
     nb, Q, _ = CS.shape
     np_ = R.shape[0]
+    Rbar = _zeros(CS, np_, Q, Q)
+    if exact:
+        (P,) = saved                                              # [np, nb (Q+1), Q] = rows (R R^T)^-1
+        Wr = (klbar.reshape(np_, nb, 1, 1) * P.reshape(np_, nb, Q + 1, Q))
+        rows_bar = Wr.sum(0)                                      # [nb, Q+1, Q]: cotangent of (mu_b ; columns of CS_b)
+        mubar = rows_bar[:, 0].contiguous()
+        CSbar = torch.tril(rows_bar[:, 1:].transpose(1, 2)).contiguous()
+        G = _zeros(CS, np_, Q, Q)
+        atb(Wr.reshape(np_, nb * (Q + 1), Q).contiguous(), P, G, 1.0)
+        kl_rbar(R, G, Rbar)
+        return CSbar, -klbar.sum(0), mubar, Rbar, klbar.sum(1)
+    t, rs = saved
     CSbar = torch.empty_like(CS)
     hldSbar = _empty(CS, nb)
     mubar = _empty(CS, nb, Q)
-    Rbar = _zeros(CS, np_, Q, Q)
     hldRbar = _empty(CS, np_)
     work = _empty(CS, np_, nb, Q)
-    check(lib().nmgp_kl_bwd(_d(klbar), _d(CS), _d(mu), _d(R), _d(t), _d(CSbar), _d(hldSbar), _d(mubar), _d(Rbar),
-                            _d(hldRbar), _d(work), c_int(np_), c_int(nb), c_int(Q), _stream()), "nmgp_kl_bwd")
+    rsb = _empty(CS, nb, Q)
+    G = _empty(CS, np_, Q, Q)
+    check(lib().nmgp_kl_bwd(_d(klbar), _d(CS), _d(R), _d(t), _d(rs), _d(CSbar), _d(hldSbar), _d(mubar), _d(Rbar),
+                            _d(hldRbar), _d(work), _d(rsb), _d(G), c_int(np_), c_int(nb), c_int(Q), _stream()),
+          "nmgp_kl_bwd")
     return CSbar, hldSbar, mubar, Rbar, hldRbar
 
 
@@ -456,14 +499,31 @@ def lcorr(L):
 
 
 # ---- SIM_code (exact / Kronecker) line --------------------------------------------------------------
-def nonstationary_cov(X1, sigma1, ell1, X2, sigma2, ell2, jitter):
+def nonstationary_cov(X1, sigma1, ell1, X2, sigma2, ell2, jitter, self_cov=False):
+    """Nonstationary_RBF_cov.  ``self_cov``: X2/sigma2/ell2 ARE X1/sigma1/ell1 (the reference's X2=None call): only the
+    tiles on and below the diagonal are evaluated and mirrored, jitter is added on the diagonal."""
     T1, dx = X1.shape
     T2 = X2.shape[0]
     K = _empty(X1, T1, T2)
     check(lib().nmgp_nonstationary_cov(_d(X1), _optd(sigma1), _optd(ell1), _d(X2), _optd(sigma2), _optd(ell2),
-                                       c_double(jitter), _d(K), c_int64(T1), c_int64(T2), c_int(dx), _stream()),
-          "nmgp_nonstationary_cov")
+                                       c_double(jitter), _d(K), c_int64(T1), c_int64(T2), c_int(dx),
+                                       c_int(1 if self_cov else 0), _stream()), "nmgp_nonstationary_cov")
     return K
+
+
+def nonstationary_cov_bwd(X1, sigma1, ell1, X2, sigma2, ell2, Kbar, want=(True, True, True, True)):
+    """Adjoint of nonstationary_cov w.r.t. (sigma1, ell1, sigma2, ell2) for 1-D inputs; entries of ``want`` switch the
+    four outputs (None where not wanted or where the argument itself was None).  For a self-covariance the caller adds the
+    row-side and the column-side gradients."""
+    T1, dx = X1.shape
+    T2 = X2.shape[0]
+    outs = []
+    for arg, w, n in ((sigma1, want[0], T1), (ell1, want[1], T1), (sigma2, want[2], T2), (ell2, want[3], T2)):
+        outs.append(_zeros(X1, n) if (w and arg is not None) else None)
+    check(lib().nmgp_nonstationary_cov_bwd(_d(X1), _optd(sigma1), _optd(ell1), _d(X2), _optd(sigma2), _optd(ell2),
+                                           _d(Kbar), _optd(outs[0]), _optd(outs[1]), _optd(outs[2]), _optd(outs[3]),
+                                           c_int64(T1), c_int64(T2), c_int(dx), _stream()), "nmgp_nonstationary_cov_bwd")
+    return tuple(outs)
 
 
 def hadamard_index_cov(Kx, Bf, indx1, indx2, diag=0.0):
@@ -474,12 +534,13 @@ def hadamard_index_cov(Kx, Bf, indx1, indx2, diag=0.0):
     return out
 
 
-def sim_rbf_cov(X1, X2, alpha, beta, jitter):
+def sim_rbf_cov(X1, X2, alpha, beta, jitter, self_cov=False):
     T1, dx = X1.shape
     T2 = X2.shape[0]
     K = _empty(X1, T1, T2)
     check(lib().nmgp_sim_rbf_cov(_d(X1), _d(X2), c_double(alpha), c_double(beta), c_double(jitter), _d(K),
-                                 c_int64(T1), c_int64(T2), c_int(dx), _stream()), "nmgp_sim_rbf_cov")
+                                 c_int64(T1), c_int64(T2), c_int(dx), c_int(1 if self_cov else 0), _stream()),
+          "nmgp_sim_rbf_cov")
     return K
 
 

@@ -205,71 +205,7 @@ NMGP_API int nmgp_gibbs_build_bwd(const double* x, const double* z, const double
     return nmgp_launch_status("nmgp_gibbs_build_bwd");
 }
 
-// ---- SIM_code builds (kernels.py) ----------------------------------------------------------------
-// dist = |x|^2 + |y|^2 - 2 x.y (GEMM form, may be slightly negative, not clamped: kernels.py:14-21)
-__device__ __forceinline__ double sim_dist(const double* __restrict__ X1, const double* __restrict__ X2, long long i,
-                                           long long j, int dx) {
-    double xn = 0.0, yn = 0.0, xy = 0.0;
-    for (int k = 0; k < dx; ++k) {
-        double a = X1[i * dx + k], b = X2[j * dx + k];
-        xn = fma(a, a, xn);
-        yn = fma(b, b, yn);
-        xy = fma(a, b, xy);
-    }
-    return xn + yn - 2.0 * xy;
-}
-// Nonstationary_RBF_cov (kernels.py:46-73): C*sqrt(2B/A)*exp(-dist/A) (+1e-6 I when self)
-__global__ void k_nonstat_cov(const double* __restrict__ X1, const double* __restrict__ sg1, const double* __restrict__ l1,
-                              const double* __restrict__ X2, const double* __restrict__ sg2, const double* __restrict__ l2,
-                              double jitter, double* __restrict__ K, long long row0, long long T2, int dx) {
-    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long i = row0 + blockIdx.y;
-    if (j >= T2) return;
-    double a = l1 ? l1[i] : 1.0, b = l2 ? l2[j] : 1.0;
-    double c = (sg1 ? sg1[i] : 1.0) * (sg2 ? sg2[j] : 1.0);
-    double A = a * a + b * b;
-    double k = c * sqrt(2.0 * (a * b) / A) * exp(-sim_dist(X1, X2, i, j, dx) / A);
-    if (i == j) k += jitter;
-    K[i * T2 + j] = k;
-}
-NMGP_API int nmgp_nonstationary_cov(const double* X1, const double* sigma1, const double* ell1, const double* X2,
-                                    const double* sigma2, const double* ell2, double jitter, double* K, long long T1,
-                                    long long T2, int dx, cudaStream_t st) {
-    NMGP_REQUIRE(T1 >= 0 && T2 >= 0 && dx > 0, "nmgp_nonstationary_cov");
-    if (T1 == 0 || T2 == 0) return 0;
-    for (long long r0 = 0; r0 < T1; r0 += 65535) {  // grid.y is limited to 65535
-        long long rows = T1 - r0 < 65535 ? T1 - r0 : 65535;
-        dim3 grid((unsigned)((T2 + 255) / 256), (unsigned)rows);
-        k_nonstat_cov<<<NMGP_L(grid), 256, 0, st>>>(X1, sigma1, ell1, X2, sigma2, ell2, jitter, K, r0, T2, dx);
-    }
-    return nmgp_launch_status("nmgp_nonstationary_cov");
-}
-// RBF_cov (kernels.py:24-43): alpha^2 exp(-0.5 dist(X1/beta, X2/beta)) (+1e-6 I when self)
-__global__ void k_sim_rbf_cov(const double* __restrict__ X1, const double* __restrict__ X2, double alpha, double beta,
-                              double jitter, double* __restrict__ K, long long T1, long long T2, int dx) {
-    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long i = blockIdx.y;
-    if (j >= T2) return;
-    double xn = 0.0, yn = 0.0, xy = 0.0;
-    for (int k = 0; k < dx; ++k) {
-        double a = X1[i * dx + k] / beta, b = X2[j * dx + k] / beta;
-        xn = fma(a, a, xn);
-        yn = fma(b, b, yn);
-        xy = fma(a, b, xy);
-    }
-    double dist = xn + yn - 2.0 * xy;
-    double k = exp(-0.5 * dist) * (alpha * alpha);
-    if (i == j) k += jitter;
-    K[i * T2 + j] = k;
-}
-NMGP_API int nmgp_sim_rbf_cov(const double* X1, const double* X2, double alpha, double beta, double jitter, double* K,
-                              long long T1, long long T2, int dx, cudaStream_t st) {
-    NMGP_REQUIRE(T1 >= 0 && T2 >= 0 && dx > 0 && T1 <= 65535, "nmgp_sim_rbf_cov");
-    if (T1 == 0 || T2 == 0) return 0;
-    dim3 grid((unsigned)((T2 + 255) / 256), (unsigned)T1);
-    k_sim_rbf_cov<<<NMGP_L(grid), 256, 0, st>>>(X1, X2, alpha, beta, jitter, K, T1, T2, dx);
-    return nmgp_launch_status("nmgp_sim_rbf_cov");
-}
+// ---- SIM_code builds (kernels.py): nmgp_simcov.cu ---------------------------------------------------
 
 // Hadamard (irregular-observation) covariance of the SIM_code line: out[i,j] = Kx[i,j] * Bf[indx1[i], indx2[j]]
 // (+ diag on i == j)   -- logpos.generate_K_index (logpos.py:87-98) fused with the elementwise product K_x * K_i

@@ -181,12 +181,11 @@ __global__ void __launch_bounds__(LQ_THREADS, 1) k_lq(const LQArgs a) {
 
     // ---- phase 1: means m[n, j] = p_n . Mu[slot] on the tensor pipe (latents / pairs as the N dimension) -----------
     double Fp[2] = {0.0, 0.0};
-    {
+    if (MODE != LQ_UB) {                                                // the adjoint needs no means
         const int o_lo = (MODE == LQ_W) ? 0 : i_lo, o_hi = (MODE == LQ_W) ? 0 : i_hi;
         for (int io = o_lo; io <= o_hi; ++io) {
             const int jcount = (MODE == LQ_W) ? D : (diag ? 1 : io);    // columns of this output's product
             if (MODE != LQ_W && (io < wlo || io > whi)) continue;
-            if (MODE == LQ_UB) break;                                   // the adjoint needs no means
             for (int jb = 0; jb * 8 < jcount; ++jb) {
                 double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
                 const int jn = 8 * jb + g;                              // B-fragment column of this lane

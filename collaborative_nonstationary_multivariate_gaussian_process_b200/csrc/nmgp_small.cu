@@ -255,116 +255,131 @@ NMGP_API int nmgp_potrf_bwd_batched(const double* C, const double* Cbar, const d
 
 // ------------------------------------------------------------------------------------------
 // KL(N(mu_b, C_b C_b^T) || N(0, R_p R_p^T)) in the reference's form (code/utils.py:346-351, quirk q10):
-//   kl[p,b] = hldR[p] - hldS[b] + 0.5 ( sum_{a,c} (C_b[a,c]/R_p[a,a])^2 + ||R_p^-1 mu_b||^2 - Q )
-// grid (ceil(nb/128), np); thread = one (p,b); R_p in shared memory; t = R_p^-1 mu_b kept in global (saved for bwd).
-__global__ void k_kl_fwd(const double* __restrict__ CS, const double* __restrict__ hldS, const double* __restrict__ mu,
-                         const double* __restrict__ R, const double* __restrict__ hldR, double* __restrict__ kl,
-                         double* __restrict__ t, int np_, int nb, int Q) {
-    extern __shared__ double Rs[];
+//   kl[p,b] = hldR[p] - hldS[b] + 0.5 ( sum_a rs[b,a] / R_p[a,a]^2 + mu_b^T (R_p R_p^T)^-1 mu_b - Q ),
+//   rs[b,a] = sum_{c<=a} C_b[a,c]^2.
+// Batched formulation (every (p,b) pair in parallel, no per-pair serial substitution):
+//   * rs once per b (one warp per matrix row, coalesced);
+//   * t[p,b,:] = (R_p R_p^T)^-1 mu_b and the Mahalanobis term mu_b . t[p,b,:] are exactly what the DMMA row-solve
+//     kernel produces for the "rows" mu_b (nmgp_solve_rows_fwd_mma: P = K (R R^T)^-1, c = rowsum(P o K));
+//   * adjoint: mubar_b = sum_p klbar t;  A_p = R_p R_p^T receives -1/2 sum_b klbar t t^T, i.e.
+//     Rbar_p -= tril(G_p R_p) with the weighted Gram matrix G_p = sum_b klbar[p,b] t t^T (DMMA reduction k_atb_mma);
+//     the diagonal-only trace term contributes Rbar_p[a,a] -= sum_b klbar rs[b,a] / d^3 and
+//     CSbar_b = tril(2 rsb[b,a] C_b), rsb[b,a] = 1/2 sum_p klbar / R_p[a,a]^2.
+int nmgp_solve_rows_fwd_mma(const double* K, const double* R, double* P, double* c, int ns, long long B, int Q,
+                            cudaStream_t st);
+int nmgp_atb_mma(const double* A, const double* Bm, double* C, double sign, int ns, long long B, int Q,
+                 const double* cbar, double* Kbar, cudaStream_t st);
+
+// rs[b,a] = sum_{c<=a} CS[b,a,c]^2 : one warp per (b,a)
+__global__ void k_kl_rowsq(const double* __restrict__ CS, double* __restrict__ rs, long long nrows, int Q) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    const int lane = threadIdx.x & 31, a = (int)(row % Q);
+    const double* src = CS + row * Q;
+    double s = 0.0;
+    for (int c = lane; c <= a; c += 32) s = fma(src[c], src[c], s);
+    s = warp_sum(s);
+    if (lane == 0) rs[row] = s;
+}
+// out[p,b,:] = mu[b,:]
+__global__ void k_kl_expand(const double* __restrict__ mu, double* __restrict__ out, int np_, long long nbQ) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nbQ) return;
+    const double v = mu[e];
+    for (int p = 0; p < np_; ++p) out[(size_t)p * nbQ + e] = v;
+}
+// kl[p,b] (in: the Mahalanobis term) = hldR[p] - hldS[b] + 0.5 (sum_a rs[b,a] w_p[a] + kl[p,b] - Q), w_p = 1/diag(R_p)^2
+__global__ void k_kl_combine(double* __restrict__ kl, const double* __restrict__ rs, const double* __restrict__ R,
+                             const double* __restrict__ hldR, const double* __restrict__ hldS, int nb, int Q) {
+    extern __shared__ double wsm[];
     const int p = blockIdx.y;
-    const double* Rp = R + (size_t)p * Q * Q;
-    for (int e = threadIdx.x; e < Q * Q; e += blockDim.x) Rs[e] = Rp[e];
-    __syncthreads();
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
-    double* tb = t + ((size_t)p * nb + b) * Q;
-    const double* mub = mu + (size_t)b * Q;
-    const double* Cb = CS + (size_t)b * Q * Q;
-    double term3 = 0.0, term2 = 0.0;
-    for (int a = 0; a < Q; ++a) {
-        double s = mub[a];
-        for (int c = 0; c < a; ++c) s = fma(-Rs[a * Q + c], tb[c], s);
-        double d = Rs[a * Q + a];
-        s /= d;
-        tb[a] = s;
-        term3 = fma(s, s, term3);
-        double rs = 0.0;
-        for (int c = 0; c <= a; ++c) {
-            double v = Cb[a * Q + c];
-            rs = fma(v, v, rs);
-        }
-        term2 += rs / (d * d);
+    for (int a = threadIdx.x; a < Q; a += blockDim.x) {
+        const double d = R[(size_t)p * Q * Q + (size_t)a * Q + a];
+        wsm[a] = 1.0 / (d * d);
     }
-    kl[(size_t)p * nb + b] = hldR[p] - hldS[b] + 0.5 * (term2 + term3 - (double)Q);
+    __syncthreads();
+    const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < nb; b += gridDim.x * wpb) {
+        double s = 0.0;
+        for (int a = lane; a < Q; a += 32) s = fma(rs[(size_t)b * Q + a], wsm[a], s);
+        s = warp_sum(s);
+        if (lane == 0) {
+            const size_t o = (size_t)p * nb + b;
+            kl[o] = hldR[p] - hldS[b] + 0.5 * (s + kl[o] - (double)Q);
+        }
+    }
 }
 NMGP_API int nmgp_kl_fwd(const double* CS, const double* hldS, const double* mu, const double* R, const double* hldR,
-                         double* kl, double* t, int np_, int nb, int Q, cudaStream_t st) {
-    NMGP_REQUIRE(np_ > 0 && nb > 0 && Q > 0, "nmgp_kl_fwd");
-    size_t smem = (size_t)Q * Q * sizeof(double);
-    if (int r = nmgp_opt_in_smem(k_kl_fwd, smem, "nmgp_kl_fwd")) return r;
-    dim3 grid((nb + 127) / 128, np_);
-    k_kl_fwd<<<NMGP_L(grid), 128, smem, st>>>(CS, hldS, mu, R, hldR, kl, t, np_, nb, Q);
+                         double* kl, double* t, double* rs, double* work, int np_, int nb, int Q, cudaStream_t st) {
+    NMGP_REQUIRE(np_ > 0 && nb > 0 && Q > 0 && Q <= 128, "nmgp_kl_fwd");
+    const long long nrows = (long long)nb * Q;
+    k_kl_rowsq<<<NMGP_L((unsigned)((nrows + 7) / 8)), 256, 0, st>>>(CS, rs, nrows, Q);
+    k_kl_expand<<<NMGP_L((unsigned)((nrows + 255) / 256)), 256, 0, st>>>(mu, work, np_, nrows);
+    if (int r = nmgp_solve_rows_fwd_mma(work, R, t, kl, np_, nb, Q, st)) return r;
+    dim3 grid((unsigned)min((nb + 7) / 8, 1024), np_);
+    k_kl_combine<<<NMGP_L(grid), 256, Q * sizeof(double), st>>>(kl, rs, R, hldR, hldS, nb, Q);
     return nmgp_launch_status("nmgp_kl_fwd");
 }
 
-// backward part 1: work[p,b,:] = R_p^-T (klbar[p,b] * t[p,b,:])
-__global__ void k_kl_bwd_solve(const double* __restrict__ klbar, const double* __restrict__ R,
-                               const double* __restrict__ t, double* __restrict__ work, int np_, int nb, int Q) {
-    extern __shared__ double Rs[];
-    const int p = blockIdx.y;
-    const double* Rp = R + (size_t)p * Q * Q;
-    for (int e = threadIdx.x; e < Q * Q; e += blockDim.x) Rs[e] = Rp[e];
-    __syncthreads();
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
-    const double kb = klbar[(size_t)p * nb + b];
-    const double* tb = t + ((size_t)p * nb + b) * Q;
-    double* wb = work + ((size_t)p * nb + b) * Q;
-    for (int a = Q - 1; a >= 0; --a) {
-        double s = kb * tb[a];
-        for (int c = a + 1; c < Q; ++c) s = fma(-Rs[c * Q + a], wb[c], s);
-        wb[a] = s / Rs[a * Q + a];
-    }
-}
-// part 2: Rbar[p][a,c] (a>=c) -= sum_b work[p,b,a] t[p,b,c];  diagonal += -2/d^3 * 0.5 sum_b klbar[p,b] rs[b,a]
-// grid (nchunks, np); each block handles a chunk of b and atomically adds its partial.
-__global__ void k_kl_bwd_R(const double* __restrict__ klbar, const double* __restrict__ CS, const double* __restrict__ R,
-                           const double* __restrict__ t, const double* __restrict__ work, double* __restrict__ Rbar,
-                           int np_, int nb, int Q, int chunk) {
-    const int p = blockIdx.y;
-    const int b0 = blockIdx.x * chunk, b1 = min(nb, b0 + chunk);
-    for (int e = threadIdx.x; e < Q * Q; e += blockDim.x) {
-        int a = e / Q, c = e - a * Q;
-        if (c > a) continue;
-        double s = 0.0;
-        for (int b = b0; b < b1; ++b) {
-            size_t o = ((size_t)p * nb + b) * Q;
-            s = fma(-work[o + a], t[o + c], s);
-        }
-        if (a == c) {
-            double d = R[(size_t)p * Q * Q + (size_t)a * Q + a];
-            double wbar = 0.0;
-            for (int b = b0; b < b1; ++b) {
-                const double* Cb = CS + (size_t)b * Q * Q + (size_t)a * Q;
-                double rs = 0.0;
-                for (int k = 0; k <= a; ++k) rs = fma(Cb[k], Cb[k], rs);
-                wbar = fma(0.5 * klbar[(size_t)p * nb + b], rs, wbar);
-            }
-            s += wbar * (-2.0) / (d * d * d);
-        }
-        atomicAdd(&Rbar[(size_t)p * Q * Q + e], s);
-    }
-}
-// part 3: mubar, CSbar, hldSbar (thread per (b, a)); hldRbar by block 0
-__global__ void k_kl_bwd_S(const double* __restrict__ klbar, const double* __restrict__ CS, const double* __restrict__ R,
-                           const double* __restrict__ work, double* __restrict__ CSbar, double* __restrict__ hldSbar,
-                           double* __restrict__ mubar, int np_, int nb, int Q) {
-    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// work[p,b,a] = klbar[p,b] t[p,b,a];  mubar[b,a] = sum_p work;  rsb[b,a] = 1/2 sum_p klbar[p,b] / R_p[a,a]^2;
+// hldSbar[b] = -sum_p klbar[p,b].   Thread per (b,a).
+__global__ void k_kl_bwd_rows(const double* __restrict__ klbar, const double* __restrict__ R, const double* __restrict__ t,
+                              double* __restrict__ work, double* __restrict__ mubar, double* __restrict__ rsb,
+                              double* __restrict__ hldSbar, int np_, int nb, int Q) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)nb * Q) return;
-    int b = (int)(gid / Q), a = (int)(gid - (long long)b * Q);
-    double mb = 0.0, rsbar = 0.0, ks = 0.0;
+    const int b = (int)(gid / Q), a = (int)(gid - (long long)b * Q);
+    double mb = 0.0, rb = 0.0, ks = 0.0;
     for (int p = 0; p < np_; ++p) {
-        double kb = klbar[(size_t)p * nb + b];
-        mb += work[((size_t)p * nb + b) * Q + a];
-        double d = R[(size_t)p * Q * Q + (size_t)a * Q + a];
-        rsbar = fma(0.5 * kb, 1.0 / (d * d), rsbar);
+        const double kb = klbar[(size_t)p * nb + b];
+        const size_t o = ((size_t)p * nb + b) * Q + a;
+        const double wv = kb * t[o];
+        work[o] = wv;
+        mb += wv;
+        const double d = R[(size_t)p * Q * Q + (size_t)a * Q + a];
+        rb = fma(0.5 * kb, 1.0 / (d * d), rb);
         ks += kb;
     }
-    mubar[(size_t)b * Q + a] = mb;
+    mubar[gid] = mb;
+    rsb[gid] = rb;
     if (a == 0) hldSbar[b] = -ks;
-    const double* Cb = CS + (size_t)b * Q * Q + (size_t)a * Q;
-    double* Ob = CSbar + (size_t)b * Q * Q + (size_t)a * Q;
-    for (int c = 0; c < Q; ++c) Ob[c] = (c <= a) ? 2.0 * rsbar * Cb[c] : 0.0;
+}
+// CSbar[b,a,c] = (c <= a) ? 2 rsb[b,a] CS[b,a,c] : 0
+__global__ void k_kl_bwd_CS(const double* __restrict__ CS, const double* __restrict__ rsb, double* __restrict__ CSbar,
+                            long long n, int Q) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const long long row = e / Q;
+    const int c = (int)(e - row * Q), a = (int)(row % Q);
+    CSbar[e] = (c <= a) ? 2.0 * rsb[row] * CS[e] : 0.0;
+}
+// Rbar_p[a,c] += -(G_p R_p)[a,c] (c <= a);  Rbar_p[a,a] += -sum_b klbar[p,b] rs[b,a] / d^3.  grid (ceil(Q/8), np), one
+// warp per row a.
+__global__ void k_kl_bwd_R(const double* __restrict__ klbar, const double* __restrict__ rs, const double* __restrict__ R,
+                           const double* __restrict__ G, double* __restrict__ Rbar, int nb, int Q) {
+    const int p = blockIdx.y, a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (a >= Q) return;
+    const double* Gp = G + (size_t)p * Q * Q + (size_t)a * Q;
+    const double* Rp = R + (size_t)p * Q * Q;
+    double* Ob = Rbar + (size_t)p * Q * Q + (size_t)a * Q;
+    for (int c = lane; c <= a; c += 32) {
+        double s0 = 0.0, s1 = 0.0;
+        int k = c;                                   // R is lower triangular: R[k,c] = 0 for k < c
+        for (; k + 1 < Q; k += 2) {
+            s0 = fma(Gp[k], Rp[(size_t)k * Q + c], s0);
+            s1 = fma(Gp[k + 1], Rp[(size_t)(k + 1) * Q + c], s1);
+        }
+        if (k < Q) s0 = fma(Gp[k], Rp[(size_t)k * Q + c], s0);
+        Ob[c] -= s0 + s1;
+    }
+    if (rs == nullptr) return;                       // exact-KL variant: no diagonal-only trace term
+    double ws = 0.0;
+    for (int b = lane; b < nb; b += 32) ws = fma(klbar[(size_t)p * nb + b], rs[(size_t)b * Q + a], ws);
+    ws = warp_sum(ws);
+    if (lane == 0) {
+        const double d = Rp[(size_t)a * Q + a];
+        Ob[a] -= ws / (d * d * d);
+    }
 }
 __global__ void k_kl_bwd_hldR(const double* __restrict__ klbar, double* __restrict__ hldRbar, int np_, int nb) {
     int p = blockIdx.x;
@@ -373,22 +388,39 @@ __global__ void k_kl_bwd_hldR(const double* __restrict__ klbar, double* __restri
     s = block_sum(s);
     if (threadIdx.x == 0) hldRbar[p] = s;
 }
-NMGP_API int nmgp_kl_bwd(const double* klbar, const double* CS, const double* mu, const double* R, const double* t,
-                         double* CSbar, double* hldSbar, double* mubar, double* Rbar /* pre-zeroed */, double* hldRbar,
-                         double* work, int np_, int nb, int Q, cudaStream_t st) {
-    (void)mu;
-    NMGP_REQUIRE(np_ > 0 && nb > 0 && Q > 0, "nmgp_kl_bwd");
-    size_t smem = (size_t)Q * Q * sizeof(double);
-    if (int r = nmgp_opt_in_smem(k_kl_bwd_solve, smem, "nmgp_kl_bwd")) return r;
-    dim3 g1((nb + 127) / 128, np_);
-    k_kl_bwd_solve<<<NMGP_L(g1), 128, smem, st>>>(klbar, R, t, work, np_, nb, Q);
-    const int chunk = 32;
-    dim3 g2((nb + chunk - 1) / chunk, np_);
-    k_kl_bwd_R<<<NMGP_L(g2), 256, 0, st>>>(klbar, CS, R, t, work, Rbar, np_, nb, Q, chunk);
-    long long n3 = (long long)nb * Q;
-    k_kl_bwd_S<<<NMGP_L((unsigned)((n3 + 127) / 128)), 128, 0, st>>>(klbar, CS, R, work, CSbar, hldSbar, mubar, np_, nb, Q);
+NMGP_API int nmgp_kl_bwd(const double* klbar, const double* CS, const double* R, const double* t, const double* rs,
+                         double* CSbar, double* hldSbar, double* mubar, double* Rbar /* += */, double* hldRbar,
+                         double* work /* [np,nb,Q] */, double* rsb /* [nb,Q] */, double* G /* [np,Q,Q] */, int np_, int nb,
+                         int Q, cudaStream_t st) {
+    NMGP_REQUIRE(np_ > 0 && nb > 0 && Q > 0 && Q <= 128, "nmgp_kl_bwd");
+    const long long n3 = (long long)nb * Q;
+    k_kl_bwd_rows<<<NMGP_L((unsigned)((n3 + 127) / 128)), 128, 0, st>>>(klbar, R, t, work, mubar, rsb, hldSbar, np_, nb, Q);
+    const long long n4 = n3 * Q;
+    k_kl_bwd_CS<<<NMGP_L((unsigned)((n4 + 255) / 256)), 256, 0, st>>>(CS, rsb, CSbar, n4, Q);
+    if (cudaMemsetAsync(G, 0, sizeof(double) * (size_t)np_ * Q * Q, st) != cudaSuccess) {
+        nmgp_set_error("nmgp_kl_bwd: cudaMemsetAsync failed");
+        return -11;
+    }
+    if (int r = nmgp_atb_mma(work, t, G, 1.0, np_, nb, Q, nullptr, nullptr, st)) return r;
+    dim3 g2((Q + 7) / 8, np_);
+    k_kl_bwd_R<<<NMGP_L(g2), 256, 0, st>>>(klbar, rs, R, G, Rbar, nb, Q);
     k_kl_bwd_hldR<<<NMGP_L(np_), 128, 0, st>>>(klbar, hldRbar, np_, nb);
     return nmgp_launch_status("nmgp_kl_bwd");
+}
+
+// Building blocks of the mathematically exact KL variant (flag of utils.KL_Gaussian / NMGP(exact_kl=True), quirk q10):
+// C[s] += sign * A[s]^T B[s] over the rows (DMMA reduction) and Rbar_p += -tril(G_p R_p).
+NMGP_API int nmgp_atb(const double* A, const double* Bm, double* C /* += */, double sign, int ns, long long B, int Q,
+                      cudaStream_t st) {
+    NMGP_REQUIRE(ns > 0 && B >= 0 && Q > 0 && Q <= 128, "nmgp_atb");
+    if (B == 0) return 0;
+    return nmgp_atb_mma(A, Bm, C, sign, ns, B, Q, nullptr, nullptr, st);
+}
+NMGP_API int nmgp_kl_rbar(const double* R, const double* G, double* Rbar /* += */, int np_, int Q, cudaStream_t st) {
+    NMGP_REQUIRE(np_ > 0 && Q > 0, "nmgp_kl_rbar");
+    dim3 g2((Q + 7) / 8, np_);
+    k_kl_bwd_R<<<NMGP_L(g2), 256, 0, st>>>(nullptr, nullptr, R, G, Rbar, 0, Q);
+    return nmgp_launch_status("nmgp_kl_rbar");
 }
 
 // ------------------------------------------------------------------------------------------

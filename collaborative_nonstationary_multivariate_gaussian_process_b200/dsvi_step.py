@@ -68,7 +68,7 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
               latent_order: Optional[torch.Tensor] = None, aux: Optional[dict] = None,
               kl_shard: Optional[tuple] = None, noise_key: Optional[tuple] = None,
               row_gid: Optional[torch.Tensor] = None, defer_pd_check: bool = False,
-              S_total: Optional[int] = None, sample_offset: int = 0):
+              S_total: Optional[int] = None, sample_offset: int = 0, exact_kl: bool = False):
     """Returns (loss, grads) for rows (x, y, I) -- I sorted ascending, int32 -- and noise
     z_v [S,Q], z_ell [S,B], z_L [S,B,D] (z_L[s,n,j] is the draw for pair (I[n], j)).
 
@@ -89,6 +89,9 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
     ``S_total`` / ``sample_offset`` (sample sharding: each rank holds ALL rows but only samples sample_offset ..
     sample_offset + S - 1 of S_total): the estimate is scaled by 1/S_total, every local sample's KL_W is evaluated
     here, and the counter-based noise is keyed by the global sample index.
+
+    ``exact_kl``: evaluate the mathematically correct KL terms instead of the reference's (quirk q10, SURVEY 8a: the
+    reference's trace term only uses diag(chol(K)); every ELBO it prints contains that).  Not the default.
 
     ``defer_pd_check`` (set under multi-rank sharding): a failed Cholesky is not raised here -- a rank that raised alone
     would leave the others waiting in the gradient all-reduce -- but returned as ``aux["pd_info"]`` (int32 device scalar,
@@ -176,18 +179,18 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
             C_U1, hld_U1 = ops.potrf(Sig_U[sl1], EPS, info=pd_info)
         if n0:
             C_U0, hld_U0 = ops.potrf(Sig_U[sl0], EPS, info=pd_info)
-        kl_v, t_v = ops.kl_fwd(C_v, hld_v, mu_v.reshape(1, Q), sysm["ell"]["R"], sysm["ell"]["hldR"])
+        kl_v, t_v = ops.kl_fwd(C_v, hld_v, mu_v.reshape(1, Q), sysm["ell"]["R"], sysm["ell"]["hldR"], exact=exact_kl)
         loss_kl = kl_weight * kl_v.sum()
         kl_W = None
         if nS:
-            kl_W, t_W = ops.kl_fwd(C_W, hld_W, mu_W, R_G[slS], hld_G[slS])
+            kl_W, t_W = ops.kl_fwd(C_W, hld_W, mu_W, R_G[slS], hld_G[slS], exact=exact_kl)
             loss_kl = loss_kl + w_sh * kl_W.sum() / S_tot
         klU_sum = zeros(())
         if n1:
-            kl_U1, t_U1 = ops.kl_fwd(C_U1, hld_U1, muU[sl1], sysm["L1"]["R"], sysm["L1"]["hldR"])
+            kl_U1, t_U1 = ops.kl_fwd(C_U1, hld_U1, muU[sl1], sysm["L1"]["R"], sysm["L1"]["hldR"], exact=exact_kl)
             klU_sum = klU_sum + kl_U1.sum()
         if n0:
-            kl_U0, t_U0 = ops.kl_fwd(C_U0, hld_U0, muU[sl0], sysm["L0"]["R"], sysm["L0"]["hldR"])
+            kl_U0, t_U0 = ops.kl_fwd(C_U0, hld_U0, muU[sl0], sysm["L0"]["R"], sysm["L0"]["hldR"], exact=exact_kl)
             klU_sum = klU_sum + kl_U0.sum()
         loss_kl = loss_kl + w_sh * klU_sum
 
@@ -196,19 +199,19 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
             CWbar = zeros(D, Q, Q); hldWbar = zeros(D); muWbar = zeros(D, Q)
             RGbar = zeros(S, Q, Q); hldGbar = zeros(S)
             if nS:
-                a, b, c_, rg, hg = ops.kl_bwd(full((nS, D), w_sh / S_tot), C_W, mu_W, R_G[slS], t_W)
+                a, b, c_, rg, hg = ops.kl_bwd(full((nS, D), w_sh / S_tot), C_W, mu_W, R_G[slS], t_W, exact=exact_kl)
                 CWbar, hldWbar, muWbar = a, b, c_
                 RGbar[slS] = rg; hldGbar[slS] = hg
             Cvbar, hldvbar, muvbar, Rellbar, hldRellbar = ops.kl_bwd(full((1, 1), kl_weight), C_v, mu_v.reshape(1, Q),
-                                                                     sysm["ell"]["R"], t_v)
+                                                                     sysm["ell"]["R"], t_v, exact=exact_kl)
             CUbar1 = hldUbar1 = CUbar0 = hldUbar0 = None
             muUbar = zeros(npair, Q)
             RL1bar = zeros(1, Q, Q); hldRL1bar = zeros(1); RL0bar = zeros(1, Q, Q); hldRL0bar = zeros(1)
             if n1:
-                CUbar1, hldUbar1, c_, RL1bar, hldRL1bar = ops.kl_bwd(full((1, n1), w_sh), C_U1, muU[sl1], sysm["L1"]["R"], t_U1)
+                CUbar1, hldUbar1, c_, RL1bar, hldRL1bar = ops.kl_bwd(full((1, n1), w_sh), C_U1, muU[sl1], sysm["L1"]["R"], t_U1, exact=exact_kl)
                 muUbar[sl1] = c_
             if n0:
-                CUbar0, hldUbar0, c_, RL0bar, hldRL0bar = ops.kl_bwd(full((1, n0), w_sh), C_U0, muU[sl0], sysm["L0"]["R"], t_U0)
+                CUbar0, hldUbar0, c_, RL0bar, hldRL0bar = ops.kl_bwd(full((1, n0), w_sh), C_U0, muU[sl0], sysm["L0"]["R"], t_U0, exact=exact_kl)
                 muUbar[sl0] = c_
             muvbar = muvbar.reshape(Q).clone()
             # Cholesky adjoints that depend on the KL terms only

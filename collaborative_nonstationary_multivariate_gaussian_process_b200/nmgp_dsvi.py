@@ -90,7 +90,7 @@ class NMGP(torch.nn.Module):
     """code/nmgp_dsvi.py:99-155 (constructor, parameters, init rules, seed)."""
 
     def __init__(self, number_observations, dim_outputs, Z, minibatch_size=None, mu_v=None, mu_W=None, mu_U=None,
-                 sqrt_v=None, sqrt_W=None, sqrt_U=None, seed=22, device=None, noise="reference"):
+                 sqrt_v=None, sqrt_W=None, sqrt_U=None, seed=22, device=None, noise="reference", exact_kl=False):
         super().__init__()
         dev = default_device() if device is None else torch.device(device)
         self.Z = torch.as_tensor(Z, dtype=F64).to(dev)
@@ -101,7 +101,8 @@ class NMGP(torch.nn.Module):
         self.noise = noise
         self.noise_seed = seed            # key of the counter-based device noise ("device" mode)
         self._noise_step = 0
-        self.step_options = {}
+        # exact_kl=True: mathematically correct KL terms instead of the reference's (quirk q10) -- explicit opt-in
+        self.step_options = {"exact_kl": True} if exact_kl else {}
         D, M = self.D, self.M
 
         torch.random.manual_seed(seed)            # same draw order as the reference (CPU generator)

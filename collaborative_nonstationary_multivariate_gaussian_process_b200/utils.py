@@ -346,28 +346,30 @@ def batch_mahalanobis(bL, bx):
 
 class _KLGaussian(Function):
     @staticmethod
-    def forward(ctx, X_mu, X_Sigma, X2_mu, X2_Sigma):
+    def forward(ctx, X_mu, X_Sigma, X2_mu, X2_Sigma, exact=False):
         M = X_mu.shape[-1]
         CS, hS = ops.potrf(X_Sigma.reshape(-1, M, M).contiguous(), tridiagonal_jitter)
         R, hR = ops.potrf(X2_Sigma.reshape(1, M, M).contiguous(), tridiagonal_jitter)
         delta = (X2_mu.reshape(1, M) - X_mu.reshape(-1, M)).contiguous()
-        kl, t = ops.kl_fwd(CS, hS, delta, R, hR)
-        ctx.save_for_backward(CS, delta, R, t)
+        kl, t = ops.kl_fwd(CS, hS, delta, R, hR, exact=exact)
+        ctx.save_for_backward(CS, delta, R)
+        ctx.kl_saved, ctx.exact = t, exact                # opaque state of the KL kernels (tensors not tracked by autograd)
         ctx.shapes = (X_mu.shape, X_Sigma.shape, X2_mu.shape, X2_Sigma.shape)
         return kl[0].reshape(X_mu.shape[:-1])
 
     @staticmethod
     def backward(ctx, g):
-        CS, delta, R, t = ctx.saved_tensors
+        CS, delta, R = ctx.saved_tensors
         nb = CS.shape[0]
-        CSb, hSb, db, Rb, hRb = ops.kl_bwd(g.reshape(1, nb).contiguous(), CS, delta, R, t)
+        CSb, hSb, db, Rb, hRb = ops.kl_bwd(g.reshape(1, nb).contiguous(), CS, delta, R, ctx.kl_saved, exact=ctx.exact)
         SigX = ops.potrf_bwd(CS, CSb, hSb)
         SigX2 = ops.potrf_bwd(R, Rb, hRb)
         s = ctx.shapes
-        return (-db).reshape(s[0]), SigX.reshape(s[1]), db.sum(0).reshape(s[2]), SigX2.reshape(s[3])
+        return (-db).reshape(s[0]), SigX.reshape(s[1]), db.sum(0).reshape(s[2]), SigX2.reshape(s[3]), None
 
 
-def KL_Gaussian(X_mu, X_Sigma, X2_mu, X2_Sigma, device0=None):
+def KL_Gaussian(X_mu, X_Sigma, X2_mu, X2_Sigma, device0=None, exact=False):
     """code/utils.py:332-351, including the diagonal-only trace term produced by ``triangular_solve(..., upper=True)``
-    on a lower factor (quirk q10): every ELBO the reference has printed contains it."""
-    return _KLGaussian.apply(X_mu, X_Sigma, X2_mu, X2_Sigma)
+    on a lower factor (quirk q10): every ELBO the reference has printed contains it.  ``exact=True`` (not in the
+    reference) evaluates the mathematically correct KL(N(X_mu, X_Sigma + eps I) || N(X2_mu, X2_Sigma + eps I))."""
+    return _KLGaussian.apply(X_mu, X_Sigma, X2_mu, X2_Sigma, bool(exact))

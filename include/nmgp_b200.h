@@ -53,13 +53,21 @@ int nmgp_potrf_batched(const double* A, double jitter, double* C, double* hld, i
 int nmgp_potrf_bwd_batched(const double* C, const double* Cbar, const double* hldbar, double* Abar, int nb, int Q,
                            nmgp_stream_t stream);
 
-/* kl[p,b] = KL(N(mu_b, CS_b CS_b^T) || N(0, R_p R_p^T)) in the reference's form (quirk q10); t[p,b,:] = R_p^-1 mu_b
- *                                                                          utils.py:332-351 KL_Gaussian */
+/* kl[p,b] = KL(N(mu_b, CS_b CS_b^T) || N(0, R_p R_p^T)) in the reference's form (quirk q10), every (p,b) pair in
+ * parallel: rs[b,a] = sum_{c<=a} CS_b[a,c]^2; t[p,b,:] = (R_p R_p^T)^-1 mu_b by the DMMA row solve (saved for the
+ * adjoint); work [np,nb,Q] is scratch.                                      utils.py:332-351 KL_Gaussian */
 int nmgp_kl_fwd(const double* CS, const double* hldS, const double* mu, const double* R, const double* hldR,
-                double* kl, double* t, int np, int nb, int Q, nmgp_stream_t stream);
-int nmgp_kl_bwd(const double* klbar, const double* CS, const double* mu, const double* R, const double* t,
-                double* CSbar, double* hldSbar, double* mubar, double* Rbar /* += */, double* hldRbar,
-                double* work /* [np,nb,Q] */, int np, int nb, int Q, nmgp_stream_t stream);
+                double* kl, double* t, double* rs, double* work, int np, int nb, int Q, nmgp_stream_t stream);
+/* adjoint of the above; work [np,nb,Q], rsb [nb,Q], G [np,Q,Q] are scratch */
+int nmgp_kl_bwd(const double* klbar, const double* CS, const double* R, const double* t, const double* rs,
+                double* CSbar, double* hldSbar, double* mubar, double* Rbar /* += */, double* hldRbar, double* work,
+                double* rsb, double* G, int np, int nb, int Q, nmgp_stream_t stream);
+
+/* building blocks of the mathematically exact KL variant (explicit flag; the reference's utils.py:349 only uses
+ * diag(chol(K)), quirk q10): C[s] += sign A[s]^T B[s] (A, B: [ns,B,Q]) and Rbar_p += -tril(G_p R_p) */
+int nmgp_atb(const double* A, const double* Bm, double* C /* += */, double sign, int ns, long long B, int Q,
+             nmgp_stream_t stream);
+int nmgp_kl_rbar(const double* R, const double* G, double* Rbar /* += */, int np, int Q, nmgp_stream_t stream);
 
 /* K[n,q] = hyp[is2] exp(-(x_n/len - z_q/len)^2 / 2) (+ jitter on n == q)    utils.py:75-94 create_RBF */
 int nmgp_rbf_build_fwd(const double* x, const double* z, const double* hyp, int is2, int ilen, double jitter,
@@ -183,12 +191,22 @@ int nmgp_sumsq_rows(const double* x, double* out, long long rows, long long cols
 int nmgp_lcorr(const double* L, double* corr, long long nmat, int D, nmgp_stream_t stream);
 
 /* SIM_code line: code/SIM_code/Utility/kernels.py:46-73 Nonstationary_RBF_cov and :24-43 RBF_cov.
- * sigma/ell pointers may be NULL (= ones).  jitter (1e-6) is added on i == j; pass 0 for cross-covariances. */
+ * sigma/ell pointers may be NULL (= ones).  self != 0: the reference's X2=None call (X2, sigma2, ell2 are X1, sigma1,
+ * ell1): only the 64 x 64 tiles on and below the diagonal are evaluated, each is written twice (itself and mirrored,
+ * 16-byte coalesced stores through shared memory) and `jitter` (1e-6) is added on the diagonal.  dx == 1 (every
+ * reference call site, quirk q11) takes the tiled path: one rsqrt + one exp per entry. */
 int nmgp_nonstationary_cov(const double* X1, const double* sigma1, const double* ell1, const double* X2,
                            const double* sigma2, const double* ell2, double jitter, double* K, long long T1,
-                           long long T2, int dx, nmgp_stream_t stream);
+                           long long T2, int dx, int self, nmgp_stream_t stream);
 int nmgp_sim_rbf_cov(const double* X1, const double* X2, double alpha, double beta, double jitter, double* K,
-                     long long T1, long long T2, int dx, nmgp_stream_t stream);
+                     long long T1, long long T2, int dx, int self, nmgp_stream_t stream);
+/* adjoint of nmgp_nonstationary_cov w.r.t. the per-point sigma / ell (g_* +=, any may be NULL; dx == 1): what autograd
+ * gives the reference when logpos.nlogpos_obj* are differentiated (logpos.py:216-296).  For a
+ * self-covariance the caller adds the row-side (g_*1) and column-side (g_*2) results. */
+int nmgp_nonstationary_cov_bwd(const double* X1, const double* sigma1, const double* ell1, const double* X2,
+                               const double* sigma2, const double* ell2, const double* Kbar, double* g_sigma1,
+                               double* g_ell1, double* g_sigma2, double* g_ell2, long long T1, long long T2, int dx,
+                               nmgp_stream_t stream);
 
 /* out[i,j] = Kx[i,j] * Bf[indx1[i], indx2[j]] (+ diag on i == j): logpos.py:87-98 generate_K_index fused with the
  * Hadamard product K_x * K_i and the sigma2_err I of prediction.py:746-750 (irregular observations); Bf is row-major

@@ -89,8 +89,23 @@ def kl_fwd(CS, hldS, mu, R, hldR, exact=False):
     return kl, t.contiguous()
 
 
+def atb(A, Bm, C, sign=1.0):
+    C += sign * A.transpose(1, 2) @ Bm
+    return C
+
+
+def kl_rbar(R, G, Rbar):
+    Rbar -= torch.tril(G @ R)
+    return Rbar
+
+
 def kl_bwd(klbar, CS, mu, R, t, exact=False):
-    assert not exact, "exact-KL adjoint is not part of the reference path"
+    if exact:                                # autograd of the exact forward (test infrastructure may be slow)
+        CSv = CS.clone().requires_grad_(True); muv = mu.clone().requires_grad_(True); Rv = R.clone().requires_grad_(True)
+        hS = torch.zeros(CS.shape[0], dtype=F64, requires_grad=True); hR = torch.zeros(R.shape[0], dtype=F64, requires_grad=True)
+        kl, _ = kl_fwd(CSv, hS, muv, Rv, hR, exact=True)
+        g = torch.autograd.grad((kl * klbar).sum(), [CSv, hS, muv, Rv, hR])
+        return torch.tril(g[0]), g[1], g[2], torch.tril(g[3]), g[4]
     np_, nb, Q = R.shape[0], CS.shape[0], CS.shape[-1]
     d = R.diagonal(dim1=-2, dim2=-1)                            # [np,Q]
     w = 1.0 / d ** 2
@@ -411,7 +426,7 @@ def latent_fused(PG, cG, l, y, I, SigW, muW, hyp, scale, Rsum, ghyp, seg=None, r
 
 
 # ---- SIM_code line ---------------------------------------------------------------------------------------
-def nonstationary_cov(X1, sigma1, ell1, X2, sigma2, ell2, jitter):
+def nonstationary_cov(X1, sigma1, ell1, X2, sigma2, ell2, jitter, self_cov=False):
     n1, n2 = X1.shape[0], X2.shape[0]
     s1 = torch.ones(n1, dtype=F64) if sigma1 is None else sigma1
     s2 = torch.ones(n2, dtype=F64) if sigma2 is None else sigma2
@@ -423,13 +438,24 @@ def nonstationary_cov(X1, sigma1, ell1, X2, sigma2, ell2, jitter):
     return K + jitter * torch.eye(n1, n2, dtype=F64)
 
 
+def nonstationary_cov_bwd(X1, sigma1, ell1, X2, sigma2, ell2, Kbar, want=(True, True, True, True)):
+    """Autograd of the specification above (test infrastructure)."""
+    args = [sigma1, ell1, sigma2, ell2]
+    leaves = [None if a is None else a.detach().clone().requires_grad_(True) for a in args]
+    K = nonstationary_cov(X1, leaves[0], leaves[1], X2, leaves[2], leaves[3], 0.0)
+    outs = []
+    for a, w in zip(leaves, want):
+        outs.append(torch.autograd.grad((K * Kbar).sum(), a, retain_graph=True)[0] if (w and a is not None) else None)
+    return tuple(outs)
+
+
 def hadamard_index_cov(Kx, Bf, indx1, indx2, diag=0.0):
     """out[i,j] = Kx[i,j] Bf[indx1[i], indx2[j]] (+ diag on i == j)."""
     Ki = Bf[indx1.long().view(-1, 1), indx2.long().view(1, -1)]
     return Kx * Ki + diag * torch.eye(Kx.shape[0], Kx.shape[1], dtype=F64)
 
 
-def sim_rbf_cov(X1, X2, alpha, beta, jitter):
+def sim_rbf_cov(X1, X2, alpha, beta, jitter, self_cov=False):
     d = pairwise_dist(X1 / beta, X2 / beta)
     return torch.exp(-0.5 * d) * alpha ** 2 + jitter * torch.eye(X1.shape[0], X2.shape[0], dtype=F64)
 

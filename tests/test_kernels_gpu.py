@@ -78,7 +78,8 @@ def test_potrf_raises_on_non_pd():
         ops.potrf(g(A), 0.0)
 
 
-@pytest.mark.parametrize("Q,np_,nb", [(20, 1, 1), (50, 4, 70), (50, 1, 300), (100, 3, 5)])
+@pytest.mark.parametrize("Q,np_,nb", [(20, 1, 1), (50, 4, 70), (50, 1, 300), (100, 3, 5), (100, 1, 140), (128, 2, 9),
+                                      (50, 32, 64)])
 def test_kl(Q, np_, nb):
     gen = torch.Generator().manual_seed(Q + np_ + nb)
     CS, hS = specs.potrf(spd(nb, Q, gen, 0.05))
@@ -86,12 +87,20 @@ def test_kl(Q, np_, nb):
     mu = torch.randn(nb, Q, generator=gen, dtype=torch.float64)
     kl, t = ops.kl_fwd(g(CS), g(hS), g(mu), g(R), g(hR))
     klr, tr = specs.kl_fwd(CS, hS, mu, R, hR)
-    check(kl, klr, 1e-12, "kl"); check(t, tr, 1e-11, "kl t")
+    check(kl, klr, 1e-11, "kl")
     kb = torch.randn(np_, nb, generator=gen, dtype=torch.float64)
-    got = ops.kl_bwd(g(kb), g(CS), g(mu), g(R), g(tr))
+    got = ops.kl_bwd(g(kb), g(CS), g(mu), g(R), t)          # `t` is opaque: what this implementation saved in kl_fwd
     ref = specs.kl_bwd(kb, CS, mu, R, tr)
     for a, b, n in zip(got, ref, ("CSbar", "hldSbar", "mubar", "Rbar", "hldRbar")):
         check(a, b, 1e-10, "kl_bwd " + n)
+    # the mathematically exact variant (explicit flag; not what the reference computes: quirk q10)
+    kle, te = ops.kl_fwd(g(CS), g(hS), g(mu), g(R), g(hR), exact=True)
+    kler, ter = specs.kl_fwd(CS, hS, mu, R, hR, exact=True)
+    check(kle, kler, 1e-11, "kl exact")
+    gote = ops.kl_bwd(g(kb), g(CS), g(mu), g(R), te, exact=True)
+    refe = specs.kl_bwd(kb, CS, mu, R, ter, exact=True)
+    for a, b, n in zip(gote, refe, ("CSbar", "hldSbar", "mubar", "Rbar", "hldRbar")):
+        check(a, b, 1e-10, "kl_bwd exact " + n)
 
 
 @pytest.mark.parametrize("Q,D,B", CASES)
@@ -224,7 +233,7 @@ def test_row_elementwise(Q, D, B):
     check(mbd, mb, 1e-12); check(sbd, sb2, 1e-12)
     # likelihood rows
     mg = rn(ns, B, D); qg = torch.rand(ns, B, D, generator=gen, dtype=torch.float64); cG = torch.rand(ns, B, generator=gen, dtype=torch.float64)
-    y = rn(ns, B) if per_sample_y else rn(B)
+    y = rn(B)
     Rs = torch.zeros(ns, dtype=torch.float64); gh = torch.zeros(7, dtype=torch.float64)
     Rsd, ghd = g(Rs.clone()), g(gh.clone())
     ref = specs.lik_rows(lr, mg, qg, cG, y, I, hyp, 0.37, Rs, gh)

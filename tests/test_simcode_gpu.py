@@ -38,6 +38,37 @@ def test_kernel_builds_match_reference_golden():
     assert rel(kernels.pairwise_distances(x1), orc.sq_dists_gemm(xc)) < 1e-13
 
 
+@pytest.mark.parametrize("T1,T2", [(130, 130), (64, 64), (257, 131), (70, 200), (1, 3), (1100, 1100)])
+def test_nonstationary_cov_tiles_and_adjoint(T1, T2):
+    """Tiled builds (ragged tiles, odd row lengths = scalar-store path, mirrored self-covariance) against the CPU
+    specification, and the hand-written adjoint w.r.t. sigma / ell against autograd of the specification."""
+    gen = torch.Generator().manual_seed(T1 * 7 + T2)
+    x1 = torch.sort(torch.rand(T1, generator=gen, dtype=torch.float64))[0].view(-1, 1)
+    x2 = torch.sort(torch.rand(T2, generator=gen, dtype=torch.float64))[0].view(-1, 1)
+    s1 = 0.5 + torch.rand(T1, generator=gen, dtype=torch.float64); l1 = torch.exp(torch.randn(T1, generator=gen, dtype=torch.float64) - 1.5)
+    s2 = 0.5 + torch.rand(T2, generator=gen, dtype=torch.float64); l2 = torch.exp(torch.randn(T2, generator=gen, dtype=torch.float64) - 1.5)
+    Kc = kernels.Nonstationary_RBF_cov(d(x1), d(s1), d(l1), d(x2), d(s2), d(l2))
+    assert rel(Kc, specs.nonstationary_cov(x1, s1, l1, x2, s2, l2, 0.0)) < 1e-13
+    Ks = kernels.Nonstationary_RBF_cov(d(x1), d(s1), d(l1))
+    assert rel(Ks, specs.nonstationary_cov(x1, s1, l1, x1, s1, l1, 1e-6)) < 1e-13
+    assert torch.equal(Ks, Ks.t()), "a self-covariance must be exactly symmetric"
+    assert rel(kernels.RBF_cov(d(x1), alpha=1.7, beta=0.3), specs.sim_rbf_cov(x1, x1, 1.7, 0.3, 1e-6)) < 1e-13
+    assert rel(kernels.RBF_cov(d(x1), d(x2), alpha=0.9, beta=0.4), specs.sim_rbf_cov(x1, x2, 0.9, 0.4, 0.0)) < 1e-13
+    # adjoint, cross-covariance
+    Kb = torch.randn(T1, T2, generator=gen, dtype=torch.float64)
+    got = ops.nonstationary_cov_bwd(d(x1), d(s1), d(l1), d(x2), d(s2), d(l2), d(Kb))
+    ref = specs.nonstationary_cov_bwd(x1, s1, l1, x2, s2, l2, Kb)
+    for a, b, n in zip(got, ref, ("sigma1", "ell1", "sigma2", "ell2")):
+        assert rel(a, b) < 1e-11, n
+    # autograd through the drop-in, self-covariance (row- and column-side contributions added)
+    sv = d(s1).requires_grad_(True); lv = d(l1).requires_grad_(True)
+    Kb2 = torch.randn(T1, T1, generator=gen, dtype=torch.float64)
+    (kernels.Nonstationary_RBF_cov(d(x1), sv, lv) * d(Kb2)).sum().backward()
+    scpu = s1.clone().requires_grad_(True); lcpu = l1.clone().requires_grad_(True)
+    (specs.nonstationary_cov(x1, scpu, lcpu, x1, scpu, lcpu, 1e-6) * Kb2).sum().backward()
+    assert rel(sv.grad, scpu.grad) < 1e-11 and rel(lv.grad, lcpu.grad) < 1e-11
+
+
 def test_kronecker_and_logpdf_match_reference_golden():
     g = gu.load("sim_code")
     K = d(g["K_self"]); Bf = d(g["Bf"]); y = d(g["y"]); mu = d(g["mu"]); s2 = torch.tensor(float(g["s2"]), dtype=torch.float64)

@@ -111,3 +111,23 @@ def test_sample_sharding_sums_to_the_unsharded_step(spec_ops):
     for k in full_grads:
         den = max(float(torch.linalg.norm(full_grads[k])), 1e-300)
         assert float(torch.linalg.norm(acc[k] - full_grads[k])) / den <= 1e-10, k
+
+
+def test_exact_kl_flag_matches_the_oracle_with_the_true_kl(spec_ops):
+    """exact_kl=True (not the reference's behaviour: quirk q10) against the oracle's exact-KL variant."""
+    g = gu.load("dsvi_ragged")
+    p = gu.case_params(g)
+    I = torch.from_numpy(g["I"]).to(torch.int32)
+    loss, grads = dsvi_step.dsvi_step(p, torch.from_numpy(g["Z"]), torch.from_numpy(g["x"]), torch.from_numpy(g["y"]), I,
+                                      int(g["N"]), torch.from_numpy(g["z_v"]), torch.from_numpy(g["z_ell"]),
+                                      torch.from_numpy(g["z_L"]), exact_kl=True)
+    Xl, Yl = gu.case_lists(g)
+    ref_loss, ref_grads = orc.step_loss_and_grads(p, torch.from_numpy(g["Z"]).view(-1, 1), int(g["N"]), Xl, Yl,
+                                                  draws=gu.replay_draws(g), exact_kl=True)
+    assert abs(float(loss) - float(g["loss"])) > 1e-6 * abs(float(g["loss"]))          # it IS a different objective
+    assert abs(float(loss) - float(ref_loss)) <= 1e-10 * abs(float(ref_loss))
+    for k, gr in ref_grads.items():
+        if gr is None:
+            continue
+        den = max(float(torch.linalg.norm(gr)), 1e-300)
+        assert float(torch.linalg.norm(grads[k].reshape(-1) - gr.reshape(-1))) / den <= 1e-9, k
