@@ -411,7 +411,8 @@ class Problem:
 
     def step_e2e(self):
         self.opt.zero_grad(set_to_none=True)
-        loss = self.model(self.Xh, self.Yh, n_mc=self.n_mc, noise="device", row_gid=self.gid)   # host lists -> H2D inside
+        loss = self.model(self.Xh, self.Yh, n_mc=self.n_mc, noise="device", row_gid=self.gid,
+                          subjects=self.subj is not None)                      # host lists -> H2D inside
         loss.backward()
         tot = self.parallel.allreduce_loss_and_grads(loss, self.params, pd_info=self.model._last_pd_info, check="defer")
         self.opt.step()

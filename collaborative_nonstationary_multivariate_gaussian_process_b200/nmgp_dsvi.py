@@ -20,7 +20,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 from torch.nn import Parameter
-from torch.utils.data import DataLoader, Dataset
+from torch.utils.data import Dataset
 
 from . import _ops as ops
 from . import dsvi_step as _step
@@ -46,14 +46,20 @@ class trainData(Dataset):
         return len(self.X_data)
 
 
-def _rows_from_lists(inputs_list, outputs_list, D, index=None):
+def _rows_from_lists(inputs_list, outputs_list, D, index=None, subjects=False):
     """Concatenate per-output lists into (x, y, I) sorted by output id (stable); also returns the
-    permutation applied so callers can restore the caller's row order."""
+    permutation applied so callers can restore the caller's row order.  ``subjects``: outputs_list[d] is [S, T_d]
+    (S subjects observed on the same inputs) and y comes back as [S, B]."""
     ids = list(range(D)) if index is None else list(index)
     sizes = [int(x.shape[0]) for x in inputs_list]
     I = np.repeat(np.asarray(ids[:len(sizes)], dtype=np.int64), sizes)
     x = torch.cat([t.reshape(-1) for t in inputs_list]) if len(inputs_list) else torch.empty(0, dtype=F64)
-    y = None if outputs_list is None else torch.cat([t.reshape(-1) for t in outputs_list])
+    if outputs_list is None:
+        y = None
+    elif subjects:
+        y = torch.cat([t.reshape(t.shape[0], -1) for t in outputs_list], dim=1)
+    else:
+        y = torch.cat([t.reshape(-1) for t in outputs_list])
     if I.size and np.any(np.diff(I) < 0):
         perm = np.argsort(I, kind="stable")
     else:
@@ -190,13 +196,18 @@ class NMGP(torch.nn.Module):
 
     # -- the hot path -----------------------------------------------------------------------------
     def forward(self, inputs_list, outputs_list, index=None, verbose=False, n_mc=1, noise=None, explicit_noise=None,
-                row_gid=None):
-        """-SELBO of one minibatch (code/nmgp_dsvi.py:157-301)."""
+                row_gid=None, subjects=False):
+        """-SELBO of one minibatch (code/nmgp_dsvi.py:157-301).  ``subjects=True`` (not in the reference):
+        outputs_list[d] is [S, T_d] -- S subjects observed on the same inputs; the result is the mean over the subjects
+        of the reference's one-draw forward on each subject's targets (n_mc must equal S)."""
         t1 = time.time() if verbose else None
-        x, y, I, perm = _rows_from_lists(inputs_list, outputs_list, self.D, index)
+        x, y, I, perm = _rows_from_lists(inputs_list, outputs_list, self.D, index, subjects)
         B = x.shape[0]
+        if subjects and y.shape[0] != n_mc:
+            raise ValueError("subjects=True needs n_mc == number of subjects (%d != %d)" % (n_mc, y.shape[0]))
         if perm is not None:
-            x, y, I = x[torch.from_numpy(perm).to(x.device)], y[torch.from_numpy(perm).to(y.device)], I[perm]
+            pt = torch.from_numpy(perm)
+            x, y, I = x[pt.to(x.device)], (y[:, pt.to(y.device)] if subjects else y[pt.to(y.device)]), I[perm]
         noise = noise or self.noise
         dev = self.device
         kw = dict(self.step_options)
@@ -276,100 +287,173 @@ def vec2list(X, Y, I, dim, device=None):
     return X_list, Y_list
 
 
-def inference(X_train_list, Y_train_list, z, batch_size, dim_outputs, hyperpars=None, fix_hyperpars=True, mu_v=None,
-              mu_W=None, mu_U=None, sqrt_v=None, sqrt_W=None, sqrt_U=None, lr=0.01, itnum=1000,
-              do_stop_criterion=False, seed=22, verbose=False, PATH="model.pt", continuous_training=False,
-              show_ELBO=True, save_model=False, X_test_list=None, Y_test_list=None, n_mc=1, noise="reference",
-              device=None):
-    """code/nmgp_dsvi.py:758-909, same arguments/returns (+ n_mc, noise, device).  Quirks kept: q3 (the
-    'sigma2_L1_log' override lands in sigma2_L0_log, :784-785) and q4 (hyperpars=None with fix_hyperpars=True
-    raises TypeError, :809)."""
-    X_train_vec = np.concatenate(X_train_list)
-    Y_train_vec = np.concatenate(Y_train_list)
-    train_index = np.concatenate([np.ones_like(Y_train_list[i]) * i for i in range(dim_outputs)]).astype(int)
-    X = torch.from_numpy(X_train_vec).type(TensorType)
-    Y = torch.from_numpy(Y_train_vec).type(TensorType)
-    I = torch.from_numpy(train_index).type(TensorType)
-    dev = default_device() if device is None else torch.device(device)
-    Z = torch.from_numpy(np.asarray(z)).type(TensorType).unsqueeze(1)
-    X_list, Y_list = vec2list(X, Y, I, dim=dim_outputs)
+class DeviceMinibatches:
+    """Shuffled minibatches gathered ON THE DEVICE (replaces the reference's CPU ``DataLoader(trainData, shuffle=True)`` +
+    ``vec2list`` regrouping, code/nmgp_dsvi.py:816-837, SURVEY 8f-4): the flattened training rows are uploaded once;
+    per epoch only a permutation is drawn and per batch only an index vector crosses PCIe, the rows are gathered by
+    ``index_select`` on the GPU already grouped by output (the order ``vec2list`` produces).
 
-    model = NMGP(number_observations=Y_train_vec.shape[0], dim_outputs=dim_outputs, Z=Z, minibatch_size=batch_size,
-                 mu_v=mu_v, mu_W=mu_W, mu_U=mu_U, sqrt_v=sqrt_v, sqrt_W=sqrt_W, sqrt_U=sqrt_U, seed=seed, device=dev,
-                 noise=noise)
-    optimizer = torch.optim.Adam(model.parameters(), lr=lr)
+    ``order="reference"``: the permutation is drawn exactly as the reference's loader draws it -- from the global CPU
+    generator, one base-seed draw for the loader iterator and one seed for the sampler's private generator -- so a
+    seeded run sees the reference's batches and, with ``noise="reference"``, reproduces its loss trace (quirk q9).
+    ``order="device"``: ``torch.randperm`` on the GPU from a private device generator; nothing is drawn on the host."""
 
+    def __init__(self, X, Y, I, dim_outputs, batch_size, device, order="reference", seed=0):
+        self.n = int(X.shape[0])
+        self.bs = int(batch_size)
+        self.D = int(dim_outputs)
+        self.dev = torch.device(device)
+        self.order = order
+        self.I_host = np.asarray(I).reshape(-1).astype(np.int64)
+        self.X = torch.as_tensor(X, dtype=F64).reshape(-1).to(self.dev)
+        self.Y = torch.as_tensor(Y, dtype=F64).reshape(-1).to(self.dev)
+        self.I = torch.from_numpy(self.I_host.astype(np.int32)).to(self.dev)
+        if order == "device":
+            self.gen = torch.Generator(device=self.dev)
+            self.gen.manual_seed(int(seed))
+        elif order != "reference":
+            raise ValueError("order must be 'reference' or 'device'")
+
+    def __len__(self):
+        return (self.n + self.bs - 1) // self.bs
+
+    @staticmethod
+    def loader_permutation(n):
+        """The permutation ``DataLoader(dataset, shuffle=True)`` would use for its next epoch, consuming the global CPU
+        generator in the same way (checked against the real DataLoader in tests/test_api_hostlogic_cpu.py)."""
+        torch.empty((), dtype=torch.int64).random_()                       # base seed of the loader's iterator
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())     # seed of the RandomSampler's generator
+        g = torch.Generator()
+        g.manual_seed(seed)
+        return torch.randperm(n, generator=g)
+
+    def epoch(self):
+        """Yields (x, y, I_sorted [int32, device], I_sorted_host or None) per batch, rows grouped by output (stable)."""
+        if self.order == "reference":
+            perm = self.loader_permutation(self.n).numpy()
+            for k in range(0, self.n, self.bs):
+                idx = perm[k:k + self.bs]
+                Ib = self.I_host[idx]
+                grp = np.argsort(Ib, kind="stable")
+                rows = torch.from_numpy(idx[grp]).to(self.dev, non_blocking=True)
+                yield self.X.index_select(0, rows), self.Y.index_select(0, rows), self.I.index_select(0, rows), Ib[grp]
+        else:
+            perm = torch.randperm(self.n, device=self.dev, generator=self.gen)
+            for k in range(0, self.n, self.bs):
+                idx = perm[k:k + self.bs]
+                Ib = self.I.index_select(0, idx)
+                grp = torch.sort(Ib, stable=True)[1]
+                rows = idx.index_select(0, grp)
+                yield self.X.index_select(0, rows), self.Y.index_select(0, rows), Ib.index_select(0, grp), None
+
+
+def _apply_hyperpars(model, hyperpars, fix_hyperpars):
+    """code/nmgp_dsvi.py:779-814 with its quirks: q3 ('sigma2_L1_log' is written into sigma2_L0_log, :784-785) and q4
+    (hyperpars=None with fix_hyperpars=True raises TypeError at the membership test, :809)."""
+    targets = {"sigma2_tildeell_log": "sigma2_tildeell_log", "sigma2_L0_log": "sigma2_L0_log",
+               "sigma2_L1_log": "sigma2_L0_log", "sigma2_err_log": "sigma2_err_log"}
     if hyperpars is not None:
-        if "sigma2_tildeell_log" in hyperpars:
-            model.sigma2_tildeell_log.data.fill_(hyperpars['sigma2_tildeell_log'])
-        if "sigma2_L0_log" in hyperpars:
-            model.sigma2_L0_log.data.fill_(hyperpars['sigma2_L0_log'])
-        if "sigma2_L1_log" in hyperpars:
-            model.sigma2_L0_log.data.fill_(hyperpars['sigma2_L1_log'])       # quirk q3, kept
-        if "sigma2_err_log" in hyperpars:
-            model.sigma2_err_log.data.fill_(hyperpars['sigma2_err_log'])
-
-    def freeze_lengthscales():
+        for key, dest in targets.items():                                   # dict order = the reference's statement order
+            if key in hyperpars:
+                getattr(model, dest).data.fill_(hyperpars[key])
+    if fix_hyperpars:
         for name in ("length_scales_tildeell_log", "length_scales_L0_log", "length_scales_L1_log"):
             getattr(model, name).requires_grad = False
             if name in hyperpars:                                           # TypeError when hyperpars is None (q4)
                 getattr(model, name).data.fill_(hyperpars[name])
 
-    if continuous_training:
+
+def inference(X_train_list, Y_train_list, z, batch_size, dim_outputs, hyperpars=None, fix_hyperpars=True, mu_v=None,
+              mu_W=None, mu_U=None, sqrt_v=None, sqrt_W=None, sqrt_U=None, lr=0.01, itnum=1000,
+              do_stop_criterion=False, seed=22, verbose=False, PATH="model.pt", continuous_training=False,
+              show_ELBO=True, save_model=False, X_test_list=None, Y_test_list=None, n_mc=1, noise="reference",
+              device=None, batch_order=None):
+    """Drop-in for code/nmgp_dsvi.py:758-909: same arguments and returns (+ n_mc, noise, device, batch_order).
+    The training rows live on the GPU and the shuffled minibatches are gathered there (``DeviceMinibatches``);
+    ``batch_order`` defaults to "reference" when ``noise == "reference"`` (seeded runs then reproduce the reference's
+    batches and loss trace) and to "device" otherwise."""
+    dev = default_device() if device is None else torch.device(device)
+    X_all = np.concatenate(X_train_list).reshape(-1)
+    Y_all = np.concatenate(Y_train_list).reshape(-1)
+    I_all = np.concatenate([np.full(len(Y_train_list[d]), d, dtype=np.int64) for d in range(dim_outputs)])
+    n_train = int(Y_all.shape[0])
+    Z = torch.from_numpy(np.asarray(z)).type(TensorType).unsqueeze(1)
+
+    model = NMGP(number_observations=n_train, dim_outputs=dim_outputs, Z=Z, minibatch_size=batch_size,
+                 mu_v=mu_v, mu_W=mu_W, mu_U=mu_U, sqrt_v=sqrt_v, sqrt_W=sqrt_W, sqrt_U=sqrt_U, seed=seed, device=dev,
+                 noise=noise)
+    optimizer = torch.optim.Adam(model.parameters(), lr=lr)
+    if continuous_training:                        # the reference overrides, then restores the checkpoint, then freezes
+        _apply_hyperpars(model, hyperpars, False)
         checkpoint = torch.load(PATH, map_location=dev, weights_only=False)
         model.load_state_dict(checkpoint["model_state_dict"])
         optimizer.load_state_dict(checkpoint["optimizer_state_dict"])
         if fix_hyperpars:
-            freeze_lengthscales()
-    elif fix_hyperpars:
-        freeze_lengthscales()
+            only_len = None if hyperpars is None else {k: v for k, v in hyperpars.items() if k.startswith("length_scales")}
+            _apply_hyperpars(model, only_len, True)
+    else:
+        _apply_hyperpars(model, hyperpars, fix_hyperpars)
 
-    train_loader = DataLoader(trainData(X, Y, I), batch_size=batch_size, shuffle=True)
-    loss_list, time_list = [], []
-    if X_test_list is not None:
-        rmse_test_list = []
-        Y_test_vec = np.concatenate(Y_test_list)
-    ts = time.time()
-    epoch = -1
-    loss = None
-    for epoch in range(itnum):
-        batch = 0
-        for X_batch, Y_batch, I_batch in train_loader:
-            batch += 1
-            optimizer.zero_grad()
-            X_batch_list, Y_batch_list = vec2list(X_batch, Y_batch, I_batch, dim=dim_outputs)
-            loss = model(X_batch_list, Y_batch_list, verbose=verbose, n_mc=n_mc)
-            loss.backward()
-            optimizer.step()
-            loss_value = loss.detach().data.cpu().numpy()
-            loss_list.append(loss_value)
-            time_list.append(time.time() - ts)
-            if X_test_list is not None:
-                est_Y_test = predict_Y(model, X_test_list)
-                rmse_test_list.append(np.sqrt(np.mean((est_Y_test[:, None] - Y_test_vec) ** 2)))
-            if verbose:
-                print("epoch: {}/{}, batch: {}/{}, loss: {}".format(epoch, itnum, batch,
-                                                                    X_train_vec.shape[0] / batch_size, loss_value))
-        if do_stop_criterion:
-            if epoch % 5 == 4 and epoch > 5:
-                loss_array = np.array(loss_list)
-                if np.sum(loss_array[-batch:]) > np.sum(loss_array[-batch * 6:-batch * 5]):
+    batches = DeviceMinibatches(X_all, Y_all, I_all, dim_outputs, batch_size, dev,
+                                order=batch_order or ("reference" if noise == "reference" else "device"), seed=seed)
+    full_lists = None
+    loss_list, time_list, rmse_test_list = [], [], []
+    Y_test_vec = np.concatenate(Y_test_list) if X_test_list is not None else None
+    steps_per_epoch = len(batches)
+    t_start = time.time()
+    epoch, loss = -1, None
+    with torch.cuda.device(dev) if dev.type == "cuda" else _nullcontext():
+        for epoch in range(itnum):
+            for step, (xb, yb, Ib, Ib_host) in enumerate(batches.epoch(), start=1):
+                optimizer.zero_grad()
+                if noise == "reference":
+                    explicit = tuple(t.to(dev) for t in model._reference_noise(int(xb.shape[0]), Ib_host, None, n_mc))
+                    loss = model.forward_rows(xb, yb, Ib, n_mc=n_mc, explicit_noise=explicit)
+                else:
+                    loss = model.forward_rows(xb, yb, Ib, n_mc=n_mc)
+                loss.backward()
+                optimizer.step()
+                loss_value = loss.detach().data.cpu().numpy()
+                loss_list.append(loss_value)
+                time_list.append(time.time() - t_start)
+                if X_test_list is not None:
+                    est = predict_Y(model, X_test_list)
+                    rmse_test_list.append(np.sqrt(np.mean((est[:, None] - Y_test_vec) ** 2)))
+                if verbose:
+                    print("epoch: {}/{}, batch: {}/{}, loss: {}".format(epoch, itnum, step, n_train / batch_size, loss_value))
+            if do_stop_criterion and epoch % 5 == 4 and epoch > 5:
+                trace = np.array(loss_list)
+                if trace[-steps_per_epoch:].sum() > trace[-6 * steps_per_epoch:-5 * steps_per_epoch].sum():
                     print("Stop criteria is satisfied.")
                     break
-        if epoch % 100 == 99 and show_ELBO:
-            elbo = model.compute_ELBO(X_list, Y_list)
-            print("epoch: {}, ELBO: {}".format(epoch + 1, elbo.detach()))
-    print("training takes {}s".format(time.time() - ts))
+            if show_ELBO and epoch % 100 == 99:
+                full_lists = full_lists or _lists_by_output(X_all, Y_all, I_all, dim_outputs)
+                print("epoch: {}, ELBO: {}".format(epoch + 1, model.compute_ELBO(*full_lists).detach()))
+    print("training takes {}s".format(time.time() - t_start))
 
     if save_model:
         torch.save({'epoch': epoch, 'model_state_dict': model.state_dict(),
                     'optimizer_state_dict': optimizer.state_dict(), 'loss': loss}, PATH)
     if show_ELBO:
-        elbo = model.compute_ELBO(X_list, Y_list)
-        print("epoch: {}, ELBO: {}".format(epoch + 1, elbo.detach()))
+        full_lists = full_lists or _lists_by_output(X_all, Y_all, I_all, dim_outputs)
+        print("epoch: {}, ELBO: {}".format(epoch + 1, model.compute_ELBO(*full_lists).detach()))
     if X_test_list is not None:
         return model, loss_list, rmse_test_list, time_list
     return model, loss_list, time_list
+
+
+def _lists_by_output(X, Y, I, D):
+    Xt, Yt = torch.from_numpy(X).type(TensorType), torch.from_numpy(Y).type(TensorType)
+    return ([Xt[torch.from_numpy(I == d)].view(-1, 1) for d in range(D)],
+            [Yt[torch.from_numpy(I == d)].view(-1, 1) for d in range(D)])
+
+
+class _nullcontext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
 
 
 def sample_Y(model, X_list, n_sample=1000):

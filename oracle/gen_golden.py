@@ -82,7 +82,9 @@ HYPER_KEYS = ("sigma2_tildeell_log", "length_scales_tildeell_log", "sigma2_L0_lo
 
 
 def dsvi_case(nmgp_dsvi, name, X_list, Y_list, z, N, hyper, seed, init=None, train_len=False,
-              store_params=True, n_forward=1):
+              store_params=True, n_forward=1, Y_lists=None):
+    """Y_lists (one Y_list per forward): the forwards see different targets on the same inputs -- the subjects of an
+    HCP-shaped step; the recorded loss / gradients are those of the mean over the forwards."""
     D = len(X_list)
     Q = z.shape[0]
     T = torch.DoubleTensor
@@ -102,9 +104,11 @@ def dsvi_case(nmgp_dsvi, name, X_list, Y_list, z, N, hyper, seed, init=None, tra
     losses = []
     zs = []
     total = 0
+    Yls = None if Y_lists is None else [[torch.from_numpy(np.asarray(y)).type(T).view(-1, 1) for y in Yl_s]
+                                        for Yl_s in Y_lists]
     for s in range(n_forward):
         with Recorder() as rec:
-            loss = model(Xl, Yl)
+            loss = model(Xl, Yl if Yls is None else Yls[s])
         total = total + loss
         losses.append(float(loss.detach()))
         log = rec.log
@@ -123,6 +127,8 @@ def dsvi_case(nmgp_dsvi, name, X_list, Y_list, z, N, hyper, seed, init=None, tra
                loss=float((total / n_forward).detach()), losses=np.array(losses),
                z_v=np.stack([a for a, _, _ in zs]), z_ell=np.stack([b for _, b, _ in zs]),
                z_L=np.stack([c for _, _, c in zs]), store_params=int(store_params))
+    if Yls is not None:
+        out["ys"] = np.stack([torch.cat(Yl_s).view(-1).numpy() for Yl_s in Yls])
     for k, v in init.items():
         out["init_" + k] = np.asarray(v)
     sd = model.state_dict()

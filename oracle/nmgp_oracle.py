@@ -312,9 +312,11 @@ def neg_selbo(p: Dict[str, torch.Tensor], Z: torch.Tensor, N: int,
 
 
 def step_loss_and_grads(p, Z, N, inputs_list, outputs_list, index=None, draws: Sequence = (reference_draw,),
-                        exact_kl=False, train_lengthscales=False):
+                        exact_kl=False, train_lengthscales=False, outputs_lists=None):
     """S-sample estimate = mean of S consecutive reference forwards on unchanged
-    parameters, plus autograd gradients for the 13 parameters."""
+    parameters, plus autograd gradients for the 13 parameters.
+    ``outputs_lists`` (one outputs_list per draw): every forward sees its own targets -- the subjects of an HCP-shaped
+    step (BASELINE.json config 3)."""
     leaves = {}
     for k in PARAM_NAMES:
         t = p[k].detach().clone()
@@ -322,8 +324,9 @@ def step_loss_and_grads(p, Z, N, inputs_list, outputs_list, index=None, draws: S
         t.requires_grad_(train_lengthscales or not is_len)
         leaves[k] = t
     total = 0.0
-    for d in draws:
-        total = total + neg_selbo(leaves, Z, N, inputs_list, outputs_list, index, d, exact_kl)
+    for s_, d in enumerate(draws):
+        Yl_s = outputs_list if outputs_lists is None else outputs_lists[s_]
+        total = total + neg_selbo(leaves, Z, N, inputs_list, Yl_s, index, d, exact_kl)
     loss = total / len(draws)
     loss.backward()
     grads = {k: (leaves[k].grad.clone() if leaves[k].grad is not None else None) for k in PARAM_NAMES}

@@ -8,7 +8,8 @@ import torch
 from oracle import nmgp_oracle as orc
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-DSVI_CASES = ("dsvi_sim_low", "dsvi_sim_high", "dsvi_sim_varying", "dsvi_ragged", "dsvi_ecog_like", "dsvi_pm25_like")
+DSVI_CASES = ("dsvi_sim_low", "dsvi_sim_high", "dsvi_sim_varying", "dsvi_ragged", "dsvi_ecog_like", "dsvi_pm25_like",
+              "dsvi_hcp_like")
 
 
 def load(name):
@@ -39,6 +40,19 @@ def case_lists(g):
     Xl = [x[torch.from_numpy(I == d)].view(-1, 1) for d in range(D)]
     Yl = [y[torch.from_numpy(I == d)].view(-1, 1) for d in range(D)]
     return Xl, Yl
+
+
+def case_targets(g):
+    """y [B], or ys [S, B] when every forward of the case has its own targets (subjects, dsvi_hcp_like)."""
+    return g["ys"] if "ys" in g else g["y"]
+
+
+def case_target_lists(g):
+    """None, or one outputs_list per forward for the oracle (cases with per-forward targets)."""
+    if "ys" not in g:
+        return None
+    I = g["I"]; D = int(g["D"])
+    return [[torch.from_numpy(ys[I == d]).view(-1, 1) for d in range(D)] for ys in g["ys"]]
 
 
 def replay_draws(g):

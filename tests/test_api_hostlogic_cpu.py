@@ -39,3 +39,43 @@ def test_compute_elbo_replay():
 
 def test_posterior_sampling_replay():
     api_cases.posterior_sampling_replay("cpu")
+
+
+def test_device_minibatches_follow_the_reference_loader_order():
+    """DeviceMinibatches(order="reference") must see the batches DataLoader(shuffle=True) would produce and leave the
+    global CPU generator in the same state (quirk q9: the reference's loss trace depends on it)."""
+    import numpy as np
+    import torch
+    from torch.utils.data import DataLoader, TensorDataset
+    from collaborative_nonstationary_multivariate_gaussian_process_b200.nmgp_dsvi import DeviceMinibatches
+    n, bs, D = 23, 5, 3
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal(n); Y = rng.standard_normal(n); I = np.sort(rng.integers(0, D, n))
+    torch.manual_seed(5)
+    dl = DataLoader(TensorDataset(torch.arange(n)), batch_size=bs, shuffle=True)
+    want = []
+    for ep in range(2):
+        for (b,) in dl:
+            idx = b.numpy()
+            grp = np.argsort(I[idx], kind="stable")           # vec2list regrouping (code/nmgp_dsvi.py:745-755)
+            want.append((X[idx[grp]], I[idx[grp]]))
+        want.append(float(torch.randn(1)))
+    torch.manual_seed(5)
+    mb = DeviceMinibatches(X, Y, I, D, bs, "cpu", order="reference")
+    got = []
+    for ep in range(2):
+        for xb, yb, Ib, Ih in mb.epoch():
+            got.append((xb.numpy(), Ib.numpy().astype(np.int64)))
+            assert np.array_equal(Ih, Ib.numpy())
+        got.append(float(torch.randn(1)))
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        if isinstance(a, float):
+            assert a == b
+        else:
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # the device order covers every row exactly once per epoch, grouped by output
+    mb2 = DeviceMinibatches(X, Y, I, D, bs, "cpu", order="device", seed=3)
+    seen = np.concatenate([xb.numpy() for xb, _, Ib, _ in mb2.epoch()])
+    assert sorted(seen.tolist()) == sorted(X.tolist())
+    assert all(bool((Ib[1:] >= Ib[:-1]).all()) for _, _, Ib, _ in mb2.epoch())

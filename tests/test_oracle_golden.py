@@ -17,7 +17,8 @@ def test_dsvi_step_matches_reference(name):
     Xl, Yl = gu.case_lists(g)
     Z = torch.from_numpy(g["Z"]).view(-1, 1)
     loss, grads = orc.step_loss_and_grads(p, Z, int(g["N"]), Xl, Yl, draws=gu.replay_draws(g),
-                                          train_lengthscales=bool(int(g["train_len"])))
+                                          train_lengthscales=bool(int(g["train_len"])),
+                                          outputs_lists=gu.case_target_lists(g))
     assert abs(float(loss) - float(g["loss"])) <= RTOL * abs(float(g["loss"]))
     for k in orc.PARAM_NAMES:
         if grads[k] is None:

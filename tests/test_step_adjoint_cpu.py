@@ -32,7 +32,7 @@ def run_step(g, sample_chunk=None):
     p = gu.case_params(g)
     I = torch.from_numpy(g["I"]).to(torch.int32)
     loss, grads = dsvi_step.dsvi_step(
-        p, torch.from_numpy(g["Z"]), torch.from_numpy(g["x"]), torch.from_numpy(g["y"]), I, int(g["N"]),
+        p, torch.from_numpy(g["Z"]), torch.from_numpy(g["x"]), torch.from_numpy(gu.case_targets(g)), I, int(g["N"]),
         torch.from_numpy(g["z_v"]), torch.from_numpy(g["z_ell"]), torch.from_numpy(g["z_L"]),
         sample_chunk=sample_chunk)
     return loss, grads
