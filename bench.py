@@ -360,7 +360,7 @@ def ncu_traffic(kernel_prefix):
 class Problem:
     """Model, optimiser and device/host copies of one rank's share of a DSVI workload."""
 
-    def __init__(self, w, rank, world, dev, noise="device"):
+    def __init__(self, w, rank, world, dev, noise="device", graph=True):
         from collaborative_nonstationary_multivariate_gaussian_process_b200 import nmgp_dsvi, parallel
         self.w, self.rank, self.world, self.dev = w, rank, world, dev
         T, D, Q, S = w["T"], w["D"], w["Q"], w["S"]
@@ -373,7 +373,7 @@ class Problem:
         for k in ("length_scales_tildeell_log", "length_scales_L0_log", "length_scales_L1_log"):
             getattr(model, k).requires_grad = False                   # fix_hyperpars=True, the drivers' setting
         self.model = model
-        self.opt = torch.optim.Adam(model.parameters(), lr=w["lr"])
+        self.opt = torch.optim.Adam(model.parameters(), lr=w["lr"], capturable=bool(graph))
         self.params = list(model.parameters())
         counts = [int(k.shape[0]) for k in keep]
         Btot = int(sum(counts))
@@ -400,8 +400,24 @@ class Problem:
         self.gid = torch.from_numpy(parallel.global_row_ids(counts, rows)).to(dev)
         self.parallel = parallel
         self.h2d_bytes = int(self.Bloc * (8 + 4) + self.yd.numel() * 8)
+        self.graphed = None
+        if graph:
+            from collaborative_nonstationary_multivariate_gaussian_process_b200.graph_step import GraphedStep
+            self.graphed = GraphedStep(model, self.opt, self.xd, self.yd, self.Id, n_mc=self.n_mc, row_gid=self.gid,
+                                       distributed=world > 1)
+            # pinned staging buffers of the end-to-end path (host lists -> pinned -> static device buffers)
+            self.x_pin = torch.empty(self.xd.shape, dtype=torch.float64).pin_memory()
+            self.y_pin = torch.empty(self.yd.shape, dtype=torch.float64).pin_memory()
+            self.I_pin = self.Id.cpu().pin_memory()
+
+    def check(self):
+        if self.graphed is not None:
+            self.graphed.check()
+        self.parallel.raise_if_pending_not_pd()
 
     def step_resident(self):
+        if self.graphed is not None:
+            return self.graphed.step()
         self.opt.zero_grad(set_to_none=True)
         loss = self.model.forward_rows(self.xd, self.yd, self.Id, n_mc=self.n_mc, row_gid=self.gid)
         loss.backward()
@@ -410,6 +426,13 @@ class Problem:
         return tot
 
     def step_e2e(self):
+        if self.graphed is not None:
+            # the caller's per-output host lists are packed into pinned memory, copied to the device, the captured
+            # iteration is replayed on them and the loss is read back
+            torch.cat([t.reshape(-1) for t in self.Xh], out=self.x_pin)
+            torch.cat(self.Yh, dim=-1, out=self.y_pin)
+            self.graphed.load_rows(self.x_pin, self.y_pin, self.I_pin)
+            return float(self.graphed.step().cpu())
         self.opt.zero_grad(set_to_none=True)
         loss = self.model(self.Xh, self.Yh, n_mc=self.n_mc, noise="device", row_gid=self.gid,
                           subjects=self.subj is not None)                      # host lists -> H2D inside
@@ -430,7 +453,7 @@ def run_b200(args, w):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     T, D, Q, S = w["T"], w["D"], w["Q"], w["S"]
-    pb = Problem(w, rank, world, dev)
+    pb = Problem(w, rank, world, dev, graph=not args.no_graph)
 
     def timed(fn, k, prof=False):
         if world > 1:
@@ -459,17 +482,21 @@ def run_b200(args, w):
     peak = fp64_yardstick(dev) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         pb.step_resident()
-    pb.parallel.raise_if_pending_not_pd()
+    pb.check()
+    # per-kernel breakdown: eager steps with CUDA events around every C-ABI call (a graph replay cannot be instrumented)
+    graphed, pb.graphed = pb.graphed, None
+    ms_inst, _, (prof, ncalls), _ = timed(lambda: (pb.step_resident(), pb.model.advance_noise_step())[0], args.steps,
+                                          prof=True)
+    pb.graphed = graphed
+    pb.check()
+    # the timed region of `value`: K steps (graph replays unless --no-graph), clocks sampled meanwhile
     clk = ClockSampler(local)
     if rank == 0:
         clk.start()
-    ms, last, (prof, ncalls), nlaunch = timed(pb.step_resident, args.steps, prof=True)
+    ms, last, _, nlaunch = timed(pb.step_resident, args.steps)
     clocks = clk.stop() if rank == 0 else None
-    pb.parallel.raise_if_pending_not_pd()
+    pb.check()
     ms_step = ms / args.steps
-    # the same steps without the per-call CUDA events of the kernel breakdown (they cost a little at small shapes)
-    ms_plain, last, _, nlaunch = timed(pb.step_resident, args.steps)
-    ms_step = min(ms_step, ms_plain / args.steps)
     e2e = None
     if not args.no_e2e:
         for _ in range(max(1, min(args.warmup, 2))):
@@ -477,14 +504,14 @@ def run_b200(args, w):
         ms2, _, _, _ = timed(pb.step_e2e, args.steps)
         e2e = {"value": 1e3 * args.steps / ms2, "unit": UNIT, "h2d_bytes_per_step": pb.h2d_bytes * world,
                "d2h_bytes_per_step": 8 * world, "ms_per_step": ms2 / args.steps}
-    pb.parallel.raise_if_pending_not_pd()
+    pb.check()
 
     small = None
     if rank == 0 and world == 1 and w["name"] == "ecog" and w["rows"] == T * D and not args.no_e2e:
         # the un-extrapolated pair of BASELINE.md 3.4: the reference driver's own minibatch (B=512 random rows, S=1),
         # end to end from host lists; `bench.py --impl reference` reports the same configuration as same_config_pair
         w2 = dict(w, rows=w["ref_rows"], S=1)
-        pb2 = Problem(w2, 0, 1, dev)
+        pb2 = Problem(w2, 0, 1, dev, graph=not args.no_graph)
         for _ in range(3):
             pb2.step_e2e()
         ks = max(args.steps, 10)
@@ -507,9 +534,9 @@ def run_b200(args, w):
             if name in prof:
                 calls, tms = prof[name]
                 flops = args.steps * nsamp * pairs_per_sample * per_pair
-                kern[name] = {"calls": calls, "ms_total": tms, "share_of_step": tms / ms,
+                kern[name] = {"calls": calls, "ms_total": tms, "share_of_step": tms / ms_inst,
                               "tflops": flops / (tms * 1e-3) / 1e12}
-        others = {k: {"calls": c, "ms_total": t_, "share_of_step": t_ / ms} for k, (c, t_) in prof.items() if k not in kern}
+        others = {k: {"calls": c, "ms_total": t_, "share_of_step": t_ / ms_inst} for k, (c, t_) in prof.items() if k not in kern}
         dom = max(kern, key=lambda k: kern[k]["ms_total"]) if kern else None
         roof = None
         if dom:
@@ -543,7 +570,9 @@ def run_b200(args, w):
                           "l2": "per-step working set (>= 5 B*Q doubles per sample chunk) exceeds the 126 MB L2"
                           if pb.Bloc * Q * 8 * 5 > 126e6 else "working set fits L2: a 256 MB buffer is not flushed between "
                           "steps because every step rewrites all its intermediates (>= L2 at the named full-batch shapes)",
-                          "noise": "device (counter-based, in-kernel)", "optimizer": "Adam lr=%g" % w["lr"]},
+                          "noise": "device (counter-based, in-kernel)", "optimizer": "Adam lr=%g" % w["lr"],
+                          "cuda_graph": "whole iteration replayed from one CUDA graph" if pb.graphed is not None else "off",
+                          "ms_per_step_eager_instrumented": ms_inst / args.steps},
                 "step_tflops_fp64": F_step / (ms_step * 1e-3) / 1e12,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(nlaunch), "abi_calls": int(ncalls),
                 "roofline": roof, "kernels": kern, "other_ops": others, "loss": float(last),

@@ -375,11 +375,13 @@ def _l(t):
 
 
 def _noise_args(noise):
-    """noise = (seed, stream_id, s0, ns, gid) for in-kernel generation; None when explicit draws are passed."""
+    """noise = (seed, stream_id, s0, ns, gid[, step_dev]) for in-kernel generation; None when explicit draws are passed.
+    step_dev: int64 device scalar holding the step counter (CUDA-graph replay), see nmgp_noise_fill."""
     if noise is None:
-        return ctypes.c_uint64(0), ctypes.c_uint64(0), c_int(0), c_void_p(0)
-    seed, stream_id, s0, _, gid = noise
-    return ctypes.c_uint64(seed), ctypes.c_uint64(stream_id), c_int(s0), _l(gid)
+        return ctypes.c_uint64(0), ctypes.c_uint64(0), c_int(0), c_void_p(0), c_void_p(0)
+    seed, stream_id, s0, _, gid = noise[:5]
+    step_dev = noise[5] if len(noise) > 5 else None
+    return ctypes.c_uint64(seed), ctypes.c_uint64(stream_id), c_int(s0), _l(gid), _l(step_dev)
 
 
 def coef_sample_fwd(m, sd, zL, I, noise=None):
@@ -388,7 +390,7 @@ def coef_sample_fwd(m, sd, zL, I, noise=None):
     l = _empty(m, ns, B, D)
     a = _noise_args(noise)
     check(lib().nmgp_coef_sample_fwd(_d(m), _d(sd), _optd(zL), _i(I), _d(l), c_int(ns), c_int64(B), c_int(D),
-                                     a[0], a[1], a[2], a[3], _stream()), "nmgp_coef_sample_fwd")
+                                     a[0], a[1], a[2], a[3], a[4], _stream()), "nmgp_coef_sample_fwd")
     return l
 
 
@@ -396,13 +398,13 @@ def coef_sample_bwd(lbar, l, zL, I, mbar, sdbar, noise=None):
     ns, B, D = l.shape
     a = _noise_args(noise)
     check(lib().nmgp_coef_sample_bwd(_d(lbar), _d(l), _optd(zL), _i(I), _d(mbar), _d(sdbar), c_int(ns), c_int64(B),
-                                     c_int(D), a[0], a[1], a[2], a[3], _stream()), "nmgp_coef_sample_bwd")
+                                     c_int(D), a[0], a[1], a[2], a[3], a[4], _stream()), "nmgp_coef_sample_bwd")
 
 
-def noise_fill(ns, B, C, seed, stream_id, s0, gid, device):
+def noise_fill(ns, B, C, seed, stream_id, s0, gid, device, step_dev=None):
     out = torch.empty(ns, B, C, dtype=F64, device=device)
     check(lib().nmgp_noise_fill(_d(out), c_int(ns), c_int64(B), c_int(C), ctypes.c_uint64(seed),
-                                ctypes.c_uint64(stream_id), c_int(s0), _l(gid), _stream()), "nmgp_noise_fill")
+                                ctypes.c_uint64(stream_id), c_int(s0), _l(gid), _l(step_dev), _stream()), "nmgp_noise_fill")
     return out
 
 

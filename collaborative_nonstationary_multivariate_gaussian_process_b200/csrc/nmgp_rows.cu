@@ -363,12 +363,12 @@ __global__ void k_coef_sample_fwd(const double* __restrict__ m, const double* __
 }
 NMGP_API int nmgp_coef_sample_fwd(const double* m, const double* sd, const double* zL, const int* I, double* l, int ns,
                                   long long B, int D, unsigned long long seed, unsigned long long stream_id, int s0,
-                                  const long long* gid, cudaStream_t st) {
+                                  const long long* gid, const unsigned long long* step_dev, cudaStream_t st) {
     NMGP_REQUIRE(ns >= 0 && ns <= 65535, "nmgp_coef_sample_fwd");
     if (B == 0 || ns == 0) return 0;
     long long n = B * ((D + 3) / 4);
     dim3 grid((unsigned)((n + 255) / 256), ns);
-    NoiseKey key{seed, stream_id};
+    NoiseKey key{seed, stream_id, step_dev};
     k_coef_sample_fwd<<<NMGP_L(grid), 256, 0, st>>>(m, sd, zL, I, l, B, D, key, s0, gid);
     return nmgp_launch_status("nmgp_coef_sample_fwd");
 }
@@ -410,10 +410,11 @@ __global__ void k_coef_sample_bwd(const double* __restrict__ lbar, const double*
 }
 NMGP_API int nmgp_coef_sample_bwd(const double* lbar, const double* l, const double* zL, const int* I, double* mbar,
                                   double* sdbar, int ns, long long B, int D, unsigned long long seed,
-                                  unsigned long long stream_id, int s0, const long long* gid, cudaStream_t st) {
+                                  unsigned long long stream_id, int s0, const long long* gid,
+                                  const unsigned long long* step_dev, cudaStream_t st) {
     if (B == 0 || ns == 0) return 0;
     long long n = B * ((D + 3) / 4);
-    NoiseKey key{seed, stream_id};
+    NoiseKey key{seed, stream_id, step_dev};
     k_coef_sample_bwd<<<NMGP_L((unsigned)((n + 255) / 256)), 256, 0, st>>>(lbar, l, zL, I, mbar, sdbar, ns, B, D, key, s0, gid);
     return nmgp_launch_status("nmgp_coef_sample_bwd");
 }
@@ -436,12 +437,13 @@ __global__ void k_noise_fill(double* __restrict__ out, long long B, int C, Noise
     }
 }
 NMGP_API int nmgp_noise_fill(double* out, int ns, long long B, int C, unsigned long long seed,
-                             unsigned long long stream_id, int s0, const long long* gid, cudaStream_t st) {
+                             unsigned long long stream_id, int s0, const long long* gid,
+                             const unsigned long long* step_dev, cudaStream_t st) {
     NMGP_REQUIRE(ns >= 0 && ns <= 65535 && B >= 0 && C > 0, "nmgp_noise_fill");
     if (B == 0 || ns == 0) return 0;
     long long n = B * ((C + 3) / 4);
     dim3 grid((unsigned)((n + 255) / 256), ns);
-    NoiseKey key{seed, stream_id};
+    NoiseKey key{seed, stream_id, step_dev};
     k_noise_fill<<<NMGP_L(grid), 256, 0, st>>>(out, B, C, key, s0, gid);
     return nmgp_launch_status("nmgp_noise_fill");
 }

@@ -5,7 +5,7 @@
 // and + jitter on the diagonal of a self-covariance.
 //
 // The builds are FP64-ALU / HBM-store co-limited (8 bytes written per entry against one rsqrt + one exp per entry), so
-//   * per-point factors are hoisted out of the pair loop: s_i sqrt(2 a_i), s_j sqrt(b_j), a_i^2, b_j^2, |x|^2 are
+//   * per-point factors are hoisted out of the pair loop: s_i sqrt(a_i), s_j sqrt(b_j), a_i^2, b_j^2, |x|^2 are
 //     staged in shared memory per 64-point strip, and sqrt(2ab/A) exp(-d/A) becomes ONE rsqrt(A) (A^-1 = rsqrt^2) and
 //     one exp per entry -- no division, no sqrt;
 //   * a self-covariance only evaluates the tiles on and below the diagonal; each 64 x 64 tile goes through shared
@@ -44,7 +44,8 @@ __device__ __forceinline__ void load_strip(Strip& s, const double* __restrict__ 
         s.x[tid] = x;
         s.n[tid] = x * x;
         s.a2[tid] = a * a;
-        s.f[tid] = row_side ? sig * sqrt(2.0 * a) : sig * sqrt(a);
+        s.f[tid] = sig * sqrt(a);          // same factor on both sides: K[i,j] and K[j,i] are then bitwise equal
+        (void)row_side;
     }
 }
 
@@ -55,7 +56,7 @@ __device__ __forceinline__ double entry(double xi, double ni, double a2i, double
     if (KIND == 1) return exp(-0.5 * dist) * alpha2;
     const double A = a2i + b2j;
     const double rs = rsqrt(A);
-    return (fi * fj) * rs * exp(-dist * (rs * rs));
+    return (fi * fj) * (rs * 1.4142135623730951) * exp(-dist * (rs * rs));
 }
 
 // SYM: blockIdx.x enumerates the tile pairs (ti >= tj) of a self-covariance; otherwise grid (tiles of T2, tiles of T1).
@@ -206,7 +207,7 @@ k_nonstat_cov_bwd(const double* __restrict__ X1, const double* __restrict__ sg1,
                 const double dist = (ni + cs_.n[c]) - 2.0 * __dmul_rn(xi, cs_.x[c]);
                 const double A = a2i + cs_.a2[c];
                 const double rsq = rsqrt(A), rA = rsq * rsq;
-                const double k = (fi * cs_.f[c]) * rsq * exp(-dist * rA);
+                const double k = (fi * cs_.f[c]) * (rsq * 1.4142135623730951) * exp(-dist * rA);
                 const double w = Kbar[(size_t)gi * T2 + gj] * k;
                 const double w1 = w * rA, w2 = w1 * dist * rA;
                 r0 += w; r1 += w1; r2 += w2;

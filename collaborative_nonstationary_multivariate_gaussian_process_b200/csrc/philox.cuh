@@ -7,6 +7,10 @@
 struct NoiseKey {
     unsigned long long seed;
     unsigned long long stream;   // (step << 8) | kind
+    // optional DEVICE step counter: the effective stream id is stream | (*step_dev << 8).  A step captured in a CUDA graph
+    // passes stream = kind and bumps the counter inside the graph, so every replay draws fresh noise -- the same noise
+    // an eager run with stream = (step << 8) | kind draws.
+    const unsigned long long* step_dev;
 };
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
@@ -28,9 +32,10 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 __device__ __forceinline__ void philox_normal4(NoiseKey key, unsigned int sample, unsigned long long gid, unsigned int q4,
                                                float z[4]) {
     uint32_t u[4];
+    const unsigned long long stream = key.step_dev ? (key.stream | (__ldg(key.step_dev) << 8)) : key.stream;
     // counter = (row gid lo, row gid hi, sample, column quad); key = seed words xor-ed with the stream id
-    philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), sample, q4, (uint32_t)key.seed ^ (uint32_t)key.stream,
-                  (uint32_t)(key.seed >> 32) ^ (uint32_t)(key.stream >> 32), u);
+    philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), sample, q4, (uint32_t)key.seed ^ (uint32_t)stream,
+                  (uint32_t)(key.seed >> 32) ^ (uint32_t)(stream >> 32), u);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const float u1 = ((float)(u[2 * h] >> 8) + 0.5f) * (1.0f / 16777216.0f);      // (0,1), 24 bits

@@ -234,7 +234,8 @@ def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: t
         if z_L is not None:
             zl_, nz_ = z_L[sl], None
         else:
-            zl_, nz_ = None, (int(noise_key[0]), int(noise_key[1]), sl.start + int(sample_offset), sl.stop - sl.start, row_gid)
+            zl_, nz_ = None, (int(noise_key[0]), int(noise_key[1]), sl.start + int(sample_offset), sl.stop - sl.start, row_gid,
+                          noise_key[2] if len(noise_key) > 2 else None)
         l = ops.coef_sample_fwd(mU[0], sdU, zl_, I, noise=nz_)
         KG = ops.gibbs_build_fwd(x, Z, ellx, ellZ[sl], 0.0)
         PG, cG = ops.solve_rows_fwd(KG, R_G[sl])

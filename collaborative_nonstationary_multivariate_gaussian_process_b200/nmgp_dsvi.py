@@ -175,13 +175,34 @@ class NMGP(torch.nn.Module):
         are sharded over ranks.  z_v and z_ell are materialised (small); the B*D coefficient draws are generated inside
         the sampling kernels and never stored (returned as None plus the key)."""
         dev = self.device
-        step = self._noise_step
-        self._noise_step += 1
         seed = int(self.noise_seed)
         sid = None if not sample_offset else torch.arange(sample_offset, sample_offset + n_mc, dtype=torch.int64, device=dev)
-        zv = ops.noise_fill(1, n_mc, self.M, seed, (step << 8) | 0, 0, sid, dev)[0]
-        zell = ops.noise_fill(n_mc, B, 1, seed, (step << 8) | 1, int(sample_offset), row_gid, dev).reshape(n_mc, B)
-        return zv, zell, None, (seed, (step << 8) | 2)
+        ctr = getattr(self, "_noise_step_dev", None)
+        if ctr is not None:
+            # CUDA-graph mode: the step index lives on the device and is bumped by the (captured) step itself
+            base, step_dev = 0, ctr
+        else:
+            base, step_dev = self._noise_step << 8, None
+            self._noise_step += 1
+        zv = ops.noise_fill(1, n_mc, self.M, seed, base | 0, 0, sid, dev, step_dev=step_dev)[0]
+        zell = ops.noise_fill(n_mc, B, 1, seed, base | 1, int(sample_offset), row_gid, dev, step_dev=step_dev).reshape(n_mc, B)
+        return zv, zell, None, (seed, base | 2, step_dev)
+
+    def use_device_step_counter(self, enable=True):
+        """Keep the noise step counter on the device (needed to replay a step from a CUDA graph: kernel arguments are
+        frozen at capture, so the step index must be data).  The caller bumps it with ``advance_noise_step()`` inside
+        the captured region.  Draws are identical to the host-counter mode."""
+        if enable:
+            if getattr(self, "_noise_step_dev", None) is None:       # idempotent: a captured graph holds this buffer
+                self._noise_step_dev = torch.full((1,), int(self._noise_step), dtype=torch.int64, device=self.device)
+        else:
+            if getattr(self, "_noise_step_dev", None) is not None:
+                self._noise_step = int(self._noise_step_dev.item())
+            self._noise_step_dev = None
+
+    def advance_noise_step(self):
+        if getattr(self, "_noise_step_dev", None) is not None:
+            self._noise_step_dev.add_(1)
 
     def forward_rows(self, x, y, I, n_mc=1, explicit_noise=None, row_gid=None):
         """Same as forward() for rows already on the device: x, y float64 [B], I int32 [B] sorted by output;

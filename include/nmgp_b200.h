@@ -140,14 +140,17 @@ int nmgp_coef_sd_bwd(const double* sdbar, const double* sd, const int* I, const 
  * from (seed, stream_id, s0 + s, gid[n] (or n), j) and never stored; the backward kernel regenerates them. */
 int nmgp_coef_sample_fwd(const double* m, const double* sd, const double* zL, const int* I, double* l, int ns,
                          long long B, int D, unsigned long long seed, unsigned long long stream_id, int s0,
-                         const long long* gid, nmgp_stream_t stream);
+                         const long long* gid, const unsigned long long* step_dev, nmgp_stream_t stream);
 int nmgp_coef_sample_bwd(const double* lbar, const double* l, const double* zL, const int* I, double* mbar /* += */,
                          double* sdbar /* += */, int ns, long long B, int D, unsigned long long seed,
-                         unsigned long long stream_id, int s0, const long long* gid, nmgp_stream_t stream);
+                         unsigned long long stream_id, int s0, const long long* gid, const unsigned long long* step_dev,
+                         nmgp_stream_t stream);
 /* out[s,n,c] = N(0,1), float32 draws widened to double (quirk q2: utils.py:123,226,234), Philox4x32-10 keyed by
  * (seed, stream_id) with counter (gid[n] or n, s0 + s, c/4): independent of how rows are sharded over ranks */
 int nmgp_noise_fill(double* out, int ns, long long B, int C, unsigned long long seed, unsigned long long stream_id,
-                    int s0, const long long* gid, nmgp_stream_t stream);
+                    int s0, const long long* gid, const unsigned long long* step_dev, nmgp_stream_t stream);
+/* step_dev (may be NULL): DEVICE step counter; the effective stream id is stream_id | (*step_dev << 8).  A step that
+ * is replayed from a CUDA graph passes stream_id = kind and increments the counter inside the graph. */
 
 /* ---- 64 < Q <= 128 (the PM2.5 / HCP drivers use Q = 100): ring-pipelined DMMA kernels, csrc/nmgp_quadform_lq.cu ----
  * The Q x Q covariances are first copied into padded, half-split records (the order the kernels stream them through

@@ -323,9 +323,11 @@ def _philox4x32_10(c, k):
     return np.stack(c, -1).astype(np.uint32)
 
 
-def noise_fill(ns, B, C, seed, stream_id, s0, gid, device=None):
+def noise_fill(ns, B, C, seed, stream_id, s0, gid, device=None, step_dev=None):
     """Counter-based N(0,1) noise of csrc/philox.cuh restated in numpy (float32 Box-Muller, widened to double)."""
     import numpy as np
+    if step_dev is not None:                      # device step counter of the CUDA-graph path: stream |= step << 8
+        stream_id = int(stream_id) | (int(step_dev) << 8)
     nq = (C + 3) // 4
     g = np.arange(B, dtype=np.uint64) if gid is None else np.asarray(gid.cpu() if torch.is_tensor(gid) else gid).astype(np.uint64)
     ctr = np.zeros((ns, B, nq, 4), dtype=np.uint32)
@@ -350,8 +352,8 @@ def noise_fill(ns, B, C, seed, stream_id, s0, gid, device=None):
 def _explicit_noise(zL, noise, B, D):
     if zL is not None:
         return zL
-    seed, stream_id, s0, ns, gid = noise
-    return noise_fill(ns, B, D, seed, stream_id, s0, gid)
+    seed, stream_id, s0, ns, gid = noise[:5]
+    return noise_fill(ns, B, D, seed, stream_id, s0, gid, step_dev=noise[5] if len(noise) > 5 else None)
 
 
 def coef_sample_fwd(m, sd, zL, I, noise=None):
