@@ -556,27 +556,53 @@ def pairwise_dist(X1, X2):
 
 
 def gemm_nt(A, Bm, alpha=1.0, beta=0.0, C=None):
-    """C = alpha * A @ Bm.T + beta * C  (A [M,K], Bm [N,K] row-major) on the FP64 tensor cores."""
+    """C = alpha * A @ Bm.T + beta * C  (A [M,K], Bm [N,K] row-major) on the FP64 tensor cores.  Row-strided 2-D views
+    (unit column stride, e.g. blocks of a larger matrix) are accepted for A, Bm and C."""
     M, K = A.shape
     N = Bm.shape[0]
     if C is None:
         C = _empty(A, M, N)
         beta = 0.0
-    check(lib().nmgp_gemm_nt(_d(A), _d(Bm), _d(C), c_int64(M), c_int64(N), c_int64(K), c_int64(K), c_int64(K),
-                             c_int64(N), c_double(alpha), c_double(beta), _stream()), "nmgp_gemm_nt")
+    for t in (A, Bm, C):
+        if not (t.is_cuda and t.dtype == F64 and t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1)):
+            raise TypeError("gemm_nt expects CUDA float64 2-D tensors with unit column stride")
+        _same_device(t)
+    ld = lambda t: int(t.stride(0)) if t.shape[0] > 1 else max(int(t.shape[1]), 1)
+    if M == 0 or N == 0:
+        return C
+    check(lib().nmgp_gemm_nt(c_void_p(A.data_ptr()), c_void_p(Bm.data_ptr()), c_void_p(C.data_ptr()), c_int64(M),
+                             c_int64(N), c_int64(K), c_int64(max(ld(A), K)), c_int64(max(ld(Bm), K)), c_int64(max(ld(C), N)),
+                             c_double(alpha), c_double(beta), _stream()), "nmgp_gemm_nt")
     return C
 
 
-def potrf_big(A):
-    """In-place blocked lower Cholesky of the square matrix A; returns (A, sum(log(diag)))."""
+def potrf_big(A, info=None, slot=0):
+    """In-place blocked lower Cholesky of the square matrix A; returns (A, sum(log(diag))).  Raises RuntimeError on a
+    non-positive pivot like torch.cholesky -- unless ``info`` (int32 device scalar, receives the order of the failing
+    leading minor, 0 if none) is given: then nothing is read back here (no host synchronisation).  ``slot`` (0..3)
+    selects the library's look-ahead scratch; factorisations running concurrently on different streams need different
+    slots."""
     T = A.shape[0]
     hld = _empty(A, 1)
-    info = torch.zeros(1, dtype=torch.int32, device=A.device)
-    check(lib().nmgp_potrf_big(_d(A), c_int64(T), c_int64(T), _d(hld), _i(info), _stream()), "nmgp_potrf_big")
-    bad = int(info.item())
-    if bad != 0:
-        raise RuntimeError("cholesky: the leading minor of order %d is not positive-definite" % bad)
+    deferred = info is not None
+    if not deferred:
+        info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    check(lib().nmgp_potrf_big_slot(_d(A), c_int64(T), c_int64(T), _d(hld), _i(info), c_int(slot), _stream()),
+          "nmgp_potrf_big")
+    if not deferred:
+        bad = int(info.item())
+        if bad != 0:
+            raise RuntimeError("cholesky: the leading minor of order %d is not positive-definite" % bad)
     return A, hld
+
+
+def tri_inv_block(L, out, scale=1.0):
+    """out = scale * inverse of the lower-triangular block L (n <= 128; 2-D views with unit column stride)."""
+    n = L.shape[0]
+    check(lib().nmgp_tri_inv_block(c_void_p(L.data_ptr()), c_int64(L.stride(0) if n > 1 else n), c_int(n),
+                                   c_void_p(out.data_ptr()), c_int64(out.stride(0) if n > 1 else n), c_double(scale),
+                                   _stream()), "nmgp_tri_inv_block")
+    return out
 
 
 def potrs_vec(L, b):
@@ -589,6 +615,14 @@ def scale_add_diag(K, alpha, sigma2):
     A = torch.empty_like(K)
     check(lib().nmgp_scale_add_diag(_d(K), _d(A), c_int64(K.shape[0]), c_double(alpha), c_double(sigma2), _stream()),
           "nmgp_scale_add_diag")
+    return A
+
+
+def scale_add_diag_dev(K, alpha_dev, sigma2_dev, out=None):
+    """A = alpha K + sigma2 I with both scalars read on the device (1-element float64 tensors / views)."""
+    A = torch.empty_like(K) if out is None else out
+    check(lib().nmgp_scale_add_diag_dev(_d(K), _d(A), c_int64(K.shape[0]), c_void_p(alpha_dev.data_ptr()),
+                                        c_void_p(sigma2_dev.data_ptr()), _stream()), "nmgp_scale_add_diag_dev")
     return A
 
 
@@ -611,6 +645,14 @@ def eigh_small(A):
 def axpby(x, y, a, b):
     out = torch.empty_like(x)
     check(lib().nmgp_axpby(_d(x), _d(y), _d(out), c_int64(x.numel()), c_double(a), c_double(b), _stream()), "nmgp_axpby")
+    return out
+
+
+def axpby_dev(x, y, a_dev, a_scale=1.0, b=1.0, out=None):
+    """out = (a_scale * a_dev[0]) * x + b * y with a_dev a 1-element device tensor (no host read)."""
+    out = torch.empty_like(x) if out is None else out
+    check(lib().nmgp_axpby_dev(_d(x), _d(y), _d(out), c_int64(x.numel()), c_void_p(a_dev.data_ptr()), c_double(a_scale),
+                               c_double(b), _stream()), "nmgp_axpby_dev")
     return out
 
 

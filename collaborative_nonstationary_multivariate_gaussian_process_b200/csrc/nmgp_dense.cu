@@ -407,29 +407,44 @@ static int factor_panel(double* Akk, long long lda, int nb, long long rest, doub
 }
 // top level with look-ahead: the next panel is factorised on a helper stream while the main stream applies the bulk
 // of the trailing update, so the latency-bound panel work hides behind the DMMA SYRK.
-static cudaStream_t g_helper_stream = nullptr;
-static cudaEvent_t g_ev_upd = nullptr, g_ev_pan = nullptr;
-static double* g_linv = nullptr;   // two 128 x 128 inverse scratch blocks (main stream, helper stream)
-static int potrf_scratch() {
-    if (!g_linv && cudaMalloc(&g_linv, sizeof(double) * 2 * DI_N * DI_N) != cudaSuccess) {
-        nmgp_set_error("nmgp_potrf_big: cannot allocate the 256 KB panel scratch");
-        return -4;
+// Library-owned scratch of the blocked Cholesky, one set per (device, slot): a highest-priority helper stream, two
+// events and two 128 x 128 inverse blocks (main stream / helper stream).  Independent factorisations that run
+// concurrently (the eigen-blocks of a Kronecker log-density, dealt round-robin to a few streams so that the panel phase
+// of one overlaps the trailing updates of the others) must use different slots.
+#define POTRF_SLOTS 4
+#define POTRF_MAXDEV 16
+struct PotrfCtx {
+    cudaStream_t helper = nullptr;
+    cudaEvent_t ev_upd = nullptr, ev_pan = nullptr;
+    double* linv = nullptr;
+};
+static PotrfCtx g_potrf_ctx[POTRF_MAXDEV][POTRF_SLOTS];
+static PotrfCtx* potrf_ctx(int slot) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= POTRF_MAXDEV || slot < 0 || slot >= POTRF_SLOTS) {
+        nmgp_set_error("nmgp_potrf_big: bad device / slot (%d, %d)", dev, slot);
+        return nullptr;
     }
-    return 0;
-}
-static int potrf_lookahead(double* A, long long T, long long lda, int pb, int* info, cudaStream_t s0) {
-    if (!g_helper_stream) {
+    PotrfCtx* c = &g_potrf_ctx[dev][slot];
+    if (!c->linv) {
         // highest priority: the panel's CTAs must get SM slots ahead of the queued tiles of the trailing update
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        if (cudaStreamCreateWithPriority(&g_helper_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
-            cudaEventCreateWithFlags(&g_ev_upd, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&g_ev_pan, cudaEventDisableTiming) != cudaSuccess) {
-            nmgp_set_error("nmgp_potrf_big: cannot create the look-ahead stream");
-            return -4;
+        if (cudaMalloc(&c->linv, sizeof(double) * 2 * DI_N * DI_N) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&c->helper, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_upd, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_pan, cudaEventDisableTiming) != cudaSuccess) {
+            c->linv = nullptr;
+            nmgp_set_error("nmgp_potrf_big: cannot create the look-ahead stream / 256 KB panel scratch");
+            return nullptr;
         }
     }
-    cudaStream_t s1 = g_helper_stream;
+    return c;
+}
+static int potrf_lookahead(PotrfCtx* ctx, double* A, long long T, long long lda, int pb, int* info, cudaStream_t s0) {
+    cudaStream_t s1 = ctx->helper;
+    cudaEvent_t g_ev_upd = ctx->ev_upd, g_ev_pan = ctx->ev_pan;
+    double* g_linv = ctx->linv;
     {   // panel 0 on the main stream
         const int nb = (int)min((long long)pb, T);
         if (int r = factor_panel(A, lda, nb, T - nb, g_linv, info, 0, s0)) return r;
@@ -465,21 +480,73 @@ static int potrf_lookahead(double* A, long long T, long long lda, int pb, int* i
 // *info = 1 + index of the first non-positive pivot (0 if none).  Reference sites: torch.logdet / torch.inverse
 // at distributions.py:109-110 and logpos.py:352-353 (dense path), and the per-eigen-block factorisations of the
 // Kronecker path.
-NMGP_API int nmgp_potrf_big(double* A, long long T, long long lda, double* hld, int* info, cudaStream_t st) {
+NMGP_API int nmgp_potrf_big_slot(double* A, long long T, long long lda, double* hld, int* info, int slot,
+                                 cudaStream_t st) {
     NMGP_REQUIRE(T > 0 && lda >= T && T < 2147483647LL, "nmgp_potrf_big");
     if (int r = nmgp_opt_in_smem(k_potrf_diag_inv, DI_SMEM, "nmgp_potrf_big")) return r;
-    if (int r = potrf_scratch()) return r;
+    PotrfCtx* ctx = potrf_ctx(slot);
+    if (!ctx) return -4;
     if (T > 1024) {
         int pb = T >= 12288 ? 512 : (T >= 6144 ? 256 : PB);   // measured best on B200 (profiles/README.md)
         if (const char* e = getenv("NMGP_POTRF_PB")) pb = atoi(e) >= 128 ? (atoi(e) / 128) * 128 : pb;   // tuning knob
-        if (int r = potrf_lookahead(A, T, lda, pb, info, st)) return r;
+        if (int r = potrf_lookahead(ctx, A, T, lda, pb, info, st)) return r;
     } else {
-        if (int r = factor_panel(A, lda, (int)T, 0, g_linv, info, 0, st)) return r;
+        if (int r = factor_panel(A, lda, (int)T, 0, ctx->linv, info, 0, st)) return r;
     }
     dim3 gz((unsigned)((T + 255) / 256), (unsigned)min(T, 65535LL));
     if (T <= 65535) k_zero_upper<<<NMGP_L(gz), 256, 0, st>>>(A, T, lda);
     if (hld) k_logdiag_sum<<<NMGP_L(1), 1024, 0, st>>>(A, T, lda, hld);
     return nmgp_launch_status("nmgp_potrf_big");
+}
+NMGP_API int nmgp_potrf_big(double* A, long long T, long long lda, double* hld, int* info, cudaStream_t st) {
+    return nmgp_potrf_big_slot(A, T, lda, hld, info, 0, st);
+}
+
+// Inverse of the lower-triangular nb x nb block at L (nb <= 128) into out (row-major, leading dimension ldo; entries
+// above the diagonal are written as zeros): one CTA, thread c solves L x = e_c by forward substitution from a shared-
+// memory copy.  Building block of the blocked triangular inverse used by the Cholesky-based log-density adjoint.
+__global__ void __launch_bounds__(PB)
+k_tri_inv_block(const double* __restrict__ L, long long lda, int nb, double* __restrict__ out, long long ldo, double scale) {
+    extern __shared__ double sm[];
+    constexpr int LD = PB + 1;
+    double* Ls = sm;                        // [PB][PB+1]
+    double* Xs = Ls + PB * LD;              // [PB][PB+1]  column c of the inverse in Xs[:, c]
+    const int tid = threadIdx.x;
+    for (int e = tid; e < PB * PB; e += blockDim.x) {
+        const int a = e / PB, b = e - a * PB;
+        Ls[a * LD + b] = (a < nb && b < nb && b <= a) ? L[(long long)a * lda + b] : (a == b ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    const int c = tid;
+    if (c < nb) {
+        for (int a = 0; a < nb; ++a) {
+            double s0 = (a == c) ? 1.0 : 0.0, s1 = 0.0;
+            if (a >= c) {
+                int k = c;
+                for (; k + 1 < a; k += 2) {
+                    s0 = fma(-Ls[a * LD + k], Xs[k * LD + c], s0);
+                    s1 = fma(-Ls[a * LD + k + 1], Xs[(k + 1) * LD + c], s1);
+                }
+                if (k < a) s0 = fma(-Ls[a * LD + k], Xs[k * LD + c], s0);
+                Xs[a * LD + c] = (s0 + s1) / Ls[a * LD + a];
+            } else {
+                Xs[a * LD + c] = 0.0;
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < nb * nb; e += blockDim.x) {
+        const int a = e / nb, b = e - a * nb;
+        out[(long long)a * ldo + b] = scale * Xs[a * LD + b];
+    }
+}
+NMGP_API int nmgp_tri_inv_block(const double* L, long long lda, int nb, double* out, long long ldo, double scale,
+                                cudaStream_t st) {
+    NMGP_REQUIRE(nb > 0 && nb <= PB && lda >= nb && ldo >= nb, "nmgp_tri_inv_block");
+    const size_t smem = sizeof(double) * 2 * PB * (PB + 1);
+    if (int r = nmgp_opt_in_smem(k_tri_inv_block, smem, "nmgp_tri_inv_block")) return r;
+    k_tri_inv_block<<<NMGP_L(1), PB, smem, st>>>(L, lda, nb, out, ldo, scale);
+    return nmgp_launch_status("nmgp_tri_inv_block");
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -589,6 +656,20 @@ __global__ void k_scale_add_diag(const double* __restrict__ K, double* __restric
                                  double sigma2) {
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y + (long long)blockIdx.z * 65535;
     if (c < T && r < T) A[r * T + c] = fma(alpha, K[r * T + c], (r == c) ? sigma2 : 0.0);
+}
+// same with alpha = alpha_dev[0] and sigma2 = sigma2_dev[0] read on the device (no host round trip for the eigenvalue)
+__global__ void k_scale_add_diag_dev(const double* __restrict__ K, double* __restrict__ A, long long T,
+                                     const double* __restrict__ alpha_dev, const double* __restrict__ sigma2_dev) {
+    const double alpha = alpha_dev[0], sigma2 = sigma2_dev[0];
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y + (long long)blockIdx.z * 65535;
+    if (c < T && r < T) A[r * T + c] = fma(alpha, K[r * T + c], (r == c) ? sigma2 : 0.0);
+}
+NMGP_API int nmgp_scale_add_diag_dev(const double* K, double* A, long long T, const double* alpha_dev,
+                                     const double* sigma2_dev, cudaStream_t st) {
+    NMGP_REQUIRE(T > 0, "nmgp_scale_add_diag_dev");
+    dim3 grid((unsigned)((T + 255) / 256), (unsigned)min(T, 65535LL), (unsigned)((T + 65534) / 65535));
+    k_scale_add_diag_dev<<<NMGP_L(grid), 256, 0, st>>>(K, A, T, alpha_dev, sigma2_dev);
+    return nmgp_launch_status("nmgp_scale_add_diag_dev");
 }
 NMGP_API int nmgp_scale_add_diag(const double* K, double* A, long long T, double alpha, double sigma2,
                                  cudaStream_t st) {
@@ -727,6 +808,19 @@ NMGP_API int nmgp_eigh_small(const double* A, double* w, double* V, double* work
 
 // ------------------------------------------------------------------------------------------------------------
 // small vector helpers of the Kronecker log-density (distributions.py:42-51)
+// out = (a_scale * a_dev[0]) * x + b * y with the scalar a read on the device
+__global__ void k_axpby_dev(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out,
+                            long long n, const double* __restrict__ a_dev, double a_scale, double b) {
+    const double a = a_scale * a_dev[0];
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = fma(a, x[i], b * y[i]);
+}
+NMGP_API int nmgp_axpby_dev(const double* x, const double* y, double* out, long long n, const double* a_dev,
+                            double a_scale, double b, cudaStream_t st) {
+    if (n <= 0) return 0;
+    k_axpby_dev<<<NMGP_L((unsigned)((n + 255) / 256)), 256, 0, st>>>(x, y, out, n, a_dev, a_scale, b);
+    return nmgp_launch_status("nmgp_axpby_dev");
+}
 __global__ void k_axpby(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out,
                         long long n, double a, double b) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -4,10 +4,25 @@ The structured operations never need an eigen-decomposition of the T x T factor 
 (D x D, Jacobi in one CTA),  sigma2 I + B (x) K = (V (x) I) blkdiag_m(sigma2 I + lam_m K) (V^T (x) I), so the
 log-determinant and solves reduce to D independent T x T blocked Cholesky factorisations whose trailing updates run
 on the FP64 tensor cores.  The reference's route is two torch.symeig calls
-(kronecker_operation.py:45-47, 66-67); results agree to rounding times the conditioning of the blocks."""
+(kronecker_operation.py:45-47, 66-67); results agree to rounding times the conditioning of the blocks.
+
+The D factorisations are independent: ``block_pipeline`` deals them round-robin to a few CUDA streams (each with its own
+look-ahead scratch slot in the library) so that the latency-bound panel phase of one block overlaps the tensor-core
+trailing updates of the others, reads the eigenvalue of each block on the device (no host round trip per block) and
+defers the positive-definiteness check to one flag per block."""
 import torch
 
 from . import _ops as ops
+
+NSLOT = 3                      # concurrent eigen-block factorisations (streams / library scratch slots / T x T buffers)
+_streams = {}
+
+
+def _slot_streams(dev):
+    key = str(dev)
+    if key not in _streams:
+        _streams[key] = [torch.cuda.Stream(device=dev) for _ in range(NSLOT)]
+    return _streams[key]
 
 
 def kronecker_product(t1, t2):
@@ -20,9 +35,75 @@ def kronecker_product_diag(d1, d2):
     return ops.kron_product(d1.contiguous().view(-1, 1), d2.contiguous().view(-1, 1)).view(-1)
 
 
+def _dev_scalar(v, dev):
+    return torch.as_tensor(v, dtype=torch.float64).detach().reshape(1).to(dev)
+
+
+def block_pipeline(sigma2, B, K, Rt=None, shard=None, per_block=None):
+    """Factorises A_m = sigma2 I + lam_m K for the eigen-blocks m of B (all, or the shard (rank, world): m = rank,
+    rank + world, ...) -- NSLOT at a time on NSLOT streams -- and per block computes hld_m = 1/2 logdet A_m and, when
+    ``Rt`` [D, T] is given, alpha_m = A_m^-1 Rt[m] and quad_m = Rt[m] . alpha_m.  ``per_block(m, L_m, slot)`` (optional)
+    runs on the block's stream right after its factorisation (the adjoint uses it).  Nothing is read back to the host.
+    Returns dict(lam, V, hld [D], quad [D], alpha [D, T] or None, info [D] int32, blocks)."""
+    D, T = B.shape[0], K.shape[0]
+    dev = K.device
+    lam, V = ops.eigh_small(B.detach().contiguous())
+    Kc = K.detach().contiguous()
+    s2 = _dev_scalar(sigma2, dev)
+    first, step = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
+    blocks = list(range(first, D, step))
+    hld = torch.zeros(D, dtype=torch.float64, device=dev)
+    quad = torch.zeros(D, dtype=torch.float64, device=dev)
+    info = torch.zeros(D, dtype=torch.int32, device=dev)
+    alpha = torch.zeros(D, T, dtype=torch.float64, device=dev) if Rt is not None else None
+    on_gpu = Kc.is_cuda
+    nslot = min(NSLOT, max(len(blocks), 1))
+    bufs = [torch.empty_like(Kc) for _ in range(nslot)]
+    streams = _slot_streams(dev)[:nslot] if on_gpu else [None] * nslot
+    main = torch.cuda.current_stream(dev) if on_gpu else None
+    for st in streams:
+        if st is not None:
+            st.wait_stream(main)
+    for idx, m in enumerate(blocks):
+        slot = idx % nslot
+        ctx = torch.cuda.stream(streams[slot]) if on_gpu else _Null()
+        with ctx:
+            A = ops.scale_add_diag_dev(Kc, lam[m:m + 1], s2, out=bufs[slot])
+            L, h = ops.potrf_big(A, info=info[m:m + 1], slot=slot)
+            hld[m:m + 1] = h
+            if Rt is not None:
+                rm = Rt[m].contiguous()
+                xm = ops.potrs_vec(L, rm)
+                alpha[m] = xm
+                quad[m:m + 1] = ops.dot(rm, xm)
+            if per_block is not None:
+                per_block(m, L, slot)
+    for st in streams:
+        if st is not None:
+            main.wait_stream(st)
+    return dict(lam=lam, V=V, hld=hld, quad=quad, alpha=alpha, info=info, blocks=blocks, bufs=bufs)
+
+
+class _Null:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+def nan_if_not_pd(value, info):
+    """The reference's eigen route yields NaN when sigma2 + lam w <= 0 somewhere (log of a non-positive number); the
+    callers in logpos.py retry with the jittered log-density then (logpos.py:267-268).  Same contract here, on the
+    device: NaN if any block failed to factorise."""
+    bad = (info != 0).any()
+    return torch.where(bad, torch.full_like(value, float("nan")), value)
+
+
 def _factor_blocks(sigma2, B, K, shard=None):
-    """Yields (m, lam_m, L_m, half_logdet_m, V) with L_m = chol(sigma2 I + lam_m K); V from the Jacobi eigensolver.
-    shard = (rank, world): only the eigen-blocks m = rank, rank + world, ... (the blocks are independent)."""
+    """Yields (m, lam_m, L_m, half_logdet_m, V) with L_m = chol(sigma2 I + lam_m K), one block at a time, every factor in
+    its own buffer (for callers that keep the factors: prediction.py).  shard = (rank, world): only the eigen-blocks
+    m = rank, rank + world, ... (the blocks are independent)."""
     lam, V = ops.eigh_small(B.contiguous())
     lam_host = lam.cpu()
     s2 = float(sigma2)
@@ -36,20 +117,38 @@ def _factor_blocks(sigma2, B, K, shard=None):
 
 def kron_logdet(sigma2, B, K):
     """kronecker_operation.py:57-69: log det(sigma2 I + B (x) K)."""
-    total = None
-    for m, lam_m, L, hld, V in _factor_blocks(sigma2, B, K):
-        total = 2.0 * hld if total is None else total + 2.0 * hld
-    return total.reshape(())
+    res = block_pipeline(sigma2, B, K)
+    return nan_if_not_pd(2.0 * res["hld"].sum(), res["info"]).reshape(())
+
+
+def chol_inverse(L):
+    """(L L^T)^-1 from the lower Cholesky factor L (T x T) with tensor-core GEMMs only: U = L^-T is built block column
+    by block column (128-wide: the diagonal blocks are inverted in one CTA each, the rest is two GEMMs per block), then
+    A^-1 = U U^T.  Used by the adjoints of the Cholesky-based log-densities."""
+    T = L.shape[0]
+    nb = 128
+    U = torch.zeros_like(L)                                  # upper triangular: U[0:i, i] blocks + diagonal blocks
+    Dinv = torch.empty(nb, nb, dtype=L.dtype, device=L.device)
+    for k0 in range(0, T, nb):
+        h = min(nb, T - k0)
+        Lkk = L[k0:k0 + h, k0:k0 + h]
+        ops.tri_inv_block(Lkk, Dinv[:h, :h])                 # Dinv = inv(L_kk) (lower)
+        U[k0:k0 + h, k0:k0 + h] = Dinv[:h, :h].t()
+        if k0 > 0:
+            # W^T = U[0:k0, 0:k0] L[k, 0:k0]^T  (k0 x h);   U[0:k0, k] = -W^T Dinv^T
+            Wt = ops.gemm_nt(U[0:k0, 0:k0], L[k0:k0 + h, 0:k0])
+            ops.gemm_nt(Wt, Dinv[:h, :h], alpha=-1.0, beta=0.0, C=U[0:k0, k0:k0 + h])
+    return ops.gemm_nt(U, U)
 
 
 def kron_inv(sigma2, B, K):
-    """kronecker_operation.py:36-54: dense (sigma2 I + B (x) K)^-1 (only sensible for small D*T, as in the reference)."""
+    """kronecker_operation.py:36-54: dense (sigma2 I + B (x) K)^-1 (only sensible for small D*T, as in the reference):
+    sum_m (v_m v_m^T) (x) A_m^-1 with A_m^-1 from the block's Cholesky factor."""
     T = K.shape[0]
     D = B.shape[0]
     out = torch.zeros(D * T, D * T, dtype=torch.float64, device=K.device)
-    eye = torch.eye(T, dtype=torch.float64, device=K.device)
     for m, lam_m, L, hld, V in _factor_blocks(sigma2, B, K):
-        Minv = torch.stack([ops.potrs_vec(L, eye[c].contiguous()) for c in range(T)], dim=1).contiguous()
+        Minv = chol_inverse(L)
         vm = V[:, m].contiguous()
         outer = ops.gemm_nt(vm.view(-1, 1).contiguous(), vm.view(-1, 1).contiguous())
         out = ops.axpby(out.view(-1), ops.kron_product(outer, Minv).view(-1), 1.0, 1.0).view(D * T, D * T)

@@ -1,8 +1,11 @@
-"""Forward values of the log joint posteriors of code/SIM_code/Utility/logpos.py (Kronecker NMGP, its stationary variant,
-and the Hadamard / irregular-observation variants), the deviance, and the index helpers next to them.
+"""Log joint posteriors of code/SIM_code/Utility/logpos.py (Kronecker NMGP, its stationary variant, and the Hadamard /
+irregular-observation variants), the deviance, and the index helpers next to them.
 
-Values only: the reference differentiates these objectives with autograd (scipy / HMC drivers); the adjoints of the
-SIM_code kernels are not built yet, so `nlogpos_obj*` here return plain values.  Every heavy step runs on
+The Kronecker family -- ``logpos`` / ``nlogpos_obj``, ``logpos_S`` / ``nlogpos_obj_S``, ``deviance`` / ``deviance_obj`` --
+is DIFFERENTIABLE w.r.t. the parameter vector, like the reference's (its drivers hand these objectives to gradient-based
+optimisers / HMC through autograd): hand-written adjoints of the Gibbs build (nmgp_nonstationary_cov_bwd), of the
+eigen-block Kronecker log-density (Cholesky-based, distributions._KronLogpdf0) and of the fixed-covariance GP priors.
+The dense (Hadamard / spatially-varying-coregionalisation) variants return forward values.  Every heavy step runs on
 the C-ABI kernels: covariance builds, the eigen-block Kronecker log-density (no symeig of K_x), dense blocked Cholesky
 in place of torch.inverse + torch.logdet and of MultivariateNormal's own factorisation.
 """
@@ -48,12 +51,59 @@ def generate_K_index(B_f, indx):
 
 
 # ---- shared pieces -----------------------------------------------------------------------------------------------------
+class _MVNLogprobFixedCov(torch.autograd.Function):
+    """log N(value | mean 1, Sigma) for a covariance that carries no gradient (the GP priors of logpos.py:271-283 use
+    RBF_cov with fixed hyper-parameters): d/d value = -Sigma^-1 (value - mean), from the same Cholesky solve."""
+
+    @staticmethod
+    def forward(ctx, value, mean, Sigma):
+        r = (value.detach() - mean).contiguous()
+        L, hld = ops.potrf_big(Sigma.detach().clone() if Sigma.requires_grad else Sigma)
+        a = ops.potrs_vec(L, r)
+        ctx.save_for_backward(a)
+        quad = ops.dot(r, a).reshape(())
+        return -0.5 * quad - hld.reshape(()) - 0.5 * r.numel() * math.log(2.0 * math.pi)
+
+    @staticmethod
+    def backward(ctx, g):
+        (a,) = ctx.saved_tensors
+        return -g * a, None, None
+
+
 def _mvn_logprob(value, mean, Sigma):
     """torch.distributions.MultivariateNormal(mean 1, covariance_matrix=Sigma).log_prob(value) through one blocked Cholesky."""
-    r = (value - mean).contiguous()
-    L, hld = ops.potrf_big(Sigma)
-    quad = ops.dot(r, ops.potrs_vec(L, r)).reshape(())
-    return -0.5 * quad - hld.reshape(()) - 0.5 * r.numel() * math.log(2.0 * math.pi)
+    return _MVNLogprobFixedCov.apply(value, mean, Sigma)
+
+
+class _GemmNT(torch.autograd.Function):
+    """C = A B^T on the tensor-core GEMM with its adjoint (Abar = Cbar B, Bbar = Cbar^T A)."""
+
+    @staticmethod
+    def forward(ctx, A, Bm):
+        ctx.save_for_backward(A.detach(), Bm.detach())
+        return ops.gemm_nt(A.detach().contiguous(), Bm.detach().contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        A, Bm = ctx.saved_tensors
+        g = g.contiguous()
+        return ops.gemm_nt(g, Bm.t().contiguous()), ops.gemm_nt(g.t().contiguous(), A.t().contiguous())
+
+
+class _NormalLogprobSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, loc, s_eff, shift):
+        vc = v.detach().contiguous().view(-1)
+        ctx.save_for_backward(vc)
+        ctx.loc, ctx.var, ctx.shape = loc, s_eff * s_eff, v.shape
+        base = ops.normal_logprob_sum(torch.full_like(vc, loc), torch.full((1,), s_eff, dtype=vc.dtype, device=vc.device),
+                                      vc).reshape(())
+        return base + shift
+
+    @staticmethod
+    def backward(ctx, g):
+        (vc,) = ctx.saved_tensors
+        return (ops.axpby(vc, torch.full_like(vc, ctx.loc), -1.0 / ctx.var, 1.0 / ctx.var) * g).reshape(ctx.shape), None, None, None
 
 
 def _normal_logprob_sum(v, loc, scale):
@@ -67,16 +117,13 @@ def _normal_logprob_sum(v, loc, scale):
     loc_t, scale_t = as_param(loc, first), as_param(scale, first)
     var = float(scale_t ** 2)
     log_scale = float(scale_t.log())
-    v = v.contiguous().view(-1)
     s_eff = math.sqrt(var)
-    base = ops.normal_logprob_sum(torch.full_like(v, float(loc_t)), torch.full((1,), s_eff, dtype=v.dtype, device=v.device),
-                                  v).reshape(())
-    return base + v.numel() * (math.log(s_eff) - log_scale)
+    return _NormalLogprobSum.apply(v, float(loc_t), s_eff, v.numel() * (math.log(s_eff) - log_scale))
 
 
 def _coregionalisation(L_vec, M):
     L = vec2lowtriangle(L_vec, M).contiguous()
-    return ops.gemm_nt(L, L)
+    return _GemmNT.apply(L, L)
 
 
 def _dense_loglik(K_x, B_f, indx, sigma2_err, y):

@@ -228,6 +228,16 @@ int nmgp_gemm_nt(const double* A, const double* B, double* C, long long M, long 
  *                                                    kronecker_operation.py:45-47,66-67; distributions.py:37-40,109-110
  * *info = 1 + index of the FIRST non-positive pivot (0 if none); strict upper triangle zeroed on return */
 int nmgp_potrf_big(double* A, long long T, long long lda, double* hld, int* info, nmgp_stream_t stream);
+/* same with an explicit scratch slot (0..3): independent factorisations running concurrently on different streams
+ * (the eigen-blocks of a Kronecker log-density) must use different slots; scratch is kept per (device, slot) */
+int nmgp_potrf_big_slot(double* A, long long T, long long lda, double* hld, int* info, int slot, nmgp_stream_t stream);
+/* out = scale * inv(L) for a lower-triangular nb x nb block (nb <= 128): building block of the blocked triangular
+ * inverse behind the Cholesky-based log-density adjoint (autograd of distributions.py:26-52) */
+int nmgp_tri_inv_block(const double* L, long long lda, int nb, double* out, long long ldo, double scale,
+                       nmgp_stream_t stream);
+/* A = alpha_dev[0] K + sigma2_dev[0] I, scalars read on the device */
+int nmgp_scale_add_diag_dev(const double* K, double* A, long long T, const double* alpha_dev, const double* sigma2_dev,
+                            nmgp_stream_t stream);
 /* x <- (L L^T)^-1 x */
 int nmgp_potrs_vec(const double* L, long long T, long long lda, double* x, nmgp_stream_t stream);
 /* A = alpha K + sigma2 I (the eigen-block sigma2 I + lambda_m K of sigma2 I + B (x) K) */
@@ -239,6 +249,9 @@ int nmgp_kron_product(const double* t1, const double* t2, double* out, int h1, i
  *                                                                          torch.symeig(B) at kronecker_operation.py:45 */
 int nmgp_eigh_small(const double* A, double* w, double* V, double* work, int n, nmgp_stream_t stream);
 int nmgp_axpby(const double* x, const double* y, double* out, long long n, double a, double b, nmgp_stream_t stream);
+/* out = (a_scale * a_dev[0]) x + b y, the scalar a_dev read on the device */
+int nmgp_axpby_dev(const double* x, const double* y, double* out, long long n, const double* a_dev, double a_scale,
+                   double b, nmgp_stream_t stream);
 int nmgp_dot(const double* x, const double* y, double* out /* += */, long long n, nmgp_stream_t stream);
 
 #ifdef __cplusplus

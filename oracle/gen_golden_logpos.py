@@ -63,6 +63,19 @@ def main():
     Lv_h = 0.4 * torch.randn(Nh * P, generator=g).double() + 0.3
     vHSVC = logpos.logpos_hadamard_SVC(tlh, Lv_h, ts2, xh, ih, yh, *hyp_i, a, b, verbose=True)
     out["logpos_hadamard_SVC_verbose"] = np.array([float(t) for t in vHSVC])
+    # gradients of the objectives w.r.t. the parameter vector: the reference's own autograd (through torch.symeig ->
+    # linalg.eigh under the shim, torch.distributions, ...).  These pin the hand-written SIM_code adjoints.
+    pg = pars.clone().requires_grad_(True)
+    logpos.nlogpos_obj(pg, Y, x, *[float(h) for h in hyp], a, b, c).backward()
+    out["grad_nlogpos_obj"] = pg.grad.numpy().copy()
+    pd_ = torch.cat([tilde_l, tilde_sigma, L_vec, ts2.view(1)]).clone().requires_grad_(True)
+    logpos.deviance_obj(pd_, Y, x).backward()
+    out["grad_deviance_obj"] = pd_.grad.numpy().copy()
+    pS = torch.cat([tlS.view(1), tsS.view(1), uL_vec, ts2.view(1)]).clone().requires_grad_(True)
+    vSo = logpos.nlogpos_obj_S(pS, Y, x, torch.tensor(-1.0).double(), torch.tensor(0.7).double(), a, b, c)
+    vSo.backward()
+    out["nlogpos_obj_S"] = float(vSo)
+    out["grad_nlogpos_obj_S"] = pS.grad.numpy().copy()
     np.savez_compressed(os.path.join(OUT, "sim_logpos.npz"), xi=xi.numpy(), tli=tli.numpy(), uLi=uLi.numpy(), Yi=Yi.numpy(),
                         hyp_i=np.array([float(h) for h in hyp_i]), Lv_h=Lv_h.numpy(), x=x.numpy(), tilde_l=tilde_l.numpy(), tilde_sigma=tilde_sigma.numpy(),
                         uL_vec=uL_vec.numpy(), L_vec=L_vec.numpy(), ts2=float(ts2), Y=Y.numpy(), hyp=np.array([float(h) for h in hyp]),

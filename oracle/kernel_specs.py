@@ -101,10 +101,11 @@ def kl_rbar(R, G, Rbar):
 
 def kl_bwd(klbar, CS, mu, R, t, exact=False):
     if exact:                                # autograd of the exact forward (test infrastructure may be slow)
-        CSv = CS.clone().requires_grad_(True); muv = mu.clone().requires_grad_(True); Rv = R.clone().requires_grad_(True)
-        hS = torch.zeros(CS.shape[0], dtype=F64, requires_grad=True); hR = torch.zeros(R.shape[0], dtype=F64, requires_grad=True)
-        kl, _ = kl_fwd(CSv, hS, muv, Rv, hR, exact=True)
-        g = torch.autograd.grad((kl * klbar).sum(), [CSv, hS, muv, Rv, hR])
+        with torch.enable_grad():
+            CSv = CS.clone().requires_grad_(True); muv = mu.clone().requires_grad_(True); Rv = R.clone().requires_grad_(True)
+            hS = torch.zeros(CS.shape[0], dtype=F64, requires_grad=True); hR = torch.zeros(R.shape[0], dtype=F64, requires_grad=True)
+            kl, _ = kl_fwd(CSv, hS, muv, Rv, hR, exact=True)
+            g = torch.autograd.grad((kl * klbar).sum(), [CSv, hS, muv, Rv, hR])
         return torch.tril(g[0]), g[1], g[2], torch.tril(g[3]), g[4]
     np_, nb, Q = R.shape[0], CS.shape[0], CS.shape[-1]
     d = R.diagonal(dim1=-2, dim2=-1)                            # [np,Q]
@@ -443,11 +444,12 @@ def nonstationary_cov(X1, sigma1, ell1, X2, sigma2, ell2, jitter, self_cov=False
 def nonstationary_cov_bwd(X1, sigma1, ell1, X2, sigma2, ell2, Kbar, want=(True, True, True, True)):
     """Autograd of the specification above (test infrastructure)."""
     args = [sigma1, ell1, sigma2, ell2]
-    leaves = [None if a is None else a.detach().clone().requires_grad_(True) for a in args]
-    K = nonstationary_cov(X1, leaves[0], leaves[1], X2, leaves[2], leaves[3], 0.0)
-    outs = []
-    for a, w in zip(leaves, want):
-        outs.append(torch.autograd.grad((K * Kbar).sum(), a, retain_graph=True)[0] if (w and a is not None) else None)
+    with torch.enable_grad():                      # may be called from inside a custom Function's backward
+        leaves = [None if a is None else a.detach().clone().requires_grad_(True) for a in args]
+        K = nonstationary_cov(X1, leaves[0], leaves[1], X2, leaves[2], leaves[3], 0.0)
+        outs = []
+        for a, w in zip(leaves, want):
+            outs.append(torch.autograd.grad((K * Kbar).sum(), a, retain_graph=True)[0] if (w and a is not None) else None)
     return tuple(outs)
 
 
@@ -474,10 +476,27 @@ def gemm_nt(A, Bm, alpha=1.0, beta=0.0, C=None):
     return out
 
 
-def potrf_big(A):
-    L = torch.linalg.cholesky(A)
+def potrf_big(A, info=None, slot=0):
+    L, bad = torch.linalg.cholesky_ex(A)
+    if int(bad) != 0:
+        if info is None:
+            raise RuntimeError("cholesky: the leading minor of order %d is not positive-definite" % int(bad))
+        info.fill_(int(bad))
     A.copy_(L)
     return A, L.diagonal().log().sum().reshape(1)
+
+
+def tri_inv_block(L, out, scale=1.0):
+    out.copy_(scale * torch.linalg.solve_triangular(torch.tril(L), torch.eye(L.shape[0], dtype=F64), upper=False))
+    return out
+
+
+def scale_add_diag_dev(K, alpha_dev, sigma2_dev, out=None):
+    A = alpha_dev.reshape(()) * K + sigma2_dev.reshape(()) * torch.eye(K.shape[0], dtype=F64)
+    if out is not None:
+        out.copy_(A)
+        return out
+    return A
 
 
 def potrs_vec(L, b):
@@ -494,6 +513,14 @@ def kron_product(t1, t2):
 
 def eigh_small(A):
     return torch.linalg.eigh(A, UPLO="U")
+
+
+def axpby_dev(x, y, a_dev, a_scale=1.0, b=1.0, out=None):
+    res = (a_scale * a_dev.reshape(())) * x + b * y
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
 
 
 def axpby(x, y, a, b):

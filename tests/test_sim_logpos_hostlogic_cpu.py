@@ -71,3 +71,25 @@ def test_logpos_values_match_reference():
     assert i1.tolist() == [0, 0, 0, 2, 2, 2] and i2.tolist() == [1, 0, 2, 1, 0, 2]
     Bf = torch.arange(9, dtype=torch.float64).view(3, 3)
     assert torch.equal(logpos.generate_K_index(Bf, torch.tensor([2, 0])), torch.tensor([[8., 6.], [2., 0.]], dtype=torch.float64))
+
+
+def test_objective_gradients_match_reference_autograd():
+    """nlogpos_obj / deviance_obj / nlogpos_obj_S are differentiable drop-ins: values and gradients w.r.t. the parameter
+    vector against the reference's own autograd (golden)."""
+    from tests import sim_logpos_cases
+    print(sim_logpos_cases.check_objective_gradients("cpu"))
+
+
+def test_nan_retry_recovers_like_the_reference():
+    """a block that is not positive definite must give NaN (as the reference's eigen route does), not an
+    exception, so the jittered retry of logpos.py:267-268 can run."""
+    from collaborative_nonstationary_multivariate_gaussian_process_b200 import distributions
+    T, D = 12, 2
+    x = torch.linspace(0, 1, T, dtype=torch.float64).view(-1, 1)
+    K = torch.exp(-0.5 * (x - x.t()) ** 2 / 0.09)
+    B = torch.tensor([[1.0, 0.2], [0.2, 0.5]], dtype=torch.float64)
+    y = torch.randn(T * D, generator=torch.Generator().manual_seed(0), dtype=torch.float64)
+    bad = distributions.multivariate_normal_logpdf0(y, torch.zeros_like(y), B, K, torch.tensor(-0.5, dtype=torch.float64))
+    assert bool(torch.isnan(bad))
+    ok = distributions.multivariate_normal_logpdf0(y, torch.zeros_like(y), B, K, torch.tensor(0.1, dtype=torch.float64))
+    assert bool(torch.isfinite(ok))
