@@ -592,6 +592,7 @@ def main():
     args = parse()
     if args.workload == "sweep":
         import bench_sweep
+        sys.modules.setdefault("bench", sys.modules[__name__])
         return bench_sweep.run(args)
     w = resolve(args)
     if args.impl == "reference":

@@ -576,6 +576,21 @@ def gemm_nt(A, Bm, alpha=1.0, beta=0.0, C=None):
     return C
 
 
+def build_augmented(K, r, alpha_dev, sigma2_dev, rnorm2_dev, out):
+    """out [T+1 rows, leading dimension out.stride(0)] = [[alpha K + sigma2 I, .], [r^T, 1 + |r|^2 / sigma2]]."""
+    T = K.shape[0]
+    check(lib().nmgp_build_augmented(_d(K), _d(r), c_void_p(out.data_ptr()), c_int64(T), c_int64(out.stride(0)),
+                                     c_void_p(alpha_dev.data_ptr()), c_void_p(sigma2_dev.data_ptr()),
+                                     c_void_p(rnorm2_dev.data_ptr()), _stream()), "nmgp_build_augmented")
+    return out
+
+
+def augmented_results(A, T, hld_aug, hld_out, quad_out):
+    check(lib().nmgp_augmented_results(c_void_p(A.data_ptr()), c_int64(T), c_int64(A.stride(0)), _d(hld_aug),
+                                       c_void_p(hld_out.data_ptr()), c_void_p(quad_out.data_ptr()), _stream()),
+          "nmgp_augmented_results")
+
+
 def potrf_big(A, info=None, slot=0):
     """In-place blocked lower Cholesky of the square matrix A; returns (A, sum(log(diag))).  Raises RuntimeError on a
     non-positive pivot like torch.cholesky -- unless ``info`` (int32 device scalar, receives the order of the failing
@@ -587,8 +602,11 @@ def potrf_big(A, info=None, slot=0):
     deferred = info is not None
     if not deferred:
         info = torch.zeros(1, dtype=torch.int32, device=A.device)
-    check(lib().nmgp_potrf_big_slot(_d(A), c_int64(T), c_int64(T), _d(hld), _i(info), c_int(slot), _stream()),
-          "nmgp_potrf_big")
+    if not (A.is_cuda and A.dtype == F64 and A.dim() == 2 and A.stride(1) == 1):
+        raise TypeError("potrf_big expects a CUDA float64 matrix with unit column stride")
+    _same_device(A)
+    check(lib().nmgp_potrf_big_slot(c_void_p(A.data_ptr()), c_int64(T), c_int64(A.stride(0) if T > 1 else 1), _d(hld),
+                                    _i(info), c_int(slot), _stream()), "nmgp_potrf_big")
     if not deferred:
         bad = int(info.item())
         if bad != 0:

@@ -411,7 +411,7 @@ static int factor_panel(double* Akk, long long lda, int nb, long long rest, doub
 // events and two 128 x 128 inverse blocks (main stream / helper stream).  Independent factorisations that run
 // concurrently (the eigen-blocks of a Kronecker log-density, dealt round-robin to a few streams so that the panel phase
 // of one overlaps the trailing updates of the others) must use different slots.
-#define POTRF_SLOTS 4
+#define POTRF_SLOTS 8
 #define POTRF_MAXDEV 16
 struct PotrfCtx {
     cudaStream_t helper = nullptr;
@@ -506,11 +506,11 @@ NMGP_API int nmgp_potrf_big(double* A, long long T, long long lda, double* hld, 
 // above the diagonal are written as zeros): one CTA, thread c solves L x = e_c by forward substitution from a shared-
 // memory copy.  Building block of the blocked triangular inverse used by the Cholesky-based log-density adjoint.
 __global__ void __launch_bounds__(PB)
-k_tri_inv_block(const double* __restrict__ L, long long lda, int nb, double* __restrict__ out, long long ldo, double scale) {
+k_tri_inv_block(const double* __restrict__ L, long long lda, int nb, double* out, long long ldo, double scale) {
     extern __shared__ double sm[];
     constexpr int LD = PB + 1;
-    double* Ls = sm;                        // [PB][PB+1]
-    double* Xs = Ls + PB * LD;              // [PB][PB+1]  column c of the inverse in Xs[:, c]
+    double* Ls = sm;                        // [PB][PB+1]; the inverse is built in `out` itself (column c by thread c:
+                                            // coalesced across the threads, each thread only re-reads its own column)
     const int tid = threadIdx.x;
     for (int e = tid; e < PB * PB; e += blockDim.x) {
         const int a = e / PB, b = e - a * PB;
@@ -520,30 +520,27 @@ k_tri_inv_block(const double* __restrict__ L, long long lda, int nb, double* __r
     const int c = tid;
     if (c < nb) {
         for (int a = 0; a < nb; ++a) {
-            double s0 = (a == c) ? 1.0 : 0.0, s1 = 0.0;
+            double v = 0.0;
             if (a >= c) {
+                double s0 = (a == c) ? 1.0 : 0.0, s1 = 0.0;
                 int k = c;
                 for (; k + 1 < a; k += 2) {
-                    s0 = fma(-Ls[a * LD + k], Xs[k * LD + c], s0);
-                    s1 = fma(-Ls[a * LD + k + 1], Xs[(k + 1) * LD + c], s1);
+                    s0 = fma(-Ls[a * LD + k], out[(long long)k * ldo + c], s0);
+                    s1 = fma(-Ls[a * LD + k + 1], out[(long long)(k + 1) * ldo + c], s1);
                 }
-                if (k < a) s0 = fma(-Ls[a * LD + k], Xs[k * LD + c], s0);
-                Xs[a * LD + c] = (s0 + s1) / Ls[a * LD + a];
-            } else {
-                Xs[a * LD + c] = 0.0;
+                if (k < a) s0 = fma(-Ls[a * LD + k], out[(long long)k * ldo + c], s0);
+                v = (s0 + s1) / Ls[a * LD + a];
             }
+            out[(long long)a * ldo + c] = v;
         }
-    }
-    __syncthreads();
-    for (int e = tid; e < nb * nb; e += blockDim.x) {
-        const int a = e / nb, b = e - a * nb;
-        out[(long long)a * ldo + b] = scale * Xs[a * LD + b];
+        if (scale != 1.0)
+            for (int a = c; a < nb; ++a) out[(long long)a * ldo + c] *= scale;
     }
 }
 NMGP_API int nmgp_tri_inv_block(const double* L, long long lda, int nb, double* out, long long ldo, double scale,
                                 cudaStream_t st) {
     NMGP_REQUIRE(nb > 0 && nb <= PB && lda >= nb && ldo >= nb, "nmgp_tri_inv_block");
-    const size_t smem = sizeof(double) * 2 * PB * (PB + 1);
+    const size_t smem = sizeof(double) * PB * (PB + 1);
     if (int r = nmgp_opt_in_smem(k_tri_inv_block, smem, "nmgp_tri_inv_block")) return r;
     k_tri_inv_block<<<NMGP_L(1), PB, smem, st>>>(L, lda, nb, out, ldo, scale);
     return nmgp_launch_status("nmgp_tri_inv_block");
@@ -670,6 +667,50 @@ NMGP_API int nmgp_scale_add_diag_dev(const double* K, double* A, long long T, co
     dim3 grid((unsigned)((T + 255) / 256), (unsigned)min(T, 65535LL), (unsigned)((T + 65534) / 65535));
     k_scale_add_diag_dev<<<NMGP_L(grid), 256, 0, st>>>(K, A, T, alpha_dev, sigma2_dev);
     return nmgp_launch_status("nmgp_scale_add_diag_dev");
+}
+// Augmented system of one eigen-block: rows 0..T-1 = alpha K + sigma2 I, row T = (r^T, c) with
+// c = 1 + |r|^2 / sigma2 >= 1 + r^T A^-1 r (A >= sigma2 I), leading dimension lda >= T + 1.  The Cholesky factor of the
+// (T+1) x (T+1) matrix carries (L^-1 r)^T in its last row, so the quadratic form r^T A^-1 r = |L^-1 r|^2 comes out of the
+// blocked factorisation itself (tensor-core panel GEMMs) instead of a chain of ~2 T/128 latency-bound substitution
+// launches per block.  Only the lower triangle is referenced by the factorisation; the upper part of the last column is
+// left unset.
+__global__ void k_build_augmented(const double* __restrict__ K, const double* __restrict__ r, double* __restrict__ A,
+                                  long long T, long long lda, const double* __restrict__ alpha_dev,
+                                  const double* __restrict__ sigma2_dev, const double* __restrict__ rnorm2_dev) {
+    const double alpha = alpha_dev[0], sigma2 = sigma2_dev[0];
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y + (long long)blockIdx.z * 65535;
+    if (row > T || c > T) return;
+    if (row < T) {
+        if (c < T) A[row * lda + c] = fma(alpha, K[row * T + c], (row == c) ? sigma2 : 0.0);
+    } else {
+        A[row * lda + c] = (c < T) ? r[c] : 1.0 + rnorm2_dev[0] / sigma2;
+    }
+}
+NMGP_API int nmgp_build_augmented(const double* K, const double* r, double* A, long long T, long long lda,
+                                  const double* alpha_dev, const double* sigma2_dev, const double* rnorm2_dev,
+                                  cudaStream_t st) {
+    NMGP_REQUIRE(T > 0 && lda >= T + 1, "nmgp_build_augmented");
+    dim3 grid((unsigned)((T + 1 + 255) / 256), (unsigned)min(T + 1, 65535LL), (unsigned)((T + 1 + 65534) / 65535));
+    k_build_augmented<<<NMGP_L(grid), 256, 0, st>>>(K, r, A, T, lda, alpha_dev, sigma2_dev, rnorm2_dev);
+    return nmgp_launch_status("nmgp_build_augmented");
+}
+// from the factor of the augmented system: quad = |row T, columns 0..T-1|^2, hld = hld_aug - log(A[T,T])
+__global__ void k_augmented_results(const double* __restrict__ A, long long T, long long lda,
+                                    const double* __restrict__ hld_aug, double* __restrict__ hld, double* __restrict__ quad) {
+    double s = 0.0;
+    const double* row = A + T * lda;
+    for (long long i = threadIdx.x; i < T; i += blockDim.x) s = fma(row[i], row[i], s);
+    s = block_sum(s);
+    if (threadIdx.x == 0) {
+        quad[0] = s;
+        hld[0] = hld_aug[0] - log(row[T]);
+    }
+}
+NMGP_API int nmgp_augmented_results(const double* A, long long T, long long lda, const double* hld_aug, double* hld,
+                                    double* quad, cudaStream_t st) {
+    NMGP_REQUIRE(T > 0 && lda >= T + 1, "nmgp_augmented_results");
+    k_augmented_results<<<NMGP_L(1), 1024, 0, st>>>(A, T, lda, hld_aug, hld, quad);
+    return nmgp_launch_status("nmgp_augmented_results");
 }
 NMGP_API int nmgp_scale_add_diag(const double* K, double* A, long long T, double alpha, double sigma2,
                                  cudaStream_t st) {

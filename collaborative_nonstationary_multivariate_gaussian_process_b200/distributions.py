@@ -35,10 +35,12 @@ class _KronLogpdf0(torch.autograd.Function):
         r = ops.axpby(y.detach().contiguous(), mu.detach().contiguous(), 1.0, -1.0)
         lam, V = ops.eigh_small(B.detach().contiguous())
         Rt = _rotate(V, r, D, T)
-        res = kronecker_operation.block_pipeline(sigma2, B, K, Rt=Rt, shard=shard)
+        needs_adjoint = any(torch.is_tensor(t) and t.requires_grad for t in (y, mu, B, K, sigma2))
+        res = kronecker_operation.block_pipeline(sigma2, B, K, Rt=Rt, shard=shard, want_alpha=needs_adjoint)
         val = -(res["hld"].sum()) - 0.5 * res["quad"].sum()
         s2 = torch.as_tensor(sigma2, dtype=torch.float64).detach().reshape(1).to(K.device)
-        ctx.save_for_backward(r, B.detach(), K.detach(), s2, res["alpha"], lam, V)
+        alpha = res["alpha"] if res["alpha"] is not None else torch.empty(0, dtype=torch.float64, device=K.device)
+        ctx.save_for_backward(r, B.detach(), K.detach(), s2, alpha, lam, V)
         ctx.shard = shard
         ctx.s2_shape = sigma2.shape if torch.is_tensor(sigma2) else None
         return kronecker_operation.nan_if_not_pd(val, res["info"]).reshape(())

@@ -14,7 +14,10 @@ import torch
 
 from . import _ops as ops
 
-NSLOT = 3                      # concurrent eigen-block factorisations (streams / library scratch slots / T x T buffers)
+import os
+
+# concurrent eigen-block factorisations (streams / library scratch slots / T x T buffers); the library has 8 slots
+NSLOT = max(1, min(8, int(os.environ.get("NMGP_KRON_SLOTS", "4"))))
 _streams = {}
 
 
@@ -39,11 +42,14 @@ def _dev_scalar(v, dev):
     return torch.as_tensor(v, dtype=torch.float64).detach().reshape(1).to(dev)
 
 
-def block_pipeline(sigma2, B, K, Rt=None, shard=None, per_block=None):
+def block_pipeline(sigma2, B, K, Rt=None, shard=None, per_block=None, want_alpha=True):
     """Factorises A_m = sigma2 I + lam_m K for the eigen-blocks m of B (all, or the shard (rank, world): m = rank,
     rank + world, ...) -- NSLOT at a time on NSLOT streams -- and per block computes hld_m = 1/2 logdet A_m and, when
     ``Rt`` [D, T] is given, alpha_m = A_m^-1 Rt[m] and quad_m = Rt[m] . alpha_m.  ``per_block(m, L_m, slot)`` (optional)
     runs on the block's stream right after its factorisation (the adjoint uses it).  Nothing is read back to the host.
+    With ``want_alpha=False`` (values only) the quadratic form comes out of the factorisation itself: the block is
+    factorised as the augmented (T+1) x (T+1) system [[A_m, r_m], [r_m^T, c]] whose factor carries (L^-1 r_m)^T in its last
+    row -- no triangular-solve launches at all.
     Returns dict(lam, V, hld [D], quad [D], alpha [D, T] or None, info [D] int32, blocks)."""
     D, T = B.shape[0], K.shape[0]
     dev = K.device
@@ -55,10 +61,16 @@ def block_pipeline(sigma2, B, K, Rt=None, shard=None, per_block=None):
     hld = torch.zeros(D, dtype=torch.float64, device=dev)
     quad = torch.zeros(D, dtype=torch.float64, device=dev)
     info = torch.zeros(D, dtype=torch.int32, device=dev)
-    alpha = torch.zeros(D, T, dtype=torch.float64, device=dev) if Rt is not None else None
+    augmented = Rt is not None and not want_alpha and per_block is None
+    alpha = torch.zeros(D, T, dtype=torch.float64, device=dev) if (Rt is not None and not augmented) else None
     on_gpu = Kc.is_cuda
     nslot = min(NSLOT, max(len(blocks), 1))
-    bufs = [torch.empty_like(Kc) for _ in range(nslot)]
+    if augmented:
+        lda = T + 8 - (T % 8) if T % 8 else T + 8                    # even, 64-byte aligned rows: 16-byte vector paths stay on
+        bufs = [torch.empty(T + 1, lda, dtype=torch.float64, device=dev) for _ in range(nslot)]
+        rn2 = (Rt * Rt).sum(1).contiguous()                          # |r_m|^2 per block (device)
+    else:
+        bufs = [torch.empty_like(Kc) for _ in range(nslot)]
     streams = _slot_streams(dev)[:nslot] if on_gpu else [None] * nslot
     main = torch.cuda.current_stream(dev) if on_gpu else None
     for st in streams:
@@ -68,6 +80,12 @@ def block_pipeline(sigma2, B, K, Rt=None, shard=None, per_block=None):
         slot = idx % nslot
         ctx = torch.cuda.stream(streams[slot]) if on_gpu else _Null()
         with ctx:
+            if augmented:
+                Aug = bufs[slot][:, :T + 1]
+                ops.build_augmented(Kc, Rt[m].contiguous(), lam[m:m + 1], s2, rn2[m:m + 1], out=bufs[slot])
+                _, h = ops.potrf_big(Aug, info=info[m:m + 1], slot=slot)
+                ops.augmented_results(bufs[slot], T, h, hld[m:m + 1], quad[m:m + 1])
+                continue
             A = ops.scale_add_diag_dev(Kc, lam[m:m + 1], s2, out=bufs[slot])
             L, h = ops.potrf_big(A, info=info[m:m + 1], slot=slot)
             hld[m:m + 1] = h

@@ -58,8 +58,13 @@ class _MVNLogprobFixedCov(torch.autograd.Function):
     @staticmethod
     def forward(ctx, value, mean, Sigma):
         r = (value.detach() - mean).contiguous()
-        L, hld = ops.potrf_big(Sigma.detach().clone() if Sigma.requires_grad else Sigma)
+        S = Sigma.detach()
+        L, hld = ops.potrf_big(S.clone())
+        # one step of FP64 iterative refinement: these prior covariances are RBF + 1e-6 I (condition number ~1e8), a plain
+        # Cholesky solve carries ~cond * eps = 1e-8, above the 1e-9 this path is compared at
         a = ops.potrs_vec(L, r)
+        res = ops.axpby(r, ops.gemm_nt(a.view(1, -1), S.contiguous()).view(-1), 1.0, -1.0)       # r - Sigma a
+        a = ops.axpby(a, ops.potrs_vec(L, res), 1.0, 1.0)
         ctx.save_for_backward(a)
         quad = ops.dot(r, a).reshape(())
         return -0.5 * quad - hld.reshape(()) - 0.5 * r.numel() * math.log(2.0 * math.pi)

@@ -84,16 +84,27 @@ class _ConditionalGP:
 
     def __init__(self, x, mu, alpha, beta):
         self.x, self.mu, self.alpha, self.beta = x, float(mu), float(alpha), float(beta)
-        self.Lc, _ = ops.potrf_big(kernels.RBF_cov(x, alpha=self.alpha, beta=self.beta))
+        self.Sigma = kernels.RBF_cov(x, alpha=self.alpha, beta=self.beta)
+        self.Lc, _ = ops.potrf_big(self.Sigma.clone())
+
+    def solve(self, b):
+        """Sigma^-1 b with one step of iterative refinement in FP64: Sigma = RBF + 1e-6 I has a condition number of
+        ~1e8, so a plain Cholesky solve carries ~cond * eps = 1e-8; the refinement step brings the solution (and the
+        conditional variance that is a cancellation of it) to rounding level, which is what lets these predictors be
+        compared with the reference at 1e-9."""
+        b = b.contiguous()
+        x = ops.potrs_vec(self.Lc, b)
+        r = ops.axpby(b, ops.gemm_nt(x.view(1, -1), self.Sigma).view(-1), 1.0, -1.0)     # b - Sigma x (Sigma symmetric)
+        return ops.axpby(x, ops.potrs_vec(self.Lc, r), 1.0, 1.0)
 
     def weights(self, tilde):
         """Sigma^-1 (tilde - mu): enough for the conditional mean."""
-        return ops.potrs_vec(self.Lc, (tilde - self.mu).contiguous())
+        return self.solve(tilde - self.mu)
 
     def projection(self, xs):
         """(k, Sigma^-1 k, k** - k . Sigma^-1 k) for the single input xs [1,1]."""
         k = kernels.RBF_cov(self.x, xs, alpha=self.alpha, beta=self.beta).view(-1).contiguous()
-        proj = ops.potrs_vec(self.Lc, k)
+        proj = self.solve(k)
         kss = kernels.RBF_cov(xs, alpha=self.alpha, beta=self.beta).view(())
         return k, proj, kss - ops.dot(proj, k).reshape(())
 

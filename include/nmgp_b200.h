@@ -235,6 +235,14 @@ int nmgp_potrf_big_slot(double* A, long long T, long long lda, double* hld, int*
  * inverse behind the Cholesky-based log-density adjoint (autograd of distributions.py:26-52) */
 int nmgp_tri_inv_block(const double* L, long long lda, int nb, double* out, long long ldo, double scale,
                        nmgp_stream_t stream);
+/* augmented eigen-block system (T+1) x (T+1), leading dimension lda: rows 0..T-1 = alpha K + sigma2 I, row T =
+ * (r^T, 1 + |r|^2 / sigma2).  Its Cholesky factor holds (L^-1 r)^T in the last row, so r^T A^-1 r needs no triangular
+ * solve launches: nmgp_augmented_results reads quad = |L^-1 r|^2 and hld = 1/2 logdet A from the factor. */
+int nmgp_build_augmented(const double* K, const double* r, double* A, long long T, long long lda,
+                         const double* alpha_dev, const double* sigma2_dev, const double* rnorm2_dev,
+                         nmgp_stream_t stream);
+int nmgp_augmented_results(const double* A, long long T, long long lda, const double* hld_aug, double* hld,
+                           double* quad, nmgp_stream_t stream);
 /* A = alpha_dev[0] K + sigma2_dev[0] I, scalars read on the device */
 int nmgp_scale_add_diag_dev(const double* K, double* A, long long T, const double* alpha_dev, const double* sigma2_dev,
                             nmgp_stream_t stream);

@@ -486,6 +486,20 @@ def potrf_big(A, info=None, slot=0):
     return A, L.diagonal().log().sum().reshape(1)
 
 
+def build_augmented(K, r, alpha_dev, sigma2_dev, rnorm2_dev, out):
+    T = K.shape[0]
+    out[:T, :T] = alpha_dev.reshape(()) * K + sigma2_dev.reshape(()) * torch.eye(T, dtype=F64)
+    out[T, :T] = r
+    out[:T, T] = r
+    out[T, T] = 1.0 + rnorm2_dev.reshape(()) / sigma2_dev.reshape(())
+    return out
+
+
+def augmented_results(A, T, hld_aug, hld_out, quad_out):
+    quad_out.copy_((A[T, :T] ** 2).sum().reshape(quad_out.shape))
+    hld_out.copy_((hld_aug.reshape(()) - torch.log(A[T, T])).reshape(hld_out.shape))
+
+
 def tri_inv_block(L, out, scale=1.0):
     out.copy_(scale * torch.linalg.solve_triangular(torch.tril(L), torch.eye(L.shape[0], dtype=F64), upper=False))
     return out

@@ -7,19 +7,25 @@ from tests import golden_util as gu
 
 ORDER = ("mu_tilde_l", "alpha_tilde_l", "beta_tilde_l", "mu_tilde_sigma", "alpha_tilde_sigma", "beta_tilde_sigma")
 # The reference solves the two GP-conditional systems Sigma + 1e-6 I (condition number ~1e8 for a smooth RBF on 60
-# points) by LU and eigendecomposes K_x; we use Cholesky factors.  Both are backward stable, so the outputs agree to
-# cond * eps; the bound below is that, not the 1e-9 of the well-conditioned DSVI path.
-RTOL = 2e-8
-# Hadamard layout: the same input appears once per output, so RBF_cov(x) + 1e-6 I has exactly repeated rows (condition
-# number ~ N alpha^2 / 1e-6 ~ 1e8) and the reference goes through symeig(K) and an explicit inverse.  Bound = cond * eps
-# with margin; measured 3e-10 with the CPU kernel specifications, 2e-8 at worst on the GPU (sampling variant, where the
-# drawn log-ell enters through exp()).
-HTOL = 5e-7
+# points) by LU and eigendecomposes K_x; we use Cholesky factors plus ONE step of FP64 iterative refinement on those
+# systems (prediction._ConditionalGP.solve), which brings our side to rounding level: what is left is the reference's
+# own LU error.  Measured (CPU specifications): <= 5.2e-10 everywhere except the SVC predictive variance (1.4e-9, a
+# cancellation of two dense (NM)^2 solves).
+RTOL = 1e-9
+# Hadamard / SVC layouts: the same input appears once per output, so RBF_cov(x) + 1e-6 I has exactly repeated rows
+# (condition number ~ N alpha^2 / 1e-6 ~ 1e8) and the reference goes through symeig(K) and an explicit inverse -- its own
+# result carries ~cond * eps.  Bound below = measured worst case (1.4e-9) with margin.
+HTOL = 5e-9
+
+
+WORST = {"max": 0.0}          # largest relative deviation seen by the last run_all (reported by the tests)
 
 
 def _rel(a, b):
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
-    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+    e = float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+    WORST["max"] = max(WORST["max"], e)
+    return e
 
 
 def run_all(dev):

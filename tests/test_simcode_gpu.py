@@ -167,3 +167,45 @@ def test_hadamard_index_cov():
     Kx = torch.randn(40, 3, generator=gen, dtype=torch.float64); Bf = torch.randn(8, 1, generator=gen, dtype=torch.float64)
     i1 = torch.randint(0, 8, (40,), generator=gen).to(torch.int32); i2 = torch.zeros(3, dtype=torch.int32)
     assert rel(ops.hadamard_index_cov(d(Kx), d(Bf), i1.cuda(), i2.cuda(), 0.0), specs.hadamard_index_cov(Kx, Bf, i1, i2, 0.0)) < 1e-15
+
+
+@pytest.mark.parametrize("T", [8192, 12288])
+def test_potrf_big_native_panels_at_sweep_sizes(T):
+    """The 256 / 512-wide panels the factorisation picks by itself above T = 6144 / 12288 (BASELINE config 5 sizes),
+    checked on the device: residual of L L^T against A (size-independent property) and log-determinant against
+    cuSOLVER's factor (a yardstick, not on the product path)."""
+    gen = torch.Generator().manual_seed(T)
+    x = torch.sort(torch.rand(T, generator=gen, dtype=torch.float64))[0].view(-1, 1)
+    K = kernels.Nonstationary_RBF_cov(d(x), ell1=d(torch.exp(3 * (x.view(-1) - 1) ** 3 - 3.0)))
+    A = ops.scale_add_diag(K, 1.0, 1e-2)
+    L, hld = ops.potrf_big(A.clone())
+    R = ops.gemm_nt(L, L)                                     # L L^T on the tensor cores
+    assert float(torch.linalg.norm(R - A) / torch.linalg.norm(A)) < 1e-13
+    Lr = torch.linalg.cholesky(A)
+    ref = float(Lr.diagonal().log().sum())
+    assert abs(float(hld) - ref) <= 1e-11 * abs(ref)
+    assert float(torch.linalg.norm(L - Lr) / torch.linalg.norm(Lr)) < 1e-9
+
+
+@pytest.mark.parametrize("T,D", [(2048, 3), (4096, 2), (8192, 2)])
+def test_kron_logpdf0_matches_the_eigen_route_at_sweep_sizes(T, D):
+    """multivariate_normal_logpdf0 through the eigen-block Cholesky pipeline (augmented systems, blocks in flight on
+    several streams) against the reference's own route -- symeig of both factors (distributions.py:37-51), evaluated
+    here with torch.linalg.eigh on the device -- at the sizes of the scale sweep.  1e-9 relative."""
+    gen = torch.Generator().manual_seed(T + D)
+    x = torch.sort(torch.rand(T, generator=gen, dtype=torch.float64))[0].view(-1, 1)
+    K = kernels.Nonstationary_RBF_cov(d(x), ell1=d(torch.exp(3 * (x.view(-1) - 1) ** 3 - 3.0)))
+    Lb = torch.tril(torch.randn(D, D, generator=gen, dtype=torch.float64)); Bf = d(Lb @ Lb.t() / D)
+    y = d(torch.randn(D * T, generator=gen, dtype=torch.float64))
+    s2 = torch.tensor(1e-2, dtype=torch.float64)
+    got = float(distributions.multivariate_normal_logpdf0(y, torch.zeros_like(y), Bf, K, s2))
+    wB, VB = torch.linalg.eigh(Bf, UPLO="U")
+    wK, VK = torch.linalg.eigh(K, UPLO="U")
+    a = (VK.t() @ y.view(D, T).t() @ VB).t().reshape(-1)        # kron_mv(V_B^T, V_K^T, y)
+    tt = torch.kron(wB, wK) + float(s2)
+    ref = float(-0.5 * torch.log(tt).sum() - 0.5 * (a * a / tt).sum())
+    assert abs(got - ref) <= 1e-9 * abs(ref), (got, ref)
+    # the adjoint-capable path (explicit solves) gives the same value
+    yv = y.clone().requires_grad_(True)
+    got2 = float(distributions.multivariate_normal_logpdf0(yv, torch.zeros_like(y), Bf, K, s2))
+    assert abs(got2 - ref) <= 1e-9 * abs(ref), (got2, ref)
