@@ -591,7 +591,7 @@ def augmented_results(A, T, hld_aug, hld_out, quad_out):
           "nmgp_augmented_results")
 
 
-def potrf_big(A, info=None, slot=0):
+def potrf_big(A, info=None, slot=0, panel=0):
     """In-place blocked lower Cholesky of the square matrix A; returns (A, sum(log(diag))).  Raises RuntimeError on a
     non-positive pivot like torch.cholesky -- unless ``info`` (int32 device scalar, receives the order of the failing
     leading minor, 0 if none) is given: then nothing is read back here (no host synchronisation).  ``slot`` (0..3)
@@ -606,7 +606,7 @@ def potrf_big(A, info=None, slot=0):
         raise TypeError("potrf_big expects a CUDA float64 matrix with unit column stride")
     _same_device(A)
     check(lib().nmgp_potrf_big_slot(c_void_p(A.data_ptr()), c_int64(T), c_int64(A.stride(0) if T > 1 else 1), _d(hld),
-                                    _i(info), c_int(slot), _stream()), "nmgp_potrf_big")
+                                    _i(info), c_int(slot), c_int(panel), _stream()), "nmgp_potrf_big")
     if not deferred:
         bad = int(info.item())
         if bad != 0:

@@ -160,6 +160,9 @@ k_gemm_nt(const double* __restrict__ A, const double* __restrict__ Bm, double* _
         }
     }
 }
+// TMA-fed variant of the 128 x 64 tile kernel (nmgp_gemm_tma.cu): 0 launched, 1 not applicable (alignment / driver)
+int nmgp_gemm_nt_tma(const double* A, const double* Bm, double* C, long long M, long long N, long long K, long long lda,
+                     long long ldb, long long ldc, double alpha, double beta, int lower_only, cudaStream_t st);
 static int g_gemm_narrow = -1;   // 1: 128x64 CTA tiles, two CTAs per SM (epilogue of one overlaps the MMAs of the other)
 static int gemm_nt_launch(const double* A, const double* Bm, double* C, long long M, long long N, long long K,
                           long long lda, long long ldb, long long ldc, double alpha, double beta, int mode,
@@ -173,6 +176,9 @@ static int gemm_nt_launch(const double* A, const double* Bm, double* C, long lon
     }
     const bool narrow = !(mode & 2) && (g_gemm_narrow || N <= 64 || K <= 256);
     if (narrow) {
+        // operand tiles by the TMA unit when the descriptors can be built (16-byte aligned rows), else cp.async staging
+        const int rt = nmgp_gemm_nt_tma(A, Bm, C, M, N, K, lda, ldb, ldc, alpha, beta, lower_only, st);
+        if (rt <= 0) return rt;
         size_t smem = sizeof(double) * 2 * (GT_M + 64) * GT_LD;
         if (int r = nmgp_opt_in_smem(k_gemm_nt<1>, smem, "nmgp_gemm_nt")) return r;
         dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + GT_M - 1) / GT_M));
@@ -480,7 +486,7 @@ static int potrf_lookahead(PotrfCtx* ctx, double* A, long long T, long long lda,
 // *info = 1 + index of the first non-positive pivot (0 if none).  Reference sites: torch.logdet / torch.inverse
 // at distributions.py:109-110 and logpos.py:352-353 (dense path), and the per-eigen-block factorisations of the
 // Kronecker path.
-NMGP_API int nmgp_potrf_big_slot(double* A, long long T, long long lda, double* hld, int* info, int slot,
+NMGP_API int nmgp_potrf_big_slot(double* A, long long T, long long lda, double* hld, int* info, int slot, int panel,
                                  cudaStream_t st) {
     NMGP_REQUIRE(T > 0 && lda >= T && T < 2147483647LL, "nmgp_potrf_big");
     if (int r = nmgp_opt_in_smem(k_potrf_diag_inv, DI_SMEM, "nmgp_potrf_big")) return r;
@@ -488,6 +494,7 @@ NMGP_API int nmgp_potrf_big_slot(double* A, long long T, long long lda, double* 
     if (!ctx) return -4;
     if (T > 1024) {
         int pb = T >= 12288 ? 512 : (T >= 6144 ? 256 : PB);   // measured best on B200 (profiles/README.md)
+        if (panel >= 128) pb = (panel / 128) * 128;            // caller's choice (concurrent blocks prefer wider panels)
         if (const char* e = getenv("NMGP_POTRF_PB")) pb = atoi(e) >= 128 ? (atoi(e) / 128) * 128 : pb;   // tuning knob
         if (int r = potrf_lookahead(ctx, A, T, lda, pb, info, st)) return r;
     } else {
@@ -499,7 +506,7 @@ NMGP_API int nmgp_potrf_big_slot(double* A, long long T, long long lda, double* 
     return nmgp_launch_status("nmgp_potrf_big");
 }
 NMGP_API int nmgp_potrf_big(double* A, long long T, long long lda, double* hld, int* info, cudaStream_t st) {
-    return nmgp_potrf_big_slot(A, T, lda, hld, info, 0, st);
+    return nmgp_potrf_big_slot(A, T, lda, hld, info, 0, 0, st);
 }
 
 // Inverse of the lower-triangular nb x nb block at L (nb <= 128) into out (row-major, leading dimension ldo; entries

@@ -65,6 +65,9 @@ def block_pipeline(sigma2, B, K, Rt=None, shard=None, per_block=None, want_alpha
     alpha = torch.zeros(D, T, dtype=torch.float64, device=dev) if (Rt is not None and not augmented) else None
     on_gpu = Kc.is_cuda
     nslot = min(NSLOT, max(len(blocks), 1))
+    # several blocks in flight hide the panel latency of each other, so wider panels (fewer, larger trailing GEMMs) pay
+    # earlier than for a single factorisation: measured 1047 -> 990 ms at T=8192, D=128 (profiles/README.md)
+    panel = 512 if (T >= 6144 and nslot > 1) else 0
     if augmented:
         lda = T + 8 - (T % 8) if T % 8 else T + 8                    # even, 64-byte aligned rows: 16-byte vector paths stay on
         bufs = [torch.empty(T + 1, lda, dtype=torch.float64, device=dev) for _ in range(nslot)]
@@ -83,11 +86,11 @@ def block_pipeline(sigma2, B, K, Rt=None, shard=None, per_block=None, want_alpha
             if augmented:
                 Aug = bufs[slot][:, :T + 1]
                 ops.build_augmented(Kc, Rt[m].contiguous(), lam[m:m + 1], s2, rn2[m:m + 1], out=bufs[slot])
-                _, h = ops.potrf_big(Aug, info=info[m:m + 1], slot=slot)
+                _, h = ops.potrf_big(Aug, info=info[m:m + 1], slot=slot, panel=panel)
                 ops.augmented_results(bufs[slot], T, h, hld[m:m + 1], quad[m:m + 1])
                 continue
             A = ops.scale_add_diag_dev(Kc, lam[m:m + 1], s2, out=bufs[slot])
-            L, h = ops.potrf_big(A, info=info[m:m + 1], slot=slot)
+            L, h = ops.potrf_big(A, info=info[m:m + 1], slot=slot, panel=panel)
             hld[m:m + 1] = h
             if Rt is not None:
                 rm = Rt[m].contiguous()

@@ -476,7 +476,7 @@ def gemm_nt(A, Bm, alpha=1.0, beta=0.0, C=None):
     return out
 
 
-def potrf_big(A, info=None, slot=0):
+def potrf_big(A, info=None, slot=0, panel=0):
     L, bad = torch.linalg.cholesky_ex(A)
     if int(bad) != 0:
         if info is None:

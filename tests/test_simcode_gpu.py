@@ -66,7 +66,9 @@ def test_nonstationary_cov_tiles_and_adjoint(T1, T2):
     (kernels.Nonstationary_RBF_cov(d(x1), sv, lv) * d(Kb2)).sum().backward()
     scpu = s1.clone().requires_grad_(True); lcpu = l1.clone().requires_grad_(True)
     (specs.nonstationary_cov(x1, scpu, lcpu, x1, scpu, lcpu, 1e-6) * Kb2).sum().backward()
-    assert rel(sv.grad, scpu.grad) < 1e-11 and rel(lv.grad, lcpu.grad) < 1e-11
+    assert rel(sv.grad, scpu.grad) < 1e-11
+    # (T = 1: the exact gradient w.r.t. ell is 0 -- compare on the scale of the sigma gradient)
+    assert float(torch.linalg.norm(lv.grad.cpu() - lcpu.grad)) < 1e-11 * max(float(torch.linalg.norm(lcpu.grad)), float(torch.linalg.norm(scpu.grad)))
 
 
 def test_kronecker_and_logpdf_match_reference_golden():
@@ -102,7 +104,9 @@ def test_t200_logpdf():
     assert abs(lp0 - float(g["logpdf0"])) <= 1e-9 * abs(lp0), (lp0, float(g["logpdf0"]))
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (300, 77, 45), (1, 5, 3), (513, 260, 129)])
+# even K (16-byte aligned rows): the TMA-fed kernel; odd K: the cp.async kernel (no tensor map possible)
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (300, 77, 45), (1, 5, 3), (513, 260, 129), (512, 256, 128), (300, 78, 46),
+                                   (1000, 130, 34), (129, 65, 2), (70, 300, 1000), (2048, 2048, 256)])
 def test_gemm_nt(M, N, K):
     gen = torch.Generator().manual_seed(M + N + K)
     A = torch.randn(M, K, generator=gen, dtype=torch.float64); B = torch.randn(N, K, generator=gen, dtype=torch.float64)
@@ -110,6 +114,19 @@ def test_gemm_nt(M, N, K):
     C = torch.randn(M, N, generator=gen, dtype=torch.float64); Cd = d(C.clone())
     ops.gemm_nt(d(A), d(B), alpha=-0.5, beta=2.0, C=Cd)
     assert rel(Cd, -0.5 * (A @ B.t()) + 2.0 * C) < 1e-14
+
+
+def test_gemm_nt_on_views_of_a_larger_matrix():
+    """Row-strided blocks (what the blocked triangular inverse and the Cholesky panels pass): tensor maps / leading
+    dimensions of the parent matrix, output written into a block of another matrix."""
+    gen = torch.Generator().manual_seed(3)
+    P = torch.randn(700, 900, generator=gen, dtype=torch.float64); Q_ = torch.randn(500, 900, generator=gen, dtype=torch.float64)
+    O = torch.randn(800, 600, generator=gen, dtype=torch.float64)
+    Pd, Qd, Od = d(P), d(Q_), d(O.clone())
+    ops.gemm_nt(Pd[100:420, 64:576], Qd[6:206, 64:576], alpha=1.5, beta=-1.0, C=Od[32:352, 100:300])
+    ref = O.clone()
+    ref[32:352, 100:300] = 1.5 * (P[100:420, 64:576] @ Q_[6:206, 64:576].t()) - O[32:352, 100:300]
+    assert rel(Od, ref) < 1e-14
 
 
 @pytest.mark.parametrize("T,pb", [(7, 0), (128, 0), (200, 0), (1000, 0), (1537, 0), (2500, 0), (1537, 256), (2100, 512)])
