@@ -585,6 +585,16 @@ def run_b200(args, w):
                                     "kind": m["kind"], "sample": m["sample"]}
         print(json.dumps(line), flush=True)
     if world > 1:
+        graph_used = pb.graphed is not None
+        torch.cuda.synchronize()
+        dist.barrier()
+        if graph_used:
+            # A captured CUDA graph that contains NCCL kernels keeps the communicator busy at teardown (observed: the
+            # process group destructor never returns); the line is out and every rank is past the barrier, so leave
+            # without running the destructors.
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
