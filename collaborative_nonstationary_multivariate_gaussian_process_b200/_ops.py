@@ -16,6 +16,7 @@ import torch
 from ._lib import check, lib
 
 F64 = torch.float64
+LQ_MIN_Q = 65          # the register-resident DMMA kernels cover Q <= 64, the ring-pipelined / right-looking ones 65..128
 MODE_W, MODE_U = 0, 1
 MAX_Q = 128
 
@@ -120,6 +121,11 @@ def raise_if_not_pd(info):
 def potrf_bwd(C, Cbar, hldbar):
     nb, Q, _ = C.shape
     out = torch.empty_like(C)
+    if Q >= LQ_MIN_Q:                       # tensor-core formulation (A^T B reduction + two DMMA right solves)
+        w1, w2 = torch.empty_like(C), torch.empty_like(C)
+        check(lib().nmgp_potrf_bwd_batched_lq(_d(C), _d(Cbar), _d(hldbar), _d(out), _d(w1), _d(w2), c_int(nb), c_int(Q),
+                                              _stream()), "nmgp_potrf_bwd_batched_lq")
+        return out
     check(lib().nmgp_potrf_bwd_batched(_d(C), _d(Cbar), _d(hldbar), _d(out), c_int(nb), c_int(Q), _stream()),
           "nmgp_potrf_bwd_batched")
     return out
@@ -259,7 +265,6 @@ def lq_pad_records(Sig):
     return rec
 
 
-LQ_MIN_Q = 65          # the register-resident DMMA kernels cover Q <= 64, the ring-pipelined ones 65..128
 
 
 def quadform_fwd(Pa, Pb, I, Sig, Mu, D, mode, seg=None, rec=None):

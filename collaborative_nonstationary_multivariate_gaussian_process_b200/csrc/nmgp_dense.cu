@@ -375,6 +375,128 @@ k_potrf_diag_inv(double* __restrict__ A, long long lda, int nb, double* Linv, in
     }
     __syncthreads();
 }
+// Batched variant of the factorisation half of k_potrf_diag_inv for the Q x Q matrices of the DSVI step with
+// 64 < Q <= 128 (one CTA of 16 warps per matrix, 16-column steps, DMMA sub-panel and trailing update):
+// C = chol(A + jitter I) (strict upper triangle zeroed), hld = sum log diag C, *info = 1 + index of a non-PD matrix.
+// Replaces the one-thread-per-row kernel of nmgp_small.cu there (Q = 100: ~130 us of serial dot products per launch).
+__global__ void __launch_bounds__(DI_THREADS)
+k_potrf_batched_blocked(const double* __restrict__ A, double jitter, double* __restrict__ C, double* __restrict__ hld,
+                        int* __restrict__ info, int nb) {
+    const double* Ain = A + (size_t)blockIdx.x * nb * nb;
+    double* Cout = C + (size_t)blockIdx.x * nb * nb;
+    extern __shared__ __align__(16) double sm[];
+    double* Ls = sm;                          // [128][DI_LD]
+    double* Xs = Ls + DI_N * DI_LD;           // [128][DI_XLD] sub-panel (DMMA operands); scratch for the inverse
+    double* Di = Xs + DI_N * DI_XLD;          // [8][16][17]   inverses of the diagonal 16 x 16 sub-blocks
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+#pragma unroll 8
+    for (int e = tid; e < DI_N * DI_N; e += DI_THREADS) {
+        const int a = e >> 7, b = e & 127;
+        Ls[a * DI_LD + b] = (a < nb && b < nb) ? Ain[(long long)a * nb + b] + (a == b ? jitter : 0.0) : (a == b ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    for (int bk = 0; bk < 8; ++bk) {
+        const int kb = 16 * bk;
+        if (w == 0) {
+            const int i = lane & 15;
+            double r[16], rd[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) r[c] = Ls[(kb + i) * DI_LD + kb + c];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const double dkk = __shfl_sync(0xffffffffu, r[k], k);
+                if (!(dkk > 0.0) && lane == 0 && kb + k < nb) atomicMax(info, (int)blockIdx.x + 1);
+                const double rinv = rsqrt(dkk);
+                rd[k] = rinv;
+                const double lik = (i == k) ? dkk * rinv : r[k] * rinv;
+                r[k] = lik;
+#pragma unroll
+                for (int j = k + 1; j < 16; ++j) {
+                    const double v = __shfl_sync(0xffffffffu, lik, j);
+                    r[j] = fma(-lik, v, r[j]);
+                }
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) Ls[(kb + i) * DI_LD + kb + c] = (c <= i) ? r[c] : 0.0;
+            }
+            __syncwarp();
+            // column i of D^-1 by forward substitution (entries above the diagonal come out as exact zeros)
+            double x[16];
+#pragma unroll
+            for (int a = 0; a < 16; ++a) {
+                double s0 = (a == i) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < a; ++k) {
+                    const double lv = Ls[(kb + a) * DI_LD + kb + k];
+                    if (k & 1) s1 = fma(-lv, x[k], s1);
+                    else s0 = fma(-lv, x[k], s0);
+                }
+                x[a] = (s0 + s1) * rd[a];
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int a = 0; a < 16; ++a) Di[(kb + a) * 17 + i] = x[a];
+            }
+        }
+        __syncthreads();
+        const int nrem = DI_N - kb - 16;
+        // sub-panel X = A[:, kb:kb+16] Dinv^T on DMMA: one warp per 8 rows (both 8-column halves), written back in place
+        // and to Xs (operand layout of the trailing update)
+        for (int ti = w; ti < (nrem >> 3); ti += DI_THREADS / 32) {
+            double* arow = &Ls[(kb + 16 + 8 * ti + g) * DI_LD + kb];
+            double xa[4][2], xb[4][2];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const double av = arow[4 * ks + t];
+                xa[ks][0] = xa[ks][1] = xb[ks][0] = xb[ks][1] = 0.0;
+                dmma884d(xa[ks][0], xa[ks][1], av, Di[(kb + g) * 17 + 4 * ks + t]);
+                dmma884d(xb[ks][0], xb[ks][1], av, Di[(kb + 8 + g) * 17 + 4 * ks + t]);
+            }
+            const double a0 = (xa[0][0] + xa[1][0]) + (xa[2][0] + xa[3][0]), a1 = (xa[0][1] + xa[1][1]) + (xa[2][1] + xa[3][1]);
+            const double b0 = (xb[0][0] + xb[1][0]) + (xb[2][0] + xb[3][0]), b1 = (xb[0][1] + xb[1][1]) + (xb[2][1] + xb[3][1]);
+            __syncwarp();
+            arow[2 * t] = a0; arow[2 * t + 1] = a1; arow[8 + 2 * t] = b0; arow[8 + 2 * t + 1] = b1;
+            double* xrow = &Xs[(8 * ti + g) * DI_XLD];
+            xrow[2 * t] = a0; xrow[2 * t + 1] = a1; xrow[8 + 2 * t] = b0; xrow[8 + 2 * t + 1] = b1;
+        }
+        __syncthreads();
+        // trailing update with DMMA: lower 8 x 8 tiles (ti >= tj) of the nrem x nrem block, one accumulator per k-step
+        const int nt = nrem >> 3, ntiles = nt * (nt + 1) / 2;
+        for (int tile = w; tile < ntiles; tile += DI_THREADS / 32) {
+            int ti = (int)((sqrtf(8.f * (float)tile + 1.f) - 1.f) * 0.5f);
+            while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+            while (ti * (ti + 1) / 2 > tile) --ti;
+            const int tj = tile - ti * (ti + 1) / 2;
+            double c[4][2];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                c[ks][0] = c[ks][1] = 0.0;
+                dmma884d(c[ks][0], c[ks][1], Xs[(8 * ti + g) * DI_XLD + 4 * ks + t], Xs[(8 * tj + g) * DI_XLD + 4 * ks + t]);
+            }
+            double2* p = reinterpret_cast<double2*>(&Ls[(kb + 16 + 8 * ti + g) * DI_LD + kb + 16 + 8 * tj + 2 * t]);
+            double2 v = *p;
+            v.x -= (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
+            v.y -= (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
+            *p = v;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < nb * nb; e += DI_THREADS) {
+        const int a = e / nb, b = e - a * nb;
+        Cout[e] = (b <= a) ? Ls[a * DI_LD + b] : 0.0;
+    }
+    double lg = (tid < nb) ? log(Ls[tid * DI_LD + tid]) : 0.0;
+    lg = block_sum(lg);
+    if (tid == 0) hld[blockIdx.x] = lg;
+}
+int nmgp_potrf_batched_blocked(const double* A, double jitter, double* C, double* hld, int* info, int nb_mat, int Q,
+                               cudaStream_t st) {
+    if (Q <= 64 || Q > DI_N) return 1;
+    if (int r = nmgp_opt_in_smem(k_potrf_batched_blocked, DI_SMEM, "nmgp_potrf_batched(blocked)")) return r;
+    k_potrf_batched_blocked<<<NMGP_L(nb_mat), DI_THREADS, DI_SMEM, st>>>(A, jitter, C, hld, info, Q);
+    return nmgp_launch_status("nmgp_potrf_batched(blocked)");
+}
 __global__ void k_zero_upper(double* __restrict__ A, long long T, long long lda) {
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
     if (c < T && c > r) A[r * lda + c] = 0.0;

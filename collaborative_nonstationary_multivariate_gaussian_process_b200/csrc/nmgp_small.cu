@@ -162,10 +162,13 @@ __global__ void k_potrf(const double* __restrict__ A, double jitter, double* __r
         C[off + e] = (b <= a) ? sm[a * ld + b] : 0.0;
     }
 }
+int nmgp_potrf_batched_blocked(const double* A, double jitter, double* C, double* hld, int* info, int nb_mat, int Q,
+                               cudaStream_t st);   // nmgp_dense.cu: DMMA blocked factorisation for 64 < Q <= 128
 NMGP_API int nmgp_potrf_batched(const double* A, double jitter, double* C, double* hld, int* info, int nb, int Q,
                                 cudaStream_t st) {
     NMGP_REQUIRE(nb >= 0 && Q > 0 && Q <= 128, "nmgp_potrf_batched");
     if (nb == 0) return 0;
+    if (Q > 64) return nmgp_potrf_batched_blocked(A, jitter, C, hld, info, nb, Q, st);
     size_t smem = (size_t)Q * (Q | 1) * sizeof(double);
     if (int r = nmgp_opt_in_smem(k_potrf, smem, "nmgp_potrf_batched")) return r;
     k_potrf<<<NMGP_L(nb), 128, smem, st>>>(A, jitter, C, hld, info, Q);
@@ -252,6 +255,62 @@ NMGP_API int nmgp_potrf_bwd_batched(const double* C, const double* Cbar, const d
     k_potrf_bwd<<<NMGP_L(nb), 128, smem, st>>>(C, Cbar, hldbar, Abar, Q);
     return nmgp_launch_status("nmgp_potrf_bwd_batched");
 }
+
+// ---- 64 < Q <= 128: the same adjoint on the tensor cores ------------------------------------------------------------
+// Abar = sym(C^-T Phi(C^T Cb) C^-1) = sym(((Phi^T C^-1)^T) C^-1): one DMMA reduction (C^T Cb, k_atb_mma) and two right
+// solves "rows x C^-1" (the row-solve kernel's second sweep) with a transpose in between -- no per-column serial
+// substitution.  work1 / work2: [nb, Q, Q] scratch.
+int nmgp_right_solve_rows(const double* K, const double* R, double* X, int ns, long long B, int Q, cudaStream_t st);
+int nmgp_atb_mma(const double* A, const double* Bm, double* C, double sign, int ns, long long B, int Q,
+                 const double* cbar, double* Kbar, cudaStream_t st);
+// W[b] = tril(Cbar[b]) + diag(hldbar[b] / diag C[b])
+__global__ void k_pbw_prep(const double* __restrict__ C, const double* __restrict__ Cbar, const double* __restrict__ hldbar,
+                           double* __restrict__ W, long long n, int Q) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const long long m = e / ((long long)Q * Q);
+    const int r = (int)(e % ((long long)Q * Q)), a = r / Q, b = r - a * Q;
+    double w = (b <= a) ? Cbar[e] : 0.0;
+    if (a == b) w += hldbar[m] / C[e];
+    W[e] = w;
+}
+// out[b] = Phi(M[b])^T  (Phi: lower triangle with halved diagonal)   or, phi == 0, plain transpose
+__global__ void k_pbw_transpose(const double* __restrict__ M, double* __restrict__ out, long long n, int Q, int phi) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const long long m = e / ((long long)Q * Q);
+    const int r = (int)(e % ((long long)Q * Q)), a = r / Q, b = r - a * Q;       // out[a,b] = f(M[b,a])
+    double v = M[m * Q * Q + (long long)b * Q + a];
+    if (phi) v = (a > b) ? 0.0 : (a == b ? 0.5 * v : v);                          // M[b,a] with b >= a kept
+    out[e] = v;
+}
+__global__ void k_pbw_sym(const double* __restrict__ M, double* __restrict__ out, long long n, int Q) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const long long m = e / ((long long)Q * Q);
+    const int r = (int)(e % ((long long)Q * Q)), a = r / Q, b = r - a * Q;
+    out[e] = 0.5 * (M[e] + M[m * Q * Q + (long long)b * Q + a]);
+}
+NMGP_API int nmgp_potrf_bwd_batched_lq(const double* C, const double* Cbar, const double* hldbar, double* Abar,
+                                       double* work1, double* work2, int nb, int Q, cudaStream_t st) {
+    NMGP_REQUIRE(nb >= 0 && Q > 64 && Q <= 128, "nmgp_potrf_bwd_batched_lq");
+    if (nb == 0) return 0;
+    const long long n = (long long)nb * Q * Q;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    k_pbw_prep<<<NMGP_L(blocks), 256, 0, st>>>(C, Cbar, hldbar, work1, n, Q);                      // work1 = Cb
+    if (cudaMemsetAsync(work2, 0, sizeof(double) * n, st) != cudaSuccess) {
+        nmgp_set_error("nmgp_potrf_bwd_batched_lq: cudaMemsetAsync failed");
+        return -11;
+    }
+    if (int r = nmgp_atb_mma(C, work1, work2, 1.0, nb, Q, Q, nullptr, nullptr, st)) return r;        // work2 = C^T Cb
+    k_pbw_transpose<<<NMGP_L(blocks), 256, 0, st>>>(work2, work1, n, Q, 1);                          // work1 = Phi^T
+    if (int r = nmgp_right_solve_rows(work1, C, work2, nb, Q, Q, st)) return r;                      // work2 = Phi^T C^-1
+    k_pbw_transpose<<<NMGP_L(blocks), 256, 0, st>>>(work2, work1, n, Q, 0);                          // work1 = C^-T Phi
+    if (int r = nmgp_right_solve_rows(work1, C, work2, nb, Q, Q, st)) return r;                      // work2 = C^-T Phi C^-1
+    k_pbw_sym<<<NMGP_L(blocks), 256, 0, st>>>(work2, Abar, n, Q);
+    return nmgp_launch_status("nmgp_potrf_bwd_batched_lq");
+}
+
 
 // ------------------------------------------------------------------------------------------
 // KL(N(mu_b, C_b C_b^T) || N(0, R_p R_p^T)) in the reference's form (code/utils.py:346-351, quirk q10):

@@ -206,7 +206,7 @@ template <int NB, bool BWD>
 __global__ void __launch_bounds__(SM_THREADS, 1)
 k_solve_rows_rl(const double* __restrict__ K, const double* __restrict__ R, double* __restrict__ P,
                 double* __restrict__ cout, const double* __restrict__ Pbar, const double* __restrict__ cbar,
-                double* __restrict__ Tout, long long B, int Q) {
+                double* __restrict__ Tout, long long B, int Q, int right_only) {
     constexpr int QP = 8 * NB;
     constexpr int LDR = QP + 4;
     extern __shared__ __align__(16) double sm[];
@@ -269,7 +269,8 @@ k_solve_rows_rl(const double* __restrict__ K, const double* __restrict__ R, doub
                 yC[mb][b][0] = v0;
                 yC[mb][b][1] = v1;
             }
-        // ---- forward sweep: Y R^T = rhs --------------------------------------------------------------------------
+        // ---- forward sweep: Y R^T = rhs  (skipped for the plain right solve X = rhs R^-1) ------------------------
+        if (!right_only)
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             double ya[2][2];
@@ -337,12 +338,13 @@ k_solve_rows_rl(const double* __restrict__ K, const double* __restrict__ R, doub
             if (!BWD) {
                 csum += __shfl_xor_sync(0xffffffffu, csum, 1);
                 csum += __shfl_xor_sync(0xffffffffu, csum, 2);
-                if (t == 0 && ok[mb]) cout[(size_t)s * B + gr_[mb]] = csum;
+                if (t == 0 && ok[mb] && cout) cout[(size_t)s * B + gr_[mb]] = csum;
             }
         }
     }
 }
 
+static thread_local int tl_right_only = 0;      // set by nmgp_right_solve_rows around its dispatch
 template <int NB, bool BWD>
 static int launch_solve_rl(const double* K, const double* R, double* P, double* c, const double* Pbar,
                            const double* cbar, const double* Pin, double* Kbar, double* Tout, int ns, long long B,
@@ -351,7 +353,7 @@ static int launch_solve_rl(const double* K, const double* R, double* P, double* 
     size_t smem = sizeof(double) * (QP * LDR + 2 * NB * 64);
     if (int r = nmgp_opt_in_smem(k_solve_rows_rl<NB, BWD>, smem, what)) return r;
     dim3 grid((unsigned)((B + SM_ROWS * RL_TILES - 1) / (SM_ROWS * RL_TILES)), ns);
-    k_solve_rows_rl<NB, BWD><<<NMGP_L(grid), SM_THREADS, smem, st>>>(K, R, P, c, Pbar, cbar, Tout, B, Q);
+    k_solve_rows_rl<NB, BWD><<<NMGP_L(grid), SM_THREADS, smem, st>>>(K, R, P, c, Pbar, cbar, Tout, B, Q, tl_right_only);
     return nmgp_launch_status(what);
 }
 #define SMM_DISPATCH(BWDFLAG, ...)                                           \
@@ -381,4 +383,14 @@ int nmgp_solve_rows_fwd_mma(const double* K, const double* R, double* P, double*
 int nmgp_solve_rows_bwd_mma(const double* Pbar, const double* cbar, const double* K, const double* P, const double* R,
                             double* Kbar, double* Tout, int ns, long long B, int Q, cudaStream_t st) {
     SMM_DISPATCH(true, K, R, nullptr, nullptr, Pbar, cbar, P, Kbar, Tout, ns, B, Q, st, "nmgp_solve_rows_bwd(mma)")
+}
+
+// X[s] = K[s] R[s]^-1 (rows of K solved against the lower-triangular R from the right; 64 < Q <= 128): the second sweep
+// of the row solve alone.  Building block of the DMMA Cholesky adjoint for large Q (nmgp_potrf_bwd_batched).
+int nmgp_right_solve_rows(const double* K, const double* R, double* X, int ns, long long B, int Q, cudaStream_t st) {
+    if (Q <= 64 || Q > 128) return 1;
+    tl_right_only = 1;
+    int r = nmgp_solve_rows_fwd_mma(K, R, X, nullptr, ns, B, Q, st);
+    tl_right_only = 0;
+    return r;
 }

@@ -52,6 +52,10 @@ int nmgp_potrf_batched(const double* A, double jitter, double* C, double* hld, i
 /* Abar = sym(C^-T Phi(C^T Cbar') C^-1), Cbar' = tril(Cbar) + diag(hldbar / diag C)   (autograd of the above) */
 int nmgp_potrf_bwd_batched(const double* C, const double* Cbar, const double* hldbar, double* Abar, int nb, int Q,
                            nmgp_stream_t stream);
+/* same adjoint for 64 < Q <= 128 on the FP64 tensor cores: one A^T B reduction and two right solves "rows x C^-1" with
+ * the DMMA row-solve kernel; work1, work2: [nb,Q,Q] scratch */
+int nmgp_potrf_bwd_batched_lq(const double* C, const double* Cbar, const double* hldbar, double* Abar, double* work1,
+                              double* work2, int nb, int Q, nmgp_stream_t stream);
 
 /* kl[p,b] = KL(N(mu_b, CS_b CS_b^T) || N(0, R_p R_p^T)) in the reference's form (quirk q10), every (p,b) pair in
  * parallel: rs[b,a] = sum_{c<=a} CS_b[a,c]^2; t[p,b,:] = (R_p R_p^T)^-1 mu_b by the DMMA row solve (saved for the
