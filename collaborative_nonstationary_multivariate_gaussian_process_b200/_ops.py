@@ -541,6 +541,19 @@ def hadamard_index_cov(Kx, Bf, indx1, indx2, diag=0.0):
     return out
 
 
+def dense_loglik_bwd(Sinv, alpha, A, Bt, indx1, indx2, g):
+    """Cotangents (Abar [N,N], Btbar like Bt, s2bar [1]) of -1/2 logdet S - 1/2 y^T S^-1 y with S = A o Bt[indx1, indx2] +
+    sigma2 I, from Sinv = S^-1, alpha = S^-1 y and the upstream cotangent g (device scalar)."""
+    N = A.shape[0]
+    Abar = _empty(A, N, N)
+    Btbar = _zeros(Bt, *Bt.shape)
+    s2bar = _zeros(A, 1)
+    check(lib().nmgp_dense_loglik_bwd(_d(Sinv), _d(alpha), _d(A), _d(Bt), _i(indx1), _i(indx2), _d(g), _d(Abar), _d(Btbar),
+                                      _d(s2bar), c_int64(N), c_int(Bt.shape[0]), c_int(Bt.shape[1]), _stream()),
+          "nmgp_dense_loglik_bwd")
+    return Abar, Btbar, s2bar
+
+
 def sim_rbf_cov(X1, X2, alpha, beta, jitter, self_cov=False):
     T1, dx = X1.shape
     T2 = X2.shape[0]

@@ -228,3 +228,54 @@ NMGP_API int nmgp_hadamard_index_cov(const double* Kx, const double* Bf, const i
     k_hadamard_index_cov<<<NMGP_L(grid), 256, 0, st>>>(Kx, Bf, indx1, indx2, diag, out, N1, N2, M);
     return nmgp_launch_status("nmgp_hadamard_index_cov");
 }
+
+// Adjoint of the dense indexed log-likelihood  -1/2 logdet S - 1/2 y^T S^-1 y,  S = A o Bt[i1, i2] + sigma2 I
+// (logpos.py:521-526 / 350-352 / 611-616 under autograd): with G = dloglik/dS = 1/2 (alpha alpha^T - S^-1), alpha = S^-1 y,
+//     Abar[a,b] = g G[a,b] Bt[i1[a], i2[b]],   Btbar[i1[a], i2[b]] += g G[a,b] A[a,b],   s2bar += g tr G.
+// G is formed on the fly from Sinv and alpha.  The table cotangent is accumulated in shared memory per CTA when the table
+// is small (M*M <= HB_SMEM doubles: the M x M coregionalisation matrix), else straight with global atomics (the N x N
+// time kernel indexed by the identity).
+#define HB_SMEM 1024
+__global__ void k_dense_loglik_bwd(const double* __restrict__ Sinv, const double* __restrict__ alpha,
+                                   const double* __restrict__ A, const double* __restrict__ Bt,
+                                   const int* __restrict__ i1, const int* __restrict__ i2, const double* __restrict__ gdev,
+                                   double* __restrict__ Abar, double* __restrict__ Btbar, double* __restrict__ s2bar,
+                                   long long N, int M, int Mrows) {
+    __shared__ double tab[HB_SMEM];
+    const bool priv = (long long)M * Mrows <= HB_SMEM;
+    if (priv) {
+        for (int e = threadIdx.x; e < M * Mrows; e += blockDim.x) tab[e] = 0.0;
+        __syncthreads();
+    }
+    const double g = gdev[0];
+    const long long a = blockIdx.y + (long long)blockIdx.z * 65535;
+    double tr = 0.0;
+    if (a < N) {
+        const double al_a = alpha[a];
+        const int ra = i1[a];
+        for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < N; b += (long long)gridDim.x * blockDim.x) {
+            const double G = 0.5 * g * (al_a * alpha[b] - Sinv[a * N + b]);
+            const size_t slot = (size_t)ra * M + i2[b];
+            Abar[a * N + b] = G * Bt[slot];
+            const double c = G * A[a * N + b];
+            if (priv) atomicAdd(&tab[slot], c);
+            else atomicAdd(&Btbar[slot], c);
+            if (a == b) tr += G;
+        }
+    }
+    if (priv) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < M * Mrows; e += blockDim.x)
+            if (tab[e] != 0.0) atomicAdd(&Btbar[e], tab[e]);
+    }
+    if (tr != 0.0) atomicAdd(s2bar, tr);
+}
+NMGP_API int nmgp_dense_loglik_bwd(const double* Sinv, const double* alpha, const double* A, const double* Bt,
+                                   const int* i1, const int* i2, const double* g, double* Abar, double* Btbar,
+                                   double* s2bar, long long N, int Mrows, int M, cudaStream_t st) {
+    NMGP_REQUIRE(N >= 0 && M > 0 && Mrows > 0, "nmgp_dense_loglik_bwd");
+    if (N == 0) return 0;
+    dim3 grid((unsigned)min((N + 255) / 256, 64LL), (unsigned)min(N, 65535LL), (unsigned)((N + 65534) / 65535));
+    k_dense_loglik_bwd<<<NMGP_L(grid), 256, 0, st>>>(Sinv, alpha, A, Bt, i1, i2, g, Abar, Btbar, s2bar, N, M, Mrows);
+    return nmgp_launch_status("nmgp_dense_loglik_bwd");
+}

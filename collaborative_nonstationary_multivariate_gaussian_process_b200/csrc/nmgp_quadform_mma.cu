@@ -631,19 +631,30 @@ struct GMShape {
     static constexpr int NG = WIDE ? 2 : 4;                // latents per CTA
     static constexpr int NP = 8 * NB;
     static constexpr int LDP = pad4mod8(NP);
-    static constexpr size_t smem_doubles = 2 * (size_t)GM_TROWS * LDP + 2 * 2 * NG * GM_TROWS;
+    // NB <= 8: the CTA is two independent 8-warp halves (own staging buffers, own named barrier) that take alternate row
+    // tiles of the same (output, latent group) and deal the block-row roles with opposite rotations.  A warp's scheduler
+    // is its index mod 4 and the four roles carry 8/8/8/4 blocks (NB = 7), so with one fixed role per scheduler the
+    // fourth tensor pipe idles half the time; with the rotations every scheduler hosts all four roles.
+    static constexpr int HALVES = WIDE ? 1 : 2;
+    static constexpr size_t half_doubles = 2 * (size_t)GM_TROWS * LDP + 2 * 2 * NG * GM_TROWS;
+    static constexpr size_t smem_doubles = HALVES * half_doubles;
 };
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 template <int NB>
-__global__ void __launch_bounds__(GM_THREADS, NB > 8 ? 1 : 2)
+__global__ void __launch_bounds__(GM_THREADS * GMShape<NB>::HALVES, 1)
 k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const int* __restrict__ seg,
            const double* __restrict__ qbar, const double* __restrict__ mbar, double* __restrict__ SigBar,
            double* __restrict__ MuBar, long long B, int Q, int D, int mode) {
     using SH = GMShape<NB>;
     constexpr int LDP = SH::LDP, GM_NG = SH::NG;
     constexpr bool WIDE = SH::WIDE;
+    constexpr int HALVES = SH::HALVES;
     extern __shared__ __align__(16) double sm[];
-    double* Pt = sm;                                        // [2][GM_TROWS][LDP]
+    const int half = HALVES == 2 ? (int)(threadIdx.x >> 8) : 0;
+    double* Pt = sm + (size_t)half * SH::half_doubles;      // [2][GM_TROWS][LDP]
     double* wq = Pt + 2 * (size_t)GM_TROWS * LDP;           // [2][GM_NG][GM_TROWS]
     double* wm = wq + 2 * GM_NG * GM_TROWS;                 // [2][GM_NG][GM_TROWS]
     const int i = blockIdx.x, s = blockIdx.z;
@@ -660,14 +671,15 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
     }
     const long long rbeg = seg[i], rend = seg[i + 1];
     if (rbeg >= rend) return;
-    const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int w = WIDE ? (tid >> 5) : ((tid >> 5) & 3), ug = WIDE ? 0 : (tid >> 7);
+    const int tid = threadIdx.x & (GM_THREADS - 1), lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int ug = WIDE ? 0 : (tid >> 7);
+    const int w = WIDE ? (tid >> 5) : (((tid >> 5) + 2 * ug + half) & 3);
     const int u0 = ug * GM_NGW;                            // this warp's latents: u0 .. u0 + GM_NGW - 1
     const int a1 = w, a2 = NB - 1 - w;
     const bool active = a1 <= a2;
     const int nslots = !active ? 0 : (a1 == a2 ? a1 + 1 : NB + 1);
 
-    for (int e = tid; e < (int)SH::smem_doubles; e += GM_THREADS) sm[e] = 0.0;
+    for (int e = threadIdx.x; e < (int)SH::smem_doubles; e += GM_THREADS * HALVES) sm[e] = 0.0;
     __syncthreads();
 
     double acc[GM_NGW][NB + 1][2];
@@ -677,9 +689,11 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
 #pragma unroll
         for (int sl = 0; sl <= NB; ++sl) acc[u][sl][0] = acc[u][sl][1] = 0.0;
 
-    const long long ntiles = (rend - rbeg + GM_TROWS - 1) / GM_TROWS;
-    auto stage = [&](long long tile, int buf) {
-        const long long r0 = rbeg + tile * GM_TROWS;
+    const long long ntiles_all = (rend - rbeg + GM_TROWS - 1) / GM_TROWS;
+    const long long ntiles = (ntiles_all - half + HALVES - 1) / HALVES;      // this half takes tiles half, half + 2, ...
+    if (ntiles <= 0) return;                                // (whole half leaves; no CTA-wide barrier follows)
+    auto stage = [&](long long tile_h, int buf) {
+        const long long r0 = rbeg + (tile_h * HALVES + half) * GM_TROWS;
         const int nr = (int)min((long long)GM_TROWS, rend - r0);
         double* Pd = Pt + (size_t)buf * GM_TROWS * LDP;
         for (int r = (tid >> 5); r < GM_TROWS; r += GM_THREADS / 32) {
@@ -713,7 +727,8 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
     for (long long tile = 0; tile < ntiles; ++tile) {
         const int buf = (int)(tile & 1);
         cp_async_wait<0>();
-        __syncthreads();
+        if (HALVES == 2) named_bar_sync(1 + half, GM_THREADS);
+        else __syncthreads();
         if (tile + 1 < ntiles) stage(tile + 1, buf ^ 1);
         cp_async_commit();
         if (!active) continue;
@@ -801,7 +816,8 @@ static int launch_gram(const double* Pa, const double* Pb, const int* seg, const
     constexpr int GM_NG = GMShape<NB>::NG;
     const int ngroups = (D + GM_NG - 1) / GM_NG;
     dim3 grid(D, ngroups + (mode == MODE_U ? 1 : 0), ns);
-    k_gram_mma<NB><<<NMGP_L(grid), GM_THREADS, smem, st>>>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, B, Q, D, mode);
+    k_gram_mma<NB><<<NMGP_L(grid), GM_THREADS * GMShape<NB>::HALVES, smem, st>>>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, B, Q,
+                                                                                  D, mode);
     return nmgp_launch_status("nmgp_weighted_gram(mma)");
 }
 

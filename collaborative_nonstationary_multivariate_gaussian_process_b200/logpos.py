@@ -131,12 +131,55 @@ def _coregionalisation(L_vec, M):
     return _GemmNT.apply(L, L)
 
 
+class _DenseIndexedLoglik(torch.autograd.Function):
+    """-1/2 logdet S - 1/2 y^T S^-1 y for S = A o Bt[i1, i2] + sigma2 I (the torch.inverse + torch.logdet likelihoods of
+    logpos.py:350-352, 521-526, 611-616, 690-694) through one blocked Cholesky, with the adjoint the reference gets from
+    autograd: dloglik/dS = 1/2 (alpha alpha^T - S^-1), alpha = S^-1 y; S^-1 from the factor by tensor-core GEMMs
+    (kronecker_operation.chol_inverse), the chain to A, the indexed table Bt and sigma2 in one kernel."""
+
+    @staticmethod
+    def forward(ctx, A, Bt, i1, i2, sigma2, y):
+        Ad, Btd = A.detach().contiguous(), Bt.detach().contiguous()
+        L, hld = ops.potrf_big(ops.hadamard_index_cov(Ad, Btd, i1, i2, float(sigma2)))
+        yc = y.detach().contiguous()
+        alpha = ops.potrs_vec(L, yc)
+        ctx.save_for_backward(Ad, Btd, L, alpha)
+        ctx.idx = (i1, i2)
+        return (-hld - 0.5 * ops.dot(yc, alpha)).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        Ad, Btd, L, alpha = ctx.saved_tensors
+        i1, i2 = ctx.idx
+        Sinv = kronecker_operation.chol_inverse(L)
+        Abar, Btbar, s2bar = ops.dense_loglik_bwd(Sinv, alpha, Ad, Btd, i1, i2, g.detach().reshape(1).contiguous())
+        return Abar, Btbar, None, None, s2bar.reshape(()), None
+
+
 def _dense_loglik(K_x, B_f, indx, sigma2_err, y):
     """-1/2 logdet(S) - 1/2 y^T S^-1 y for S = K_x * K_i + sigma2 I (logpos.py:521-526), dense Cholesky."""
     ii = indx.to(torch.int32).contiguous()
-    L, hld = ops.potrf_big(ops.hadamard_index_cov(K_x, B_f, ii, ii, float(sigma2_err)))
-    yc = y.contiguous()
-    return (-hld - 0.5 * ops.dot(yc, ops.potrs_vec(L, yc))).reshape(())
+    return _DenseIndexedLoglik.apply(K_x, B_f, ii, ii, sigma2_err, y)
+
+
+class _StationaryRBF(torch.autograd.Function):
+    """kernels.RBF_cov(x, alpha, beta) for scalar tensors alpha, beta that carry gradient (logpos_hadamard_S,
+    logpos.py:685): alpha^2 exp(-|x_i - x_j|^2 / (2 beta^2)) is the Gibbs kernel with constant sigma = alpha, ell = beta,
+    so the adjoint is the per-point Gibbs adjoint summed over the points."""
+
+    @staticmethod
+    def forward(ctx, xc, alpha, beta):
+        ctx.save_for_backward(xc, alpha.detach(), beta.detach())
+        return kernels.RBF_cov(xc, alpha=float(alpha), beta=float(beta))
+
+    @staticmethod
+    def backward(ctx, Kbar):
+        xc, alpha, beta = ctx.saved_tensors
+        one = torch.ones(xc.shape[0], dtype=torch.float64, device=xc.device)
+        s, l = (alpha * one).contiguous(), (beta * one).contiguous()
+        g1, gl1, g2, gl2 = ops.nonstationary_cov_bwd(xc, s, l, xc, s, l, Kbar.contiguous())
+        return None, ops.dot(one, ops.axpby(g1, g2, 1.0, 1.0)).reshape(alpha.shape), \
+            ops.dot(one, ops.axpby(gl1, gl2, 1.0, 1.0)).reshape(beta.shape)
 
 
 # ---- deviance (logpos.py:176-213) --------------------------------------------------------------------------------------
@@ -247,7 +290,7 @@ def logpos_hadamard_S(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y,
     M = int(torch.unique(indx).numel())
     B_f = _coregionalisation(L_vec, M)
     sigma2_err = torch.exp(tilde_sigma2_err)
-    K_x = kernels.RBF_cov(x.contiguous().view(-1, 1), alpha=float(torch.exp(tilde_sigma)), beta=float(torch.exp(tilde_l)))
+    K_x = _StationaryRBF.apply(x.contiguous().view(-1, 1), torch.exp(tilde_sigma), torch.exp(tilde_l))
     loglik = _dense_loglik(K_x, B_f, indx, sigma2_err, y)
     lp_l = _normal_logprob_sum(tilde_l.reshape(1), mu_tilde_l, sigma_tilde_l)
     lp_L = _normal_logprob_sum(L_vec, 0.0, c)
@@ -308,15 +351,35 @@ def _triangles(L_vecs, N, M):
     return Lmat
 
 
+class _GPPriorColumns(torch.autograd.Function):
+    """sum over the columns of V [N, P] of MultivariateNormal(mu 1, Sigma).log_prob(V[:, p]) for a fixed Sigma: one
+    factorisation, P solves; d/dV[:, p] = -Sigma^-1 (V[:, p] - mu) from the same solves."""
+
+    @staticmethod
+    def forward(ctx, V, mu, Sigma):
+        Sd = Sigma.detach().contiguous()
+        L, hld = ops.potrf_big(Sd.clone())
+        N, P = V.shape
+        total = -P * (hld.reshape(()) + 0.5 * N * math.log(2.0 * math.pi))
+        sols = []
+        for p_ in range(P):
+            r = (V.detach()[:, p_] - mu).contiguous()
+            a = ops.potrs_vec(L, r)
+            res = ops.axpby(r, ops.gemm_nt(a.view(1, -1), Sd).view(-1), 1.0, -1.0)       # one refinement step (cond ~1e8)
+            a = ops.axpby(a, ops.potrs_vec(L, res), 1.0, 1.0)
+            sols.append(a)
+            total = total - 0.5 * ops.dot(r, a).reshape(())
+        ctx.save_for_backward(torch.stack(sols, dim=1))
+        return total
+
+    @staticmethod
+    def backward(ctx, g):
+        (sol,) = ctx.saved_tensors
+        return -g * sol, None, None
+
+
 def _gp_prior_entries(V, mu, Sigma):
-    """sum over the columns of V [N, P] of MultivariateNormal(mu 1, Sigma).log_prob(V[:, p]): one factorisation, P solves."""
-    L, hld = ops.potrf_big(Sigma)
-    N, P = V.shape
-    total = -P * (hld.reshape(()) + 0.5 * N * math.log(2.0 * math.pi))
-    for p_ in range(P):
-        r = (V[:, p_] - mu).contiguous()
-        total = total - 0.5 * ops.dot(r, ops.potrs_vec(L, r)).reshape(())
-    return total
+    return _GPPriorColumns.apply(V, mu, Sigma)
 
 
 def logpos_SVC(tilde_l, uL_vecs, tilde_sigma2_err, Y, x, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L, a, b,
@@ -330,9 +393,7 @@ def logpos_SVC(tilde_l, uL_vecs, tilde_sigma2_err, Y, x, mu_tilde_l, alpha_tilde
     sigma2_err = torch.exp(tilde_sigma2_err)
     xc = x.contiguous().view(-1, 1)
     K_x = kernels.Nonstationary_RBF_cov(xc, ell1=torch.exp(tilde_l))
-    S = ops.hadamard_index_cov(ops.gemm_nt(Lrow, Lrow), K_x, nidx, nidx, float(sigma2_err))
-    Lc, hld = ops.potrf_big(S)
-    loglik = (-hld - 0.5 * ops.dot(y, ops.potrs_vec(Lc, y))).reshape(())
+    loglik = _DenseIndexedLoglik.apply(_GemmNT.apply(Lrow, Lrow), K_x, nidx, nidx, sigma2_err, y)
     lp_l = _mvn_logprob(tilde_l, float(mu_tilde_l), kernels.RBF_cov(xc, alpha=float(alpha_tilde_l), beta=float(beta_tilde_l)))
     lp_L = _gp_prior_entries(uL_vecs.reshape(N, P), float(mu_L), kernels.RBF_cov(xc, alpha=float(alpha_L), beta=float(beta_L)))
     lp_e = distributions.inverse_gamma_logpdf(sigma2_err, alpha=a, beta=b)
@@ -361,10 +422,7 @@ def logpos_hadamard_SVC(tilde_l, L_vecs, tilde_sigma2_err, x, indx, y, mu_tilde_
     sigma2_err = torch.exp(tilde_sigma2_err)
     xc = x.contiguous().view(-1, 1)
     K_x = kernels.Nonstationary_RBF_cov(xc, ell1=torch.exp(tilde_l))
-    S = ops.hadamard_index_cov(ops.gemm_nt(Lsel, Lsel), K_x, ident, ident, float(sigma2_err))
-    Lc, hld = ops.potrf_big(S)
-    yc = y.contiguous()
-    loglik = (-hld - 0.5 * ops.dot(yc, ops.potrs_vec(Lc, yc))).reshape(())
+    loglik = _DenseIndexedLoglik.apply(_GemmNT.apply(Lsel, Lsel), K_x, ident, ident, sigma2_err, y)
     lp_l = _mvn_logprob(tilde_l, float(mu_tilde_l), kernels.RBF_cov(xc, alpha=float(alpha_tilde_l), beta=float(beta_tilde_l)))
     lp_L = _gp_prior_entries(L_vecs.reshape(N, P), float(mu_L), kernels.RBF_cov(xc, alpha=float(alpha_L), beta=float(beta_L)))
     lp_e = distributions.inverse_gamma_logpdf_u(sigma2_err, alpha=a, beta=b)

@@ -221,6 +221,14 @@ int nmgp_nonstationary_cov_bwd(const double* X1, const double* sigma1, const dou
 int nmgp_hadamard_index_cov(const double* Kx, const double* Bf, const int* indx1, const int* indx2, double diag,
                             double* out, long long N1, long long N2, int M, nmgp_stream_t stream);
 
+/* adjoint of the dense indexed log-likelihood -1/2 logdet S - 1/2 y^T S^-1 y, S = A o Bt[i1, i2] + sigma2 I, i.e. what
+ * autograd gives the reference for the torch.inverse / torch.logdet likelihoods of the Hadamard and spatially-varying
+ * coregionalisation posteriors (logpos.py:350-352, 521-526, 611-616, 690-694).  Sinv = S^-1, alpha = S^-1 y, g = upstream
+ * cotangent (device scalar); Abar [N,N] =, Btbar [Mrows,M] += , s2bar[1] += */
+int nmgp_dense_loglik_bwd(const double* Sinv, const double* alpha, const double* A, const double* Bt, const int* i1,
+                          const int* i2, const double* g, double* Abar, double* Btbar, double* s2bar, long long N,
+                          int Mrows, int M, nmgp_stream_t stream);
+
 int nmgp_pairwise_dist(const double* X1, const double* X2, double* out, long long T1, long long T2, int dx,
                        nmgp_stream_t stream);                               /* kernels.py:5-21 */
 

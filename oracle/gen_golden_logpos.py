@@ -76,6 +76,25 @@ def main():
     vSo.backward()
     out["nlogpos_obj_S"] = float(vSo)
     out["grad_nlogpos_obj_S"] = pS.grad.numpy().copy()
+    # dense (Hadamard / spatially-varying-coregionalisation) objectives: value + reference autograd gradient
+    fh = [float(h) for h in hyp]
+    fhi = [float(h) for h in hyp_i]
+    pH = parsH.clone().requires_grad_(True)
+    logpos.nlogpos_obj_hadamard(pH, xh, ih, yh, *fh, a, b, c).backward()
+    out["grad_nlogpos_obj_hadamard"] = pH.grad.numpy().copy()
+    pHS = torch.cat([tlS.view(1), tsS.view(1), L_vec, ts2.view(1)]).clone().requires_grad_(True)
+    vHSo = logpos.nlogpos_obj_hadamard_S(pHS, xh, ih, yh, torch.tensor(-1.0).double(), torch.tensor(0.7).double(), a, b, c)
+    vHSo.backward()
+    out["nlogpos_obj_hadamard_S"] = float(vHSo)
+    out["grad_nlogpos_obj_hadamard_S"] = pHS.grad.numpy().copy()
+    pSVC = torch.cat([tli, uLi, ts2.view(1)]).clone().requires_grad_(True)
+    logpos.nlogpos_obj_SVC(pSVC, Yi, xi, *fhi, a, b).backward()
+    out["grad_nlogpos_obj_SVC"] = pSVC.grad.numpy().copy()
+    pHSVC = torch.cat([tlh, Lv_h, ts2.view(1)]).clone().requires_grad_(True)
+    vHSVCo = logpos.nlogpos_obj_hadamard_SVC(pHSVC, xh, ih, yh, *fhi, a, b)
+    vHSVCo.backward()
+    out["nlogpos_obj_hadamard_SVC"] = float(vHSVCo)
+    out["grad_nlogpos_obj_hadamard_SVC"] = pHSVC.grad.numpy().copy()
     np.savez_compressed(os.path.join(OUT, "sim_logpos.npz"), xi=xi.numpy(), tli=tli.numpy(), uLi=uLi.numpy(), Yi=Yi.numpy(),
                         hyp_i=np.array([float(h) for h in hyp_i]), Lv_h=Lv_h.numpy(), x=x.numpy(), tilde_l=tilde_l.numpy(), tilde_sigma=tilde_sigma.numpy(),
                         uL_vec=uL_vec.numpy(), L_vec=L_vec.numpy(), ts2=float(ts2), Y=Y.numpy(), hyp=np.array([float(h) for h in hyp]),

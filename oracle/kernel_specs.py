@@ -459,6 +459,16 @@ def hadamard_index_cov(Kx, Bf, indx1, indx2, diag=0.0):
     return Kx * Ki + diag * torch.eye(Kx.shape[0], Kx.shape[1], dtype=F64)
 
 
+def dense_loglik_bwd(Sinv, alpha, A, Bt, indx1, indx2, g):
+    """Cotangents of -1/2 logdet S - 1/2 y^T S^-1 y, S = A o Bt[indx1, indx2] + sigma2 I (G = 1/2 (alpha alpha^T - S^-1))."""
+    G = 0.5 * g.reshape(()) * (torch.outer(alpha, alpha) - Sinv)
+    i1, i2 = indx1.long().view(-1, 1), indx2.long().view(1, -1)
+    Abar = G * Bt[i1, i2]
+    Btbar = torch.zeros_like(Bt)
+    Btbar.index_put_((i1.expand_as(G), i2.expand_as(G)), G * A, accumulate=True)
+    return Abar, Btbar, torch.diagonal(G).sum().reshape(1)
+
+
 def sim_rbf_cov(X1, X2, alpha, beta, jitter, self_cov=False):
     d = pairwise_dist(X1 / beta, X2 / beta)
     return torch.exp(-0.5 * d) * alpha ** 2 + jitter * torch.eye(X1.shape[0], X2.shape[0], dtype=F64)

@@ -79,3 +79,27 @@ def test_device_minibatches_follow_the_reference_loader_order():
     seen = np.concatenate([xb.numpy() for xb, _, Ib, _ in mb2.epoch()])
     assert sorted(seen.tolist()) == sorted(X.tolist())
     assert all(bool((Ib[1:] >= Ib[:-1]).all()) for _, _, Ib, _ in mb2.epoch())
+
+
+def test_whole_module_pickle_round_trip():
+    """The reference's drivers pickle the whole nn.Module next to the loss trace (NMGP_PM25.py:101-106,
+    NMGP_ECoG_full.py:169-174): the drop-in model must survive pickle.dump / pickle.load with its parameters, its
+    inducing grid Z (a plain attribute, not in the state dict) and its shapes, and keep the reference's state-dict keys."""
+    import io
+    import pickle
+    import numpy as np
+    import torch
+    from collaborative_nonstationary_multivariate_gaussian_process_b200.nmgp_dsvi import NMGP
+    Z = np.linspace(0.0, 1.0, 6)
+    m = NMGP(number_observations=40, dim_outputs=3, Z=Z, minibatch_size=10, seed=3, device="cpu")
+    buf = io.BytesIO()
+    pickle.dump([m, [1.0, 2.0], [0.1, 0.2]], buf)               # [model, loss_list, time_list] as the drivers write it
+    m2, losses, times = pickle.loads(buf.getvalue())
+    assert losses == [1.0, 2.0] and times == [0.1, 0.2]
+    sd, sd2 = m.state_dict(), m2.state_dict()
+    assert list(sd) == list(sd2)
+    assert set(sd) >= {"mu_W", "sqrt_W", "mu_v", "sqrt_v", "mu_U", "sqrt_U", "sigma2_err_log"}
+    for k in sd:
+        assert torch.equal(sd[k], sd2[k]), k
+    assert torch.equal(torch.as_tensor(m.Z), torch.as_tensor(m2.Z))
+    assert (m2.N, m2.D, m2.M) == (m.N, m.D, m.M)
