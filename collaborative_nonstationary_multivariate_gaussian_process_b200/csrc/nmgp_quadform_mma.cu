@@ -12,6 +12,7 @@
 //
 // Register-resident design: valid for Q <= 64 (NB = ceil(Q/8) <= 8); larger Q uses the shared-memory FMA kernels.
 #include "common.cuh"
+#include <stdlib.h>
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -625,17 +626,21 @@ int nmgp_coef_quadform_mma(bool bwd, const double* Pa, const double* Pb, const i
                         // it accumulates.  8 < NB <= 16 (WIDE): 8 block-row roles, 2 latents per CTA, both in every warp
 #define GM_NGW 2        // latents accumulated per warp
 
-template <int NB>
+template <int NB, int HV = 1>
 struct GMShape {
     static constexpr bool WIDE = NB > 8;
     static constexpr int NG = WIDE ? 2 : 4;                // latents per CTA
     static constexpr int NP = 8 * NB;
     static constexpr int LDP = pad4mod8(NP);
-    // NB <= 8: the CTA is two independent 8-warp halves (own staging buffers, own named barrier) that take alternate row
-    // tiles of the same (output, latent group) and deal the block-row roles with opposite rotations.  A warp's scheduler
-    // is its index mod 4 and the four roles carry 8/8/8/4 blocks (NB = 7), so with one fixed role per scheduler the
-    // fourth tensor pipe idles half the time; with the rotations every scheduler hosts all four roles.
-    static constexpr int HALVES = WIDE ? 1 : 2;
+    // Block-row roles.  Even NB: role w owns block rows (w, NB-1-w): NB+1 blocks each.  Odd NB: rows (w, NB-2-w) for
+    // w < (NB-1)/2 and the last row alone: NB blocks each -- e.g. NB = 7 (Q = 50): 7/7/7/7 instead of 8/8/8/4 with the
+    // even rule, which left the fourth warp scheduler's tensor pipe idle half of the time (a warp's scheduler is its
+    // index mod 4, so a light role is a light scheduler).
+    static constexpr int NSLOT = (NB & 1) ? NB : NB + 1;
+    // HV = 2 (tuning variant, NMGP_GRAM_HALVES=2, NB <= 8): the CTA is two independent 8-warp halves (own staging buffers,
+    // own named barrier) that take alternate row tiles of the same (output, latent group) with the roles rotated
+    // against each other, one 16-warp CTA per SM instead of two 8-warp ones.
+    static constexpr int HALVES = HV;
     static constexpr size_t half_doubles = 2 * (size_t)GM_TROWS * LDP + 2 * 2 * NG * GM_TROWS;
     static constexpr size_t smem_doubles = HALVES * half_doubles;
 };
@@ -643,13 +648,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int NB>
-__global__ void __launch_bounds__(GM_THREADS * GMShape<NB>::HALVES, 1)
+template <int NB, int HV>
+__global__ void __launch_bounds__(GM_THREADS * HV, (NB > 8 || HV == 2) ? 1 : 2)
 k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const int* __restrict__ seg,
            const double* __restrict__ qbar, const double* __restrict__ mbar, double* __restrict__ SigBar,
            double* __restrict__ MuBar, long long B, int Q, int D, int mode) {
-    using SH = GMShape<NB>;
-    constexpr int LDP = SH::LDP, GM_NG = SH::NG;
+    using SH = GMShape<NB, HV>;
+    constexpr int LDP = SH::LDP, GM_NG = SH::NG, NSLOT = SH::NSLOT;
     constexpr bool WIDE = SH::WIDE;
     constexpr int HALVES = SH::HALVES;
     extern __shared__ __align__(16) double sm[];
@@ -673,21 +678,30 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
     if (rbeg >= rend) return;
     const int tid = threadIdx.x & (GM_THREADS - 1), lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int ug = WIDE ? 0 : (tid >> 7);
-    const int w = WIDE ? (tid >> 5) : (((tid >> 5) + 2 * ug + half) & 3);
+    const int w = WIDE ? (tid >> 5) : (HALVES == 2 ? (((tid >> 5) + 2 * ug + half) & 3) : ((tid >> 5) & 3));
     const int u0 = ug * GM_NGW;                            // this warp's latents: u0 .. u0 + GM_NGW - 1
-    const int a1 = w, a2 = NB - 1 - w;
-    const bool active = a1 <= a2;
-    const int nslots = !active ? 0 : (a1 == a2 ? a1 + 1 : NB + 1);
+    int a1, a2;
+    bool active;
+    if (NB & 1) {
+        constexpr int NPAIR = (NB - 1) / 2;
+        active = w <= NPAIR;
+        a1 = w < NPAIR ? w : NB - 1;
+        a2 = w < NPAIR ? NB - 2 - w : NB - 1;
+    } else {
+        a1 = w; a2 = NB - 1 - w;
+        active = a1 <= a2;
+    }
+    const int nslots = !active ? 0 : (a1 == a2 ? a1 + 1 : a1 + a2 + 2);
 
     for (int e = threadIdx.x; e < (int)SH::smem_doubles; e += GM_THREADS * HALVES) sm[e] = 0.0;
     __syncthreads();
 
-    double acc[GM_NGW][NB + 1][2];
+    double acc[GM_NGW][NSLOT][2];
     double accm[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
     for (int u = 0; u < GM_NGW; ++u)
 #pragma unroll
-        for (int sl = 0; sl <= NB; ++sl) acc[u][sl][0] = acc[u][sl][1] = 0.0;
+        for (int sl = 0; sl < NSLOT; ++sl) acc[u][sl][0] = acc[u][sl][1] = 0.0;
 
     const long long ntiles_all = (rend - rbeg + GM_TROWS - 1) / GM_TROWS;
     const long long ntiles = (ntiles_all - half + HALVES - 1) / HALVES;      // this half takes tiles half, half + 2, ...
@@ -746,7 +760,7 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
                 sa2[u] = ra2 * wv;
             }
 #pragma unroll
-            for (int sl = 0; sl <= NB; ++sl) {
+            for (int sl = 0; sl < NSLOT; ++sl) {
                 if (sl < nslots) {
                     const bool first = sl <= a1;
                     const int bb = first ? sl : sl - a1 - 1;
@@ -774,7 +788,7 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
             const int idx = (mode == MODE_U) ? pair_slot(i, j0 + u, D) : j0 + u;
             double* Sb = SigBar + (size_t)idx * Q * Q;
 #pragma unroll
-            for (int sl = 0; sl <= NB; ++sl) {
+            for (int sl = 0; sl < NSLOT; ++sl) {
                 if (sl < nslots) {
                     const bool first = sl <= a1;
                     const int a = first ? a1 : a2, bb = first ? sl : sl - a1 - 1;
@@ -808,17 +822,26 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
     }
 }
 
+template <int NB, int HV>
+static int launch_gram_v(const double* Pa, const double* Pb, const int* seg, const double* qbar, const double* mbar,
+                         double* SigBar, double* MuBar, int ns, long long B, int Q, int D, int mode, cudaStream_t st) {
+    using SH = GMShape<NB, HV>;
+    size_t smem = SH::smem_doubles * sizeof(double);
+    if (int r = nmgp_opt_in_smem(k_gram_mma<NB, HV>, smem, "nmgp_weighted_gram")) return r;
+    constexpr int GM_NG = SH::NG;
+    const int ngroups = (D + GM_NG - 1) / GM_NG;
+    dim3 grid(D, ngroups + (mode == MODE_U ? 1 : 0), ns);
+    k_gram_mma<NB, HV><<<NMGP_L(grid), GM_THREADS * HV, smem, st>>>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, B, Q, D, mode);
+    return nmgp_launch_status("nmgp_weighted_gram(mma)");
+}
 template <int NB>
 static int launch_gram(const double* Pa, const double* Pb, const int* seg, const double* qbar, const double* mbar,
                        double* SigBar, double* MuBar, int ns, long long B, int Q, int D, int mode, cudaStream_t st) {
-    size_t smem = GMShape<NB>::smem_doubles * sizeof(double);
-    if (int r = nmgp_opt_in_smem(k_gram_mma<NB>, smem, "nmgp_weighted_gram")) return r;
-    constexpr int GM_NG = GMShape<NB>::NG;
-    const int ngroups = (D + GM_NG - 1) / GM_NG;
-    dim3 grid(D, ngroups + (mode == MODE_U ? 1 : 0), ns);
-    k_gram_mma<NB><<<NMGP_L(grid), GM_THREADS * GMShape<NB>::HALVES, smem, st>>>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, B, Q,
-                                                                                  D, mode);
-    return nmgp_launch_status("nmgp_weighted_gram(mma)");
+    if constexpr (NB <= 8) {
+        static const int halves = [] { const char* e = getenv("NMGP_GRAM_HALVES"); return e ? atoi(e) : 1; }();
+        if (halves == 2) return launch_gram_v<NB, 2>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+    }
+    return launch_gram_v<NB, 1>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
 }
 
 // returns 1 if Q is outside the register-resident range (caller falls back to the FMA kernel)
