@@ -74,10 +74,20 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
             : "memory");
     }
 }
-// rec[j] = [ Sigma_W[j] padded to KP x LDS | mu_W[j] padded to NP ], zeros in the padding
+// rec[j] = [ Sigma_W[j] padded to KP x LDS | mu_W[j] padded to NP ], zeros in the padding; block D appends the padded
+// mean block  mu[DP][LDM]  (DP = D rounded up to 8) that the fused kernel brings in by one bulk copy for its two mean-path
+// products (phase 1 and the mbar mu_W part of Pbar)
 __global__ void k_pad_records(const double* __restrict__ SigW, const double* __restrict__ muW, double* __restrict__ rec,
-                              int Q, int KP, int LDS, int NP) {
+                              int Q, int KP, int LDS, int NP, int D, int DP, int LDM) {
     const int j = blockIdx.x, REC = KP * LDS + NP;
+    if (j == D) {
+        double* out = rec + (size_t)D * REC;
+        for (int e = threadIdx.x; e < DP * LDM; e += blockDim.x) {
+            const int jj = e / LDM, c = e - jj * LDM;
+            out[e] = (jj < D && c < Q) ? muW[(size_t)jj * Q + c] : 0.0;
+        }
+        return;
+    }
     double* out = rec + (size_t)j * REC;
     for (int e = threadIdx.x; e < KP * LDS; e += blockDim.x) {
         const int a = e / LDS, b = e - a * LDS;
@@ -105,7 +115,12 @@ struct LFShape {
     static constexpr int LDP = pad8mod16(NP > KP ? NP : KP);
     static constexpr int LDS = pad4mod8(NP);
     static constexpr int REC = KP * LDS + NP;              // one latent's padded record: Sigma_W[j] then mu_W[j]
-    static constexpr size_t smem_doubles = (size_t)LFK_ROWS * LDP + 2 * (size_t)REC + 2 * LFK_ROWS + 2;
+    // padded mean block mu[DP][LDM] (row = latent): staged in a record buffer when it fits (D <= MU_DMAX)
+    static constexpr int LDM = pad4mod8(NP > KP ? NP : KP);
+    static constexpr int MU_DMAX = 64;
+    static constexpr int MUB = MU_DMAX * LDM;
+    static constexpr int BUF = REC > MUB ? REC : MUB;      // doubles per staging buffer
+    static constexpr size_t smem_doubles = (size_t)LFK_ROWS * LDP + 2 * (size_t)BUF + 2 * LFK_ROWS + 4;
     static constexpr size_t smem_bytes = smem_doubles * 8 + LFK_ROWS * 4;
 };
 
@@ -118,14 +133,14 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
                double* __restrict__ mgbar, double* __restrict__ qgbar, double* __restrict__ cGbar,
                double* __restrict__ PGbar, long long B, int Q, int D, long long ystride) {
     using SH = LFShape<NB, KS>;
-    constexpr int LDP = SH::LDP, LDS = SH::LDS, REC = SH::REC;
+    constexpr int LDP = SH::LDP, LDS = SH::LDS, REC = SH::REC, LDM = SH::LDM, BUF = SH::BUF;
     extern __shared__ __align__(16) double sm[];
     double* Ps = sm;                                   // [LFK_ROWS][LDP]
-    double* Ss = Ps + (size_t)LFK_ROWS * LDP;           // [2][REC]: double-buffered records of the latent j
-    double* rrs = Ss + 2 * (size_t)REC;                // [LFK_ROWS]
+    double* Ss = Ps + (size_t)LFK_ROWS * LDP;           // [2][BUF]: double-buffered records of the latent j / mean block
+    double* rrs = Ss + 2 * (size_t)BUF;                // [LFK_ROWS]
     double* omcs = rrs + LFK_ROWS;                      // [LFK_ROWS]
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(omcs + LFK_ROWS);   // [2]
-    int* Is = reinterpret_cast<int*>(mbar + 2);        // [LFK_ROWS]
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(omcs + LFK_ROWS);   // [3] (+1 pad)
+    int* Is = reinterpret_cast<int*>(mbar + 4);        // [LFK_ROWS]
 
     const int s = blockIdx.y;
     const long long row0 = (long long)blockIdx.x * LFK_ROWS;
@@ -133,20 +148,48 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
     const size_t rbase = (size_t)s * B + row0;          // first row of this tile in [ns*B]
     const double s2e = hyp[H_S2_ERR];
+    const int DP = (D + 7) & ~7;
+    const bool mu_smem = DP <= SH::MU_DMAX && DP * LDM <= BUF;   // the padded mean block fits a staging buffer
+    const double* mublk = rec + (size_t)D * REC;
+    const bool bulk_rows = (Q & 1) == 0;                // 16-byte aligned rows of P: one bulk copy per row
 
-    for (int e = tid; e < LFK_ROWS * LDP; e += LFK_THREADS) {
-        int r = e / LDP, a = e - r * LDP;
-        Ps[e] = (r < nrows && a < Q) ? PG[(rbase + r) * Q + a] : 0.0;
-    }
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
+        mbar_init(&mbar[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    // everything the prologue needs is put in flight at once on the bulk-copy engine: the P rows of the tile (mbar[2]),
+    // the mean block into buffer 1 (mbar[2]) and the record of latent 0 into buffer 0 (mbar[0])
+    if (tid == 0) {
+        const unsigned bytes = (bulk_rows ? (unsigned)nrows * (unsigned)Q * 8u : 0u) + (mu_smem ? (unsigned)(DP * LDM) * 8u : 0u);
+        mbar_expect_tx(&mbar[2], bytes);
+        if (mu_smem) bulk_g2s(Ss + BUF, mublk, (unsigned)(DP * LDM) * 8u, &mbar[2]);
+        mbar_expect_tx(&mbar[0], (unsigned)(REC * sizeof(double)));
+        bulk_g2s(Ss, rec, (unsigned)(REC * sizeof(double)), &mbar[0]);
+    }
+    if (bulk_rows) {
+        if (tid < nrows) bulk_g2s(Ps + (size_t)tid * LDP, PG + (rbase + tid) * Q, (unsigned)Q * 8u, &mbar[2]);
+        for (int e = tid; e < LFK_ROWS * (LDP - Q); e += LFK_THREADS) {       // padding columns
+            const int r = e / (LDP - Q), a = Q + (e - r * (LDP - Q));
+            Ps[r * LDP + a] = 0.0;
+        }
+        for (int e = tid; e < (LFK_ROWS - nrows) * Q; e += LFK_THREADS) {     // rows past the end of the batch
+            const int r = nrows + e / Q, a = e - (e / Q) * Q;
+            Ps[r * LDP + a] = 0.0;
+        }
+    } else {
+        for (int e = tid; e < LFK_ROWS * LDP; e += LFK_THREADS) {
+            int r = e / LDP, a = e - r * LDP;
+            Ps[e] = (r < nrows && a < Q) ? PG[(rbase + r) * Q + a] : 0.0;
+        }
     }
     for (int r = tid; r < LFK_ROWS; r += LFK_THREADS) {
         Is[r] = r < nrows ? I[row0 + r] : -1;
         omcs[r] = r < nrows ? 1.0 - cG[rbase + r] : 0.0;
     }
+    mbar_wait(&mbar[2], 0u);
     __syncthreads();
 
     // A fragments of this warp's 16 rows: rows 16w + 8mb + g, k = 4ks + t
@@ -163,12 +206,30 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
     for (int jb = 0; jb * 8 < D; ++jb) {
         double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
         const int jn = 8 * jb + g;                       // B-fragment column (latent) of this lane
+        double lv[2][2];                                 // coefficients of this lane's (row, latent) results, loaded ahead
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            const int k = 4 * ks + t;
-            double b = (jn < D && k < Q) ? __ldg(&muW[(size_t)jn * Q + k]) : 0.0;
-            dmma884(acc[0][0], acc[0][1], afr[0][ks], b);
-            dmma884(acc[1][0], acc[1][1], afr[1][ks], b);
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = 8 * jb + 2 * t + e;
+                lv[mb][e] = (rloc[mb] < nrows && j <= myI[mb]) ? __ldg(&l[(rbase + rloc[mb]) * D + j]) : 0.0;
+            }
+        if (mu_smem) {
+            const double* Mu = Ss + BUF;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const double b = Mu[jn * LDM + 4 * ks + t];
+                dmma884(acc[0][0], acc[0][1], afr[0][ks], b);
+                dmma884(acc[1][0], acc[1][1], afr[1][ks], b);
+            }
+        } else {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const int k = 4 * ks + t;
+                double b = (jn < D && k < Q) ? __ldg(&muW[(size_t)jn * Q + k]) : 0.0;
+                dmma884(acc[0][0], acc[0][1], afr[0][ks], b);
+                dmma884(acc[1][0], acc[1][1], afr[1][ks], b);
+            }
         }
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {
@@ -176,12 +237,9 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int j = 8 * jb + 2 * t + e;
-                    if (j < D) {
-                        const size_t o = (rbase + rloc[mb]) * D + j;
-                        if (j <= myI[mb]) {
-                            Fp[mb] = fma(l[o], acc[mb][e], Fp[mb]);
-                            mgbar[o] = acc[mb][e];        // m[n,j] parked in the slot its cotangent overwrites at latent j
-                        }
+                    if (j <= myI[mb]) {
+                        Fp[mb] = fma(lv[mb][e], acc[mb][e], Fp[mb]);
+                        mgbar[(rbase + rloc[mb]) * D + j] = acc[mb][e];   // m[n,j] parked in the slot its cotangent overwrites at latent j
                     }
                 }
             }
@@ -220,7 +278,11 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
     const int warpmaxI = (16 * w < nrows) ? Is[min(16 * w + 15, nrows - 1)] : -1;
     auto stage = [&](int j, int buf) {                    // one thread: whole record by the bulk-copy engine
         mbar_expect_tx(&mbar[buf], (unsigned)(REC * sizeof(double)));
-        bulk_g2s(Ss + (size_t)buf * REC, rec + (size_t)j * REC, (unsigned)(REC * sizeof(double)), &mbar[buf]);
+        bulk_g2s(Ss + (size_t)buf * BUF, rec + (size_t)j * REC, (unsigned)(REC * sizeof(double)), &mbar[buf]);
+    };
+    auto stage_mu = [&](int buf) {                        // the mean block as "record jmax + 1" (for the product after the loop)
+        mbar_expect_tx(&mbar[buf], (unsigned)(DP * LDM) * 8u);
+        bulk_g2s(Ss + (size_t)buf * BUF, mublk, (unsigned)(DP * LDM) * 8u, &mbar[buf]);
     };
     double pacc[2][NB][2];
 #pragma unroll
@@ -229,8 +291,7 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
         for (int nb = 0; nb < NB; ++nb) pacc[mb][nb][0] = pacc[mb][nb][1] = 0.0;
     double pen[2] = {0.0, 0.0}, gsum[2] = {0.0, 0.0};
 
-    if (tid == 0 && jmax >= 0) stage(0, 0);
-    double lnext[2], mnext[2];
+    double lnext[2], mnext[2];                             // (record 0 is already in flight since the prologue)
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb) {
         lnext[mb] = (rloc[mb] < nrows) ? __ldg(&l[(rbase + rloc[mb]) * D]) : 0.0;
@@ -239,7 +300,10 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
     for (int j = 0; j <= jmax; ++j) {
         const int buf = j & 1;
         __syncthreads();                                  // everyone is done with the other buffer (latent j - 1)
-        if (tid == 0 && j + 1 <= jmax) stage(j + 1, buf ^ 1);
+        if (tid == 0) {
+            if (j + 1 <= jmax) stage(j + 1, buf ^ 1);
+            else if (mu_smem) stage_mu(buf ^ 1);
+        }
         if (warpmaxI < j) continue;                        // warp-uniform: none of this warp's rows uses latent j
         const double lcur[2] = {lnext[0], lnext[1]}, mcur[2] = {mnext[0], mnext[1]};
         if (j + 1 < D) {
@@ -250,7 +314,7 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
             }
         }
         mbar_wait(&mbar[buf], (unsigned)((j >> 1) & 1));  // record j landed
-        const double* Sd = Ss + (size_t)buf * REC;
+        const double* Sd = Ss + (size_t)buf * BUF;
         double V[2][NB][2];
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb)
@@ -303,18 +367,45 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
     // Pbar += mbar mu_W (the mean-path part of the adjoint) as one DMMA product over the latents: A = mbar rows of this
     // warp (just written to mgbar; zeros beyond I[n]), B = mu_W.  Replaces 28 FMAs per thread and latent in the loop.
     __syncthreads();
-    for (int ks = 0; 4 * ks < D; ++ks) {
-        const int jj = 4 * ks + t;
-        double av[2];
+    if (mu_smem) {
+        // B = the mean block staged as record jmax + 1; A = this warp's mbar rows, all loads issued before the first DMMA
+        const int bm = (jmax + 1) & 1;
+        const double* Mu = Ss + (size_t)bm * BUF;
+        constexpr int KSM = SH::MU_DMAX / 4;
+        double av[2][KSM];
 #pragma unroll
-        for (int mb = 0; mb < 2; ++mb)
-            av[mb] = (rloc[mb] < nrows && jj < D) ? __ldcg(&mgbar[(rbase + rloc[mb]) * D + jj]) : 0.0;
+        for (int ks = 0; ks < KSM; ++ks)
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-            const int c = 8 * nb + g;
-            const double b = (jj < D && c < Q) ? __ldg(&muW[(size_t)jj * Q + c]) : 0.0;
-            dmma884(pacc[0][nb][0], pacc[0][nb][1], av[0], b);
-            dmma884(pacc[1][nb][0], pacc[1][nb][1], av[1], b);
+            for (int mb = 0; mb < 2; ++mb) {
+                const int jj = 4 * ks + t;
+                av[mb][ks] = (rloc[mb] < nrows && jj < D) ? __ldcg(&mgbar[(rbase + rloc[mb]) * D + jj]) : 0.0;
+            }
+        mbar_wait(&mbar[bm], (unsigned)(((jmax + 1) >> 1) & 1));
+#pragma unroll
+        for (int ks = 0; ks < KSM; ++ks) {
+            if (4 * ks < D) {
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    const double b = Mu[(4 * ks + t) * LDM + 8 * nb + g];
+                    dmma884(pacc[0][nb][0], pacc[0][nb][1], av[0][ks], b);
+                    dmma884(pacc[1][nb][0], pacc[1][nb][1], av[1][ks], b);
+                }
+            }
+        }
+    } else {
+        for (int ks = 0; 4 * ks < D; ++ks) {
+            const int jj = 4 * ks + t;
+            double av[2];
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+                av[mb] = (rloc[mb] < nrows && jj < D) ? __ldcg(&mgbar[(rbase + rloc[mb]) * D + jj]) : 0.0;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                const int c = 8 * nb + g;
+                const double b = (jj < D && c < Q) ? __ldg(&muW[(size_t)jj * Q + c]) : 0.0;
+                dmma884(pacc[0][nb][0], pacc[0][nb][1], av[0], b);
+                dmma884(pacc[1][nb][0], pacc[1][nb][1], av[1], b);
+            }
         }
     }
 
@@ -357,7 +448,8 @@ static int launch_latent_fused(const double* PG, const double* cG, const double*
     // padded records of (Sigma_W[j], mu_W[j]) in a library-owned scratch buffer (grown on demand, one per process)
     static double* rec = nullptr;
     static size_t rec_cap = 0;
-    const size_t need = (size_t)D * SH::REC;
+    const int DP = (D + 7) & ~7;
+    const size_t need = (size_t)D * SH::REC + (size_t)DP * SH::LDM;
     if (need > rec_cap) {
         if (rec) {
             cudaDeviceSynchronize();
@@ -371,7 +463,7 @@ static int launch_latent_fused(const double* PG, const double* cG, const double*
         }
         rec_cap = need;
     }
-    k_pad_records<<<NMGP_L(D), 256, 0, st>>>(SigW, muW, rec, Q, SH::KP, SH::LDS, SH::NP);
+    k_pad_records<<<NMGP_L(D + 1), 256, 0, st>>>(SigW, muW, rec, Q, SH::KP, SH::LDS, SH::NP, D, DP, SH::LDM);
     dim3 grid((unsigned)((B + LFK_ROWS - 1) / LFK_ROWS), ns);
     k_latent_fused<NB, KS><<<NMGP_L(grid), LFK_THREADS, smem, st>>>(PG, cG, l, y, I, rec, muW, hyp, scale, Rsum, ghyp, lbar,
                                                            mgbar, qgbar, cGbar, PGbar, B, Q, D, ystride);
@@ -844,10 +936,227 @@ static int launch_gram(const double* Pa, const double* Pb, const int* seg, const
     return launch_gram_v<NB, 1>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// k_gram_tma: the same weighted Gram products for NB <= 8, fed by the bulk-copy engine through a GT_STAGES-deep ring of
+// (P tile, qbar / mbar chunk) stages with full / empty mbarriers.  ncu on k_gram_mma<7> (profiles/r2): a quarter of every
+// warp's time went to the per-tile staging code (cp.async address arithmetic in all 8 warps) and the CTA barrier behind
+// it.  Here one warp issues three bulk copies per row (P row, 4 consecutive qbar, 4 consecutive mbar) for the tile
+// GT_STAGES - 1 ahead, nobody executes a CTA barrier inside the loop, and the warps may drift by up to three tiles.
+// Requires 16-byte aligned rows: Q even, D % 4 == 0 (else k_gram_mma).
+#define GT_STAGES 4
+template <int NB>
+struct GTShape {
+    static constexpr int NP = 8 * NB;
+    static constexpr int LDP = pad4mod8(NP);
+    static constexpr int NSLOT = (NB & 1) ? NB : NB + 1;
+    static constexpr int stage_doubles = GM_TROWS * LDP + 2 * GM_TROWS * 4;
+    static constexpr size_t smem_bytes = (size_t)GT_STAGES * stage_doubles * 8 + 2 * GT_STAGES * 8;
+};
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
+}
+
+template <int NB>
+__global__ void __launch_bounds__(GM_THREADS, 2)
+k_gram_tma(const double* __restrict__ Pa, const double* __restrict__ Pb, const int* __restrict__ seg,
+           const double* __restrict__ qbar, const double* __restrict__ mbar_, double* __restrict__ SigBar,
+           double* __restrict__ MuBar, long long B, int Q, int D, int mode) {
+    using SH = GTShape<NB>;
+    constexpr int LDP = SH::LDP, NSLOT = SH::NSLOT, STG = SH::stage_doubles;
+    extern __shared__ __align__(16) double sm[];
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + (size_t)GT_STAGES * STG);
+    unsigned long long* empty = full + GT_STAGES;
+    const int i = blockIdx.x, s = blockIdx.z;
+    const int ngroups = (D + 3) / 4;
+    int jc, nj, usel = -1;                                  // chunk of 4 latent columns jc .. jc+3; live: u < nj (or u == usel)
+    const double* P = Pa;
+    if (mode == MODE_U && (int)blockIdx.y == ngroups) {     // the diagonal coefficient pair (i,i): L1 system rows
+        jc = i & ~3; usel = i & 3; nj = 4; P = Pb;
+    } else {
+        jc = 4 * blockIdx.y;
+        const int jlast = (mode == MODE_U) ? i - 1 : i;      // MODE_U groups cover the strictly-lower pairs only
+        if (jc > jlast) return;
+        nj = min(4, jlast - jc + 1);
+    }
+    const long long rbeg = seg[i], rend = seg[i + 1];
+    if (rbeg >= rend) return;
+    const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3, warp = tid >> 5;
+    const int w = warp & 3, ug = warp >> 2;
+    const int u0 = ug * GM_NGW;
+    int a1, a2;
+    bool active;
+    if (NB & 1) {
+        constexpr int NPAIR = (NB - 1) / 2;
+        active = w <= NPAIR;
+        a1 = w < NPAIR ? w : NB - 1;
+        a2 = w < NPAIR ? NB - 2 - w : NB - 1;
+    } else {
+        a1 = w; a2 = NB - 1 - w;
+        active = a1 <= a2;
+    }
+    const int nslots = !active ? 0 : (a1 == a2 ? a1 + 1 : a1 + a2 + 2);
+
+    // zero the stages once (rows past the end of the last tile keep finite values; their weights are zeroed per tile)
+    for (int e = tid; e < GT_STAGES * STG; e += GM_THREADS) sm[e] = 0.0;
+    if (tid == 0) {
+        for (int k = 0; k < GT_STAGES; ++k) {
+            mbar_init(&full[k], 1);
+            mbar_init(&empty[k], GM_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+
+    const long long ntiles = (rend - rbeg + GM_TROWS - 1) / GM_TROWS;
+    const size_t sB = (size_t)s * B;
+    auto issue = [&](long long tile) {                      // warp 0, all lanes: one row per lane
+        const int st = (int)(tile % GT_STAGES);
+        const long long r0 = rbeg + tile * GM_TROWS;
+        const int nr = (int)min((long long)GM_TROWS, rend - r0);
+        double* Pd = sm + (size_t)st * STG;
+        double* wq = Pd + GM_TROWS * LDP;                   // [GM_TROWS][4]
+        double* wm = wq + GM_TROWS * 4;
+        if (lane >= nr) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) wq[lane * 4 + u] = wm[lane * 4 + u] = 0.0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_expect_tx(&full[st], (unsigned)nr * ((unsigned)Q * 8u + 64u));
+        __syncwarp();
+        if (lane < nr) {
+            const size_t row = sB + r0 + lane;
+            bulk_g2s(Pd + lane * LDP, P + row * Q, (unsigned)Q * 8u, &full[st]);
+            bulk_g2s(wq + lane * 4, qbar + row * D + jc, 32u, &full[st]);
+            bulk_g2s(wm + lane * 4, mbar_ + row * D + jc, 32u, &full[st]);
+        }
+    };
+    if (warp == 0)
+        for (long long tl = 0; tl < GT_STAGES - 1 && tl < ntiles; ++tl) issue(tl);
+
+    double acc[GM_NGW][NSLOT][2];
+    double accm[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+    for (int u = 0; u < GM_NGW; ++u)
+#pragma unroll
+        for (int sl = 0; sl < NSLOT; ++sl) acc[u][sl][0] = acc[u][sl][1] = 0.0;
+
+    for (long long tile = 0; tile < ntiles; ++tile) {
+        const int st = (int)(tile % GT_STAGES);
+        if (warp == 0) {
+            const long long nt = tile + GT_STAGES - 1;
+            if (nt < ntiles) {
+                if (nt >= GT_STAGES) mbar_wait(&empty[nt % GT_STAGES], (unsigned)(((nt / GT_STAGES) - 1) & 1));
+                issue(nt);
+            }
+        }
+        mbar_wait(&full[st], (unsigned)((tile / GT_STAGES) & 1));
+        if (active) {
+            const double* Pd = sm + (size_t)st * STG;
+            const double* wq = Pd + GM_TROWS * LDP;
+            const double* wm = wq + GM_TROWS * 4;
+#pragma unroll
+            for (int kk = 0; kk < GM_TROWS / 4; ++kk) {
+                const int n = 4 * kk + t;                    // row of the tile this lane feeds as k index
+                const double ra1 = Pd[n * LDP + 8 * a1 + g]; // A fragment (a = 8 a1 + g, k = n), unscaled
+                const double ra2 = Pd[n * LDP + 8 * a2 + g];
+                double sa1[GM_NGW], sa2[GM_NGW];
+#pragma unroll
+                for (int u = 0; u < GM_NGW; ++u) {
+                    const double wv = wq[n * 4 + u0 + u];
+                    sa1[u] = ra1 * wv;
+                    sa2[u] = ra2 * wv;
+                }
+#pragma unroll
+                for (int sl = 0; sl < NSLOT; ++sl) {
+                    if (sl < nslots) {
+                        const bool first = sl <= a1;
+                        const int bb = first ? sl : sl - a1 - 1;
+                        const double bf = Pd[n * LDP + 8 * bb + g];   // B fragment (k = n, col = 8 bb + g)
+#pragma unroll
+                        for (int u = 0; u < GM_NGW; ++u)
+                            dmma884(acc[u][sl][0], acc[u][sl][1], first ? sa1[u] : sa2[u], bf);
+                    }
+                }
+                if (ug == 0) {                               // MuBar: B fragment column g carries mbar of latent g (< 4)
+                    const double bm = (g < 4) ? wm[n * 4 + g] : 0.0;
+                    dmma884(accm[0][0], accm[0][1], ra1, bm);
+                    if (a2 != a1) dmma884(accm[1][0], accm[1][1], ra2, bm);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+    }
+    if (!active) return;
+    // ---- write-out: block (a, bb) holds rows 8a+g, cols 8bb+2t+e; mirror the strictly-lower blocks ----------
+    auto live = [&](int u) { return usel >= 0 ? (u == usel) : (u < nj); };
+    auto slot_of = [&](int u) { return (mode == MODE_U) ? pair_slot(i, usel >= 0 ? i : jc + u, D) : jc + u; };
+#pragma unroll
+    for (int uu = 0; uu < GM_NGW; ++uu) {
+        const int u = u0 + uu;
+        if (live(u)) {
+            double* Sb = SigBar + (size_t)slot_of(u) * Q * Q;
+#pragma unroll
+            for (int sl = 0; sl < NSLOT; ++sl) {
+                if (sl < nslots) {
+                    const bool first = sl <= a1;
+                    const int a = first ? a1 : a2, bb = first ? sl : sl - a1 - 1;
+                    const int r = 8 * a + g;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int c = 8 * bb + 2 * t + e;
+                        if (r < Q && c < Q) {
+                            atomicAdd(&Sb[(size_t)r * Q + c], acc[uu][sl][e]);
+                            if (a != bb) atomicAdd(&Sb[(size_t)c * Q + r], acc[uu][sl][e]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (ug != 0) return;
+#pragma unroll
+    for (int st2 = 0; st2 < 2; ++st2) {
+        if (st2 == 1 && a2 == a1) break;
+        const int a = st2 == 0 ? a1 : a2;
+        const int r = 8 * a + g;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int u = 2 * t + e;
+            if (u < 4 && live(u) && r < Q) atomicAdd(&MuBar[(size_t)slot_of(u) * Q + r], accm[st2][e]);
+        }
+    }
+}
+
+template <int NB>
+static int launch_gram_tma(const double* Pa, const double* Pb, const int* seg, const double* qbar, const double* mbar,
+                           double* SigBar, double* MuBar, int ns, long long B, int Q, int D, int mode, cudaStream_t st) {
+    size_t smem = GTShape<NB>::smem_bytes;
+    if (int r = nmgp_opt_in_smem(k_gram_tma<NB>, smem, "nmgp_weighted_gram")) return r;
+    const int ngroups = (D + 3) / 4;
+    dim3 grid(D, ngroups + (mode == MODE_U ? 1 : 0), ns);
+    k_gram_tma<NB><<<NMGP_L(grid), GM_THREADS, smem, st>>>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, B, Q, D, mode);
+    return nmgp_launch_status("nmgp_weighted_gram(tma)");
+}
+
 // returns 1 if Q is outside the register-resident range (caller falls back to the FMA kernel)
 int nmgp_weighted_gram_mma(const double* Pa, const double* Pb, const int* seg, const double* qbar, const double* mbar,
                            double* SigBar, double* MuBar, int ns, long long B, int Q, int D, int mode,
                            cudaStream_t st) {
+    static const int use_tma = [] { const char* e = getenv("NMGP_GRAM_TMA"); return e ? atoi(e) : 1; }();
+    if (use_tma && (Q & 1) == 0 && (D & 3) == 0 && Q <= 64) {
+        switch ((Q + 7) / 8) {
+            case 1: return launch_gram_tma<1>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+            case 2: return launch_gram_tma<2>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+            case 3: return launch_gram_tma<3>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+            case 4: return launch_gram_tma<4>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+            case 5: return launch_gram_tma<5>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+            case 6: return launch_gram_tma<6>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+            case 7: return launch_gram_tma<7>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+            case 8: return launch_gram_tma<8>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
+        }
+    }
     switch ((Q + 7) / 8) {
         case 1: return launch_gram<1>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
         case 2: return launch_gram<2>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
