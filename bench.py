@@ -60,6 +60,9 @@ def parse():
     ap.add_argument("--cpu-baseline", default="auto", choices=["auto", "skip"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph")
+    ap.add_argument("--others", default="auto", choices=["auto", "skip"],
+                    help="auto: the default (ecog, full batch) run also measures short lines of BASELINE's other configs "
+                         "(pm25, hcp, sim, scale sweep) and attaches them as `other_configs`")
     ap.add_argument("--ref-budget", type=float, default=float(os.environ.get("NMGP_REF_BUDGET_S", "300")),
                     help="wall-clock budget (s) of the reference arm's calls; it stops early when the requested "
                          "steps do not fit and reports the steps it timed")
@@ -342,18 +345,23 @@ def fp64_yardstick(dev, n=8192, reps=3):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def ncu_traffic(kernel_prefix):
-    """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture (static; see profiles/README.md)."""
-    for name in ("ncu_r2_full_summary.json", "ncu_r1_full_summary.json"):
-        try:
-            summ = json.load(open(os.path.join(ROOT, "profiles", name)))
-        except Exception:
-            continue
-        for kname, rec in summ.items():
-            if kname.startswith(kernel_prefix):
-                u = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-                return (rec["dram__bytes_read.sum"] * u.get(rec["units"]["dram__bytes_read.sum"], 1.0)
-                        + rec["dram__bytes_write.sum"] * u.get(rec["units"]["dram__bytes_write.sum"], 1.0)), "profiles/" + name
+def ncu_traffic(dom, Q):
+    """DRAM bytes per launch of the dominant kernel from this round's committed `ncu --set full` captures
+    (profiles/r2/ncu_r2_*_full_summary.json, written by profiles/scripts/ncu_summarize.py).  Static: the capture is a
+    separate profiler run of the same bench command at the shape named in the returned source string."""
+    if Q <= 64:
+        fname, shape = "profiles/r2/ncu_r2_ecog_full_summary.json", "ECoG shape, 4 samples per launch"
+        prefix = {"latent_fused": "void k_latent_fused", "weighted_gram": "void k_gram"}.get(dom)
+    else:
+        fname, shape = "profiles/r2/ncu_r2_pm25_full_summary.json", "PM2.5 shape, 8 samples per launch"
+        prefix = {"latent_fused": "void <unnamed>::k_lq<13, 0>", "weighted_gram": "void k_gram"}.get(dom)
+    try:
+        summ = json.load(open(os.path.join(ROOT, fname)))
+    except Exception:
+        return None, None
+    for kname, rec in summ.items():
+        if prefix and kname.startswith(prefix) and "dram_bytes_per_launch" in rec:
+            return rec["dram_bytes_per_launch"], "%s (%s)" % (fname, shape)
     return None, None
 
 
@@ -441,6 +449,37 @@ class Problem:
         tot = self.parallel.allreduce_loss_and_grads(loss, self.params, pd_info=self.model._last_pd_info, check="defer")
         self.opt.step()
         return float(tot.cpu())                                       # D2H read of the step's result
+
+
+def other_configs(args, rank, world, dev, timed, peak):
+    """Short measured lines of BASELINE.json's other configurations, taken in the same process right after the headline
+    workload so that the driver's record holds them too: PM2.5-shaped and simulation-shaped steps (single GPU only: they
+    are one-GPU configurations), the HCP-shaped subject-sharded step and the scale-sweep evaluation (every N).  Same
+    timing rules as the headline (warm-up >= 3, CUDA events, max over ranks); `e2e` from pinned host lists."""
+    out = {}
+    k2 = max(args.steps, 5)
+    names = ["hcp"] + (["pm25", "sim"] if world == 1 else [])
+    for name in names:
+        w2 = dict(WORKLOADS[name]); w2["rows"] = w2["T"] * w2["D"]; w2["name"] = name
+        pb2 = Problem(w2, rank, world, dev, graph=not args.no_graph)
+        for _ in range(3):
+            pb2.step_resident()
+        pb2.check()
+        ms, last, _, nl = timed(pb2.step_resident, k2)
+        for _ in range(2):
+            pb2.step_e2e()
+        ms2, _, _, _ = timed(pb2.step_e2e, k2)
+        pb2.check()
+        out[name] = {"metric": w2["metric"], "config": config_of(w2), "n_gpus": world, "steps": k2, "warmup": 3,
+                     "value": 1e3 * k2 / ms, "unit": UNIT, "ms_per_step": ms / k2, "gpu_launches": int(nl),
+                     "e2e": {"value": 1e3 * k2 / ms2, "unit": UNIT, "ms_per_step": ms2 / k2,
+                             "h2d_bytes_per_step": pb2.h2d_bytes * world, "d2h_bytes_per_step": 8 * world},
+                     "loss": float(last)}
+        del pb2
+        torch.cuda.empty_cache()
+    import bench_sweep
+    out["sweep"] = bench_sweep.quick_line(args.sweep_T, args.sweep_D, rank, world, dev, timed, peak)
+    return out
 
 
 def run_b200(args, w):
@@ -541,7 +580,16 @@ def run_b200(args, w):
         dom = max(kern, key=lambda k: kern[k]["ms_total"]) if kern else None
         roof = None
         if dom:
-            traffic, tsrc = ncu_traffic({"latent_fused": "k_latent_fused", "weighted_gram": "k_gram_mma"}.get(dom, "?"))
+            traffic, tsrc = ncu_traffic(dom, Q)
+            # algorithmic DRAM bytes of one launch of the dominant kernel: the fused kernel reads P [B,Q],
+            # l [B,D], y, c and writes lbar, qbar, mbar [B,D], Pbar [B,Q], cbar per sample; the Gram kernel reads P and
+            # the live halves of qbar / mbar
+            ns_launch = max(1, round(n_mc * args.steps / max(kern[dom]["calls"], 1))) if dom == "latent_fused" else None
+            alg_bytes = None
+            if dom == "latent_fused":
+                alg_bytes = 8.0 * ns_launch * pb.Bloc * (2 * Q + 4 * D + 3)
+            elif dom == "weighted_gram":
+                alg_bytes = 8.0 * (n_mc * args.steps / max(kern[dom]["calls"] - args.steps, 1)) * pb.Bloc * (Q + D)
             # flops the kernel really issues per (row, pair): one padded V = P Sigma GEMM (latent_fused) / the lower
             # 8x8 blocks of the Gram matrix (weighted_gram) -- the dense convention counts 4 Q^2 / 2 Q^2
             KSp, NBp = (Q + 3) // 4, (Q + 7) // 8
@@ -550,7 +598,9 @@ def run_b200(args, w):
             roof = {"kernel": dom, "bound": "tensor", "achieved": kern[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
                     "frac": kern[dom]["tflops"] / peak, "traffic": traffic,
                     "traffic_source": None if traffic is None else
-                    "static: committed ncu --set full capture %s (ECoG shape), not measured in this run" % tsrc,
+                    "static: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full "
+                    "capture %s; a separate profiler run of this command, not measured in this run" % tsrc,
+                    "algorithmic_bytes_per_launch": alg_bytes,
                     "peak_source": "FP64 DGEMM (torch.matmul, cuBLAS) 8192^3 measured in this run; "
                                    "MEASURED_PEAKS.json holds no FP64 figure",
                     "convention": "achieved = dense-convention flops of SURVEY.md 8d (2 Q^2 per quadratic form and per "
@@ -578,15 +628,22 @@ def run_b200(args, w):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(nlaunch), "abi_calls": int(ncalls),
                 "roofline": roof, "kernels": kern, "other_ops": others, "loss": float(last),
                 "same_config_pair": small}
+    graph_used = pb.graphed is not None
+    extra = None
+    if args.others == "auto" and w["name"] == "ecog" and w["rows"] == T * D and args.S == 0 and not args.no_e2e:
+        del pb
+        torch.cuda.empty_cache()
+        extra = other_configs(args, rank, world, dev, timed, peak)
+    if rank == 0:
+        line["other_configs"] = extra
         if args.cpu_baseline == "auto" and world == 1:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
-            m = reference_measure(w, 1 if w["rows"] * S > 4096 else 5, 1, 90.0, fit=False)
+            m = reference_measure(w, 3 if w["rows"] * S > 4096 else 5, 1, 90.0, fit=False)
             line["cpu_baseline"] = {"value": m["value"], "unit": UNIT, "cores": torch.get_num_threads(),
                                     "kind": m["kind"], "sample": m["sample"]}
         print(json.dumps(line), flush=True)
     if world > 1:
-        graph_used = pb.graphed is not None
         torch.cuda.synchronize()
         dist.barrier()
         if graph_used:

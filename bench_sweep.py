@@ -135,6 +135,39 @@ def sweep_config(args):
                         % (args.sweep_T, args.sweep_D), "T": args.sweep_T, "D": args.sweep_D}
 
 
+def quick_line(T, D, rank, world, dev, timed, peak):
+    """One short measured line of the scale-sweep configuration for bench.py's `other_configs` (same step as `run`)."""
+    from collaborative_nonstationary_multivariate_gaussian_process_b200 import parallel
+    xh, ellh, Bfh, yh, s2 = sweep_problem(T, D, None)
+    xh, ellh, yh, Bfh = xh.pin_memory(), ellh.pin_memory(), yh.pin_memory(), Bfh.pin_memory()
+    x, ell, Bf, y = xh.to(dev), ellh.to(dev), Bfh.to(dev), yh.to(dev)
+    mu = torch.zeros_like(y)
+
+    def step():
+        return parallel.kron_logpdf0_sharded(y, mu, Bf, kernels.Nonstationary_RBF_cov(x, ell1=ell), s2)
+
+    def step_e2e():
+        xd, elld, Bd, yd = (t.to(dev, non_blocking=True) for t in (xh, ellh, Bfh, yh))
+        return float(parallel.kron_logpdf0_sharded(yd, torch.zeros_like(yd), Bd, kernels.Nonstationary_RBF_cov(xd, ell1=elld), s2).cpu())
+    for _ in range(3):
+        step()
+    k = 2
+    ms, lp, _, nl = timed(step, k)
+    ms2, _, _, _ = timed(step_e2e, k)
+    blocks_local = (D + world - 1) // world
+    tf = blocks_local * T ** 3 / 3.0 / (ms / k * 1e-3) / 1e12
+    return {"metric": SWEEP_METRIC % (T, D), "config": {"workload": "scale sweep: T=%d x D=%d, nonstationary kernel build + "
+                                                        "multivariate_normal_logpdf0 (eigen-blocks dealt to the ranks)" % (T, D),
+                                                        "T": T, "D": D},
+            "n_gpus": world, "steps": k, "warmup": 3, "value": 1e3 * k / ms, "unit": "evals/s", "ms_per_step": ms / k,
+            "gpu_launches": int(nl), "logpdf0": float(lp),
+            "e2e": {"value": 1e3 * k / ms2, "unit": "evals/s", "ms_per_step": ms2 / k,
+                    "h2d_bytes_per_step": int(8 * (2 * T + D * D + D * T)) * world, "d2h_bytes_per_step": 8 * world},
+            "roofline": {"kernel": "nmgp_potrf_big (blocked Cholesky, %d eigen-blocks per GPU in flight on streams)" % blocks_local,
+                         "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (tf / peak) if peak else None, "algorithmic": "T^3/3 flop per block (build included in the time)"}}
+
+
 def run(args):
     """bench.py --workload sweep: one step = build K (T x T, HBM roofline) + Kronecker log-density (D blocked Cholesky
     factorisations on the FP64 tensor cores, sharded over the ranks, one all-reduce of a double)."""

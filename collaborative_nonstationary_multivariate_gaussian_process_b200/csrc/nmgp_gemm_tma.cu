@@ -210,18 +210,11 @@ bool encode_map(CUtensorMap* map, const double* base, long long rows, long long 
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-}  // namespace
-
-// returns 0 when the GEMM was launched, 1 when this path does not apply (caller falls back to the cp.async kernel),
-// < 0 on error.  Requirements of the TMA descriptors: 16-byte aligned base pointers and row strides.
-int nmgp_gemm_nt_tma(const double* A, const double* Bm, double* C, long long M, long long N, long long K, long long lda,
-                     long long ldb, long long ldc, double alpha, double beta, int lower_only, cudaStream_t st) {
+bool ensure_encode() {
     if (g_encode_state == 0) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
-        const char* off = getenv("NMGP_GEMM_TMA");
-        if (!(off && off[0] == '0') &&
-            cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
             qres == cudaDriverEntryPointSuccess) {
             g_encode = reinterpret_cast<EncodeTiledFn>(fn);
             g_encode_state = 1;
@@ -229,7 +222,17 @@ int nmgp_gemm_nt_tma(const double* A, const double* Bm, double* C, long long M, 
             g_encode_state = -1;
         }
     }
-    if (g_encode_state < 0) return 1;
+    return g_encode_state > 0;
+}
+
+}  // namespace
+
+// returns 0 when the GEMM was launched, 1 when this path does not apply (caller falls back to the cp.async kernel),
+// < 0 on error.  Requirements of the TMA descriptors: 16-byte aligned base pointers and row strides.
+int nmgp_gemm_nt_tma(const double* A, const double* Bm, double* C, long long M, long long N, long long K, long long lda,
+                     long long ldb, long long ldc, double alpha, double beta, int lower_only, cudaStream_t st) {
+    static const bool off = [] { const char* e = getenv("NMGP_GEMM_TMA"); return e && e[0] == '0'; }();
+    if (off || !ensure_encode()) return 1;
     if ((lda & 1) || (ldb & 1) || (((size_t)A) & 15) || (((size_t)Bm) & 15) || K < 1 || M >= (1LL << 31) ||
         N >= (1LL << 31) || K >= (1LL << 31))
         return 1;

@@ -63,6 +63,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  "l"(src), "r"(bytes), "r"(smem_u32(b))
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
     unsigned done = 0;
     const unsigned a = smem_u32(b);
@@ -120,7 +123,7 @@ struct LFShape {
     static constexpr int MU_DMAX = 64;
     static constexpr int MUB = MU_DMAX * LDM;
     static constexpr int BUF = REC > MUB ? REC : MUB;      // doubles per staging buffer
-    static constexpr size_t smem_doubles = (size_t)LFK_ROWS * LDP + 2 * (size_t)BUF + 2 * LFK_ROWS + 4;
+    static constexpr size_t smem_doubles = (size_t)LFK_ROWS * LDP + 2 * (size_t)BUF + 2 * LFK_ROWS + 6;
     static constexpr size_t smem_bytes = smem_doubles * 8 + LFK_ROWS * 4;
 };
 
@@ -139,8 +142,9 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
     double* Ss = Ps + (size_t)LFK_ROWS * LDP;           // [2][BUF]: double-buffered records of the latent j / mean block
     double* rrs = Ss + 2 * (size_t)BUF;                // [LFK_ROWS]
     double* omcs = rrs + LFK_ROWS;                      // [LFK_ROWS]
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(omcs + LFK_ROWS);   // [3] (+1 pad)
-    int* Is = reinterpret_cast<int*>(mbar + 4);        // [LFK_ROWS]
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(omcs + LFK_ROWS);   // full[2], prologue, pad, empty[2]
+    unsigned long long* mempty = mbar + 4;
+    int* Is = reinterpret_cast<int*>(mbar + 6);        // [LFK_ROWS]
 
     const int s = blockIdx.y;
     const long long row0 = (long long)blockIdx.x * LFK_ROWS;
@@ -157,6 +161,8 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         mbar_init(&mbar[2], 1);
+        mbar_init(&mempty[0], LFK_THREADS / 32);
+        mbar_init(&mempty[1], LFK_THREADS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
@@ -291,6 +297,7 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
         for (int nb = 0; nb < NB; ++nb) pacc[mb][nb][0] = pacc[mb][nb][1] = 0.0;
     double pen[2] = {0.0, 0.0}, gsum[2] = {0.0, 0.0};
 
+    __syncthreads();                                       // phase 1 is done with the mean block in buffer 1 (refilled at j = 0)
     double lnext[2], mnext[2];                             // (record 0 is already in flight since the prologue)
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb) {
@@ -299,12 +306,24 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
     }
     for (int j = 0; j <= jmax; ++j) {
         const int buf = j & 1;
-        __syncthreads();                                  // everyone is done with the other buffer (latent j - 1)
-        if (tid == 0) {
-            if (j + 1 <= jmax) stage(j + 1, buf ^ 1);
-            else if (mu_smem) stage_mu(buf ^ 1);
+        // No CTA barrier in the loop: a warp releases a record buffer (empty mbarrier, one arrival per warp) as soon as its
+        // DMMA run over it is done, and warp 0 refills the other buffer once all four warps have released it -- the
+        // epilogue of a slow warp no longer holds the others back, and the refill starts one epilogue earlier.
+        if (w == 0) {
+            if (j >= 1) mbar_wait(&mempty[buf ^ 1], (unsigned)(((j - 1) >> 1) & 1));    // latent j - 1 is done everywhere
+            if (lane == 0) {
+                if (j + 1 <= jmax) stage(j + 1, buf ^ 1);
+                else if (mu_smem) stage_mu(buf ^ 1);
+            }
+            __syncwarp();
         }
-        if (warpmaxI < j) continue;                        // warp-uniform: none of this warp's rows uses latent j
+        if (warpmaxI < j) {                                // warp-uniform: none of this warp's rows uses latent j
+            // a skipping warp reads no record, so nothing paces it: it must not arrive for latent j while the buffer's
+            // previous phase (latent j - 2) is still open, or that phase would complete with two of its arrivals
+            if (j >= 2) mbar_wait(&mempty[buf], (unsigned)(((j - 2) >> 1) & 1));
+            if (lane == 0) mbar_arrive(&mempty[buf]);
+            continue;
+        }
         const double lcur[2] = {lnext[0], lnext[1]}, mcur[2] = {mnext[0], mnext[1]};
         if (j + 1 < D) {
 #pragma unroll
@@ -329,6 +348,8 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
                 dmma884(V[1][nb][0], V[1][nb][1], afr[1][ks], b);
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mempty[buf]);          // this warp is done reading record j
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {
             const int rl = rloc[mb];
@@ -718,7 +739,7 @@ int nmgp_coef_quadform_mma(bool bwd, const double* Pa, const double* Pb, const i
                         // it accumulates.  8 < NB <= 16 (WIDE): 8 block-row roles, 2 latents per CTA, both in every warp
 #define GM_NGW 2        // latents accumulated per warp
 
-template <int NB, int HV = 1>
+template <int NB>
 struct GMShape {
     static constexpr bool WIDE = NB > 8;
     static constexpr int NG = WIDE ? 2 : 4;                // latents per CTA
@@ -729,29 +750,19 @@ struct GMShape {
     // even rule, which left the fourth warp scheduler's tensor pipe idle half of the time (a warp's scheduler is its
     // index mod 4, so a light role is a light scheduler).
     static constexpr int NSLOT = (NB & 1) ? NB : NB + 1;
-    // HV = 2 (tuning variant, NMGP_GRAM_HALVES=2, NB <= 8): the CTA is two independent 8-warp halves (own staging buffers,
-    // own named barrier) that take alternate row tiles of the same (output, latent group) with the roles rotated
-    // against each other, one 16-warp CTA per SM instead of two 8-warp ones.
-    static constexpr int HALVES = HV;
-    static constexpr size_t half_doubles = 2 * (size_t)GM_TROWS * LDP + 2 * 2 * NG * GM_TROWS;
-    static constexpr size_t smem_doubles = HALVES * half_doubles;
+    static constexpr size_t smem_doubles = 2 * (size_t)GM_TROWS * LDP + 2 * 2 * NG * GM_TROWS;
 };
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
-}
 
-template <int NB, int HV>
-__global__ void __launch_bounds__(GM_THREADS * HV, (NB > 8 || HV == 2) ? 1 : 2)
+template <int NB>
+__global__ void __launch_bounds__(GM_THREADS, NB > 8 ? 1 : 2)
 k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const int* __restrict__ seg,
            const double* __restrict__ qbar, const double* __restrict__ mbar, double* __restrict__ SigBar,
            double* __restrict__ MuBar, long long B, int Q, int D, int mode) {
-    using SH = GMShape<NB, HV>;
+    using SH = GMShape<NB>;
     constexpr int LDP = SH::LDP, GM_NG = SH::NG, NSLOT = SH::NSLOT;
     constexpr bool WIDE = SH::WIDE;
-    constexpr int HALVES = SH::HALVES;
     extern __shared__ __align__(16) double sm[];
-    const int half = HALVES == 2 ? (int)(threadIdx.x >> 8) : 0;
-    double* Pt = sm + (size_t)half * SH::half_doubles;      // [2][GM_TROWS][LDP]
+    double* Pt = sm;                                        // [2][GM_TROWS][LDP]
     double* wq = Pt + 2 * (size_t)GM_TROWS * LDP;           // [2][GM_NG][GM_TROWS]
     double* wm = wq + 2 * GM_NG * GM_TROWS;                 // [2][GM_NG][GM_TROWS]
     const int i = blockIdx.x, s = blockIdx.z;
@@ -768,9 +779,8 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
     }
     const long long rbeg = seg[i], rend = seg[i + 1];
     if (rbeg >= rend) return;
-    const int tid = threadIdx.x & (GM_THREADS - 1), lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int ug = WIDE ? 0 : (tid >> 7);
-    const int w = WIDE ? (tid >> 5) : (HALVES == 2 ? (((tid >> 5) + 2 * ug + half) & 3) : ((tid >> 5) & 3));
+    const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int w = WIDE ? (tid >> 5) : ((tid >> 5) & 3), ug = WIDE ? 0 : (tid >> 7);
     const int u0 = ug * GM_NGW;                            // this warp's latents: u0 .. u0 + GM_NGW - 1
     int a1, a2;
     bool active;
@@ -785,7 +795,7 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
     }
     const int nslots = !active ? 0 : (a1 == a2 ? a1 + 1 : a1 + a2 + 2);
 
-    for (int e = threadIdx.x; e < (int)SH::smem_doubles; e += GM_THREADS * HALVES) sm[e] = 0.0;
+    for (int e = tid; e < (int)SH::smem_doubles; e += GM_THREADS) sm[e] = 0.0;
     __syncthreads();
 
     double acc[GM_NGW][NSLOT][2];
@@ -795,11 +805,9 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
 #pragma unroll
         for (int sl = 0; sl < NSLOT; ++sl) acc[u][sl][0] = acc[u][sl][1] = 0.0;
 
-    const long long ntiles_all = (rend - rbeg + GM_TROWS - 1) / GM_TROWS;
-    const long long ntiles = (ntiles_all - half + HALVES - 1) / HALVES;      // this half takes tiles half, half + 2, ...
-    if (ntiles <= 0) return;                                // (whole half leaves; no CTA-wide barrier follows)
-    auto stage = [&](long long tile_h, int buf) {
-        const long long r0 = rbeg + (tile_h * HALVES + half) * GM_TROWS;
+    const long long ntiles = (rend - rbeg + GM_TROWS - 1) / GM_TROWS;
+    auto stage = [&](long long tile, int buf) {
+        const long long r0 = rbeg + tile * GM_TROWS;
         const int nr = (int)min((long long)GM_TROWS, rend - r0);
         double* Pd = Pt + (size_t)buf * GM_TROWS * LDP;
         for (int r = (tid >> 5); r < GM_TROWS; r += GM_THREADS / 32) {
@@ -833,8 +841,7 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
     for (long long tile = 0; tile < ntiles; ++tile) {
         const int buf = (int)(tile & 1);
         cp_async_wait<0>();
-        if (HALVES == 2) named_bar_sync(1 + half, GM_THREADS);
-        else __syncthreads();
+        __syncthreads();
         if (tile + 1 < ntiles) stage(tile + 1, buf ^ 1);
         cp_async_commit();
         if (!active) continue;
@@ -863,10 +870,12 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
                 }
             }
             // MuBar: (Q x rows)(rows x NG): B fragment column g carries mbar of latent g (< NG), k = n
-            if (ug == 0) {
+            // (one product gives all NG latents of the CTA, so the two latent halves share the work: half 0 takes block
+            // row a1, half 1 block row a2 -- 15/15 DMMAs per k-step instead of 16/14 at NB = 7)
+            if (WIDE || ug == 0 || a2 != a1) {
                 const double bm = (g < GM_NG) ? wm[(buf * GM_NG + g) * GM_TROWS + n] : 0.0;
-                dmma884(accm[0][0], accm[0][1], ra1, bm);
-                if (a2 != a1) dmma884(accm[1][0], accm[1][1], ra2, bm);
+                if (WIDE || ug == 0) dmma884(accm[0][0], accm[0][1], ra1, bm);
+                if ((WIDE || ug == 1) && a2 != a1) dmma884(accm[1][0], accm[1][1], ra2, bm);
             }
         }
     }
@@ -897,10 +906,10 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
             }
         }
     }
-    if (ug != 0) return;
 #pragma unroll
     for (int st2 = 0; st2 < 2; ++st2) {
         if (st2 == 1 && a2 == a1) break;
+        if (!WIDE && ug != st2) continue;                   // half 0 accumulated block row a1, half 1 block row a2
         const int a = st2 == 0 ? a1 : a2;
         const int r = 8 * a + g;
 #pragma unroll
@@ -914,249 +923,22 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
     }
 }
 
-template <int NB, int HV>
-static int launch_gram_v(const double* Pa, const double* Pb, const int* seg, const double* qbar, const double* mbar,
-                         double* SigBar, double* MuBar, int ns, long long B, int Q, int D, int mode, cudaStream_t st) {
-    using SH = GMShape<NB, HV>;
-    size_t smem = SH::smem_doubles * sizeof(double);
-    if (int r = nmgp_opt_in_smem(k_gram_mma<NB, HV>, smem, "nmgp_weighted_gram")) return r;
-    constexpr int GM_NG = SH::NG;
-    const int ngroups = (D + GM_NG - 1) / GM_NG;
-    dim3 grid(D, ngroups + (mode == MODE_U ? 1 : 0), ns);
-    k_gram_mma<NB, HV><<<NMGP_L(grid), GM_THREADS * HV, smem, st>>>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, B, Q, D, mode);
-    return nmgp_launch_status("nmgp_weighted_gram(mma)");
-}
 template <int NB>
 static int launch_gram(const double* Pa, const double* Pb, const int* seg, const double* qbar, const double* mbar,
                        double* SigBar, double* MuBar, int ns, long long B, int Q, int D, int mode, cudaStream_t st) {
-    if constexpr (NB <= 8) {
-        static const int halves = [] { const char* e = getenv("NMGP_GRAM_HALVES"); return e ? atoi(e) : 1; }();
-        if (halves == 2) return launch_gram_v<NB, 2>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
-    }
-    return launch_gram_v<NB, 1>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// k_gram_tma: the same weighted Gram products for NB <= 8, fed by the bulk-copy engine through a GT_STAGES-deep ring of
-// (P tile, qbar / mbar chunk) stages with full / empty mbarriers.  ncu on k_gram_mma<7> (profiles/r2): a quarter of every
-// warp's time went to the per-tile staging code (cp.async address arithmetic in all 8 warps) and the CTA barrier behind
-// it.  Here one warp issues three bulk copies per row (P row, 4 consecutive qbar, 4 consecutive mbar) for the tile
-// GT_STAGES - 1 ahead, nobody executes a CTA barrier inside the loop, and the warps may drift by up to three tiles.
-// Requires 16-byte aligned rows: Q even, D % 4 == 0 (else k_gram_mma).
-#define GT_STAGES 4
-template <int NB>
-struct GTShape {
-    static constexpr int NP = 8 * NB;
-    static constexpr int LDP = pad4mod8(NP);
-    static constexpr int NSLOT = (NB & 1) ? NB : NB + 1;
-    static constexpr int stage_doubles = GM_TROWS * LDP + 2 * GM_TROWS * 4;
-    static constexpr size_t smem_bytes = (size_t)GT_STAGES * stage_doubles * 8 + 2 * GT_STAGES * 8;
-};
-__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
-}
-
-template <int NB>
-__global__ void __launch_bounds__(GM_THREADS, 2)
-k_gram_tma(const double* __restrict__ Pa, const double* __restrict__ Pb, const int* __restrict__ seg,
-           const double* __restrict__ qbar, const double* __restrict__ mbar_, double* __restrict__ SigBar,
-           double* __restrict__ MuBar, long long B, int Q, int D, int mode) {
-    using SH = GTShape<NB>;
-    constexpr int LDP = SH::LDP, NSLOT = SH::NSLOT, STG = SH::stage_doubles;
-    extern __shared__ __align__(16) double sm[];
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + (size_t)GT_STAGES * STG);
-    unsigned long long* empty = full + GT_STAGES;
-    const int i = blockIdx.x, s = blockIdx.z;
-    const int ngroups = (D + 3) / 4;
-    int jc, nj, usel = -1;                                  // chunk of 4 latent columns jc .. jc+3; live: u < nj (or u == usel)
-    const double* P = Pa;
-    if (mode == MODE_U && (int)blockIdx.y == ngroups) {     // the diagonal coefficient pair (i,i): L1 system rows
-        jc = i & ~3; usel = i & 3; nj = 4; P = Pb;
-    } else {
-        jc = 4 * blockIdx.y;
-        const int jlast = (mode == MODE_U) ? i - 1 : i;      // MODE_U groups cover the strictly-lower pairs only
-        if (jc > jlast) return;
-        nj = min(4, jlast - jc + 1);
-    }
-    const long long rbeg = seg[i], rend = seg[i + 1];
-    if (rbeg >= rend) return;
-    const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3, warp = tid >> 5;
-    const int w = warp & 3, ug = warp >> 2;
-    const int u0 = ug * GM_NGW;
-    int a1, a2;
-    bool active;
-    if (NB & 1) {
-        constexpr int NPAIR = (NB - 1) / 2;
-        active = w <= NPAIR;
-        a1 = w < NPAIR ? w : NB - 1;
-        a2 = w < NPAIR ? NB - 2 - w : NB - 1;
-    } else {
-        a1 = w; a2 = NB - 1 - w;
-        active = a1 <= a2;
-    }
-    const int nslots = !active ? 0 : (a1 == a2 ? a1 + 1 : a1 + a2 + 2);
-
-    // zero the stages once (rows past the end of the last tile keep finite values; their weights are zeroed per tile)
-    for (int e = tid; e < GT_STAGES * STG; e += GM_THREADS) sm[e] = 0.0;
-    if (tid == 0) {
-        for (int k = 0; k < GT_STAGES; ++k) {
-            mbar_init(&full[k], 1);
-            mbar_init(&empty[k], GM_THREADS / 32);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    __syncthreads();
-
-    const long long ntiles = (rend - rbeg + GM_TROWS - 1) / GM_TROWS;
-    const size_t sB = (size_t)s * B;
-    auto issue = [&](long long tile) {                      // warp 0, all lanes: one row per lane
-        const int st = (int)(tile % GT_STAGES);
-        const long long r0 = rbeg + tile * GM_TROWS;
-        const int nr = (int)min((long long)GM_TROWS, rend - r0);
-        double* Pd = sm + (size_t)st * STG;
-        double* wq = Pd + GM_TROWS * LDP;                   // [GM_TROWS][4]
-        double* wm = wq + GM_TROWS * 4;
-        if (lane >= nr) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) wq[lane * 4 + u] = wm[lane * 4 + u] = 0.0;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_expect_tx(&full[st], (unsigned)nr * ((unsigned)Q * 8u + 64u));
-        __syncwarp();
-        if (lane < nr) {
-            const size_t row = sB + r0 + lane;
-            bulk_g2s(Pd + lane * LDP, P + row * Q, (unsigned)Q * 8u, &full[st]);
-            bulk_g2s(wq + lane * 4, qbar + row * D + jc, 32u, &full[st]);
-            bulk_g2s(wm + lane * 4, mbar_ + row * D + jc, 32u, &full[st]);
-        }
-    };
-    if (warp == 0)
-        for (long long tl = 0; tl < GT_STAGES - 1 && tl < ntiles; ++tl) issue(tl);
-
-    double acc[GM_NGW][NSLOT][2];
-    double accm[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-#pragma unroll
-    for (int u = 0; u < GM_NGW; ++u)
-#pragma unroll
-        for (int sl = 0; sl < NSLOT; ++sl) acc[u][sl][0] = acc[u][sl][1] = 0.0;
-
-    for (long long tile = 0; tile < ntiles; ++tile) {
-        const int st = (int)(tile % GT_STAGES);
-        if (warp == 0) {
-            const long long nt = tile + GT_STAGES - 1;
-            if (nt < ntiles) {
-                if (nt >= GT_STAGES) mbar_wait(&empty[nt % GT_STAGES], (unsigned)(((nt / GT_STAGES) - 1) & 1));
-                issue(nt);
-            }
-        }
-        mbar_wait(&full[st], (unsigned)((tile / GT_STAGES) & 1));
-        if (active) {
-            const double* Pd = sm + (size_t)st * STG;
-            const double* wq = Pd + GM_TROWS * LDP;
-            const double* wm = wq + GM_TROWS * 4;
-#pragma unroll
-            for (int kk = 0; kk < GM_TROWS / 4; ++kk) {
-                const int n = 4 * kk + t;                    // row of the tile this lane feeds as k index
-                const double ra1 = Pd[n * LDP + 8 * a1 + g]; // A fragment (a = 8 a1 + g, k = n), unscaled
-                const double ra2 = Pd[n * LDP + 8 * a2 + g];
-                double sa1[GM_NGW], sa2[GM_NGW];
-#pragma unroll
-                for (int u = 0; u < GM_NGW; ++u) {
-                    const double wv = wq[n * 4 + u0 + u];
-                    sa1[u] = ra1 * wv;
-                    sa2[u] = ra2 * wv;
-                }
-#pragma unroll
-                for (int sl = 0; sl < NSLOT; ++sl) {
-                    if (sl < nslots) {
-                        const bool first = sl <= a1;
-                        const int bb = first ? sl : sl - a1 - 1;
-                        const double bf = Pd[n * LDP + 8 * bb + g];   // B fragment (k = n, col = 8 bb + g)
-#pragma unroll
-                        for (int u = 0; u < GM_NGW; ++u)
-                            dmma884(acc[u][sl][0], acc[u][sl][1], first ? sa1[u] : sa2[u], bf);
-                    }
-                }
-                if (ug == 0) {                               // MuBar: B fragment column g carries mbar of latent g (< 4)
-                    const double bm = (g < 4) ? wm[n * 4 + g] : 0.0;
-                    dmma884(accm[0][0], accm[0][1], ra1, bm);
-                    if (a2 != a1) dmma884(accm[1][0], accm[1][1], ra2, bm);
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
-    }
-    if (!active) return;
-    // ---- write-out: block (a, bb) holds rows 8a+g, cols 8bb+2t+e; mirror the strictly-lower blocks ----------
-    auto live = [&](int u) { return usel >= 0 ? (u == usel) : (u < nj); };
-    auto slot_of = [&](int u) { return (mode == MODE_U) ? pair_slot(i, usel >= 0 ? i : jc + u, D) : jc + u; };
-#pragma unroll
-    for (int uu = 0; uu < GM_NGW; ++uu) {
-        const int u = u0 + uu;
-        if (live(u)) {
-            double* Sb = SigBar + (size_t)slot_of(u) * Q * Q;
-#pragma unroll
-            for (int sl = 0; sl < NSLOT; ++sl) {
-                if (sl < nslots) {
-                    const bool first = sl <= a1;
-                    const int a = first ? a1 : a2, bb = first ? sl : sl - a1 - 1;
-                    const int r = 8 * a + g;
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int c = 8 * bb + 2 * t + e;
-                        if (r < Q && c < Q) {
-                            atomicAdd(&Sb[(size_t)r * Q + c], acc[uu][sl][e]);
-                            if (a != bb) atomicAdd(&Sb[(size_t)c * Q + r], acc[uu][sl][e]);
-                        }
-                    }
-                }
-            }
-        }
-    }
-    if (ug != 0) return;
-#pragma unroll
-    for (int st2 = 0; st2 < 2; ++st2) {
-        if (st2 == 1 && a2 == a1) break;
-        const int a = st2 == 0 ? a1 : a2;
-        const int r = 8 * a + g;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int u = 2 * t + e;
-            if (u < 4 && live(u) && r < Q) atomicAdd(&MuBar[(size_t)slot_of(u) * Q + r], accm[st2][e]);
-        }
-    }
-}
-
-template <int NB>
-static int launch_gram_tma(const double* Pa, const double* Pb, const int* seg, const double* qbar, const double* mbar,
-                           double* SigBar, double* MuBar, int ns, long long B, int Q, int D, int mode, cudaStream_t st) {
-    size_t smem = GTShape<NB>::smem_bytes;
-    if (int r = nmgp_opt_in_smem(k_gram_tma<NB>, smem, "nmgp_weighted_gram")) return r;
-    const int ngroups = (D + 3) / 4;
+    size_t smem = GMShape<NB>::smem_doubles * sizeof(double);
+    if (int r = nmgp_opt_in_smem(k_gram_mma<NB>, smem, "nmgp_weighted_gram")) return r;
+    constexpr int GM_NG = GMShape<NB>::NG;
+    const int ngroups = (D + GM_NG - 1) / GM_NG;
     dim3 grid(D, ngroups + (mode == MODE_U ? 1 : 0), ns);
-    k_gram_tma<NB><<<NMGP_L(grid), GM_THREADS, smem, st>>>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, B, Q, D, mode);
-    return nmgp_launch_status("nmgp_weighted_gram(tma)");
+    k_gram_mma<NB><<<NMGP_L(grid), GM_THREADS, smem, st>>>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, B, Q, D, mode);
+    return nmgp_launch_status("nmgp_weighted_gram(mma)");
 }
 
 // returns 1 if Q is outside the register-resident range (caller falls back to the FMA kernel)
 int nmgp_weighted_gram_mma(const double* Pa, const double* Pb, const int* seg, const double* qbar, const double* mbar,
                            double* SigBar, double* MuBar, int ns, long long B, int Q, int D, int mode,
                            cudaStream_t st) {
-    static const int use_tma = [] { const char* e = getenv("NMGP_GRAM_TMA"); return e ? atoi(e) : 1; }();
-    if (use_tma && (Q & 1) == 0 && (D & 3) == 0 && Q <= 64) {
-        switch ((Q + 7) / 8) {
-            case 1: return launch_gram_tma<1>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
-            case 2: return launch_gram_tma<2>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
-            case 3: return launch_gram_tma<3>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
-            case 4: return launch_gram_tma<4>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
-            case 5: return launch_gram_tma<5>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
-            case 6: return launch_gram_tma<6>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
-            case 7: return launch_gram_tma<7>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
-            case 8: return launch_gram_tma<8>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
-        }
-    }
     switch ((Q + 7) / 8) {
         case 1: return launch_gram<1>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
         case 2: return launch_gram<2>(Pa, Pb, seg, qbar, mbar, SigBar, MuBar, ns, B, Q, D, mode, st);
