@@ -673,7 +673,8 @@ def kron_product(t1, t2):
 
 def eigh_small(A):
     n = A.shape[0]
-    w = _empty(A, n); V = _empty(A, n, n); work = _empty(A, n, n)
+    lib().nmgp_eigh_small_work.restype = ctypes.c_longlong
+    w = _empty(A, n); V = _empty(A, n, n); work = _empty(A, int(lib().nmgp_eigh_small_work(c_int(n))))
     check(lib().nmgp_eigh_small(_d(A), _d(w), _d(V), _d(work), c_int(n), _stream()), "nmgp_eigh_small")
     return w, V
 

@@ -869,31 +869,43 @@ NMGP_API int nmgp_kron_product(const double* t1, const double* t2, double* out, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Cyclic Jacobi eigen-decomposition of a small symmetric n x n matrix (n <= 128), one CTA.  Reads the UPPER triangle
+// Cyclic Jacobi eigen-decomposition of a small symmetric n x n matrix (n <= 128).  Reads the UPPER triangle
 // (torch.symeig's default, kronecker_operation.py:45).  Eigenvalues ascending in w, eigenvectors in the columns of V.
 // Parallel (round-robin tournament) ordering: every step rotates n/2 disjoint index pairs at once -- all (c, s) from the
-// current matrix, then S <- S J (columns; U <- U J alongside) and S <- J^T S (rows) -- so a sweep costs n - 1 steps of
-// three barriers instead of n(n-1)/2 sequential rotations (n = 128: 223 ms -> a few ms).
+// current matrix, then S <- S J (columns) and S <- J^T S (rows) -- so a sweep costs n - 1 steps of three barriers.
+// Two kernels: k_eigh_jacobi (one CTA) keeps only S, in shared memory, and LOGS every step's rotations; the
+// eigenvector matrix U = J_1 J_2 ... never enters that serial chain (at n = 128 S and U do not fit shared memory
+// together, and updating U in global memory was 90 % of the 37 ms the one-kernel version took).  k_eigh_replay then
+// applies the logged rotations to the n rows of the identity independently -- one warp per row, the row in shared
+// memory, the next step's parameters prefetched -- which is embarrassingly parallel.
 #define EJ_THREADS 512
+#define EJ_MAXSWEEP 30
+struct EJMeta { int nsteps; int pad; };
+__host__ __device__ inline long long ej_work_doubles(int n) {
+    const long long m = (n + (n & 1)) / 2, steps = (long long)EJ_MAXSWEEP * (n + (n & 1) - 1);
+    return 8 + 128 + steps * m * 3;      // meta | order (ints) | cs (double2 per rotation) | pq (int2 per rotation)
+}
 __global__ void __launch_bounds__(EJ_THREADS)
-k_eigh_jacobi(const double* __restrict__ A, double* __restrict__ w, double* __restrict__ V,
-              double* __restrict__ Vwork, int n) {
+k_eigh_jacobi(const double* __restrict__ A, double* __restrict__ w, double* __restrict__ work, int n) {
     extern __shared__ double sm[];
     double* S = sm;              // [n][n]
-    double* U = Vwork;           // [n][n] eigenvector accumulator (global scratch, L2-resident)
     __shared__ double cs[64][2];
     __shared__ int pq[64][2];
-    __shared__ int order[128];
     const int tid = threadIdx.x;
+    const int ne = n + (n & 1);          // players of the tournament (a dummy index n when n is odd)
+    const int m = ne / 2, N1 = ne - 1;
+    EJMeta* meta = reinterpret_cast<EJMeta*>(work);
+    int* order = reinterpret_cast<int*>(work + 8);
+    double2* lcs = reinterpret_cast<double2*>(work + 8 + 128);
+    int2* lpq = reinterpret_cast<int2*>(work + 8 + 128 + (size_t)EJ_MAXSWEEP * N1 * m * 2);
     for (int e = tid; e < n * n; e += blockDim.x) {
         int a = e / n, b = e - a * n;
         S[e] = (b >= a) ? A[a * n + b] : A[b * n + a];
-        U[e] = (a == b) ? 1.0 : 0.0;
     }
     __syncthreads();
-    const int ne = n + (n & 1);          // players of the tournament (a dummy index n when n is odd)
-    const int m = ne / 2, N1 = ne - 1;
-    for (int sweep = 0; sweep < 30; ++sweep) {
+    int step = 0;
+    double prev_off = 1e300;
+    for (int sweep = 0; sweep < EJ_MAXSWEEP; ++sweep) {
         double off = 0.0;
         for (int e = tid; e < n * n; e += blockDim.x) {
             int a = e / n, b = e - a * n;
@@ -903,8 +915,12 @@ k_eigh_jacobi(const double* __restrict__ A, double* __restrict__ w, double* __re
         double diag = 0.0;
         for (int a = tid; a < n; a += blockDim.x) diag = fma(S[a * n + a], S[a * n + a], diag);
         diag = block_sum(diag);
-        if (off <= 1e-34 * diag) break;
-        for (int r = 0; r < N1; ++r) {
+        // converged: quadratic convergence takes the ratio from ~1e-12 to the rounding floor in one sweep; the floor itself
+        // (rotated entries are not exact zeros) sits around 1e-32, so a fixed 1e-34 never triggered and all EJ_MAXSWEEP
+        // sweeps ran (measured: 24 ms at n = 128 for 10 useful sweeps)
+        if (off <= 1e-30 * diag || (sweep >= 3 && off <= 1e-24 * diag && off >= 0.25 * prev_off)) break;
+        prev_off = off;
+        for (int r = 0; r < N1; ++r, ++step) {
             if (tid < m) {                // pair i of round r (circle method): (r, ne-1), ((r+i) mod N1, (r-i) mod N1)
                 int a_ = tid == 0 ? r : (r + tid) % N1, b_ = tid == 0 ? ne - 1 : (r - tid + N1) % N1;
                 int p = min(a_, b_), q = max(a_, b_);
@@ -922,30 +938,31 @@ k_eigh_jacobi(const double* __restrict__ A, double* __restrict__ w, double* __re
                 }
                 pq[tid][0] = p; pq[tid][1] = q;
                 cs[tid][0] = c; cs[tid][1] = sn;
+                lcs[(size_t)step * m + tid] = make_double2(c, sn);
+                lpq[(size_t)step * m + tid] = make_int2(p, q);
             }
             __syncthreads();
-            for (int e = tid; e < m * n; e += blockDim.x) {          // columns p, q of S and U
-                const int i = e % m, k = e / m;
+            for (int i = tid & 63; i < m; i += 64) {                  // columns p, q of S: lane group = pair, rows strided
                 const double c = cs[i][0], sn = cs[i][1];
                 if (sn != 0.0) {
                     const int p = pq[i][0], q = pq[i][1];
-                    const double skp = S[k * n + p], skq = S[k * n + q];
-                    S[k * n + p] = c * skp - sn * skq;
-                    S[k * n + q] = sn * skp + c * skq;
-                    const double ukp = U[k * n + p], ukq = U[k * n + q];
-                    U[k * n + p] = c * ukp - sn * ukq;
-                    U[k * n + q] = sn * ukp + c * ukq;
+                    for (int k = tid >> 6; k < n; k += EJ_THREADS / 64) {
+                        const double skp = S[k * n + p], skq = S[k * n + q];
+                        S[k * n + p] = c * skp - sn * skq;
+                        S[k * n + q] = sn * skp + c * skq;
+                    }
                 }
             }
             __syncthreads();
-            for (int e = tid; e < m * n; e += blockDim.x) {          // rows p, q of S
-                const int k = e % n, i = e / n;
+            for (int i = tid >> 7; i < m; i += EJ_THREADS / 128) {    // rows p, q of S: consecutive threads = consecutive columns
                 const double c = cs[i][0], sn = cs[i][1];
                 if (sn != 0.0) {
                     const int p = pq[i][0], q = pq[i][1];
-                    const double spk = S[p * n + k], sqk = S[q * n + k];
-                    S[p * n + k] = c * spk - sn * sqk;
-                    S[q * n + k] = sn * spk + c * sqk;
+                    for (int k = tid & 127; k < n; k += 128) {
+                        const double spk = S[p * n + k], sqk = S[q * n + k];
+                        S[p * n + k] = c * spk - sn * sqk;
+                        S[q * n + k] = sn * spk + c * sqk;
+                    }
                 }
             }
             __syncthreads();
@@ -960,19 +977,64 @@ k_eigh_jacobi(const double* __restrict__ A, double* __restrict__ w, double* __re
             if (u < v || (u == v && k < tid)) ++rank;
         }
         order[rank] = tid;
+        w[rank] = v;
     }
-    __syncthreads();
-    if (tid < n) w[tid] = S[order[tid] * n + order[tid]];
-    for (int e = tid; e < n * n; e += blockDim.x) {
-        int a = e / n, b = e - a * n;
-        V[e] = U[a * n + order[b]];
-    }
+    if (tid == 0) meta->nsteps = step;
 }
-NMGP_API int nmgp_eigh_small(const double* A, double* w, double* V, double* work /* n*n */, int n, cudaStream_t st) {
+// V[k][rank] = (e_k^T J_1 J_2 ... J_nsteps)[order[rank]]: one warp per row k
+#define ER_WARPS 4
+__global__ void __launch_bounds__(32 * ER_WARPS)
+k_eigh_replay(const double* __restrict__ work, double* __restrict__ V, int n) {
+    __shared__ double rows[ER_WARPS][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * ER_WARPS + warp;
+    if (k >= n) return;
+    const int ne = n + (n & 1), m = ne / 2, N1 = ne - 1;
+    const EJMeta* meta = reinterpret_cast<const EJMeta*>(work);
+    const int* order = reinterpret_cast<const int*>(work + 8);
+    const double2* lcs = reinterpret_cast<const double2*>(work + 8 + 128);
+    const int2* lpq = reinterpret_cast<const int2*>(work + 8 + 128 + (size_t)EJ_MAXSWEEP * N1 * m * 2);
+    double* row = rows[warp];
+    for (int c = lane; c < n; c += 32) row[c] = (c == k) ? 1.0 : 0.0;
+    __syncwarp();
+    const int nsteps = meta->nsteps;
+    // rotations of one step touch disjoint index pairs: lanes take pairs lane, lane + 32 (m <= 64)
+    double2 c0 = make_double2(1.0, 0.0), c1 = c0;
+    int2 q0 = make_int2(0, 0), q1 = q0;
+    if (nsteps > 0) {
+        if (lane < m) { c0 = __ldg(&lcs[lane]); q0 = __ldg(&lpq[lane]); }
+        if (lane + 32 < m) { c1 = __ldg(&lcs[lane + 32]); q1 = __ldg(&lpq[lane + 32]); }
+    }
+    for (int st = 0; st < nsteps; ++st) {
+        const double2 a0 = c0, a1 = c1;
+        const int2 p0 = q0, p1 = q1;
+        if (st + 1 < nsteps) {                                        // prefetch the next step's parameters
+            const size_t o = (size_t)(st + 1) * m;
+            if (lane < m) { c0 = __ldg(&lcs[o + lane]); q0 = __ldg(&lpq[o + lane]); }
+            if (lane + 32 < m) { c1 = __ldg(&lcs[o + lane + 32]); q1 = __ldg(&lpq[o + lane + 32]); }
+        }
+        if (lane < m && a0.y != 0.0) {
+            const double up = row[p0.x], uq = row[p0.y];
+            row[p0.x] = a0.x * up - a0.y * uq;
+            row[p0.y] = a0.y * up + a0.x * uq;
+        }
+        if (lane + 32 < m && a1.y != 0.0) {
+            const double up = row[p1.x], uq = row[p1.y];
+            row[p1.x] = a1.x * up - a1.y * uq;
+            row[p1.y] = a1.y * up + a1.x * uq;
+        }
+        __syncwarp();
+    }
+    for (int c = lane; c < n; c += 32) V[(size_t)k * n + c] = row[order[c]];
+}
+NMGP_API long long nmgp_eigh_small_work(int n) { return ej_work_doubles(n); }
+NMGP_API int nmgp_eigh_small(const double* A, double* w, double* V, double* work /* nmgp_eigh_small_work(n) doubles */,
+                             int n, cudaStream_t st) {
     NMGP_REQUIRE(n > 0 && n <= 128 && work != nullptr, "nmgp_eigh_small");
     size_t smem = sizeof(double) * n * n;
     if (int r = nmgp_opt_in_smem(k_eigh_jacobi, smem, "nmgp_eigh_small")) return r;
-    k_eigh_jacobi<<<NMGP_L(1), EJ_THREADS, smem, st>>>(A, w, V, work, n);
+    k_eigh_jacobi<<<NMGP_L(1), EJ_THREADS, smem, st>>>(A, w, work, n);
+    k_eigh_replay<<<NMGP_L((n + ER_WARPS - 1) / ER_WARPS), 32 * ER_WARPS, 0, st>>>(work, V, n);
     return nmgp_launch_status("nmgp_eigh_small");
 }
 

@@ -753,6 +753,55 @@ struct GMShape {
     static constexpr size_t smem_doubles = 2 * (size_t)GM_TROWS * LDP + 2 * 2 * NG * GM_TROWS;
 };
 
+// block-row roles (see GMShape): role w of a CTA with NB block rows
+__host__ __device__ constexpr bool gm_active(int NB, int w) { return (NB & 1) ? w <= (NB - 1) / 2 : w <= NB - 1 - w; }
+__host__ __device__ constexpr int gm_a1(int NB, int w) { return (NB & 1) ? (w < (NB - 1) / 2 ? w : NB - 1) : w; }
+__host__ __device__ constexpr int gm_a2(int NB, int w) { return (NB & 1) ? (w < (NB - 1) / 2 ? NB - 2 - w : NB - 1) : NB - 1 - w; }
+
+// One staged tile (GM_TROWS rows) for a warp whose role (block rows A1 <= A2) is known at compile time.  The A fragment
+// of block row a and the B fragment of block column a are the same shared-memory element (Gram matrix: both operands
+// are P), so the warp loads the A2 + 1 distinct fragments of a k-step once and uses them on both sides: 4-7 shared
+// loads per k-step at NB = 7 instead of 9-11 when the slot -> block mapping was resolved at run time.
+template <int NB, int A1, int A2, bool WIDE, int NG, int NSLOT, int LDP>
+__device__ __forceinline__ void gram_tile(double (&acc)[GM_NGW][NSLOT][2], double (&accm)[2][2], const double* __restrict__ Pd,
+                                          const double* __restrict__ wqb, const double* __restrict__ wmb, int g, int t, int ug) {
+    const int u0 = ug * GM_NGW;
+#pragma unroll
+    for (int kk = 0; kk < GM_TROWS / 4; ++kk) {
+        const int n = 4 * kk + t;                            // row of the tile this lane feeds as k index
+        double f[A2 + 1];
+#pragma unroll
+        for (int b = 0; b <= A2; ++b) f[b] = Pd[n * LDP + 8 * b + g];
+        double sa1[GM_NGW], sa2[GM_NGW];
+#pragma unroll
+        for (int u = 0; u < GM_NGW; ++u) {
+            const double wv = wqb[(u0 + u) * GM_TROWS + n];
+            sa1[u] = f[A1] * wv;
+            sa2[u] = f[A2] * wv;
+        }
+#pragma unroll
+        for (int b = 0; b <= A2; ++b) {
+#pragma unroll
+            for (int u = 0; u < GM_NGW; ++u) {
+                if (b <= A1) dmma884(acc[u][b][0], acc[u][b][1], sa1[u], f[b]);
+                if (A2 != A1) dmma884(acc[u][A1 + 1 + b][0], acc[u][A1 + 1 + b][1], sa2[u], f[b]);
+            }
+        }
+        // MuBar: (Q x rows)(rows x NG): B fragment column g carries mbar of latent g (< NG), k = n.  One product gives all
+        // NG latents of the CTA, so the two latent halves share the work: half 0 takes block row A1, half 1 block row A2
+        if (WIDE || ug == 0 || A2 != A1) {
+            const double bm = (g < NG) ? wmb[g * GM_TROWS + n] : 0.0;
+            if (WIDE || ug == 0) dmma884(accm[0][0], accm[0][1], f[A1], bm);
+            if ((WIDE || ug == 1) && A2 != A1) dmma884(accm[1][0], accm[1][1], f[A2], bm);
+        }
+    }
+}
+#define GM_ROLE(W)                                                                                                     \
+    case W:                                                                                                            \
+        if constexpr (gm_active(NB, W))                                                                                \
+            gram_tile<NB, gm_a1(NB, W), gm_a2(NB, W), WIDE, GM_NG, NSLOT, LDP>(acc, accm, Pd, wqb, wmb, g, t, ug);     \
+        break;
+
 template <int NB>
 __global__ void __launch_bounds__(GM_THREADS, NB > 8 ? 1 : 2)
 k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const int* __restrict__ seg,
@@ -782,17 +831,8 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
     const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int w = WIDE ? (tid >> 5) : ((tid >> 5) & 3), ug = WIDE ? 0 : (tid >> 7);
     const int u0 = ug * GM_NGW;                            // this warp's latents: u0 .. u0 + GM_NGW - 1
-    int a1, a2;
-    bool active;
-    if (NB & 1) {
-        constexpr int NPAIR = (NB - 1) / 2;
-        active = w <= NPAIR;
-        a1 = w < NPAIR ? w : NB - 1;
-        a2 = w < NPAIR ? NB - 2 - w : NB - 1;
-    } else {
-        a1 = w; a2 = NB - 1 - w;
-        active = a1 <= a2;
-    }
+    const int a1 = gm_a1(NB, w), a2 = gm_a2(NB, w);
+    const bool active = gm_active(NB, w);
     const int nslots = !active ? 0 : (a1 == a2 ? a1 + 1 : a1 + a2 + 2);
 
     for (int e = tid; e < (int)SH::smem_doubles; e += GM_THREADS) sm[e] = 0.0;
@@ -846,37 +886,11 @@ k_gram_mma(const double* __restrict__ Pa, const double* __restrict__ Pb, const i
         cp_async_commit();
         if (!active) continue;
         const double* Pd = Pt + (size_t)buf * GM_TROWS * LDP;
-#pragma unroll
-        for (int kk = 0; kk < GM_TROWS / 4; ++kk) {
-            const int n = 4 * kk + t;                        // row of the tile this lane feeds as k index
-            const double ra1 = Pd[n * LDP + 8 * a1 + g];     // A fragment (a = 8 a1 + g, k = n), unscaled
-            const double ra2 = Pd[n * LDP + 8 * a2 + g];
-            double sa1[GM_NGW], sa2[GM_NGW];
-#pragma unroll
-            for (int u = 0; u < GM_NGW; ++u) {
-                const double wv = wq[(buf * GM_NG + u0 + u) * GM_TROWS + n];
-                sa1[u] = ra1 * wv;
-                sa2[u] = ra2 * wv;
-            }
-#pragma unroll
-            for (int sl = 0; sl < NSLOT; ++sl) {
-                if (sl < nslots) {
-                    const bool first = sl <= a1;
-                    const int bb = first ? sl : sl - a1 - 1;
-                    const double bf = Pd[n * LDP + 8 * bb + g];   // B fragment (k = n, col = 8 bb + g)
-#pragma unroll
-                    for (int u = 0; u < GM_NGW; ++u)
-                        dmma884(acc[u][sl][0], acc[u][sl][1], first ? sa1[u] : sa2[u], bf);
-                }
-            }
-            // MuBar: (Q x rows)(rows x NG): B fragment column g carries mbar of latent g (< NG), k = n
-            // (one product gives all NG latents of the CTA, so the two latent halves share the work: half 0 takes block
-            // row a1, half 1 block row a2 -- 15/15 DMMAs per k-step instead of 16/14 at NB = 7)
-            if (WIDE || ug == 0 || a2 != a1) {
-                const double bm = (g < GM_NG) ? wm[(buf * GM_NG + g) * GM_TROWS + n] : 0.0;
-                if (WIDE || ug == 0) dmma884(accm[0][0], accm[0][1], ra1, bm);
-                if ((WIDE || ug == 1) && a2 != a1) dmma884(accm[1][0], accm[1][1], ra2, bm);
-            }
+        const double* wqb = wq + (size_t)buf * GM_NG * GM_TROWS;
+        const double* wmb = wm + (size_t)buf * GM_NG * GM_TROWS;
+        switch (w) {                                         // the role is warp-uniform; each case is fully static
+            GM_ROLE(0) GM_ROLE(1) GM_ROLE(2) GM_ROLE(3) GM_ROLE(4) GM_ROLE(5) GM_ROLE(6) GM_ROLE(7)
+            default: break;
         }
     }
     cp_async_wait<0>();

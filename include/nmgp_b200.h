@@ -269,6 +269,7 @@ int nmgp_kron_product(const double* t1, const double* t2, double* out, int h1, i
 /* Jacobi eigen-decomposition of a small symmetric matrix (upper triangle read), ascending eigenvalues
  *                                                                          torch.symeig(B) at kronecker_operation.py:45 */
 int nmgp_eigh_small(const double* A, double* w, double* V, double* work, int n, nmgp_stream_t stream);
+long long nmgp_eigh_small_work(int n);   /* doubles of scratch nmgp_eigh_small needs (rotation log of the Jacobi sweeps) */
 int nmgp_axpby(const double* x, const double* y, double* out, long long n, double a, double b, nmgp_stream_t stream);
 /* out = (a_scale * a_dev[0]) x + b y, the scalar a_dev read on the device */
 int nmgp_axpby_dev(const double* x, const double* y, double* out, long long n, const double* a_dev, double a_scale,
