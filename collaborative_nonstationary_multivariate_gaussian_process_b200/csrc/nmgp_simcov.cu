@@ -246,6 +246,44 @@ k_nonstat_cov_bwd(const double* __restrict__ X1, const double* __restrict__ sg1,
     }
 }
 
+// adjoint for a generic input dimension (dx > 1; no call site of the reference, which views x as (-1, 1) everywhere):
+// one CTA per (row, 256 columns); row sums through a block reduction, column sums by one atomic per entry
+__global__ void k_nonstat_cov_bwd_generic(const double* __restrict__ X1, const double* __restrict__ sg1,
+                                          const double* __restrict__ l1, const double* __restrict__ X2,
+                                          const double* __restrict__ sg2, const double* __restrict__ l2,
+                                          const double* __restrict__ Kbar, double* __restrict__ g_sg1,
+                                          double* __restrict__ g_l1, double* __restrict__ g_sg2, double* __restrict__ g_l2,
+                                          long long T1, long long T2, int dx) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = blockIdx.y; i < T1; i += gridDim.y) {
+        double w = 0.0, w1 = 0.0, w2 = 0.0;
+        const double a = l1 ? l1[i] : 1.0, si = sg1 ? sg1[i] : 1.0;
+        if (j < T2) {
+            double xn = 0.0, yn = 0.0, xy = 0.0;
+            for (int k = 0; k < dx; ++k) {
+                const double u = X1[i * dx + k], v = X2[j * dx + k];
+                xn = fma(u, u, xn);
+                yn = fma(v, v, yn);
+                xy = fma(u, v, xy);
+            }
+            const double dist = xn + yn - 2.0 * xy;
+            const double b = l2 ? l2[j] : 1.0, sj = sg2 ? sg2[j] : 1.0;
+            const double A = a * a + b * b;
+            const double kv = si * sj * sqrt(2.0 * (a * b) / A) * exp(-dist / A);
+            w = Kbar[i * T2 + j] * kv;
+            w1 = w / A;
+            w2 = w1 * dist / A;
+            if (g_sg2) atomicAdd(&g_sg2[j], w / sj);
+            if (g_l2) atomicAdd(&g_l2[j], w / (2.0 * b) - b * w1 + 2.0 * b * w2);
+        }
+        const double r0 = block_sum(w), r1 = block_sum(w1), r2 = block_sum(w2);
+        if (threadIdx.x == 0) {
+            if (g_sg1) atomicAdd(&g_sg1[i], r0 / si);
+            if (g_l1) atomicAdd(&g_l1[i], r0 / (2.0 * a) - a * r1 + 2.0 * a * r2);
+        }
+    }
+}
+
 template <int KIND>
 int launch_simcov(const double* X1, const double* sg1, const double* l1, const double* X2, const double* sg2,
                   const double* l2, double alpha, double beta, double jitter, double* K, long long T1, long long T2,
@@ -294,14 +332,21 @@ NMGP_API int nmgp_sim_rbf_cov(const double* X1, const double* X2, double alpha, 
     return nmgp_launch_status("nmgp_sim_rbf_cov");
 }
 
-// g_* (+=, any of them may be NULL): adjoint of nmgp_nonstationary_cov w.r.t. the per-point sigma / ell, dx == 1.
+// g_* (+=, any of them may be NULL): adjoint of nmgp_nonstationary_cov w.r.t. the per-point sigma / ell (tiled kernel for
+// dx == 1, the reference's case; a plain one for dx > 1).
 // For a self-covariance the caller adds the row-side and column-side results.
 NMGP_API int nmgp_nonstationary_cov_bwd(const double* X1, const double* sigma1, const double* ell1, const double* X2,
                                         const double* sigma2, const double* ell2, const double* Kbar, double* g_sigma1,
                                         double* g_ell1, double* g_sigma2, double* g_ell2, long long T1, long long T2,
                                         int dx, cudaStream_t st) {
-    NMGP_REQUIRE(T1 >= 0 && T2 >= 0 && dx == 1 && T1 < (1LL << 22) && T2 < (1LL << 31), "nmgp_nonstationary_cov_bwd");
+    NMGP_REQUIRE(T1 >= 0 && T2 >= 0 && dx >= 1 && T1 < (1LL << 22) && T2 < (1LL << 31), "nmgp_nonstationary_cov_bwd");
     if (T1 == 0 || T2 == 0) return 0;
+    if (dx != 1) {
+        dim3 gg((unsigned)((T2 + 255) / 256), (unsigned)min(T1, 65535LL));
+        k_nonstat_cov_bwd_generic<<<NMGP_L(gg), 256, 0, st>>>(X1, sigma1, ell1, X2, sigma2, ell2, Kbar, g_sigma1, g_ell1,
+                                                               g_sigma2, g_ell2, T1, T2, dx);
+        return nmgp_launch_status("nmgp_nonstationary_cov_bwd");
+    }
     dim3 grid((unsigned)((T2 + SC_T - 1) / SC_T), (unsigned)((T1 + SC_T - 1) / SC_T));
     k_nonstat_cov_bwd<<<NMGP_L(grid), SC_THREADS, 0, st>>>(X1, sigma1, ell1, X2, sigma2, ell2, Kbar, g_sigma1, g_ell1,
                                                             g_sigma2, g_ell2, T1, T2);

@@ -45,9 +45,6 @@ class _NonstatCov(torch.autograd.Function):
             want = (need[1], need[2], need[1], need[2])
         else:
             want = (need[1], need[2], need[4], need[5])
-        if X1d.shape[1] != 1:
-            raise NotImplementedError("the adjoint of Nonstationary_RBF_cov is built for 1-D inputs (every call site of the "
-                                      "reference views x as (-1, 1))")
         g1, gl1, g2, gl2 = ops.nonstationary_cov_bwd(X1d, s1, l1, X2d, s2, l2, _c(Kbar), want)
         if ctx.self_cov:
             gs = None if g1 is None else ops.axpby(g1, g2, 1.0, 1.0)

@@ -207,7 +207,7 @@ int nmgp_nonstationary_cov(const double* X1, const double* sigma1, const double*
                            long long T2, int dx, int self, nmgp_stream_t stream);
 int nmgp_sim_rbf_cov(const double* X1, const double* X2, double alpha, double beta, double jitter, double* K,
                      long long T1, long long T2, int dx, int self, nmgp_stream_t stream);
-/* adjoint of nmgp_nonstationary_cov w.r.t. the per-point sigma / ell (g_* +=, any may be NULL; dx == 1): what autograd
+/* adjoint of nmgp_nonstationary_cov w.r.t. the per-point sigma / ell (g_* +=, any may be NULL; any dx): what autograd
  * gives the reference when logpos.nlogpos_obj* are differentiated (logpos.py:216-296).  For a
  * self-covariance the caller adds the row-side (g_*1) and column-side (g_*2) results. */
 int nmgp_nonstationary_cov_bwd(const double* X1, const double* sigma1, const double* ell1, const double* X2,

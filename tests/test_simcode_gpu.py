@@ -226,3 +226,45 @@ def test_kron_logpdf0_matches_the_eigen_route_at_sweep_sizes(T, D):
     yv = y.clone().requires_grad_(True)
     got2 = float(distributions.multivariate_normal_logpdf0(yv, torch.zeros_like(y), Bf, K, s2))
     assert abs(got2 - ref) <= 1e-9 * abs(ref), (got2, ref)
+
+
+def test_nonstationary_cov_adjoint_multidimensional_inputs():
+    """dx > 1 (no reference call site uses it, but kernels.Nonstationary_RBF_cov accepts it): forward and the (sigma, ell)
+    adjoint against autograd of the specification."""
+    gen = torch.Generator().manual_seed(11)
+    T1, T2, dx = 70, 45, 3
+    x1 = torch.rand(T1, dx, generator=gen, dtype=torch.float64); x2 = torch.rand(T2, dx, generator=gen, dtype=torch.float64)
+    s1 = 0.5 + torch.rand(T1, generator=gen, dtype=torch.float64); l1 = torch.exp(torch.randn(T1, generator=gen, dtype=torch.float64) - 1.0)
+    s2 = 0.5 + torch.rand(T2, generator=gen, dtype=torch.float64); l2 = torch.exp(torch.randn(T2, generator=gen, dtype=torch.float64) - 1.0)
+    assert rel(kernels.Nonstationary_RBF_cov(d(x1), d(s1), d(l1), d(x2), d(s2), d(l2)),
+               specs.nonstationary_cov(x1, s1, l1, x2, s2, l2, 0.0)) < 1e-13
+    Kb = torch.randn(T1, T2, generator=gen, dtype=torch.float64)
+    got = ops.nonstationary_cov_bwd(d(x1), d(s1), d(l1), d(x2), d(s2), d(l2), d(Kb))
+    ref = specs.nonstationary_cov_bwd(x1, s1, l1, x2, s2, l2, Kb)
+    for a, b, n in zip(got, ref, ("sigma1", "ell1", "sigma2", "ell2")):
+        assert rel(a, b) < 1e-11, n
+    sv = d(s1).requires_grad_(True); lv = d(l1).requires_grad_(True)
+    Kb2 = torch.randn(T1, T1, generator=gen, dtype=torch.float64)
+    (kernels.Nonstationary_RBF_cov(d(x1), sv, lv) * d(Kb2)).sum().backward()
+    scpu = s1.clone().requires_grad_(True); lcpu = l1.clone().requires_grad_(True)
+    (specs.nonstationary_cov(x1, scpu, lcpu, x1, scpu, lcpu, 1e-6) * Kb2).sum().backward()
+    assert rel(sv.grad, scpu.grad) < 1e-11 and rel(lv.grad, lcpu.grad) < 1e-11
+
+
+@pytest.mark.parametrize("N,M,table", [(37, 3, "small"), (300, 5, "small"), (90, 90, "identity")])
+def test_dense_loglik_bwd(N, M, table):
+    """Adjoint kernel of the dense indexed log-likelihood (shared-memory privatised table / global atomics) vs its spec."""
+    gen = torch.Generator().manual_seed(N + M)
+    A = torch.randn(N, N, generator=gen, dtype=torch.float64); A = A @ A.t() / N
+    Bt = torch.randn(M, M, generator=gen, dtype=torch.float64); Bt = Bt @ Bt.t() / M
+    if table == "identity":
+        i1 = torch.arange(N, dtype=torch.int32)
+    else:
+        i1 = torch.randint(0, M, (N,), generator=gen, dtype=torch.int32)
+    Sinv = torch.randn(N, N, generator=gen, dtype=torch.float64); Sinv = Sinv + Sinv.t()
+    alpha = torch.randn(N, generator=gen, dtype=torch.float64)
+    g = torch.tensor([0.7], dtype=torch.float64)
+    got = ops.dense_loglik_bwd(d(Sinv), d(alpha), d(A), d(Bt), i1.cuda(), i1.cuda(), d(g))
+    ref = specs.dense_loglik_bwd(Sinv, alpha, A, Bt, i1, i1, g)
+    for a, b, n in zip(got, ref, ("Abar", "Btbar", "s2bar")):
+        assert rel(a, b) < 1e-12, n
