@@ -248,7 +248,8 @@ def test_cpu_tensors_are_rejected():
         ops.tril_syrk_fwd(torch.zeros(1, 4, 4, dtype=torch.float64))
 
 
-@pytest.mark.parametrize("Q,D,B", [(20, 3, 37), (50, 8, 300), (50, 70, 517), (64, 5, 131), (100, 4, 90), (8, 2, 129)]
+@pytest.mark.parametrize("Q,D,B", [(20, 3, 37), (50, 8, 300), (50, 70, 517), (64, 5, 131), (100, 4, 90), (8, 2, 129),
+                                   (21, 5, 150), (35, 66, 200)]
                          + LQ_CASES + [(100, 40, 517), (100, 2, 1)])
 @pytest.mark.parametrize("per_sample_y", [False, True])
 def test_latent_fused(Q, D, B, per_sample_y):
