@@ -22,12 +22,29 @@ def sources():
     return sorted(glob.glob(os.path.join(HERE, "*.cu")))
 
 
+INFO = os.path.join(HERE, "BUILD_INFO.json")
+
+
+def source_digest():
+    """SHA-256 over every source / header, this script and the flags: what the built library corresponds to."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in sources() + sorted(glob.glob(os.path.join(HERE, "*.cuh"))) + [os.path.abspath(__file__)]:
+        h.update(os.path.basename(d).encode())
+        h.update(open(d, "rb").read())
+    h.update(repr((ARCH, sorted(PTXAS_OPT.items()))).encode())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(OUT):
+    """Content-based (not mtime-based): the library is rebuilt whenever a source, header, flag or this script changed."""
+    if not os.path.exists(OUT) or not os.path.exists(INFO):
         return True
-    t = os.path.getmtime(OUT)
-    deps = sources() + glob.glob(os.path.join(HERE, "*.cuh")) + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        import json
+        return json.load(open(INFO)).get("digest") != source_digest()
+    except Exception:
+        return True
 
 
 def build(force=False, verbose=False):
@@ -57,6 +74,11 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc compilation failed")
     cmd = [nvcc, "-shared", *ARCH, "-o", OUT, *objs, "-lcudart"]
     subprocess.check_call(cmd)
+    import json
+    import time
+    ver = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    json.dump({"digest": source_digest(), "built_at": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), "nvcc": ver,
+               "arch": ARCH, "sources": [os.path.basename(x) for x in sources()]}, open(INFO, "w"), indent=1)
     return OUT
 
 

@@ -1,5 +1,5 @@
-"""Size-independent properties at BASELINE.json's full ECoG size (T=4096, D=64, Q=50, full batch B=262144), where the
-CPU oracle cannot run: (1) the row-sharded step sums to the unsharded step (linearity of every adjoint + rank-invariant
+"""Size-independent properties at BASELINE.json's full sizes -- ECoG (T=4096, D=64, Q=50, full batch B=262144), PM2.5
+(T=2048, D=16, Q=100) and HCP (T=1200, D=15, Q=100, one target vector per subject) -- where the CPU oracle cannot run: (1) the row-sharded step sums to the unsharded step (linearity of every adjoint + rank-invariant
 counter-based noise); (2) the hand-written gradient agrees with central finite differences of the loss along random
 directions of the parameters (same noise); (3) the loss is finite and the zero-gradient blocks (quirk q8) are exact
 zeros."""
@@ -12,14 +12,28 @@ pytestmark = pytest.mark.gpu
 from collaborative_nonstationary_multivariate_gaussian_process_b200 import dsvi_step, nmgp_dsvi, parallel  # noqa: E402
 
 DEV = "cuda:0"
-T, D, Q, S = 4096, 64, 50, 2          # S=2 keeps the test short; the per-sample work is what scales with S
+S = 2                                 # S=2 keeps the test short; the per-sample work is what scales with S
+# name -> (T, D, Q, driver hyper-parameters, per-subject targets)
+SHAPES = {
+    "ecog": (4096, 64, 50, {"length_scales_L0_log": 10., "length_scales_L1_log": 10., "length_scales_tildeell_log": 5.,
+                            "sigma2_err_log": -5.}, False),
+    "pm25": (2048, 16, 100, {"length_scales_L0_log": 10., "length_scales_L1_log": 10., "length_scales_tildeell_log": 10.}, False),
+    "hcp": (1200, 15, 100, {"length_scales_L0_log": 5., "length_scales_L1_log": 5., "length_scales_tildeell_log": 5.}, True),
+}
+T, D, Q, HYPER, SUBJECTS = SHAPES["ecog"]
+
+
+@pytest.fixture(params=sorted(SHAPES), autouse=True)
+def shape(request):
+    global T, D, Q, HYPER, SUBJECTS
+    T, D, Q, HYPER, SUBJECTS = SHAPES[request.param]
+    return request.param
 
 
 def make_model():
     m = nmgp_dsvi.NMGP(T * D, D, torch.linspace(0, T - 1, Q, dtype=torch.float64).view(-1, 1), mu_v=np.ones(Q), seed=22,
                        device=DEV, noise="device")
-    for k, v in {"length_scales_L0_log": 10., "length_scales_L1_log": 10., "length_scales_tildeell_log": 5.,
-                 "sigma2_err_log": -5.}.items():
+    for k, v in HYPER.items():
         getattr(m, k).data.fill_(v)
     return m
 
@@ -28,10 +42,12 @@ def rows(rank, world):
     r = parallel.shard_rows_per_output([T] * D, rank, world)
     gid = parallel.global_row_ids([T] * D, r)
     g = torch.Generator().manual_seed(0)
-    Y = torch.randn(D, T, generator=g, dtype=torch.float64).reshape(-1)
+    nsub = S if SUBJECTS else 1
+    Y = torch.randn(nsub, D * T, generator=g, dtype=torch.float64)
     x = torch.from_numpy((gid % T).astype(np.float64))
     I = torch.from_numpy((gid // T).astype(np.int32))
-    return x.to(DEV), Y[torch.from_numpy(gid)].to(DEV), I.to(DEV), torch.from_numpy(gid).to(DEV)
+    y = Y[:, torch.from_numpy(gid)]
+    return x.to(DEV), (y if SUBJECTS else y[0]).contiguous().to(DEV), I.to(DEV), torch.from_numpy(gid).to(DEV)
 
 
 def step(model, world=1, params=None, want_grads=True):
