@@ -298,3 +298,24 @@ def test_counter_noise_kernel_and_in_kernel_sampling():
     ops.coef_sample_bwd(g(lb), l_in, None, g(I), mb1, sb1, noise=noise)
     ops.coef_sample_bwd(g(lb), l_ex, z, g(I), mb2, sb2)
     assert torch.equal(mb1, mb2) and torch.equal(sb1, sb2)
+
+
+@pytest.mark.parametrize("Q", [8, 16, 24, 32, 40, 48, 56, 64, 72, 80, 88, 96, 104, 112, 120, 128, 13, 51, 99])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_weighted_gram_every_block_count(Q, mode):
+    """The Gram kernel's block-row roles are compile-time specialised per block count NB = ceil(Q/8) (odd / even dealing,
+    narrow / wide CTAs): every NB from 1 to 16, both modes, ragged segments."""
+    D, B, ns = 5, 203, 2 if mode == 0 else 1
+    gen = torch.Generator().manual_seed(Q * 2 + mode)
+    I = make_I(gen, B, D, empty=(1,))
+    nm = D if mode == 0 else D * (D + 1) // 2
+    Pa = torch.randn(ns, B, Q, generator=gen, dtype=torch.float64)
+    Pb = torch.randn(ns, B, Q, generator=gen, dtype=torch.float64) if mode == 1 else Pa
+    qb = torch.randn(ns, B, D, generator=gen, dtype=torch.float64)
+    mb = torch.randn(ns, B, D, generator=gen, dtype=torch.float64)
+    SB = torch.randn(nm, Q, Q, generator=gen, dtype=torch.float64); MB = torch.randn(nm, Q, generator=gen, dtype=torch.float64)
+    SBd, MBd = g(SB.clone()), g(MB.clone())
+    seg = ops.segment_offsets(g(I), D)
+    specs.weighted_gram(Pa, Pb, I, qb, mb, mode, SB, MB)
+    ops.weighted_gram(g(Pa), g(Pb), g(I), g(qb), g(mb), mode, SBd, MBd, seg=seg)
+    check(SBd, SB, 1e-12, "gram Sig"); check(MBd, MB, 1e-12, "gram Mu")
