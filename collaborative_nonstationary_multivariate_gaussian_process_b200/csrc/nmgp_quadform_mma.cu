@@ -147,7 +147,7 @@ k_latent_fused(const double* __restrict__ PG, const double* __restrict__ cG, con
     int* Is = reinterpret_cast<int*>(mbar + 6);        // [LFK_ROWS]
 
     const int s = blockIdx.y;
-    const long long row0 = (long long)blockIdx.x * LFK_ROWS;
+    const long long row0 = (long long)blockIdx.x * LFK_ROWS;   // (longest-tiles-first order measured: no gain)
     const int nrows = (int)min((long long)LFK_ROWS, B - row0);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
     const size_t rbase = (size_t)s * B + row0;          // first row of this tile in [ns*B]

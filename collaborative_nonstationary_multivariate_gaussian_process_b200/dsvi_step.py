@@ -55,10 +55,22 @@ def packed_pair_index(D: int, device) -> torch.Tensor:
     return _pair_cache[key]
 
 
-def default_sample_chunk(S: int, B: int, Q: int, D: int, budget_bytes: float = 6e9) -> int:
+def _sample_budget_bytes() -> float:
+    """Bytes the [ns,B,*] temporaries of one pass may take: NMGP_SAMPLE_BUDGET_GB, default 6 GB.  (Larger launches do not
+    pay: 4 samples per launch already fill 55 waves at the ECoG shape; 131.3 / 131.4 / 130.5 ms per step at 6 / 13 / 50 GB,
+    profiles/README.md.)"""
+    import os
+    try:
+        return float(os.environ.get("NMGP_SAMPLE_BUDGET_GB", "6")) * 1e9
+    except ValueError:
+        return 6e9
+
+
+def default_sample_chunk(S: int, B: int, Q: int, D: int, budget_bytes: Optional[float] = None) -> int:
     """Samples processed per pass so the [ns,B,*] temporaries stay within a budget."""
     per_sample = 8.0 * B * (5 * Q + 7 * D + 8)
-    return max(1, min(S, int(budget_bytes // max(per_sample, 1.0))))
+    budget = _sample_budget_bytes() if budget_bytes is None else budget_bytes
+    return max(1, min(S, int(budget // max(per_sample, 1.0))))
 
 
 def dsvi_step(p: Dict[str, torch.Tensor], Z: torch.Tensor, x: torch.Tensor, y: torch.Tensor,
