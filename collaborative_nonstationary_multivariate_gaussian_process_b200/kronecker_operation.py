@@ -68,6 +68,10 @@ def block_pipeline(sigma2, B, K, Rt=None, shard=None, per_block=None, want_alpha
     # several blocks in flight hide the panel latency of each other, so wider panels (fewer, larger trailing GEMMs) pay
     # earlier than for a single factorisation: measured 1047 -> 990 ms at T=8192, D=128 (profiles/README.md)
     panel = 512 if (T >= 6144 and nslot > 1) else 0
+    # a negative panel tells the library that other factorisations run concurrently (cp.async operand staging in its
+    # GEMMs: the TMA-fed kernel was not bit-reproducible with four blocks in flight at T = 12288, profiles/README.md)
+    if nslot > 1:
+        panel = -panel if panel else -1
     if augmented:
         lda = T + 8 - (T % 8) if T % 8 else T + 8                    # even, 64-byte aligned rows: 16-byte vector paths stay on
         bufs = [torch.empty(T + 1, lda, dtype=torch.float64, device=dev) for _ in range(nslot)]

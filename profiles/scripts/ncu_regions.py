@@ -14,8 +14,10 @@ import sys
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
     mark = sys.argv[3] if len(sys.argv) > 3 else "DMMA"
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern],
-                         capture_output=True, text=True, check=True).stdout
+    # KERNEL_REGEX may carry an invocation index ("k_lq:2" = second captured launch matching k_lq)
+    kern, _, inv = kern.partition(":")
+    sel = ["--kernel-id", "::regex:%s:%s" % (kern, inv)] if inv else ["--kernel-name", "regex:" + kern]
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr = rows[1]
     data = []
@@ -38,6 +40,7 @@ def main():
     for a, b in runs:
         bounds += [a, b + 1]
     bounds.append(len(data))
+    print(rows[0][1][:90] if rows and len(rows[0]) > 1 else "")
     print("kernel %s: %d instructions, %d samples, %d %s in %d runs" % (kern, len(data), tot, len(marks), mark, len(runs)))
     for n, (lo, hi) in enumerate(zip(bounds[:-1], bounds[1:])):
         if hi <= lo:
