@@ -632,6 +632,12 @@ def potrf_big(A, info=None, slot=0, panel=0):
     return A, hld
 
 
+def gemm_concurrent_mode(on):
+    """Tell the library that several of its GEMMs / factorisations are about to run concurrently on different streams (its
+    GEMMs then stage operands with cp.async, see nmgp_gemm_concurrent_mode)."""
+    lib().nmgp_gemm_concurrent_mode(c_int(1 if on else 0))
+
+
 def tri_inv_block(L, out, scale=1.0):
     """out = scale * inverse of the lower-triangular block L (n <= 128; 2-D views with unit column stride)."""
     n = L.shape[0]

@@ -163,6 +163,8 @@ k_gemm_nt(const double* __restrict__ A, const double* __restrict__ Bm, double* _
 // TMA-fed variant of the 128 x 64 tile kernel (nmgp_gemm_tma.cu): 0 launched, 1 not applicable (alignment / driver)
 int nmgp_gemm_nt_tma(const double* A, const double* Bm, double* C, long long M, long long N, long long K, long long lda,
                      long long ldb, long long ldc, double alpha, double beta, int lower_only, cudaStream_t st);
+static int g_gemm_cp_async_only = 0;
+NMGP_API void nmgp_gemm_concurrent_mode(int on) { g_gemm_cp_async_only = on ? 1 : 0; }
 static int g_gemm_narrow = -1;   // 1: 128x64 CTA tiles, two CTAs per SM (epilogue of one overlaps the MMAs of the other)
 static int gemm_nt_launch(const double* A, const double* Bm, double* C, long long M, long long N, long long K,
                           long long lda, long long ldb, long long ldc, double alpha, double beta, int mode,
@@ -177,12 +179,12 @@ static int gemm_nt_launch(const double* A, const double* Bm, double* C, long lon
     const bool narrow = !(mode & 2) && (g_gemm_narrow || N <= 64 || K <= 256);
     if (narrow) {
         // operand tiles by the TMA unit when the descriptors can be built (16-byte aligned rows), else cp.async staging.
-        // mode bit 2: cp.async staging requested -- set by factorisations that run concurrently with others (several
-        // eigen-blocks in flight): with four of them in flight at T = 12288 the TMA-fed kernel gave run-to-run different
-        // factors (relative 2e-7, profiles/microbench/kron_determinism.py) while the cp.async kernel and every
-        // single-factorisation run stayed bit-reproducible; until that is understood the concurrent pipeline does not
+        // g_gemm_cp_async_only (nmgp_gemm_concurrent_mode): set by the eigen-block pipeline while it keeps several
+        // factorisations in flight on different streams: with four of them in flight at T = 12288 the TMA-fed kernel gave
+        // run-to-run different factors (relative 2e-7, profiles/microbench/kron_determinism.py) while the cp.async kernel
+        // and every single-factorisation run stayed bit-reproducible; until that is understood concurrent work does not
         // use it.
-        if (!(mode & 4)) {
+        if (!g_gemm_cp_async_only) {
             const int rt = nmgp_gemm_nt_tma(A, Bm, C, M, N, K, lda, ldb, ldc, alpha, beta, lower_only, st);
             if (rt <= 0) return rt;
         }
@@ -520,14 +522,14 @@ __global__ void k_logdiag_sum(const double* __restrict__ A, long long T, long lo
 //   rows below it:  X = A Linv^T                                                                    (DMMA GEMM, in place)
 // linv: 128 x 128 scratch owned by the stream the panel runs on.
 static int factor_panel(double* Akk, long long lda, int nb, long long rest, double* linv, int* info, int pivot_base,
-                        cudaStream_t st, int gflags = 0) {
+                        cudaStream_t st) {
     for (int c0 = 0; c0 < nb; c0 += DI_N) {
         const int h = nb - c0 > DI_N ? DI_N : nb - c0;
         double* Dcc = Akk + (long long)c0 * lda + c0;
         const long long rows = (nb - c0) + rest;            // rows from the diagonal block down
         if (c0 > 0)
             if (int r = gemm_nt_launch(Akk + (long long)c0 * lda, Akk + (long long)c0 * lda, Dcc, rows, h, c0, lda, lda, lda,
-                                       -1.0, 1.0, gflags, st))
+                                       -1.0, 1.0, 0, st))
                 return r;
         k_potrf_diag_inv<<<NMGP_L(1), DI_THREADS, DI_SMEM, st>>>(Dcc, lda, h, linv, info, pivot_base + c0);
         const long long below = rows - h;
@@ -576,14 +578,13 @@ static PotrfCtx* potrf_ctx(int slot) {
     }
     return c;
 }
-static int potrf_lookahead(PotrfCtx* ctx, double* A, long long T, long long lda, int pb, int* info, cudaStream_t s0,
-                           int gflags) {
+static int potrf_lookahead(PotrfCtx* ctx, double* A, long long T, long long lda, int pb, int* info, cudaStream_t s0) {
     cudaStream_t s1 = ctx->helper;
     cudaEvent_t g_ev_upd = ctx->ev_upd, g_ev_pan = ctx->ev_pan;
     double* g_linv = ctx->linv;
     {   // panel 0 on the main stream
         const int nb = (int)min((long long)pb, T);
-        if (int r = factor_panel(A, lda, nb, T - nb, g_linv, info, 0, s0, gflags)) return r;
+        if (int r = factor_panel(A, lda, nb, T - nb, g_linv, info, 0, s0)) return r;
     }
     for (long long k = 0; k < T; k += pb) {
         const int nb = (int)min((long long)pb, T - k);
@@ -593,18 +594,18 @@ static int potrf_lookahead(PotrfCtx* ctx, double* A, long long T, long long lda,
         double* A22 = A + (k + nb) * lda + (k + nb);     // rest x rest (trailing matrix)
         const int nb2 = (int)min((long long)pb, rest);   // width of the next panel
         // 1. bring the next panel's columns up to date (main stream)
-        if (int r = gemm_nt_launch(A21, A21, A22, rest, nb2, nb, lda, lda, lda, -1.0, 1.0, gflags, s0)) return r;
+        if (int r = gemm_nt_launch(A21, A21, A22, rest, nb2, nb, lda, lda, lda, -1.0, 1.0, 0, s0)) return r;
         cudaEventRecord(g_ev_upd, s0);
         // 2. factorise the next panel on the helper stream
         cudaStreamWaitEvent(s1, g_ev_upd, 0);
-        if (int r = factor_panel(A22, lda, nb2, rest - nb2, g_linv + DI_N * DI_N, info, (int)(k + nb), s1, gflags)) return r;
+        if (int r = factor_panel(A22, lda, nb2, rest - nb2, g_linv + DI_N * DI_N, info, (int)(k + nb), s1)) return r;
         cudaEventRecord(g_ev_pan, s1);
         // 3. rest of the trailing update (columns beyond the next panel, lower tiles only) on the main stream
         const long long rest2 = rest - nb2;
         if (rest2 > 0) {
             double* B21 = A21 + (long long)nb2 * lda;
             if (int r = gemm_nt_launch(B21, B21, A22 + (long long)nb2 * lda + nb2, rest2, rest2, nb, lda, lda, lda, -1.0, 1.0,
-                                       1 | gflags, s0))
+                                       1, s0))
                 return r;
         }
         // 4. the next iteration (and anything after us on the main stream) needs the factorised panel
@@ -618,10 +619,6 @@ static int potrf_lookahead(PotrfCtx* ctx, double* A, long long T, long long lda,
 // Kronecker path.
 NMGP_API int nmgp_potrf_big_slot(double* A, long long T, long long lda, double* hld, int* info, int slot, int panel,
                                  cudaStream_t st) {
-    // panel < 0: "other factorisations are in flight" (the eigen-block pipeline): |panel| is the requested width (-1: by
-    // size) and the GEMMs stage their operands with cp.async (see gemm_nt_launch)
-    const int gflags = panel < 0 ? 4 : 0;
-    if (panel < 0) panel = panel == -1 ? 0 : -panel;
     NMGP_REQUIRE(T > 0 && lda >= T && T < 2147483647LL, "nmgp_potrf_big");
     if (int r = nmgp_opt_in_smem(k_potrf_diag_inv, DI_SMEM, "nmgp_potrf_big")) return r;
     PotrfCtx* ctx = potrf_ctx(slot);
@@ -630,9 +627,9 @@ NMGP_API int nmgp_potrf_big_slot(double* A, long long T, long long lda, double* 
         int pb = T >= 12288 ? 512 : (T >= 6144 ? 256 : PB);   // measured best on B200 (profiles/README.md)
         if (panel >= 128) pb = (panel / 128) * 128;            // caller's choice (concurrent blocks prefer wider panels)
         if (const char* e = getenv("NMGP_POTRF_PB")) pb = atoi(e) >= 128 ? (atoi(e) / 128) * 128 : pb;   // tuning knob
-        if (int r = potrf_lookahead(ctx, A, T, lda, pb, info, st, gflags)) return r;
+        if (int r = potrf_lookahead(ctx, A, T, lda, pb, info, st)) return r;
     } else {
-        if (int r = factor_panel(A, lda, (int)T, 0, ctx->linv, info, 0, st, gflags)) return r;
+        if (int r = factor_panel(A, lda, (int)T, 0, ctx->linv, info, 0, st)) return r;
     }
     dim3 gz((unsigned)((T + 255) / 256), (unsigned)min(T, 65535LL));
     if (T <= 65535) k_zero_upper<<<NMGP_L(gz), 256, 0, st>>>(A, T, lda);

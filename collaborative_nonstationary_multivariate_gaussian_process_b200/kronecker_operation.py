@@ -68,10 +68,6 @@ def block_pipeline(sigma2, B, K, Rt=None, shard=None, per_block=None, want_alpha
     # several blocks in flight hide the panel latency of each other, so wider panels (fewer, larger trailing GEMMs) pay
     # earlier than for a single factorisation: measured 1047 -> 990 ms at T=8192, D=128 (profiles/README.md)
     panel = 512 if (T >= 6144 and nslot > 1) else 0
-    # a negative panel tells the library that other factorisations run concurrently (cp.async operand staging in its
-    # GEMMs: the TMA-fed kernel was not bit-reproducible with four blocks in flight at T = 12288, profiles/README.md)
-    if nslot > 1:
-        panel = -panel if panel else -1
     if augmented:
         lda = T + 8 - (T % 8) if T % 8 else T + 8                    # even, 64-byte aligned rows: 16-byte vector paths stay on
         bufs = [torch.empty(T + 1, lda, dtype=torch.float64, device=dev) for _ in range(nslot)]
@@ -83,6 +79,25 @@ def block_pipeline(sigma2, B, K, Rt=None, shard=None, per_block=None, want_alpha
     for st in streams:
         if st is not None:
             st.wait_stream(main)
+    # several factorisations in flight: the library stages its GEMM operands with cp.async meanwhile (the TMA-fed kernel was
+    # not bit-reproducible with four blocks in flight at T = 12288, profiles/README.md); also covers per_block callbacks
+    concurrent = on_gpu and nslot > 1
+    if concurrent:
+        ops.gemm_concurrent_mode(True)
+    try:
+        _run_blocks(blocks, nslot, streams, on_gpu, augmented, bufs, Kc, Rt, lam, s2, rn2 if augmented else None, info, hld,
+                    quad, alpha, panel, per_block, T)
+    finally:
+        if concurrent:
+            ops.gemm_concurrent_mode(False)
+    for st in streams:
+        if st is not None:
+            main.wait_stream(st)
+    return dict(lam=lam, V=V, hld=hld, quad=quad, alpha=alpha, info=info, blocks=blocks, bufs=bufs)
+
+
+def _run_blocks(blocks, nslot, streams, on_gpu, augmented, bufs, Kc, Rt, lam, s2, rn2, info, hld, quad, alpha, panel,
+                per_block, T):
     for idx, m in enumerate(blocks):
         slot = idx % nslot
         ctx = torch.cuda.stream(streams[slot]) if on_gpu else _Null()
@@ -103,10 +118,6 @@ def block_pipeline(sigma2, B, K, Rt=None, shard=None, per_block=None, want_alpha
                 quad[m:m + 1] = ops.dot(rm, xm)
             if per_block is not None:
                 per_block(m, L, slot)
-    for st in streams:
-        if st is not None:
-            main.wait_stream(st)
-    return dict(lam=lam, V=V, hld=hld, quad=quad, alpha=alpha, info=info, blocks=blocks, bufs=bufs)
 
 
 class _Null:

@@ -243,9 +243,10 @@ int nmgp_potrf_big(double* A, long long T, long long lda, double* hld, int* info
 /* same with an explicit scratch slot (0..3): independent factorisations running concurrently on different streams
  * (the eigen-blocks of a Kronecker log-density) must use different slots; scratch is kept per (device, slot) */
 int nmgp_potrf_big_slot(double* A, long long T, long long lda, double* hld, int* info, int slot,
-                        int panel /* panel width, multiple of 128; 0 = chosen from T; negative: other factorisations run concurrently
-                                      (|panel| = width, -1 = chosen from T): GEMM operands staged by cp.async */,
-                        nmgp_stream_t stream);
+                        int panel /* panel width, multiple of 128; 0 = chosen from T */, nmgp_stream_t stream);
+/* on != 0 while the caller keeps several factorisations / GEMMs in flight on different streams: operand tiles are then
+ * staged with cp.async instead of TMA tensor copies (reproducibility finding in profiles/README.md) */
+void nmgp_gemm_concurrent_mode(int on);
 /* out = scale * inv(L) for a lower-triangular nb x nb block (nb <= 128): building block of the blocked triangular
  * inverse behind the Cholesky-based log-density adjoint (autograd of distributions.py:26-52) */
 int nmgp_tri_inv_block(const double* L, long long lda, int nb, double* out, long long ldo, double scale,

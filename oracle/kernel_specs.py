@@ -486,6 +486,11 @@ def gemm_nt(A, Bm, alpha=1.0, beta=0.0, C=None):
     return out
 
 
+def gemm_concurrent_mode(on):
+    """No-op on the CPU specification."""
+    return None
+
+
 def potrf_big(A, info=None, slot=0, panel=0):
     L, bad = torch.linalg.cholesky_ex(A)
     if int(bad) != 0:
