@@ -164,7 +164,10 @@ k_gemm_nt(const double* __restrict__ A, const double* __restrict__ Bm, double* _
 int nmgp_gemm_nt_tma(const double* A, const double* Bm, double* C, long long M, long long N, long long K, long long lda,
                      long long ldb, long long ldc, double alpha, double beta, int lower_only, cudaStream_t st);
 static int g_gemm_cp_async_only = 0;
-NMGP_API void nmgp_gemm_concurrent_mode(int on) { g_gemm_cp_async_only = on ? 1 : 0; }
+NMGP_API void nmgp_gemm_concurrent_mode(int on) {
+    static const bool keep_tma = [] { const char* e = getenv("NMGP_TMA_CONCURRENT"); return e && e[0] == '1'; }();   // probe
+    g_gemm_cp_async_only = (on && !keep_tma) ? 1 : 0;
+}
 static int g_gemm_narrow = -1;   // 1: 128x64 CTA tiles, two CTAs per SM (epilogue of one overlaps the MMAs of the other)
 static int gemm_nt_launch(const double* A, const double* Bm, double* C, long long M, long long N, long long K,
                           long long lda, long long ldb, long long ldc, double alpha, double beta, int mode,

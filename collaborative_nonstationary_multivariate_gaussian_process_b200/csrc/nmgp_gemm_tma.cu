@@ -80,7 +80,7 @@ k_gemm_nt_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     unsigned long long* full = reinterpret_cast<unsigned long long*>(stage0 + TG_STAGES * TG_STAGE_DOUBLES);
     unsigned long long* empty = full + TG_STAGES;
     const long long m0 = (long long)blockIdx.y * TG_M, n0 = (long long)blockIdx.x * TG_N;
-    if (lower_only && n0 > m0 + TG_M - 1) return;
+    if ((lower_only & 1) && n0 > m0 + TG_M - 1) return;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
     if (tid == 0) {
         for (int s = 0; s < TG_STAGES; ++s) {
@@ -105,8 +105,12 @@ k_gemm_nt_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         tma_load_2d(Bs + TG_N * TG_KBOX, &mapB, k0 + TG_KBOX, (int)n0, &full[s]);
     };
     if (tid == 0) {
-        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapA) : "memory");
-        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapB) : "memory");
+        if (lower_only >= 0) {      // (bit 1 of the flags switches the descriptor prefetch off: experiment knob)
+            if (!(lower_only & 2)) {
+                asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapA) : "memory");
+                asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapB) : "memory");
+            }
+        }
         issue(0);
     }
 
@@ -205,8 +209,11 @@ bool encode_map(CUtensorMap* map, const double* base, long long rows, long long 
     cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
     cuuint32_t box[2] = {TG_KBOX, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
+    static const int promo = [] { const char* e = getenv("NMGP_TMA_L2PROMO"); return e ? atoi(e) : 256; }();
     return g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (promo == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                                                 : CU_TENSOR_MAP_L2_PROMOTION_L2_256B),
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -240,6 +247,8 @@ int nmgp_gemm_nt_tma(const double* A, const double* Bm, double* C, long long M, 
     if (!encode_map(&mapA, A, M, K, lda, TG_M) || !encode_map(&mapB, Bm, N, K, ldb, TG_N)) return 1;
     if (int r = nmgp_opt_in_smem(k_gemm_nt_tma, TG_SMEM, "nmgp_gemm_nt(tma)")) return r;
     dim3 grid((unsigned)((N + TG_N - 1) / TG_N), (unsigned)((M + TG_M - 1) / TG_M));
-    k_gemm_nt_tma<<<NMGP_L(grid), TG_THREADS, TG_SMEM, st>>>(mapA, mapB, C, M, N, K, ldc, alpha, beta, lower_only);
+    static const int noprefetch = [] { const char* e = getenv("NMGP_TMA_NOPREFETCH"); return e && e[0] == '1' ? 2 : 0; }();
+    k_gemm_nt_tma<<<NMGP_L(grid), TG_THREADS, TG_SMEM, st>>>(mapA, mapB, C, M, N, K, ldc, alpha, beta,
+                                                              (lower_only ? 1 : 0) | noprefetch);
     return nmgp_launch_status("nmgp_gemm_nt(tma)");
 }
