@@ -183,3 +183,58 @@ def test_two_rank_kronecker_logpdf_matches_reference(tmp_path):
     res = torch.load(out, weights_only=False)
     g = gu.load("sim_code")
     assert abs(res["logpdf0"] - float(g["logpdf0"])) <= 1e-9 * abs(float(g["logpdf0"]))
+
+
+def _subject_worker(rank, world, port, out):
+    """HCP-style step: two subjects observed on the same rows, one Monte-Carlo draw each; rank r keeps all rows and
+    subject r only (shard="samples").  Rank 0 also evaluates the unsharded two-subject step for comparison."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import kernel_specs as specs
+    from collaborative_nonstationary_multivariate_gaussian_process_b200 import _ops, nmgp_dsvi, parallel
+    for n, f in inspect.getmembers(specs, inspect.isfunction):
+        if not n.startswith("_"):
+            setattr(_ops, n, f)
+    g = gu.load("dsvi_ragged")
+    D, B = int(g["D"]), g["x"].shape[0]
+    S = 2
+    gen = torch.Generator().manual_seed(9)
+    x = torch.from_numpy(g["x"]); I = torch.from_numpy(g["I"].astype(np.int32))
+    Y = torch.stack([torch.from_numpy(g["y"]), torch.from_numpy(g["y"]) + 0.3 * torch.randn(B, generator=gen, dtype=torch.float64)])
+    Q = g["Z"].shape[0]
+    zv = torch.randn(S, Q, generator=gen, dtype=torch.float64)
+    zell = torch.randn(S, B, generator=gen, dtype=torch.float64)
+    zL = torch.randn(S, B, D, generator=gen, dtype=torch.float64)
+
+    def fresh():
+        m = nmgp_dsvi.NMGP(int(g["N"]), D, torch.from_numpy(g["Z"]).view(-1, 1), device="cpu")
+        m.load_state_dict(gu.case_params(g))
+        return m
+    model = fresh()
+    parallel.configure_model_for_sharding(model, B, rank, world, shard="samples", n_samples_total=S)
+    lo, hi = parallel.shard_samples(S, rank, world)
+    loss = model.forward_rows(x, Y[lo:hi], I, explicit_noise=(zv[lo:hi], zell[lo:hi], zL[lo:hi]))
+    loss.backward()
+    tot = parallel.allreduce_loss_and_grads(loss, list(model.parameters()), pd_info=model._last_pd_info)
+    if rank == 0:
+        ref = fresh()
+        lref = ref.forward_rows(x, Y, I, explicit_noise=(zv, zell, zL))
+        lref.backward()
+        res = {"loss": float(tot), "loss_ref": float(lref)}
+        for (k, prm), (_, pr) in zip(model.named_parameters(), ref.named_parameters()):
+            res[k] = prm.grad.detach().numpy().copy()
+            res["ref_" + k] = pr.grad.detach().numpy().copy()
+        torch.save(res, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_subject_sharding_matches_unsharded(tmp_path):
+    out = str(tmp_path / "res_subjects.pt")
+    port = 35500 + (os.getpid() % 2000)
+    mp.spawn(_subject_worker, args=(2, port, out), nprocs=2, join=True)
+    res = torch.load(out, weights_only=False)
+    assert abs(res["loss"] - res["loss_ref"]) <= 1e-12 * abs(res["loss_ref"])
+    for k in ("mu_W", "sqrt_W", "mu_v", "sqrt_v", "mu_U", "sqrt_U", "sigma2_err_log", "sigma2_L0_log"):
+        a, b = res[k].reshape(-1), res["ref_" + k].reshape(-1)
+        assert np.linalg.norm(a - b) <= 1e-11 * max(np.linalg.norm(b), 1e-300), k
