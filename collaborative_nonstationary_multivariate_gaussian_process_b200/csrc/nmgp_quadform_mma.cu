@@ -466,9 +466,19 @@ static int launch_latent_fused(const double* PG, const double* cG, const double*
     using SH = LFShape<NB, KS>;
     size_t smem = SH::smem_bytes;
     if (int r = nmgp_opt_in_smem(k_latent_fused<NB, KS>, smem, "nmgp_latent_fused")) return r;
-    // padded records of (Sigma_W[j], mu_W[j]) in a library-owned scratch buffer (grown on demand, one per process)
-    static double* rec = nullptr;
-    static size_t rec_cap = 0;
+    // padded records of (Sigma_W[j], mu_W[j]) in a library-owned scratch buffer (grown on demand, one per device and
+    // kernel shape; a process drives one GPU in the intended one-rank-per-GPU use, but a second device must not be handed
+    // the first one's pointer)
+    constexpr int MAXDEV = 16;
+    static double* recs[MAXDEV] = {nullptr};
+    static size_t rec_caps[MAXDEV] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) {
+        nmgp_set_error("nmgp_latent_fused: unsupported device ordinal %d", dev);
+        return -4;
+    }
+    double*& rec = recs[dev];
+    size_t& rec_cap = rec_caps[dev];
     const int DP = (D + 7) & ~7;
     const size_t need = (size_t)D * SH::REC + (size_t)DP * SH::LDM;
     if (need > rec_cap) {
